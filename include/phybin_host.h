@@ -1,0 +1,88 @@
+/* phybin_host.h -- C interface of libphybin_host.so: the HOST side of the path, i.e. what stays
+ * in the Haskell program in a real integration (Newick parsing, the global label table, the
+ * HashRF leaf-count filter, bipartition extraction `allBips`, printDistMat) re-stated in C++
+ * because this image has no GHC.  It produces exactly the arrays include/phybin_rf.h consumes.
+ * It contains no CUDA and never touches the oracle.
+ *
+ * Reference interfaces mirrored (all under /root/reference/src/Bio/Phylogeny/PhyBin/):
+ *   parseNewicks      Parser.hs:57-75      (label order: last file first, children right-to-left)
+ *   numLeaves         CoreTypes.hs:289-291
+ *   allBips/normBip   RFDistance.hs:207-248
+ *   treeLabels        RFDistance.hs:200-203
+ *   printDistMat      RFDistance.hs:352-361
+ *   HashRF filter     ../PhyBin.hs:187-194
+ */
+#ifndef PHYBIN_HOST_H
+#define PHYBIN_HOST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PHB_API __attribute__((visibility("default")))
+#else
+#define PHB_API
+#endif
+
+typedef struct phb_forest phb_forest;
+
+/* Synthetic tree families (BASELINE.md section 3 / SURVEY.md 8d). */
+typedef enum phb_family {
+  PHB_RANDOM_TOPOLOGY = 0, /* uniform unrooted binary tree by random-edge insertion */
+  PHB_NNI_FAMILY = 1       /* one random base tree + r ~ U{0..nni_max} random NNI moves per tree */
+} phb_family;
+
+/* Parses `nfiles` Newick texts (command-line order); name_prefix >= 0 applies `take n` to leaf
+ * names (-p, Main.hs:290).  Never returns NULL; check phb_error(). */
+PHB_API phb_forest* phb_parse(int nfiles, const char* const* texts, int name_prefix);
+/* T trees on taxa t0..t{n-1}; splitmix64 stream seeded with `seed`; each taxon is dropped from a
+ * tree independently with probability p_missing (at least 4 are kept).  Labels are assigned as
+ * parseNewicks would assign them to the emitted Newick text. */
+PHB_API phb_forest* phb_synth(uint32_t T, uint32_t n, uint64_t seed, int family, uint32_t nni_max,
+                              double p_missing);
+PHB_API void phb_free(phb_forest* f);
+PHB_API const char* phb_error(const phb_forest* f); /* NULL when fine */
+
+PHB_API uint32_t phb_num_trees(const phb_forest* f);
+PHB_API uint32_t phb_num_labels(const phb_forest* f);
+PHB_API const char* phb_label_name(const phb_forest* f, uint32_t label);
+PHB_API uint32_t phb_tree_num_leaves(const phb_forest* f, uint32_t t);
+/* Drops trees whose numLeaves != expected (PhyBin.hs:187-194); returns the number kept. */
+PHB_API uint32_t phb_filter_num_leaves(phb_forest* f, uint32_t expected);
+/* Keeps only trees [t0, t1). */
+PHB_API uint32_t phb_slice(phb_forest* f, uint32_t t0, uint32_t t1);
+/* 1 when some tree repeats a leaf label. */
+PHB_API int phb_has_duplicate_leaves(const phb_forest* f);
+
+/* Newick text of trees [t0, t1), one per line; free with phb_free_buf. */
+PHB_API char* phb_to_newick(const phb_forest* f, uint32_t t0, uint32_t t1);
+
+/* Words per bit set needed for this forest: ceil(max(#labels, max numLeaves) / 64). */
+PHB_API uint32_t phb_words(const phb_forest* f);
+
+/* allBips of every tree, canonicalised exactly as normBip does and bit-packed (hashRF's input).
+ * *bips: nnz*W words, *tree_off: T+1 offsets; both malloc'd, free with phb_free_buf.
+ * threads <= 0: use all hardware threads. */
+PHB_API int phb_allbips(const phb_forest* f, uint32_t W, int threads, uint64_t** bips,
+                        uint64_t** tree_off, uint64_t* nnz);
+
+/* Tolerant-mode inputs: un-normalised leaf sets of the non-root interior nodes + per-tree taxon
+ * sets.  *clades: nnz*W, *tree_off: T+1, *leafsets: T*W. */
+PHB_API int phb_raw_clades(const phb_forest* f, uint32_t W, int threads, uint64_t** clades,
+                           uint64_t** tree_off, uint64_t** leafsets, uint64_t* nnz);
+
+/* printDistMat text of a packed uint16 upper triangle; free with phb_free_buf. */
+PHB_API char* phb_print_dist_mat(const uint16_t* upper, uint32_t T);
+/* Streams the same text to a file; returns 0 on success. */
+PHB_API int phb_write_dist_mat(const char* path, const uint16_t* upper, uint32_t T);
+
+PHB_API void phb_free_buf(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHYBIN_HOST_H */

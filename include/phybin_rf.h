@@ -1,0 +1,177 @@
+/* phybin_rf.h -- C ABI of libphybin_rf.so, the B200 (sm_100a) implementation of PhyBin's
+ * all-to-all Robinson-Foulds distance-matrix path.
+ *
+ * The reference has no FFI: its boundary for this path is two pure Haskell functions and one type
+ * (all in /root/reference/src/Bio/Phylogeny/PhyBin/RFDistance.hs):
+ *
+ *     hashRF          :: Int -> [NewickTree a] -> DistanceMatrix              -- RFDistance.hs:284
+ *     naiveDistMatrix :: [NewickTree DefDecor]
+ *                     -> (DistanceMatrix, V.Vector (S.Set DenseLabelSet))     -- RFDistance.hs:168
+ *     type DistanceMatrix = V.Vector (U.Vector Int)                           -- RFDistance.hs:156
+ *
+ * called from exactly one production site, doCluster (PhyBin.hs:343-364).  The entry points below
+ * are what a `foreign import ccall` inside drop-in replacements for those two functions binds
+ * (INTEGRATION.md shows the Haskell shim).  The host keeps Newick parsing, --prune/--minbootstrap
+ * preprocessing and bipartition extraction (allBips, RFDistance.hs:247); the device receives
+ * bit-packed taxon sets and returns the matrix.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns PRF_OK (0) or a negative prf_status
+ *     and never throws, aborts or prints; prf_last_error() has the message.
+ *   - the caller owns every pointer it passes; the library owns all device memory of a context.
+ *   - one calling thread per context; no global state; work is issued on the context's stream.
+ *   - bit sets: taxon label l (the reference's `Label = Int`, CoreTypes.hs:139) is bit (l % 64) of
+ *     64-bit word (l / 64); a set is W consecutive little-endian uint64 words.
+ *   - matrix layout: PACKED ROW-MAJOR UPPER TRIANGLE of uint16.  For trees a < b,
+ *         d(a,b) lives at  p(a,b) = a*T - a*(a+1)/2 + (b - a - 1)        (64-bit arithmetic)
+ *     which is the reference's row b, column a (DistanceMatrix row i holds d(i,0..i-1),
+ *     RFDistance.hs:306-311).  The diagonal is implicit 0.  There are P = T*(T-1)/2 entries.
+ *   - the optional edit-distance mask has bit (p % 32) of uint32 word (p / 32) set iff
+ *     d(p) <= editdist (the --editdist value, Main.hs:100-102); ceil(P/32) words.
+ *   - there is no CPU fallback: without a CUDA device prf_create fails.
+ */
+#ifndef PHYBIN_RF_H
+#define PHYBIN_RF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PRF_API __attribute__((visibility("default")))
+#else
+#define PRF_API
+#endif
+
+typedef struct prf_ctx prf_ctx;
+
+typedef enum prf_status {
+  PRF_OK = 0,
+  PRF_E_INVALID = -1,     /* bad argument (null pointer, T or W out of range, p range unordered) */
+  PRF_E_CUDA = -2,        /* a CUDA runtime call or kernel failed; see prf_last_error */
+  PRF_E_NOMEM = -3,       /* host or device allocation failed */
+  PRF_E_RANGE = -4,       /* a distance does not fit uint16 (a tree with > 32767 bipartitions) */
+  PRF_E_STATE = -5,       /* call order: compute/fetch before a successful load */
+  PRF_E_UNSUPPORTED = -6  /* shape outside what the kernels are built for (see prf_limits) */
+} prf_status;
+
+typedef enum prf_variant {
+  PRF_VARIANT_AUTO = 0,   /* pick by measured split density (stats.hits vs stats.n_shared) */
+  PRF_VARIANT_SPARSE = 1, /* inverted-list join in shared memory, HBM-write bound */
+  PRF_VARIANT_DENSE = 2   /* int8 tcgen05 Gram product S = A*A^T, tensor-pipe bound */
+} prf_variant;
+
+typedef enum prf_memkind {
+  PRF_MEM_HOST = 0,   /* pointer is host memory (pageable or pinned) */
+  PRF_MEM_DEVICE = 1  /* pointer is device memory on the context's device */
+} prf_memkind;
+
+/* Filled by the load / compute calls; all times are CUDA-event milliseconds on the context's
+ * stream (0 when the phase did not run). */
+typedef struct prf_stats {
+  uint64_t n_trees;      /* T */
+  uint64_t n_words;      /* W */
+  uint64_t nnz;          /* bipartition entries handed in (sum of per-tree counts) */
+  uint64_t n_unique;     /* U: distinct bipartitions over all trees (size of hashRF's Map, :289) */
+  uint64_t n_shared;     /* distinct bipartitions present in >= 2 trees */
+  uint64_t n_shared_nnz; /* entries that belong to those */
+  uint64_t n_hits;       /* sum over bipartitions of m*(m-1)/2 = sum over pairs of |B_i n B_j| */
+  uint64_t n_pairs;      /* T*(T-1)/2 */
+  uint32_t max_bips;     /* max per-tree |B_i| */
+  uint32_t min_bips;
+  int32_t variant_used;  /* prf_variant actually run by the last compute */
+  int32_t gpu_launches;  /* kernels launched by the last call */
+  float ms_h2d, ms_dedup, ms_incidence, ms_matrix, ms_d2h, ms_total;
+} prf_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+
+/* Creates a context on CUDA device `device` (>= 0).  Returns NULL when there is no such device or
+ * CUDA is unavailable (there is no CPU fallback). */
+PRF_API prf_ctx* prf_create(int device);
+PRF_API void prf_destroy(prf_ctx* ctx);
+/* Message of the last failure on this context ("" if none).  ctx may be NULL: returns the message
+ * of the last failed prf_create on this thread. */
+PRF_API const char* prf_last_error(const prf_ctx* ctx);
+PRF_API const char* prf_version(void);
+/* The context's CUDA stream (a cudaStream_t) so callers holding device buffers can order work. */
+PRF_API void* prf_stream(prf_ctx* ctx);
+
+/* ---- hashRF: one-shot (replaces the body of hashRF, RFDistance.hs:284-341) ------------------- */
+
+/* bips      nnz*W words: for tree t the canonical bipartitions allBips(t) (RFDistance.hs:247) are
+ *           entries tree_off[t] .. tree_off[t+1]-1.  A tree's entries are treated as a SET
+ *           (duplicates count once), like S.Set DenseLabelSet.  Host memory.
+ * tree_off  T+1 ascending offsets, tree_off[0] = 0, tree_off[T] = nnz.  Host memory.
+ * editdist  < 0: no mask.  >= 0: also produce the d <= editdist bit mask.
+ * out_upper host buffer of T*(T-1)/2 uint16, or NULL to leave the result on the device
+ *           (read it later with prf_fetch / prf_fetch_rows).
+ * out_mask  host buffer of ceil(P/32) uint32 or NULL.
+ * stats     optional. */
+PRF_API int prf_hashrf(prf_ctx* ctx, const uint64_t* bips, const uint64_t* tree_off, uint32_t T,
+                       uint32_t W, int32_t editdist, uint16_t* out_upper, uint32_t* out_mask,
+                       prf_stats* stats);
+
+/* ---- hashRF: staged (large T, device-resident inputs, multi-GPU sharding) -------------------- */
+
+/* Stage 1 -- the `build` phase of hashRF (RFDistance.hs:289-297): global bipartition dedup and
+ * the trees x bipartitions incidence, kept on the device.  `kind` says where bips/tree_off live. */
+PRF_API int prf_hashrf_load(prf_ctx* ctx, const uint64_t* bips, const uint64_t* tree_off,
+                            uint32_t T, uint32_t W, int kind /* prf_memkind */, prf_stats* stats);
+
+/* Stage 2 -- the `ingest` phase (RFDistance.hs:300-341) for packed positions [p_begin, p_end):
+ * d = |B_a| + |B_b| - 2|B_a n B_b|.  p_begin must be a multiple of prf_shard_align().
+ * d_out   DEVICE buffer of (p_end - p_begin) uint16 (16-byte aligned) or NULL to use a buffer the
+ *         context owns (readable with prf_fetch);
+ * d_mask  DEVICE buffer of ceil((p_end - p_begin)/32) uint32 or NULL (ctx-owned when editdist>=0).
+ * Ranks of a multi-GPU job call this with disjoint ranges; no exchange is needed. */
+PRF_API int prf_hashrf_compute(prf_ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist,
+                               int variant /* prf_variant */, uint16_t* d_out, uint32_t* d_mask,
+                               prf_stats* stats);
+
+/* Copies packed positions [p_begin, p_end) of the last ctx-owned result to host memory. */
+PRF_API int prf_fetch(prf_ctx* ctx, uint64_t p_begin, uint64_t p_end, uint16_t* dst);
+PRF_API int prf_fetch_mask(prf_ctx* ctx, uint64_t p_begin, uint64_t p_end, uint32_t* dst);
+/* Copies the packed entries of upper-triangle rows [row0, row1) (row a holds d(a, a+1..T-1)). */
+PRF_API int prf_fetch_rows(prf_ctx* ctx, uint32_t row0, uint32_t row1, uint16_t* dst);
+
+/* ---- tolerant mode (replaces fst . naiveDistMatrix, RFDistance.hs:168-198) ------------------- */
+
+/* clades    nnz*W words: for tree t, the UN-normalised leaf set of every non-root interior node
+ *           (the sets labelBips attaches to interior nodes, RFDistance.hs:218-221).  Singleton
+ *           leaf sets need not be passed (the kernel derives them from `leafsets`).
+ * tree_off  T+1 offsets into clades.
+ * leafsets  T*W words: the tree's taxon set (treeLabels, RFDistance.hs:200-203).
+ * Each tree's leaf labels must be distinct.  Per pair the kernel restricts both trees to the
+ * shared taxa, re-normalises (normBip with size = #shared, RFDistance.hs:229-239, including its
+ * [0,size) complement universe and odd-size tie rule) and counts the symmetric difference. */
+PRF_API int prf_tolerant(prf_ctx* ctx, const uint64_t* clades, const uint64_t* tree_off,
+                         const uint64_t* leafsets, uint32_t T, uint32_t W, int32_t editdist,
+                         uint16_t* out_upper, uint32_t* out_mask, prf_stats* stats);
+PRF_API int prf_tolerant_load(prf_ctx* ctx, const uint64_t* clades, const uint64_t* tree_off,
+                              const uint64_t* leafsets, uint32_t T, uint32_t W, int kind,
+                              prf_stats* stats);
+PRF_API int prf_tolerant_compute(prf_ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist,
+                                 uint16_t* d_out, uint32_t* d_mask, prf_stats* stats);
+
+/* ---- helpers -------------------------------------------------------------------------------- */
+
+/* p(a,b) for a < b < T (see layout above); UINT64_MAX on bad arguments. */
+PRF_API uint64_t prf_packed_index(uint32_t T, uint32_t a, uint32_t b);
+/* Shard boundaries handed to *_compute must be multiples of this many entries (or equal P). */
+PRF_API uint64_t prf_shard_align(void);
+/* Balanced, aligned split of [0, P) over `world` ranks: writes rank's [*p_begin, *p_end). */
+PRF_API int prf_shard_range(uint32_t T, uint32_t rank, uint32_t world, uint64_t* p_begin,
+                            uint64_t* p_end);
+/* Largest W and per-tree bipartition count the kernels accept. */
+PRF_API void prf_limits(uint32_t* max_words, uint32_t* max_bips_per_tree);
+/* Kernels launched by this context since it was created (bench.py reports it as gpu_launches). */
+PRF_API uint64_t prf_launch_count(const prf_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHYBIN_RF_H */

@@ -1,0 +1,489 @@
+// prf_api.cu -- the C ABI of include/phybin_rf.h.  One translation unit: the kernels live in the
+// .cuh files next to this one.  Built for sm_100a only (see phybin_b200/build.py); there is no CPU
+// path here and no dependency on the oracle.
+
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "prf_common.cuh"
+#include "prf_primitives.cuh"
+#include "prf_incidence.cuh"
+#include "prf_sparse.cuh"
+#include "prf_tolerant.cuh"
+
+using namespace prf;
+
+struct prf_ctx {
+  Ctx c;
+};
+
+static thread_local std::string g_create_error;
+
+namespace {
+
+int check_range(Ctx* ctx, uint64_t P, uint64_t p_begin, uint64_t p_end) {
+  if (p_begin > p_end || p_end > P)
+    return ctx->fail(PRF_E_INVALID, "packed range [%llu, %llu) outside [0, %llu]",
+                     (unsigned long long)p_begin, (unsigned long long)p_end, (unsigned long long)P);
+  if (p_begin % kShardAlign != 0 && p_begin != P)
+    return ctx->fail(PRF_E_INVALID, "p_begin=%llu is not a multiple of prf_shard_align()=%llu",
+                     (unsigned long long)p_begin, (unsigned long long)kShardAlign);
+  return PRF_OK;
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return 0.f; }
+  return ms;
+}
+
+// Points *d_out / *d_mask at context-owned buffers covering [p_begin, p_end) when the caller
+// passed none.
+int own_output(Ctx* ctx, uint64_t p_begin, uint64_t p_end, bool want_mask, uint16_t** d_out, uint32_t** d_mask) {
+  uint64_t n = p_end - p_begin;
+  if (!*d_out) {
+    ctx->out_valid = false;
+    if (ctx->out.n < n) PRF_CK(ctx, ctx->out.alloc(n, ctx->stream));
+    *d_out = ctx->out.p;
+    ctx->out_begin = p_begin;
+    ctx->out_end = p_end;
+    ctx->out_valid = true;
+  }
+  if (want_mask && !*d_mask) {
+    ctx->mask_valid = false;
+    uint64_t words = (n + 31) / 32;
+    if (ctx->mask.n < words) PRF_CK(ctx, ctx->mask.alloc(words, ctx->stream));
+    *d_mask = ctx->mask.p;
+    ctx->mask_begin = p_begin;
+    ctx->mask_end = p_end;
+    ctx->mask_valid = true;
+  }
+  return PRF_OK;
+}
+
+int upload(Ctx* ctx, void* dst, const void* src, size_t bytes, int kind) {
+  if (!bytes) return PRF_OK;
+  PRF_CK(ctx, cudaMemcpyAsync(dst, src, bytes,
+                              kind == PRF_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                              ctx->stream));
+  return PRF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+PRF_API const char* prf_version(void) { return "phybin_rf 0.1 (sm_100a)"; }
+
+PRF_API prf_ctx* prf_create(int device) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                     " (phybin_rf has no CPU fallback)";
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (device < 0 || device >= ndev) {
+    g_create_error = "device index out of range";
+    return nullptr;
+  }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    return nullptr;
+  }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    return nullptr;
+  }
+  if (prop.major != 10) {
+    g_create_error = "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                     "; this library is built for sm_100a (B200) only";
+    return nullptr;
+  }
+  prf_ctx* h = new (std::nothrow) prf_ctx;
+  if (!h) { g_create_error = "out of host memory"; return nullptr; }
+  Ctx& c = h->c;
+  c.device = device;
+  c.sm_count = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    delete h;
+    return nullptr;
+  }
+  for (auto& ev : c.ev) cudaEventCreate(&ev);
+  // keep freed blocks in the pool: repeated load/compute cycles reuse them without cudaMalloc
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  g_create_error.clear();
+  return h;
+}
+
+PRF_API void prf_destroy(prf_ctx* h) {
+  if (!h) return;
+  Ctx& c = h->c;
+  cudaSetDevice(c.device);
+  c.h = HashRFState{};
+  c.tol = TolerantState{};
+  c.out.release();
+  c.mask.release();
+  cudaStreamSynchronize(c.stream);
+  for (auto& ev : c.ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(c.stream);
+  delete h;
+}
+
+PRF_API const char* prf_last_error(const prf_ctx* h) { return h ? h->c.err.c_str() : g_create_error.c_str(); }
+PRF_API void* prf_stream(prf_ctx* h) { return h ? (void*)h->c.stream : nullptr; }
+PRF_API uint64_t prf_launch_count(const prf_ctx* h) { return h ? h->c.launches : 0; }
+PRF_API uint64_t prf_shard_align(void) { return kShardAlign; }
+PRF_API void prf_limits(uint32_t* max_words, uint32_t* max_bips) {
+  if (max_words) *max_words = kMaxWords;
+  if (max_bips) *max_bips = kMaxBipsPerTree;
+}
+
+PRF_API uint64_t prf_packed_index(uint32_t T, uint32_t a, uint32_t b) {
+  if (!(a < b && b < T)) return ~0ull;
+  return row_start(a, T) + (b - a - 1);
+}
+
+PRF_API int prf_shard_range(uint32_t T, uint32_t rank, uint32_t world, uint64_t* p_begin, uint64_t* p_end) {
+  if (!world || rank >= world || !p_begin || !p_end) return PRF_E_INVALID;
+  uint64_t P = (uint64_t)T * (T ? T - 1 : 0) / 2;
+  uint64_t units = (P + kShardAlign - 1) / kShardAlign;  // aligned blocks, the last may be partial
+  uint64_t b = units * rank / world, e = units * (rank + 1) / world;
+  *p_begin = std::min(P, b * kShardAlign);
+  *p_end = std::min(P, e * kShardAlign);
+  return PRF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// hashRF
+// ---------------------------------------------------------------------------------------------
+
+PRF_API int prf_hashrf_load(prf_ctx* h, const uint64_t* bips, const uint64_t* tree_off, uint32_t T, uint32_t W,
+                            int kind, prf_stats* stats) {
+  if (!h) return PRF_E_INVALID;
+  Ctx* ctx = &h->c;
+  ctx->err.clear();
+  if (!tree_off) return ctx->fail(PRF_E_INVALID, "tree_off is NULL");
+  if (W == 0 || W > kMaxWords) return ctx->fail(PRF_E_UNSUPPORTED, "W=%u words per set; supported 1..%u", W, kMaxWords);
+  if (kind != PRF_MEM_HOST && kind != PRF_MEM_DEVICE) return ctx->fail(PRF_E_INVALID, "bad memory kind %d", kind);
+  PRF_CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  uint64_t launches0 = ctx->launches;
+  ctx->h.loaded = false;
+  ctx->out_valid = ctx->mask_valid = false;
+
+  PRF_CK(ctx, cudaEventRecord(ctx->ev[0], s));
+  // offsets first: nnz = tree_off[T]
+  DevBuf<uint64_t> d_off_own, d_bips_own;
+  const uint64_t* d_off = tree_off;
+  uint64_t nnz = 0;
+  if (kind == PRF_MEM_HOST) {
+    if (tree_off[0] != 0) return ctx->fail(PRF_E_INVALID, "tree_off[0] must be 0");
+    for (uint32_t t = 0; t < T; ++t)
+      if (tree_off[t + 1] < tree_off[t]) return ctx->fail(PRF_E_INVALID, "tree_off is not ascending at tree %u", t);
+    nnz = tree_off[T];
+    PRF_CK(ctx, d_off_own.alloc((size_t)T + 1, s));
+    int rc = upload(ctx, d_off_own.p, tree_off, ((size_t)T + 1) * 8, kind);
+    if (rc) return rc;
+    d_off = d_off_own.p;
+  } else {
+    PRF_CK(ctx, cudaMemcpyAsync(&nnz, tree_off + T, 8, cudaMemcpyDeviceToHost, s));
+    PRF_CK(ctx, cudaStreamSynchronize(s));
+  }
+  if (nnz >= 0xffffffffull) return ctx->fail(PRF_E_UNSUPPORTED, "nnz=%llu entries; supported < 2^32 - 1", (unsigned long long)nnz);
+  if (nnz && !bips) return ctx->fail(PRF_E_INVALID, "bips is NULL");
+  const uint64_t* d_bips = bips;
+  if (kind == PRF_MEM_HOST) {
+    PRF_CK(ctx, d_bips_own.alloc(nnz * W, s));
+    int rc = upload(ctx, d_bips_own.p, bips, nnz * W * 8, kind);
+    if (rc) return rc;
+    d_bips = d_bips_own.p;
+  } else if (nnz && (reinterpret_cast<uintptr_t>(bips) & 15)) {
+    return ctx->fail(PRF_E_INVALID, "device bips pointer must be 16-byte aligned");
+  }
+  int rc = hashrf_build(ctx, d_bips, d_off, T, W, nnz);
+  if (rc) return rc;
+  prf_stats& st = ctx->h.stats;
+  st.ms_h2d = ev_ms(ctx->ev[0], ctx->ev[1]);
+  st.ms_dedup = ev_ms(ctx->ev[1], ctx->ev[2]);
+  st.ms_incidence = ev_ms(ctx->ev[2], ctx->ev[3]);
+  st.ms_total = ev_ms(ctx->ev[0], ctx->ev[3]);
+  st.gpu_launches = (int32_t)(ctx->launches - launches0);
+  if (stats) *stats = st;
+  return PRF_OK;
+}
+
+PRF_API int prf_hashrf_compute(prf_ctx* h, uint64_t p_begin, uint64_t p_end, int32_t editdist, int variant,
+                               uint16_t* d_out, uint32_t* d_mask, prf_stats* stats) {
+  if (!h) return PRF_E_INVALID;
+  Ctx* ctx = &h->c;
+  ctx->err.clear();
+  HashRFState& H = ctx->h;
+  if (!H.loaded) return ctx->fail(PRF_E_STATE, "prf_hashrf_compute before a successful prf_hashrf_load");
+  int rc = check_range(ctx, H.P, p_begin, p_end);
+  if (rc) return rc;
+  if (d_out && (reinterpret_cast<uintptr_t>(d_out) & 15))
+    return ctx->fail(PRF_E_INVALID, "d_out must be 16-byte aligned");
+  if (variant != PRF_VARIANT_AUTO && variant != PRF_VARIANT_SPARSE && variant != PRF_VARIANT_DENSE)
+    return ctx->fail(PRF_E_INVALID, "unknown variant %d", variant);
+  PRF_CK(ctx, cudaSetDevice(ctx->device));
+  uint64_t launches0 = ctx->launches;
+  if ((rc = own_output(ctx, p_begin, p_end, editdist >= 0, &d_out, &d_mask))) return rc;
+  if (editdist < 0) d_mask = nullptr;
+
+  int use = variant == PRF_VARIANT_AUTO ? PRF_VARIANT_SPARSE : variant;
+  if (use == PRF_VARIANT_DENSE)
+    return ctx->fail(PRF_E_UNSUPPORTED, "dense (tcgen05) variant is not built into this library version");
+  PRF_CK(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+  if (p_end > p_begin) {
+    if ((rc = launch_sparse<16384>(ctx, p_begin, p_end, editdist, d_out, d_mask))) return rc;
+  }
+  PRF_CK(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
+  H.stats.variant_used = use;
+  if (stats) {
+    PRF_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    prf_stats st = H.stats;
+    st.ms_matrix = ev_ms(ctx->ev[4], ctx->ev[5]);
+    st.gpu_launches = (int32_t)(ctx->launches - launches0);
+    *stats = st;
+  }
+  return PRF_OK;
+}
+
+static int fetch_common(Ctx* ctx, uint64_t p_begin, uint64_t p_end, uint16_t* dst) {
+  if (!ctx->out_valid) return ctx->fail(PRF_E_STATE, "no context-owned result to fetch");
+  if (p_begin > p_end || p_begin < ctx->out_begin || p_end > ctx->out_end)
+    return ctx->fail(PRF_E_INVALID, "fetch range outside the computed range");
+  if (!dst) return ctx->fail(PRF_E_INVALID, "dst is NULL");
+  PRF_CK(ctx, cudaSetDevice(ctx->device));
+  if (p_end > p_begin)
+    PRF_CK(ctx, cudaMemcpyAsync(dst, ctx->out.p + (p_begin - ctx->out_begin), (p_end - p_begin) * 2,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  PRF_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return PRF_OK;
+}
+
+PRF_API int prf_fetch(prf_ctx* h, uint64_t p_begin, uint64_t p_end, uint16_t* dst) {
+  if (!h) return PRF_E_INVALID;
+  h->c.err.clear();
+  return fetch_common(&h->c, p_begin, p_end, dst);
+}
+
+PRF_API int prf_fetch_mask(prf_ctx* h, uint64_t p_begin, uint64_t p_end, uint32_t* dst) {
+  if (!h) return PRF_E_INVALID;
+  Ctx* ctx = &h->c;
+  ctx->err.clear();
+  if (!ctx->mask_valid) return ctx->fail(PRF_E_STATE, "no context-owned mask to fetch");
+  if (p_begin > p_end || p_begin < ctx->mask_begin || p_end > ctx->mask_end || (p_begin - ctx->mask_begin) % 32)
+    return ctx->fail(PRF_E_INVALID, "mask fetch range must lie in the computed range and start on a 32-entry boundary");
+  if (!dst) return ctx->fail(PRF_E_INVALID, "dst is NULL");
+  PRF_CK(ctx, cudaSetDevice(ctx->device));
+  uint64_t words = (p_end - p_begin + 31) / 32;
+  if (words)
+    PRF_CK(ctx, cudaMemcpyAsync(dst, ctx->mask.p + (p_begin - ctx->mask_begin) / 32, words * 4,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  PRF_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return PRF_OK;
+}
+
+PRF_API int prf_fetch_rows(prf_ctx* h, uint32_t row0, uint32_t row1, uint16_t* dst) {
+  if (!h) return PRF_E_INVALID;
+  Ctx* ctx = &h->c;
+  ctx->err.clear();
+  uint32_t T = ctx->h.loaded ? ctx->h.T : (ctx->tol.loaded ? ctx->tol.T : 0);
+  if (row0 > row1 || row1 > T) return ctx->fail(PRF_E_INVALID, "row range [%u, %u) outside [0, %u]", row0, row1, T);
+  uint64_t P = (uint64_t)T * (T ? T - 1 : 0) / 2;
+  uint64_t b = row0 + 1 >= T ? P : row_start(row0, T);
+  uint64_t e = row1 + 1 >= T ? P : row_start(row1, T);
+  return fetch_common(ctx, b, e, dst);
+}
+
+PRF_API int prf_hashrf(prf_ctx* h, const uint64_t* bips, const uint64_t* tree_off, uint32_t T, uint32_t W,
+                       int32_t editdist, uint16_t* out_upper, uint32_t* out_mask, prf_stats* stats) {
+  if (!h) return PRF_E_INVALID;
+  Ctx* ctx = &h->c;
+  prf_stats st{};
+  int rc = prf_hashrf_load(h, bips, tree_off, T, W, PRF_MEM_HOST, &st);
+  if (rc) return rc;
+  uint64_t P = ctx->h.P;
+  prf_stats st2{};
+  if ((rc = prf_hashrf_compute(h, 0, P, editdist, PRF_VARIANT_AUTO, nullptr, nullptr, &st2))) return rc;
+  PRF_CK(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
+  if (out_upper && (rc = prf_fetch(h, 0, P, out_upper))) return rc;
+  if (out_mask && editdist >= 0 && (rc = prf_fetch_mask(h, 0, P, out_mask))) return rc;
+  PRF_CK(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
+  PRF_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (stats) {
+    *stats = st2;
+    stats->ms_h2d = st.ms_h2d;
+    stats->ms_dedup = st.ms_dedup;
+    stats->ms_incidence = st.ms_incidence;
+    stats->ms_d2h = ev_ms(ctx->ev[6], ctx->ev[7]);
+    stats->ms_total = ev_ms(ctx->ev[0], ctx->ev[7]);
+    stats->gpu_launches = st.gpu_launches + st2.gpu_launches;
+  }
+  return PRF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tolerant
+// ---------------------------------------------------------------------------------------------
+
+PRF_API int prf_tolerant_load(prf_ctx* h, const uint64_t* clades, const uint64_t* tree_off,
+                              const uint64_t* leafsets, uint32_t T, uint32_t W, int kind, prf_stats* stats) {
+  if (!h) return PRF_E_INVALID;
+  Ctx* ctx = &h->c;
+  ctx->err.clear();
+  if (!tree_off || (T && !leafsets)) return ctx->fail(PRF_E_INVALID, "tree_off / leafsets is NULL");
+  if (W == 0 || W > kTolMaxWords) return ctx->fail(PRF_E_UNSUPPORTED, "tolerant mode supports W in 1..%u, got %u", kTolMaxWords, W);
+  if (kind != PRF_MEM_HOST && kind != PRF_MEM_DEVICE) return ctx->fail(PRF_E_INVALID, "bad memory kind %d", kind);
+  PRF_CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  uint64_t launches0 = ctx->launches;
+  TolerantState& S = ctx->tol;
+  S = TolerantState{};
+  ctx->out_valid = ctx->mask_valid = false;
+  PRF_CK(ctx, cudaEventRecord(ctx->ev[0], s));
+  std::vector<uint64_t> hoff((size_t)T + 1);
+  if (kind == PRF_MEM_HOST) {
+    std::memcpy(hoff.data(), tree_off, ((size_t)T + 1) * 8);
+  } else {
+    PRF_CK(ctx, cudaMemcpyAsync(hoff.data(), tree_off, ((size_t)T + 1) * 8, cudaMemcpyDeviceToHost, s));
+    PRF_CK(ctx, cudaStreamSynchronize(s));
+  }
+  if (hoff[0] != 0) return ctx->fail(PRF_E_INVALID, "tree_off[0] must be 0");
+  uint32_t maxc = 0;
+  for (uint32_t t = 0; t < T; ++t) {
+    if (hoff[t + 1] < hoff[t]) return ctx->fail(PRF_E_INVALID, "tree_off is not ascending at tree %u", t);
+    maxc = std::max<uint64_t>(maxc, hoff[t + 1] - hoff[t]);
+  }
+  uint64_t nnz = hoff[T];
+  if (nnz && !clades) return ctx->fail(PRF_E_INVALID, "clades is NULL");
+  if (maxc > kTolMaxClades)
+    return ctx->fail(PRF_E_UNSUPPORTED, "a tree has %u interior clades; tolerant mode supports <= %u", maxc, kTolMaxClades);
+  PRF_CK(ctx, S.off.alloc((size_t)T + 1, s));
+  PRF_CK(ctx, S.clades.alloc(nnz * W, s));
+  PRF_CK(ctx, S.leafsets.alloc((size_t)T * W, s));
+  int rc;
+  if ((rc = upload(ctx, S.off.p, hoff.data(), ((size_t)T + 1) * 8, PRF_MEM_HOST))) return rc;
+  if ((rc = upload(ctx, S.clades.p, clades, nnz * W * 8, kind))) return rc;
+  if ((rc = upload(ctx, S.leafsets.p, leafsets, (size_t)T * W * 8, kind))) return rc;
+  PRF_CK(ctx, cudaEventRecord(ctx->ev[1], s));
+  PRF_CK(ctx, cudaStreamSynchronize(s));
+  S.T = T;
+  S.W = W;
+  S.nnz = nnz;
+  S.max_clades = maxc;
+  S.P = (uint64_t)T * (T ? T - 1 : 0) / 2;
+  S.loaded = true;
+  ctx->h.loaded = false;
+  S.stats = prf_stats{};
+  S.stats.n_trees = T;
+  S.stats.n_words = W;
+  S.stats.nnz = nnz;
+  S.stats.n_pairs = S.P;
+  S.stats.max_bips = maxc;
+  S.stats.ms_h2d = ev_ms(ctx->ev[0], ctx->ev[1]);
+  S.stats.gpu_launches = (int32_t)(ctx->launches - launches0);
+  if (stats) *stats = S.stats;
+  return PRF_OK;
+}
+
+PRF_API int prf_tolerant_compute(prf_ctx* h, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out,
+                                 uint32_t* d_mask, prf_stats* stats) {
+  if (!h) return PRF_E_INVALID;
+  Ctx* ctx = &h->c;
+  ctx->err.clear();
+  TolerantState& S = ctx->tol;
+  if (!S.loaded) return ctx->fail(PRF_E_STATE, "prf_tolerant_compute before a successful prf_tolerant_load");
+  int rc = check_range(ctx, S.P, p_begin, p_end);
+  if (rc) return rc;
+  PRF_CK(ctx, cudaSetDevice(ctx->device));
+  uint64_t launches0 = ctx->launches;
+  if ((rc = own_output(ctx, p_begin, p_end, editdist >= 0, &d_out, &d_mask))) return rc;
+  if (editdist < 0) d_mask = nullptr;
+  PRF_CK(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+  if (p_end > p_begin && (rc = launch_tolerant(ctx, p_begin, p_end, editdist, d_out, d_mask))) return rc;
+  PRF_CK(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
+  if (stats) {
+    PRF_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    prf_stats st = S.stats;
+    st.ms_matrix = ev_ms(ctx->ev[4], ctx->ev[5]);
+    st.gpu_launches = (int32_t)(ctx->launches - launches0);
+    *stats = st;
+  }
+  return PRF_OK;
+}
+
+PRF_API int prf_tolerant(prf_ctx* h, const uint64_t* clades, const uint64_t* tree_off, const uint64_t* leafsets,
+                         uint32_t T, uint32_t W, int32_t editdist, uint16_t* out_upper, uint32_t* out_mask,
+                         prf_stats* stats) {
+  if (!h) return PRF_E_INVALID;
+  Ctx* ctx = &h->c;
+  prf_stats st{}, st2{};
+  int rc = prf_tolerant_load(h, clades, tree_off, leafsets, T, W, PRF_MEM_HOST, &st);
+  if (rc) return rc;
+  uint64_t P = ctx->tol.P;
+  if ((rc = prf_tolerant_compute(h, 0, P, editdist, nullptr, nullptr, &st2))) return rc;
+  PRF_CK(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
+  if (out_upper && (rc = prf_fetch(h, 0, P, out_upper))) return rc;
+  if (out_mask && editdist >= 0 && (rc = prf_fetch_mask(h, 0, P, out_mask))) return rc;
+  PRF_CK(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
+  PRF_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (stats) {
+    *stats = st2;
+    stats->ms_h2d = st.ms_h2d;
+    stats->ms_d2h = ev_ms(ctx->ev[6], ctx->ev[7]);
+    stats->ms_total = ev_ms(ctx->ev[0], ctx->ev[7]);
+    stats->gpu_launches = st.gpu_launches + st2.gpu_launches;
+  }
+  return PRF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Debug entry points for tests of the primitives (not part of phybin_rf.h).
+// ---------------------------------------------------------------------------------------------
+
+PRF_API int prf_debug_scan(prf_ctx* h, const uint32_t* host_in, uint64_t n, uint32_t* host_out, uint32_t* total) {
+  if (!h) return PRF_E_INVALID;
+  Ctx* ctx = &h->c;
+  cudaStream_t s = ctx->stream;
+  DevBuf<uint32_t> in, out, tot;
+  PRF_CK(ctx, in.alloc(n, s));
+  PRF_CK(ctx, out.alloc(n, s));
+  PRF_CK(ctx, tot.alloc(1, s));
+  PRF_CK(ctx, cudaMemcpyAsync(in.p, host_in, n * 4, cudaMemcpyHostToDevice, s));
+  int rc = exclusive_scan(ctx, LoadU32{in.p}, n, out.p, tot.p);
+  if (rc) return rc;
+  PRF_CK(ctx, cudaMemcpyAsync(host_out, out.p, n * 4, cudaMemcpyDeviceToHost, s));
+  PRF_CK(ctx, cudaMemcpyAsync(total, tot.p, 4, cudaMemcpyDeviceToHost, s));
+  PRF_CK(ctx, cudaStreamSynchronize(s));
+  return PRF_OK;
+}
+
+PRF_API int prf_debug_sort(prf_ctx* h, uint32_t* host_keys, uint32_t* host_vals, uint32_t n, int nbits) {
+  if (!h) return PRF_E_INVALID;
+  Ctx* ctx = &h->c;
+  cudaStream_t s = ctx->stream;
+  DevBuf<uint32_t> k, v;
+  PRF_CK(ctx, k.alloc(n, s));
+  PRF_CK(ctx, v.alloc(n, s));
+  PRF_CK(ctx, cudaMemcpyAsync(k.p, host_keys, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  PRF_CK(ctx, cudaMemcpyAsync(v.p, host_vals, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  int rc = radix_sort_pairs(ctx, k.p, v.p, n, nbits);
+  if (rc) return rc;
+  PRF_CK(ctx, cudaMemcpyAsync(host_keys, k.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  PRF_CK(ctx, cudaMemcpyAsync(host_vals, v.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  PRF_CK(ctx, cudaStreamSynchronize(s));
+  return PRF_OK;
+}
+
+}  // extern "C"

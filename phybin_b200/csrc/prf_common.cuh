@@ -1,0 +1,155 @@
+// prf_common.cuh -- context, error plumbing and small device helpers shared by every kernel file.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "phybin_rf.h"
+
+namespace prf {
+
+constexpr uint32_t kMaxWords = 16;            // W <= 16 (1024 taxa); kernels are templated on W
+constexpr uint32_t kMaxBipsPerTree = 32767;   // so that |B_a| + |B_b| fits uint16
+constexpr uint64_t kShardAlign = 65536;       // multiple of every chunk size the sparse kernel uses
+
+struct Ctx;
+
+// Stream-ordered device buffer (cudaMallocAsync on the context's stream).
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaStream_t s = nullptr;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  cudaError_t alloc(size_t count, cudaStream_t stream) {
+    release();
+    s = stream;
+    n = count;
+    return cudaMallocAsync((void**)&p, (count ? count : 1) * sizeof(T), stream);
+  }
+  void release() {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr;
+    n = 0;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+// Device-resident state of a loaded hashRF problem (the incidence in the form the kernels use).
+struct HashRFState {
+  bool loaded = false;
+  uint32_t T = 0, W = 0;
+  uint64_t nnz = 0, P = 0;
+  bool uniform_nb = false;       // every tree has the same |B|
+  uint32_t nb_uniform = 0;
+  DevBuf<uint16_t> nb;           // [T]   |B_t| (distinct bipartitions)
+  DevBuf<uint32_t> roff;         // [T+1] per-tree offsets into `ranges`
+  DevBuf<uint2> ranges;          // member-list suffixes (begin, end) into `members`, tree-major
+  DevBuf<uint32_t> members;      // inverted lists of the shared bipartitions, ascending tree ids
+  // tree-major incidence over shared bipartition ids (dense variant input)
+  uint32_t n_shared = 0;
+  uint64_t n_shared_nnz = 0;
+  DevBuf<uint32_t> sh_tree;      // [n_shared_nnz] tree of the k-th shared entry (tree order)
+  DevBuf<uint32_t> sh_sid;       // [n_shared_nnz] its shared bipartition id
+  prf_stats stats{};
+};
+
+struct TolerantState {
+  bool loaded = false;
+  uint32_t T = 0, W = 0, max_clades = 0;
+  uint64_t nnz = 0, P = 0;
+  DevBuf<uint64_t> clades;    // [nnz*W]
+  DevBuf<uint64_t> off;       // [T+1]
+  DevBuf<uint64_t> leafsets;  // [T*W]
+  prf_stats stats{};
+};
+
+struct Ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  std::string err;
+  uint64_t launches = 0;
+  HashRFState h;
+  TolerantState tol;
+  // ctx-owned result of the last compute
+  DevBuf<uint16_t> out;
+  DevBuf<uint32_t> mask;
+  uint64_t out_begin = 0, out_end = 0, mask_begin = 0, mask_end = 0;
+  bool out_valid = false, mask_valid = false;
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+};
+
+#define PRF_CK(ctx, call)                                                                      \
+  do {                                                                                         \
+    cudaError_t _e = (call);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return (ctx)->fail(PRF_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,                \
+                         cudaGetErrorString(_e));                                              \
+  } while (0)
+
+// Counts a launch and checks it was accepted.
+#define PRF_LAUNCHED(ctx)                                                                      \
+  do {                                                                                         \
+    ++(ctx)->launches;                                                                         \
+    cudaError_t _e = cudaGetLastError();                                                       \
+    if (_e != cudaSuccess)                                                                     \
+      return (ctx)->fail(PRF_E_CUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__,            \
+                         cudaGetErrorString(_e));                                              \
+  } while (0)
+
+__host__ __device__ inline uint64_t row_start(uint64_t a, uint64_t T) {
+  // first packed position of upper-triangle row a: a*T - a(a+1)/2 = a(2T - a - 1)/2
+  return a * (2 * T - a - 1) / 2;
+}
+
+// Largest row a (0 <= a <= T-2) with row_start(a) <= p, for p < T(T-1)/2.
+__host__ __device__ inline uint32_t row_of(uint64_t p, uint64_t T) {
+  double tt = 2.0 * (double)T - 1.0;
+  double disc = tt * tt - 8.0 * (double)p;
+  double r = (tt - sqrt(disc > 0.0 ? disc : 0.0)) * 0.5;
+  int64_t a = (int64_t)r;
+  if (a < 0) a = 0;
+  if (a > (int64_t)T - 2) a = (int64_t)T - 2;
+  while (a > 0 && row_start((uint64_t)a, T) > p) --a;
+  while (a + 1 <= (int64_t)T - 2 && row_start((uint64_t)a + 1, T) <= p) ++a;
+  return (uint32_t)a;
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t lanemask_lt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+}  // namespace prf

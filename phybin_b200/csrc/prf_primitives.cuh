@@ -1,0 +1,231 @@
+// prf_primitives.cuh -- device-wide exclusive scan and stable LSD radix sort of (key, value) pairs.
+// Hand-written (no CUB/Thrust): three-kernel scan (tile reduce, one-CTA scan of tile sums, tile
+// scan) and an 8-bit-digit radix sort (tile histogram, scan of digit-major histograms, stable
+// warp-multisplit scatter).  Both are HBM-streaming kernels far off the critical path: at the
+// headline shape they touch < 1 % of the bytes the matrix kernel writes.
+#pragma once
+
+#include "prf_common.cuh"
+
+namespace prf {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;  // 4096
+
+// Block-wide exclusive scan of one value per thread; returns the exclusive prefix and writes the
+// block total to `total` (same value in every thread).
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t& total) {
+  __shared__ uint32_t warp_sums[kScanThreads / 32];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= (uint32_t)d) inc += o;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  uint32_t wprefix = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kScanThreads / 32; ++w) {
+    uint32_t s = warp_sums[w];
+    if ((uint32_t)w < warp) wprefix += s;
+    tot += s;
+  }
+  __syncthreads();  // warp_sums may be reused by the caller's next call
+  total = tot;
+  return wprefix + inc - v;
+}
+
+// F: struct with __device__ uint32_t operator()(uint64_t i) const
+template <class F>
+__global__ void __launch_bounds__(kScanThreads) scan_tile_reduce_kernel(F f, uint64_t n,
+                                                                         uint32_t* tile_sums) {
+  const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    uint64_t i = base + k;
+    if (i < n) s += f(i);
+  }
+  uint32_t tot;
+  block_exclusive_scan(s, tot);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+// One CTA: in-place exclusive scan of `m` tile sums; the grand total goes to *total.
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(uint32_t* tile_sums, uint32_t m,
+                                                                       uint32_t* total) {
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < m; base += kScanThreads) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < m ? tile_sums[i] : 0;
+    uint32_t tot;
+    uint32_t ex = block_exclusive_scan(v, tot);
+    if (i < m) tile_sums[i] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0 && total) *total = carry;
+}
+
+template <class F>
+__global__ void __launch_bounds__(kScanThreads) scan_tile_apply_kernel(F f, uint64_t n,
+                                                                        const uint32_t* tile_offs,
+                                                                        uint32_t* out) {
+  const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    uint64_t i = base + k;
+    v[k] = i < n ? f(i) : 0;
+    s += v[k];
+  }
+  uint32_t tot;
+  uint32_t ex = block_exclusive_scan(s, tot) + tile_offs[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    uint64_t i = base + k;
+    if (i < n) out[i] = ex;
+    ex += v[k];
+  }
+}
+
+// out[i] = sum_{j<i} f(j) for i in [0, n); *d_total = sum of all (device pointer, may be null).
+// out must not alias anything f reads unless f reads element i only (in-place is then safe:
+// every tile is fully read into registers before it is written).
+template <class F>
+int exclusive_scan(Ctx* ctx, F f, uint64_t n, uint32_t* out, uint32_t* d_total) {
+  cudaStream_t s = ctx->stream;
+  if (n == 0) {
+    if (d_total) PRF_CK(ctx, cudaMemsetAsync(d_total, 0, sizeof(uint32_t), s));
+    return PRF_OK;
+  }
+  uint32_t tiles = (uint32_t)((n + kScanTile - 1) / kScanTile);
+  DevBuf<uint32_t> sums;
+  PRF_CK(ctx, sums.alloc(tiles, s));
+  scan_tile_reduce_kernel<F><<<tiles, kScanThreads, 0, s>>>(f, n, sums.p);
+  PRF_LAUNCHED(ctx);
+  scan_tile_sums_kernel<<<1, kScanThreads, 0, s>>>(sums.p, tiles, d_total);
+  PRF_LAUNCHED(ctx);
+  scan_tile_apply_kernel<F><<<tiles, kScanThreads, 0, s>>>(f, n, sums.p, out);
+  PRF_LAUNCHED(ctx);
+  return PRF_OK;
+}
+
+struct LoadU32 {
+  const uint32_t* p;
+  __device__ uint32_t operator()(uint64_t i) const { return p[i]; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Stable LSD radix sort of (key, value) uint32 pairs on key bits [0, nbits).
+// ---------------------------------------------------------------------------------------------
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;  // per thread
+constexpr int kSortTile = kSortThreads * kSortItems;  // 4096: 8 warps x 16 rounds x 32 lanes
+
+__global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const uint32_t* __restrict__ keys,
+                                                                  uint32_t n, int shift,
+                                                                  uint32_t* __restrict__ hist,
+                                                                  uint32_t tiles) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t base = blockIdx.x * kSortTile;
+#pragma unroll
+  for (int k = 0; k < kSortItems; ++k) {
+    uint32_t i = base + k * kSortThreads + threadIdx.x;
+    if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[(uint32_t)threadIdx.x * tiles + blockIdx.x] = h[threadIdx.x];  // digit-major
+}
+
+__global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(
+    const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t n,
+    int shift, const uint32_t* __restrict__ hist_scanned, uint32_t tiles,
+    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+  __shared__ uint32_t whist[kSortThreads / 32][256];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (kSortThreads / 32) * 256; i += kSortThreads) (&whist[0][0])[i] = 0;
+  __syncthreads();
+  // warp w owns the contiguous sub-tile [base + w*512, base + (w+1)*512), 16 rounds of 32
+  const uint32_t wbase = blockIdx.x * kSortTile + warp * (kSortItems * 32);
+  uint32_t k[kSortItems], v[kSortItems];
+  const uint32_t lt = lanemask_lt();
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    uint32_t i = wbase + r * 32 + lane;
+    bool valid = i < n;
+    k[r] = valid ? keys_in[i] : 0;
+    v[r] = valid ? vals_in[i] : 0;
+    uint32_t act = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+      uint32_t d = (k[r] >> shift) & 255u;
+      uint32_t peers = __match_any_sync(act, d);
+      if ((peers & lt) == 0) whist[warp][d] += __popc(peers);  // lowest lane of the group
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  {  // thread d: turn per-warp counts of digit d into global start offsets
+    uint32_t d = threadIdx.x;
+    uint32_t run = hist_scanned[d * tiles + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < kSortThreads / 32; ++w) {
+      uint32_t t = whist[w][d];
+      whist[w][d] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    uint32_t i = wbase + r * 32 + lane;
+    bool valid = i < n;
+    uint32_t act = __ballot_sync(0xffffffffu, valid);
+    uint32_t d = 0, peers = 0;
+    if (valid) {
+      d = (k[r] >> shift) & 255u;
+      peers = __match_any_sync(act, d);
+      uint32_t pos = whist[warp][d] + __popc(peers & lt);
+      keys_out[pos] = k[r];
+      vals_out[pos] = v[r];
+    }
+    __syncwarp();  // everyone has read whist before the group leaders bump it
+    if (valid && (peers & lt) == 0) whist[warp][d] += __popc(peers);
+    __syncwarp();
+  }
+}
+
+// Sorts in place (result ends in keys/vals); tmp buffers of the same size are allocated inside.
+inline int radix_sort_pairs(Ctx* ctx, uint32_t* keys, uint32_t* vals, uint32_t n, int nbits) {
+  if (n < 2 || nbits <= 0) return PRF_OK;
+  cudaStream_t s = ctx->stream;
+  uint32_t tiles = (n + kSortTile - 1) / kSortTile;
+  DevBuf<uint32_t> k2, v2, hist;
+  PRF_CK(ctx, k2.alloc(n, s));
+  PRF_CK(ctx, v2.alloc(n, s));
+  PRF_CK(ctx, hist.alloc((size_t)256 * tiles, s));
+  uint32_t *ki = keys, *vi = vals, *ko = k2.p, *vo = v2.p;
+  for (int shift = 0; shift < nbits; shift += 8) {
+    sort_hist_kernel<<<tiles, kSortThreads, 0, s>>>(ki, n, shift, hist.p, tiles);
+    PRF_LAUNCHED(ctx);
+    int rc = exclusive_scan(ctx, LoadU32{hist.p}, (uint64_t)256 * tiles, hist.p, nullptr);
+    if (rc) return rc;
+    sort_scatter_kernel<<<tiles, kSortThreads, 0, s>>>(ki, vi, n, shift, hist.p, tiles, ko, vo);
+    PRF_LAUNCHED(ctx);
+    uint32_t* t;
+    t = ki; ki = ko; ko = t;
+    t = vi; vi = vo; vo = t;
+  }
+  if (ki != keys) {
+    PRF_CK(ctx, cudaMemcpyAsync(keys, ki, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    PRF_CK(ctx, cudaMemcpyAsync(vals, vi, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  return PRF_OK;
+}
+
+}  // namespace prf

@@ -1,0 +1,296 @@
+// prf_tolerant.cuh -- naiveDistMatrix (RFDistance.hs:168-198), the --tolerant path.
+//
+// Per pair (a, b) the reference prunes both trees to the shared taxa S (pruneTreeLeaves,
+// PreProcessor.hs:21-32), recomputes allBips with size = |S| (RFDistance.hs:207-248) unless the
+// tree already has exactly S (cached bips, :186-191), and counts the symmetric difference of the two
+// bipartition sets (:193-194).  On bit sets that is:
+//     raw_t = { c & S : c clade of a non-root node of t } minus {0} minus {S unless L_t == S}
+//     F_t   = { normBip_k(r) : r in raw_t, |normBip_k(r)| > 1 }            (a SET: dedup needed)
+//     d     = |F_a xor F_b|
+// where normBip_k complements inside {0..k-1} (NOT inside S: invertDense, :127-131) and breaks
+// |r| == k/2 ties with IntSet's lexicographic order (:239).  Distinct clades can collapse to one
+// masked set and the two sides of one split normalise to the same set, so a masked-popcount Gram
+// product is not equivalent; each pair needs an exact set computation.
+//
+// One warp per pair.  Lanes normalise the clades of both trees and insert them into a small
+// per-warp open-addressing table in shared memory (hash routes, equality is decided on the full
+// key); each slot accumulates "seen in a" / "seen in b" flags; d = number of slots with exactly one.
+#pragma once
+
+#include "prf_common.cuh"
+
+namespace prf {
+
+constexpr uint32_t kTolMaxWords = 8;
+constexpr uint32_t kTolMaxClades = 1000;  // per tree; slot word keeps an 11-bit key index
+constexpr int kTolPairsPerWarp = 8;
+
+template <int W>
+struct BitSet {
+  uint64_t w[W];
+};
+
+template <int W>
+__device__ __forceinline__ uint32_t popc_set(const BitSet<W>& s) {
+  uint32_t c = 0;
+#pragma unroll
+  for (int i = 0; i < W; ++i) c += __popcll(s.w[i]);
+  return c;
+}
+
+// normBip (RFDistance.hs:229-239) with universe R = {0..k-1}.  Returns the cardinality of the
+// canonical side written to `out`.
+template <int W>
+__device__ __forceinline__ uint32_t norm_bip(const BitSet<W>& m, uint32_t pc, const BitSet<W>& R, uint32_t half,
+                                             BitSet<W>& out) {
+  if (pc < half) {
+    out = m;
+    return pc;
+  }
+  BitSet<W> fl;
+#pragma unroll
+  for (int i = 0; i < W; ++i) fl.w[i] = R.w[i] & ~m.w[i];  // invertDense k m
+  bool take_fl = true;
+  if (pc == half) {
+    // min m fl on ascending element lists; m and fl are disjoint so their first elements decide,
+    // and the empty list is smallest.
+    bool decided = false;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      uint64_t u = m.w[i] | fl.w[i];
+      if (!decided && u) {
+        uint64_t low = u & (0 - u);
+        take_fl = (fl.w[i] & low) != 0;
+        decided = true;
+      }
+    }
+    uint32_t fc = popc_set<W>(fl);
+    if (fc == 0) take_fl = true;
+  }
+  out = take_fl ? fl : m;
+  return popc_set<W>(out);
+}
+
+template <int W>
+__device__ __forceinline__ uint32_t hash_set(const BitSet<W>& s) {
+  uint64_t h = 0x9E3779B97F4A7C15ull;
+#pragma unroll
+  for (int i = 0; i < W; ++i) h = (h ^ s.w[i]) * 0xD6E8FEB86659FD93ull + (h >> 29);
+  h ^= h >> 32;
+  h *= 0xD6E8FEB86659FD93ull;
+  h ^= h >> 29;
+  return (uint32_t)h;
+}
+
+// slot word: [31:30] flags (1 = in a, 2 = in b), [29:11] tag, [10:0] key index + 1; 0 = empty
+template <int W>
+__device__ __forceinline__ void table_insert(uint32_t* table, uint32_t tmask, uint64_t* keys, uint32_t idx,
+                                             const BitSet<W>& key, uint32_t flag) {
+  const uint32_t h = hash_set<W>(key);
+  const uint32_t tag = (h >> 13) & 0x7ffffu;
+  const uint32_t mine = (flag << 30) | (tag << 11) | (idx + 1);
+  uint32_t s = h & tmask;
+  for (;;) {
+    uint32_t cur = *((volatile uint32_t*)&table[s]);
+    if (cur == 0) {
+      cur = atomicCAS(&table[s], 0u, mine);
+      if (cur == 0) return;
+    }
+    if (((cur >> 11) & 0x7ffffu) == tag) {
+      const uint64_t* other = keys + (size_t)((cur & 0x7ffu) - 1) * W;
+      bool eq = true;
+#pragma unroll
+      for (int i = 0; i < W; ++i) eq &= (other[i] == key.w[i]);
+      if (eq) {
+        atomicOr(&table[s], flag << 30);
+        return;
+      }
+    }
+    s = (s + 1) & tmask;
+  }
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) tolerant_kernel(uint32_t T, uint64_t p_begin, uint64_t p_end,
+                                                       const uint64_t* __restrict__ clades,
+                                                       const uint64_t* __restrict__ off,
+                                                       const uint64_t* __restrict__ leafsets, uint32_t tsize,
+                                                       uint32_t key_cap, int32_t editdist,
+                                                       uint16_t* __restrict__ out, uint32_t* __restrict__ mask) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t warps = blockDim.x >> 5;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // layout: per-warp key areas (uint64), then per-warp tables (uint32), then the CTA's results
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw) + (size_t)warp * key_cap * W;
+  uint32_t* table = reinterpret_cast<uint32_t*>(reinterpret_cast<uint64_t*>(smem_raw) + (size_t)warps * key_cap * W) +
+                    (size_t)warp * tsize;
+  uint16_t* res = reinterpret_cast<uint16_t*>(reinterpret_cast<uint32_t*>(
+      reinterpret_cast<uint64_t*>(smem_raw) + (size_t)warps * key_cap * W) + (size_t)warps * tsize);
+  const uint32_t tmask = tsize - 1;
+  for (uint32_t s = lane; s < tsize; s += 32) table[s] = 0;
+  __syncwarp();
+
+  const uint32_t per_cta = warps * kTolPairsPerWarp;
+  const uint64_t n_blocks = (p_end - p_begin + per_cta - 1) / per_cta;
+  for (uint64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    const uint64_t pb = p_begin + blk * per_cta;
+    for (int q = 0; q < kTolPairsPerWarp; ++q) {
+      const uint32_t local = warp * kTolPairsPerWarp + q;
+      const uint64_t p = pb + local;
+      if (p >= p_end) break;
+      const uint32_t a = row_of(p, T);
+      const uint32_t b = a + 1 + (uint32_t)(p - row_start(a, T));
+      BitSet<W> La, Lb, S, R;
+#pragma unroll
+      for (int i = 0; i < W; ++i) {
+        La.w[i] = leafsets[(size_t)a * W + i];
+        Lb.w[i] = leafsets[(size_t)b * W + i];
+        S.w[i] = La.w[i] & Lb.w[i];
+      }
+      const uint32_t k = popc_set<W>(S);
+      uint32_t d = 0;
+      if (k != 0) {  // inBoth empty -> 0 (RFDistance.hs:195-196)
+        const uint32_t half = k >> 1;
+        bool fullA = true, fullB = true;
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+          fullA &= La.w[i] == S.w[i];
+          fullB &= Lb.w[i] == S.w[i];
+          int64_t rem = (int64_t)k - 64 * i;
+          R.w[i] = rem >= 64 ? ~0ull : (rem <= 0 ? 0ull : ((1ull << rem) - 1));
+        }
+        const uint64_t oa = off[a], na = off[a + 1] - oa, ob = off[b], nbb = off[b + 1] - ob;
+        // both trees, one pass each: tree index 0 -> a (flag 1), 1 -> b (flag 2)
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+          const uint64_t o = t ? ob : oa;
+          const uint32_t cnt = (uint32_t)(t ? nbb : na);
+          const bool full = t ? fullB : fullA;
+          const uint32_t idx0 = t ? (uint32_t)na : 0u;
+          for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            bool have = false;
+            BitSet<W> key;
+            if (c < cnt) {
+              BitSet<W> m;
+              const uint64_t* src = clades + (o + c) * W;
+#pragma unroll
+              for (int i = 0; i < W; ++i) m.w[i] = src[i] & S.w[i];
+              const uint32_t pc = popc_set<W>(m);
+              // drop the empty set, and the full set unless the cached (unpruned) bips are used
+              if (pc != 0 && (pc != k || full)) have = norm_bip<W>(m, pc, R, half, key) > 1;
+              if (have) {
+                uint64_t* dst = keys + (size_t)(idx0 + c) * W;
+#pragma unroll
+                for (int i = 0; i < W; ++i) dst[i] = key.w[i];
+              }
+            }
+            __syncwarp();
+            if (have) table_insert<W>(table, tmask, keys, idx0 + c, key, t ? 2u : 1u);
+            __syncwarp();
+          }
+        }
+        if (k <= 3) {
+          // singleton leaf sets survive the `> 1` filter only here; both pruned trees have every
+          // leaf of S, so they enter with both flags (they still matter: another clade of one tree
+          // may normalise to the same set).
+          const uint32_t idx0 = (uint32_t)(na + nbb);
+          uint32_t seen = 0;
+          bool have = false;
+          BitSet<W> key, m;
+#pragma unroll
+          for (int i = 0; i < W; ++i) {
+            m.w[i] = 0;
+            uint64_t word = S.w[i];
+            while (word) {
+              uint64_t low = word & (0 - word);
+              if (seen == lane) m.w[i] = low;
+              ++seen;
+              word ^= low;
+            }
+          }
+          if (lane < k) {
+            have = norm_bip<W>(m, 1, R, half, key) > 1;
+            if (have) {
+              uint64_t* dst = keys + (size_t)(idx0 + lane) * W;
+#pragma unroll
+              for (int i = 0; i < W; ++i) dst[i] = key.w[i];
+            }
+          }
+          __syncwarp();
+          if (have) table_insert<W>(table, tmask, keys, idx0 + lane, key, 3u);
+          __syncwarp();
+        }
+        // count slots seen in exactly one tree, and clear the table for the next pair
+        for (uint32_t s = lane; s < tsize; s += 32) {
+          const uint32_t fl = table[s] >> 30;
+          d += (fl == 1u) | (fl == 2u);
+          table[s] = 0;
+        }
+#pragma unroll
+        for (int sh = 16; sh; sh >>= 1) d += __shfl_xor_sync(0xffffffffu, d, sh);
+        __syncwarp();
+      }
+      if (lane == 0) res[local] = (uint16_t)d;
+    }
+    __syncthreads();
+    const uint32_t nvalid = (uint32_t)min((uint64_t)per_cta, p_end - pb);
+    const uint64_t rel = pb - p_begin;
+    for (uint32_t i = threadIdx.x; i < nvalid; i += blockDim.x) out[rel + i] = res[i];
+    if (editdist >= 0) {
+      // per_cta is a multiple of 32 and so is rel
+      for (uint32_t g = warp; g * 32 < nvalid; g += warps) {
+        const uint32_t i = g * 32 + lane;
+        const bool hit = i < nvalid && (int32_t)res[i] <= editdist;
+        const uint32_t bits = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) mask[rel / 32 + g] = bits;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int W>
+static int launch_tolerant_w(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out,
+                             uint32_t* d_mask) {
+  const TolerantState& S = ctx->tol;
+  const uint32_t key_cap = 2 * S.max_clades + 4;
+  uint32_t tsize = 64;
+  while (tsize < key_cap + key_cap / 2) tsize <<= 1;  // load factor <= 2/3 even if no key repeats
+  const size_t per_warp = (size_t)key_cap * W * 8 + (size_t)tsize * 4;
+  uint32_t warps = 8;
+  while (warps > 1 && warps * per_warp + warps * kTolPairsPerWarp * 2 > 100 * 1024) warps >>= 1;
+  // pairs per CTA must be a multiple of 32 so mask words never straddle CTAs: 8 pairs/warp -> warps % 4 == 0
+  if (warps < 4) {
+    warps = 4;
+    if (warps * per_warp + warps * kTolPairsPerWarp * 2 > 220 * 1024)
+      return ctx->fail(PRF_E_UNSUPPORTED, "tolerant mode: %u clades x %d words per tree needs too much shared memory",
+                       S.max_clades, W);
+  }
+  const size_t smem = warps * per_warp + warps * kTolPairsPerWarp * 2;
+  PRF_CK(ctx, cudaFuncSetAttribute(tolerant_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const uint32_t per_cta = warps * kTolPairsPerWarp;
+  const uint64_t n_blocks = (p_end - p_begin + per_cta - 1) / per_cta;
+  const uint32_t grid = (uint32_t)std::min<uint64_t>(n_blocks, (uint64_t)ctx->sm_count * 64);
+  tolerant_kernel<W><<<grid, warps * 32, smem, ctx->stream>>>(S.T, p_begin, p_end, S.clades.p, S.off.p,
+                                                             S.leafsets.p, tsize, key_cap, editdist, d_out, d_mask);
+  PRF_LAUNCHED(ctx);
+  return PRF_OK;
+}
+
+static int launch_tolerant(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out,
+                           uint32_t* d_mask) {
+  switch (ctx->tol.W) {
+    case 1: return launch_tolerant_w<1>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    case 2: return launch_tolerant_w<2>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    case 3: return launch_tolerant_w<3>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    case 4: return launch_tolerant_w<4>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    case 5: return launch_tolerant_w<5>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    case 6: return launch_tolerant_w<6>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    case 7: return launch_tolerant_w<7>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    case 8: return launch_tolerant_w<8>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    default: return ctx->fail(PRF_E_UNSUPPORTED, "tolerant mode supports W in 1..%u", kTolMaxWords);
+  }
+}
+
+}  // namespace prf

@@ -1,0 +1,123 @@
+"""Host side of the path: trees, the global label table and bipartition extraction.
+
+Thin Python face of libphybin_host.so (C++).  Mirrors what PhyBin's driver does before it calls
+hashRF / naiveDistMatrix (PhyBin.hs:125-194): parseNewicks, the numLeaves filter, allBips.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ._native import host_lib, u64p
+
+RANDOM_TOPOLOGY = 0
+NNI_FAMILY = 1
+
+
+def _take(ptr, n_words: int) -> np.ndarray:
+    """Copies a malloc'd uint64 buffer into a numpy array and frees it."""
+    L = host_lib()
+    n = max(int(n_words), 0)
+    arr = np.empty(n, dtype=np.uint64)
+    if n:
+        C.memmove(arr.ctypes.data, ptr, n * 8)
+    L.phb_free_buf(ptr)
+    return arr
+
+
+class Forest:
+    """A list of NewickTrees sharing one LabelTable (the `[FullTree]` parseNewicks returns)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        err = host_lib().phb_error(handle)
+        if err:
+            msg = err.decode()
+            host_lib().phb_free(handle)
+            self._h = None
+            raise ValueError(msg)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            host_lib().phb_free(self._h)
+            self._h = None
+
+    # -- construction -------------------------------------------------------------------------
+    @classmethod
+    def parse(cls, texts: Sequence[str], name_prefix: int = -1) -> "Forest":
+        arr = (C.c_char_p * len(texts))(*[t.encode() for t in texts])
+        return cls(host_lib().phb_parse(len(texts), arr, name_prefix))
+
+    @classmethod
+    def synthetic(cls, T: int, n: int, seed: int, family: int = RANDOM_TOPOLOGY, nni_max: int = 8,
+                  p_missing: float = 0.0) -> "Forest":
+        return cls(host_lib().phb_synth(T, n, seed & (2**64 - 1), family, nni_max, p_missing))
+
+    # -- queries ------------------------------------------------------------------------------
+    def __len__(self) -> int:
+        return host_lib().phb_num_trees(self._h)
+
+    @property
+    def num_labels(self) -> int:
+        return host_lib().phb_num_labels(self._h)
+
+    @property
+    def labels(self) -> List[str]:
+        L = host_lib()
+        return [L.phb_label_name(self._h, i).decode() for i in range(self.num_labels)]
+
+    def num_leaves(self, t: int) -> int:
+        return host_lib().phb_tree_num_leaves(self._h, t)
+
+    def filter_num_leaves(self, expected: int) -> int:
+        return host_lib().phb_filter_num_leaves(self._h, expected)
+
+    def slice(self, t0: int, t1: int) -> int:
+        return host_lib().phb_slice(self._h, t0, t1)
+
+    def has_duplicate_leaves(self) -> bool:
+        return bool(host_lib().phb_has_duplicate_leaves(self._h))
+
+    def to_newick(self, t0: int = 0, t1: Optional[int] = None) -> str:
+        L = host_lib()
+        p = L.phb_to_newick(self._h, t0, len(self) if t1 is None else t1)
+        s = C.string_at(p).decode()
+        L.phb_free_buf(p)
+        return s
+
+    @property
+    def words(self) -> int:
+        return host_lib().phb_words(self._h)
+
+    # -- device inputs ------------------------------------------------------------------------
+    def all_bips(self, W: Optional[int] = None, threads: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+        """(bips[nnz, W] uint64, tree_off[T+1] uint64): allBips of every tree, bit-packed."""
+        W = W or self.words
+        bp, op, nnz = u64p(), u64p(), C.c_uint64(0)
+        if host_lib().phb_allbips(self._h, W, threads, C.byref(bp), C.byref(op), C.byref(nnz)):
+            raise RuntimeError("phb_allbips failed (W too small or out of memory)")
+        return _take(bp, nnz.value * W).reshape(-1, W), _take(op, len(self) + 1)
+
+    def raw_clades(self, W: Optional[int] = None, threads: int = 0):
+        """(clades[nnz, W], tree_off[T+1], leafsets[T, W]) for the tolerant path."""
+        W = W or self.words
+        cp, op, lp, nnz = u64p(), u64p(), u64p(), C.c_uint64(0)
+        if host_lib().phb_raw_clades(self._h, W, threads, C.byref(cp), C.byref(op), C.byref(lp),
+                                     C.byref(nnz)):
+            raise RuntimeError("phb_raw_clades failed (W too small or out of memory)")
+        T = len(self)
+        return (_take(cp, nnz.value * W).reshape(-1, W), _take(op, T + 1),
+                _take(lp, T * W).reshape(T, W))
+
+
+def bits_to_labels(row: np.ndarray) -> Tuple[int, ...]:
+    """One W-word bit set -> ascending label tuple (for tests and debugging)."""
+    out = []
+    for w, word in enumerate(row.tolist()):
+        while word:
+            b = (word & -word).bit_length() - 1
+            out.append(w * 64 + b)
+            word &= word - 1
+    return tuple(out)

@@ -1,0 +1,266 @@
+"""Host-side mirror of Bio.Phylogeny.PhyBin.RFDistance's public face for the distance-matrix path
+(same names, argument meaning and results), computed by libphybin_rf.so on a B200.
+
+    hashRF          :: Int -> [NewickTree a] -> DistanceMatrix                 RFDistance.hs:284
+    naiveDistMatrix :: [NewickTree DefDecor] -> (DistanceMatrix, Vector (Set DenseLabelSet))   :168
+    printDistMat    :: Handle -> DistanceMatrix -> IO ()                       :352
+
+There is no CPU implementation in this module: every matrix comes from the CUDA library, and the
+calls raise if it is missing or no device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import IO, List, Optional, Tuple
+
+import numpy as np
+
+from . import _native
+from ._native import prf_stats, rf_lib, host_lib
+from .host import Forest, bits_to_labels
+
+VARIANT_AUTO, VARIANT_SPARSE, VARIANT_DENSE = 0, 1, 2
+MEM_HOST, MEM_DEVICE = 0, 1
+
+
+class PhyBinRFError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"phybin_rf error {code}: {msg}")
+        self.code = code
+
+
+def packed_index(T: int, a, b):
+    """p(a, b) for a < b: position of d(a, b) in the packed row-major upper triangle."""
+    a = np.asarray(a, dtype=np.int64)
+    b = np.asarray(b, dtype=np.int64)
+    return a * T - a * (a + 1) // 2 + (b - a - 1)
+
+
+class DistanceMatrix:
+    """`V.Vector (U.Vector Int)`: row i holds d(i, 0..i-1) (RFDistance.hs:156, :306-311), stored as
+    the uint16 packed upper triangle the device produces."""
+
+    def __init__(self, upper: np.ndarray, T: int):
+        self.upper = upper
+        self.T = T
+
+    def __len__(self) -> int:
+        return self.T
+
+    def row(self, i: int) -> np.ndarray:
+        j = np.arange(i, dtype=np.int64)
+        return self.upper[packed_index(self.T, j, i)].astype(np.int64)
+
+    def __getitem__(self, i: int) -> np.ndarray:
+        return self.row(i)
+
+    def rows(self) -> List[List[int]]:
+        return [self.row(i).tolist() for i in range(self.T)]
+
+    def lower_flat(self) -> np.ndarray:
+        """(i, j), j < i at i(i-1)/2 + j -- the reference's rows back to back."""
+        T = self.T
+        if T < 2:
+            return np.zeros(0, dtype=np.int64)
+        ii, jj = np.tril_indices(T, -1)
+        return self.upper[packed_index(T, jj, ii)].astype(np.int64)
+
+    def __repr__(self) -> str:  # `show` of the Haskell value for small matrices
+        return str(self.rows()).replace(" ", "")
+
+
+class RFContext:
+    """One prf_ctx: a CUDA device, a stream, and the device-resident state of one problem."""
+
+    def __init__(self, device: int = 0):
+        self._L = rf_lib()
+        self._h = self._L.prf_create(device)
+        if not self._h:
+            raise PhyBinRFError(-2, self._L.prf_last_error(None).decode())
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.prf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise PhyBinRFError(rc, self._L.prf_last_error(self._h).decode())
+
+    @property
+    def launches(self) -> int:
+        return int(self._L.prf_launch_count(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(self._L.prf_stream(self._h) or 0)
+
+    # ---- hashRF ------------------------------------------------------------------------------
+    def hashrf(self, bips: np.ndarray, tree_off: np.ndarray, editdist: int = -1,
+               fetch: bool = True) -> Tuple[Optional[np.ndarray], Optional[np.ndarray], dict]:
+        """One-shot prf_hashrf on host arrays.  Returns (upper uint16[P], mask uint32[...] | None, stats)."""
+        bips = np.ascontiguousarray(bips, dtype=np.uint64)
+        tree_off = np.ascontiguousarray(tree_off, dtype=np.uint64)
+        T = len(tree_off) - 1
+        W = bips.shape[1] if bips.ndim == 2 else 1
+        P = T * (T - 1) // 2 if T else 0
+        out = np.empty(P, dtype=np.uint16) if fetch else None
+        mask = np.empty((P + 31) // 32, dtype=np.uint32) if (fetch and editdist >= 0) else None
+        st = prf_stats()
+        self._ck(self._L.prf_hashrf(self._h, bips.ctypes.data, tree_off.ctypes.data, T, W, editdist,
+                                    out.ctypes.data if out is not None else None,
+                                    mask.ctypes.data if mask is not None else None, C.byref(st)))
+        return out, mask, st.as_dict()
+
+    def hashrf_load(self, bips, tree_off, T: Optional[int] = None, W: Optional[int] = None,
+                    kind: int = MEM_HOST) -> dict:
+        """prf_hashrf_load.  With kind=MEM_DEVICE pass raw device pointers (ints) plus T and W."""
+        st = prf_stats()
+        if kind == MEM_HOST:
+            bips = np.ascontiguousarray(bips, dtype=np.uint64)
+            tree_off = np.ascontiguousarray(tree_off, dtype=np.uint64)
+            T = len(tree_off) - 1
+            W = bips.shape[1] if bips.ndim == 2 else 1
+            self._keep = (bips, tree_off)
+            bp, op = bips.ctypes.data, tree_off.ctypes.data
+        else:
+            bp, op = int(bips), int(tree_off)
+        self._ck(self._L.prf_hashrf_load(self._h, bp, op, T, W, kind, C.byref(st)))
+        self.T = T
+        self.P = T * (T - 1) // 2 if T else 0
+        return st.as_dict()
+
+    def hashrf_compute(self, p_begin: int = 0, p_end: Optional[int] = None, editdist: int = -1,
+                       variant: int = VARIANT_AUTO, d_out: int = 0, d_mask: int = 0,
+                       want_stats: bool = True) -> Optional[dict]:
+        p_end = self.P if p_end is None else p_end
+        st = prf_stats()
+        self._ck(self._L.prf_hashrf_compute(self._h, p_begin, p_end, editdist, variant, d_out or None,
+                                            d_mask or None, C.byref(st) if want_stats else None))
+        return st.as_dict() if want_stats else None
+
+    # ---- tolerant ----------------------------------------------------------------------------
+    def tolerant(self, clades: np.ndarray, tree_off: np.ndarray, leafsets: np.ndarray, editdist: int = -1,
+                 fetch: bool = True):
+        clades = np.ascontiguousarray(clades, dtype=np.uint64)
+        tree_off = np.ascontiguousarray(tree_off, dtype=np.uint64)
+        leafsets = np.ascontiguousarray(leafsets, dtype=np.uint64)
+        T = len(tree_off) - 1
+        W = leafsets.shape[1] if leafsets.ndim == 2 else 1
+        P = T * (T - 1) // 2 if T else 0
+        out = np.empty(P, dtype=np.uint16) if fetch else None
+        mask = np.empty((P + 31) // 32, dtype=np.uint32) if (fetch and editdist >= 0) else None
+        st = prf_stats()
+        self._ck(self._L.prf_tolerant(self._h, clades.ctypes.data, tree_off.ctypes.data, leafsets.ctypes.data,
+                                      T, W, editdist, out.ctypes.data if out is not None else None,
+                                      mask.ctypes.data if mask is not None else None, C.byref(st)))
+        return out, mask, st.as_dict()
+
+    def tolerant_load(self, clades, tree_off, leafsets, T: Optional[int] = None, W: Optional[int] = None,
+                      kind: int = MEM_HOST) -> dict:
+        st = prf_stats()
+        if kind == MEM_HOST:
+            clades = np.ascontiguousarray(clades, dtype=np.uint64)
+            tree_off = np.ascontiguousarray(tree_off, dtype=np.uint64)
+            leafsets = np.ascontiguousarray(leafsets, dtype=np.uint64)
+            T = len(tree_off) - 1
+            W = leafsets.shape[1] if leafsets.ndim == 2 else 1
+            cp, op, lp = clades.ctypes.data, tree_off.ctypes.data, leafsets.ctypes.data
+        else:
+            cp, op, lp = int(clades), int(tree_off), int(leafsets)
+        self._ck(self._L.prf_tolerant_load(self._h, cp, op, lp, T, W, kind, C.byref(st)))
+        self.T = T
+        self.P = T * (T - 1) // 2 if T else 0
+        return st.as_dict()
+
+    def tolerant_compute(self, p_begin: int = 0, p_end: Optional[int] = None, editdist: int = -1,
+                         d_out: int = 0, d_mask: int = 0, want_stats: bool = True) -> Optional[dict]:
+        p_end = self.P if p_end is None else p_end
+        st = prf_stats()
+        self._ck(self._L.prf_tolerant_compute(self._h, p_begin, p_end, editdist, d_out or None, d_mask or None,
+                                              C.byref(st) if want_stats else None))
+        return st.as_dict() if want_stats else None
+
+    # ---- results -----------------------------------------------------------------------------
+    def fetch(self, p_begin: int = 0, p_end: Optional[int] = None) -> np.ndarray:
+        p_end = self.P if p_end is None else p_end
+        out = np.empty(p_end - p_begin, dtype=np.uint16)
+        self._ck(self._L.prf_fetch(self._h, p_begin, p_end, out.ctypes.data))
+        return out
+
+    def fetch_mask(self, p_begin: int = 0, p_end: Optional[int] = None) -> np.ndarray:
+        p_end = self.P if p_end is None else p_end
+        out = np.empty((p_end - p_begin + 31) // 32, dtype=np.uint32)
+        self._ck(self._L.prf_fetch_mask(self._h, p_begin, p_end, out.ctypes.data))
+        return out
+
+    def fetch_rows(self, row0: int, row1: int) -> np.ndarray:
+        T = self.T
+        n = sum(T - 1 - a for a in range(row0, min(row1, T)))
+        out = np.empty(n, dtype=np.uint16)
+        self._ck(self._L.prf_fetch_rows(self._h, row0, row1, out.ctypes.data))
+        return out
+
+
+_default_ctx: Optional[RFContext] = None
+
+
+def default_context() -> RFContext:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = RFContext(0)
+    return _default_ctx
+
+
+def shard_range(T: int, rank: int, world: int) -> Tuple[int, int]:
+    """Aligned, balanced slice of the packed triangle for `rank` of `world` (prf_shard_range)."""
+    b, e = C.c_uint64(0), C.c_uint64(0)
+    rc = rf_lib().prf_shard_range(T, rank, world, C.byref(b), C.byref(e))
+    if rc:
+        raise PhyBinRFError(rc, "prf_shard_range: bad arguments")
+    return b.value, e.value
+
+
+# ---- the reference's names ---------------------------------------------------------------------
+
+def hashRF(num_taxa: int, trees: Forest, ctx: Optional[RFContext] = None) -> DistanceMatrix:
+    """hashRF num_taxa trees (RFDistance.hs:284).  `num_taxa` is accepted and ignored exactly as in
+    the reference's IntSet build (it only reaches mkSingleDense, :295/:119).  The caller is
+    expected to have applied the numLeaves filter (PhyBin.hs:187-194; Forest.filter_num_leaves)."""
+    del num_taxa
+    ctx = ctx or default_context()
+    bips, off = trees.all_bips()
+    upper, _, _ = ctx.hashrf(bips, off)
+    return DistanceMatrix(upper, len(trees))
+
+
+def naiveDistMatrix(trees: Forest, ctx: Optional[RFContext] = None):
+    """naiveDistMatrix trees (RFDistance.hs:168): (matrix, per-tree allBips as sets of label tuples)."""
+    if trees.has_duplicate_leaves():
+        raise PhyBinRFError(-6, "tolerant mode on the device needs distinct leaf labels within a tree")
+    ctx = ctx or default_context()
+    clades, off, leafsets = trees.raw_clades()
+    upper, _, _ = ctx.tolerant(clades, off, leafsets)
+    bips, boff = trees.all_bips()
+    eachbips = [frozenset(bits_to_labels(b) for b in bips[int(boff[t]):int(boff[t + 1])])
+                for t in range(len(trees))]
+    return DistanceMatrix(upper, len(trees)), eachbips
+
+
+def printDistMat(handle: IO[str], mat: DistanceMatrix) -> None:
+    """printDistMat h mat (RFDistance.hs:352-361), byte-identical text."""
+    L = host_lib()
+    up = np.ascontiguousarray(mat.upper, dtype=np.uint16)
+    p = L.phb_print_dist_mat(up.ctypes.data, mat.T)
+    handle.write(C.string_at(p).decode())
+    L.phb_free_buf(p)

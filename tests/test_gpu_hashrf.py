@@ -1,0 +1,218 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+the CPU oracle on the same inputs.  Bit-exact -- this is integer work."""
+import ctypes as C
+import io
+import random
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from phybin_b200 import _native
+from phybin_b200.host import Forest, NNI_FAMILY
+from phybin_b200.rfdistance import (DistanceMatrix, PhyBinRFError, RFContext, hashRF, naiveDistMatrix,
+                                    packed_index, printDistMat, shard_range)
+from tests.util import oracle_packed, random_multifurcating_newicks
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = RFContext(0)
+    yield c
+    c.close()
+
+
+# ---- primitives ---------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n", [1, 31, 4096, 4097, 100003, 1 << 21])
+def test_scan_primitive(ctx, n):
+    L = _native.rf_lib()
+    rng = np.random.default_rng(n)
+    x = rng.integers(0, 5, size=n, dtype=np.uint32)
+    out = np.empty_like(x)
+    tot = C.c_uint32(0)
+    assert L.prf_debug_scan(ctx._h, x.ctypes.data, C.c_uint64(n), out.ctypes.data, C.byref(tot)) == 0
+    want = np.concatenate([[0], np.cumsum(x, dtype=np.uint64)[:-1]]).astype(np.uint32)
+    assert np.array_equal(out, want) and tot.value == int(x.sum())
+
+
+@pytest.mark.parametrize("n,bits", [(2, 1), (1000, 8), (4096, 9), (50001, 17), (300000, 22)])
+def test_sort_primitive_is_stable(ctx, n, bits):
+    L = _native.rf_lib()
+    rng = np.random.default_rng(n)
+    k = rng.integers(0, 1 << bits, size=n, dtype=np.uint32)
+    v = np.arange(n, dtype=np.uint32)
+    k2, v2 = k.copy(), v.copy()
+    assert L.prf_debug_sort(ctx._h, k2.ctypes.data, v2.ctypes.data, n, bits) == 0
+    order = np.argsort(k, kind="stable")
+    assert np.array_equal(k2, k[order]) and np.array_equal(v2, v[order])
+
+
+# ---- golden fixtures ----------------------------------------------------------------------------
+
+def test_reference_kat_t30_on_device(golden, ctx):
+    c = golden["t30_literal"]
+    mat, eachbips = naiveDistMatrix(Forest.parse(c["texts"], c["name_prefix"]), ctx)
+    assert repr(mat) == "[[],[0],[1,0]]"  # TestAll.hs:31-32
+    assert [sorted(list(b) for b in bs) for bs in eachbips] == [sorted(x) for x in c["all_bips"]]
+    buf = io.StringIO()
+    printDistMat(buf, mat)
+    assert buf.getvalue().splitlines()[2:5] == ["0", "0 0", "1 0 0"]
+
+
+@pytest.mark.parametrize("name", ["t30_file", "t1", "t2", "t4", "t5", "t3"])
+def test_golden_hashrf_and_naive(golden, ctx, name):
+    c = golden[name]
+    f = Forest.parse(c["texts"], c["name_prefix"])
+    mat, _ = naiveDistMatrix(f, ctx)
+    assert mat.rows() == c["naive"]
+    f.filter_num_leaves(len(c["labels"]))
+    assert len(f) == c["hashrf_num_trees"]
+    mat = hashRF(len(c["labels"]), f, ctx)
+    assert mat.rows() == c["hashrf"]
+    s = c.get("survey", {})
+    if "sum" in s:
+        assert int(mat.upper.astype(np.int64).sum()) == s["sum"] and int(mat.upper.max(initial=0)) == s["max"]
+
+
+# ---- synthetic, against the literal oracle --------------------------------------------------------
+
+def run_hashrf(ctx, f: Forest, editdist=-1):
+    bips, off = f.all_bips()
+    return ctx.hashrf(bips, off, editdist)
+
+
+@pytest.mark.parametrize("T,n,family", [(100, 10, 0), (300, 30, 0), (700, 64, 0), (700, 65, 0),
+                                        (400, 100, NNI_FAMILY), (2, 5, 0), (1, 8, 0)])
+def test_synthetic_vs_literal_oracle(ctx, T, n, family):
+    f = Forest.synthetic(T, n, seed=0x5EED0001 + T, family=family)
+    o = orc.Forest([f.to_newick()])
+    up, _, st = run_hashrf(ctx, f)
+    assert np.array_equal(up.astype(np.int64), oracle_packed(o, "hashrf", "literal"))
+    ost = {}
+    o.hashrf(n, "closed", ost)
+    assert st["n_unique"] == ost["n_unique"] and st["n_pairs"] == T * (T - 1) // 2
+
+
+def test_config2_shape_vs_closed_form_oracle(ctx):
+    # BASELINE config 2 family at a size the oracle finishes in seconds: 2500 x 100
+    T, n = 2500, 100
+    f = Forest.synthetic(T, n, seed=0x5EED0002)
+    o = orc.Forest([f.to_newick()])
+    small = orc.Forest([f.to_newick(0, 300)])
+    assert np.array_equal(small.hashrf(n, "closed"), small.hashrf(n, "literal"))  # closed form is trusted only after this
+    up, mask, st = run_hashrf(ctx, f, editdist=190)
+    want = oracle_packed(o, "hashrf", "closed")
+    assert np.array_equal(up.astype(np.int64), want)
+    bits = np.unpackbits(mask.view(np.uint8), bitorder="little")[: len(want)]
+    assert np.array_equal(bits.astype(bool), want <= 190)
+    assert 0 < bits.sum() < len(want)
+    assert st["gpu_launches"] > 0 and st["variant_used"] == 1
+
+
+def test_multifurcating_nonuniform_bip_counts(ctx):
+    rng = random.Random(11)
+    text = [random_multifurcating_newicks(rng, 500, 40)]
+    f, o = Forest.parse(text), orc.Forest(text)
+    up, _, st = run_hashrf(ctx, f)
+    assert st["min_bips"] < st["max_bips"]
+    assert np.array_equal(up.astype(np.int64), oracle_packed(o, "hashrf", "literal"))
+
+
+def test_quirk_q1_odd_taxa_on_device(ctx):
+    # odd n: the tie rule makes rootings of one topology differ; device must agree
+    rng = random.Random(5)
+    text = [random_multifurcating_newicks(rng, 200, 9)]
+    f, o = Forest.parse(text), orc.Forest(text)
+    up, _, _ = run_hashrf(ctx, f)
+    assert np.array_equal(up.astype(np.int64), oracle_packed(o, "hashrf", "literal"))
+
+
+def test_duplicate_bips_within_a_tree_count_once(ctx):
+    f = Forest.synthetic(50, 12, seed=3)
+    bips, off = f.all_bips()
+    want, _, _ = ctx.hashrf(bips, off)
+    # repeat every entry of every tree twice: a tree's bipartitions are a Set
+    rep = np.repeat(bips, 2, axis=0)
+    got, _, st = ctx.hashrf(rep, off * 2)
+    assert np.array_equal(got, want)
+
+
+def test_editdist_mask_and_sharded_compute(ctx):
+    T, n = 900, 30
+    f = Forest.synthetic(T, n, seed=9, family=NNI_FAMILY, nni_max=4)
+    bips, off = f.all_bips()
+    full, mask, _ = ctx.hashrf(bips, off, editdist=4)
+    P = T * (T - 1) // 2
+    bits = np.unpackbits(mask.view(np.uint8), bitorder="little")[:P].astype(bool)
+    assert np.array_equal(bits, full <= 4) and bits.any() and not bits.all()
+    # staged API: 3 "ranks" each compute their aligned slice; slices tile [0, P) exactly
+    ctx.hashrf_load(bips, off)
+    got = np.empty(P, dtype=np.uint16)
+    prev = 0
+    for r in range(3):
+        b, e = shard_range(T, r, 3)
+        assert b == prev
+        prev = e
+        ctx.hashrf_compute(b, e, editdist=4)
+        got[b:e] = ctx.fetch(b, e)
+        m = np.unpackbits(ctx.fetch_mask(b, e).view(np.uint8), bitorder="little")[: e - b].astype(bool)
+        assert np.array_equal(m, full[b:e] <= 4)
+    assert prev == P and np.array_equal(got, full)
+    ctx.hashrf_compute(0, P)
+    rows = ctx.fetch_rows(10, 12)
+    assert np.array_equal(rows, full[packed_index(T, 10, 11): packed_index(T, 12, 13)])
+
+
+def test_error_codes_not_aborts(ctx):
+    fresh = RFContext(0)
+    fresh.P = 0
+    with pytest.raises(PhyBinRFError) as ei:
+        fresh.hashrf_compute(0, 0)
+    assert ei.value.code == -5  # PRF_E_STATE: compute before load
+    fresh.close()
+    f = Forest.synthetic(10, 8, seed=1)
+    bips, off = f.all_bips()
+    ctx.hashrf_load(bips, off)
+    with pytest.raises(PhyBinRFError) as ei:
+        ctx.hashrf_compute(1, 40)  # unaligned begin
+    assert ei.value.code == -1
+    bad = off.copy()
+    bad[3] = bad[2] - 1
+    with pytest.raises(PhyBinRFError):
+        ctx.hashrf_load(bips, bad)
+
+
+# ---- tolerant -------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("seed", range(6))
+def test_tolerant_random_shapes_vs_oracle(ctx, seed):
+    rng = random.Random(100 + seed)
+    n = rng.choice([3, 5, 8, 12, 30, 70])
+    T = rng.randint(2, 60)
+    text = [random_multifurcating_newicks(rng, T, n, p_missing=0.25, unary=0.1)]
+    f, o = Forest.parse(text), orc.Forest(text)
+    mat, _ = naiveDistMatrix(f, ctx)
+    assert np.array_equal(mat.upper.astype(np.int64), oracle_packed(o, "naive")), text
+
+
+def test_tolerant_config5_family_vs_oracle(ctx):
+    # BASELINE config 5 family (150 taxa, each dropped w.p. 0.10) at an oracle-sized T
+    T, n = 160, 150
+    f = Forest.synthetic(T, n, seed=0x5EED0005, p_missing=0.10)
+    o = orc.Forest([f.to_newick()])
+    clades, off, leaf = f.raw_clades()
+    up, mask, st = ctx.tolerant(clades, off, leaf, editdist=250)
+    want = oracle_packed(o, "naive")
+    assert np.array_equal(up.astype(np.int64), want)
+    bits = np.unpackbits(mask.view(np.uint8), bitorder="little")[: len(want)].astype(bool)
+    assert np.array_equal(bits, want <= 250)
+
+
+def test_tolerant_equals_hashrf_on_complete_taxa(ctx):
+    f = Forest.synthetic(300, 24, seed=77)
+    a = hashRF(24, f, ctx)
+    b, _ = naiveDistMatrix(f, ctx)
+    assert np.array_equal(a.upper, b.upper)

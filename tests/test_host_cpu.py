@@ -1,0 +1,158 @@
+"""CPU tests (no GPU): the C++ host side against the oracle, the C-ABI library's exported
+symbols, and loud failure without a device."""
+import ctypes
+import io
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from phybin_b200 import _native, build
+from phybin_b200.host import Forest, NNI_FAMILY, bits_to_labels
+from tests.util import random_multifurcating_newicks
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def host_bips(f: Forest, t: int, bips, off):
+    return sorted(bits_to_labels(b) for b in bips[int(off[t]):int(off[t + 1])])
+
+
+@pytest.mark.parametrize("name", ["t30_literal", "t30_file", "t1", "t2", "t4", "t5", "t3"])
+def test_host_allbips_matches_golden(golden, name):
+    c = golden[name]
+    f = Forest.parse(c["texts"], c["name_prefix"])
+    assert f.labels == c["labels"]  # Parser.hs label order (quirk Q4)
+    bips, off = f.all_bips()
+    for t in range(len(f)):
+        assert host_bips(f, t, bips, off) == sorted(tuple(b) for b in c["all_bips"][t])
+
+
+def test_host_matches_oracle_on_random_shapes():
+    rng = random.Random(7)
+    for trial in range(30):
+        n = rng.randint(2, 40)
+        text = [random_multifurcating_newicks(rng, rng.randint(1, 6), n, p_missing=0.2, unary=0.1)]
+        f, o = Forest.parse(text), orc.Forest(text)
+        assert f.labels == o.labels
+        bips, off = f.all_bips()
+        for t in range(len(f)):
+            assert f.num_leaves(t) == o.num_leaves(t)
+            assert host_bips(f, t, bips, off) == sorted(o.all_bips(t)), (text, t)
+
+
+def test_host_duplicate_labels_and_wide_sets():
+    # duplicate taxa: numLeaves counts them twice (CoreTypes.hs:289) and so does the host
+    text = ["((a,b),(a,c),(d,(e,f)));((a,b),(c,d),(e,f));"]
+    f, o = Forest.parse(text), orc.Forest(text)
+    assert f.has_duplicate_leaves()
+    bips, off = f.all_bips()
+    for t in range(2):
+        assert host_bips(f, t, bips, off) == sorted(o.all_bips(t))
+    # > 64 taxa: multi-word sets
+    rng = random.Random(3)
+    text = [random_multifurcating_newicks(rng, 4, 150)]
+    f, o = Forest.parse(text), orc.Forest(text)
+    assert f.words == 3
+    bips, off = f.all_bips()
+    for t in range(4):
+        assert host_bips(f, t, bips, off) == sorted(o.all_bips(t))
+
+
+@pytest.mark.parametrize("family,p_missing", [(0, 0.0), (NNI_FAMILY, 0.0), (0, 0.15)])
+def test_synthetic_forest_roundtrips_through_newick(family, p_missing):
+    f = Forest.synthetic(40, 37, seed=0x5EED0001, family=family, nni_max=6, p_missing=p_missing)
+    text = f.to_newick()
+    g, o = Forest.parse([text]), orc.Forest([text])
+    assert f.labels == g.labels == o.labels  # generator numbers taxa exactly as the parser would
+    b1, o1 = f.all_bips()
+    b2, o2 = g.all_bips()
+    assert np.array_equal(b1, b2) and np.array_equal(o1, o2)
+    for t in range(len(f)):
+        assert host_bips(f, t, b1, o1) == sorted(o.all_bips(t))
+    if p_missing == 0:
+        assert all(f.num_leaves(t) == 37 for t in range(40))
+        assert all(int(o1[t + 1] - o1[t]) == 37 - 3 for t in range(40))  # binary: n - 3 bips
+
+
+def test_synthetic_is_deterministic_and_seeded():
+    a = Forest.synthetic(10, 20, seed=1).to_newick()
+    assert a == Forest.synthetic(10, 20, seed=1).to_newick()
+    assert a != Forest.synthetic(10, 20, seed=2).to_newick()
+
+
+def test_raw_clades_shapes():
+    text = ["((a,b),(c,(d,e)),f);(a,(b,c));"]
+    f = Forest.parse(text)
+    clades, off, leaf = f.raw_clades()
+    lab = {n: i for i, n in enumerate(f.labels)}
+    got0 = sorted(bits_to_labels(c) for c in clades[int(off[0]):int(off[1])])
+    want0 = sorted(tuple(sorted(lab[x] for x in s)) for s in [("a", "b"), ("d", "e"), ("c", "d", "e")])
+    assert got0 == want0
+    assert bits_to_labels(leaf[1]) == tuple(sorted(lab[x] for x in "abc"))
+
+
+def test_filter_num_leaves_is_the_hashrf_input_filter(golden):
+    c = golden["t30_literal"]
+    f = Forest.parse(c["texts"])
+    assert len(f) == 3 and f.filter_num_leaves(10) == 2  # PhyBin.hs:187-194 drops the 9-taxon tree
+
+
+def test_print_dist_mat_text():
+    L = _native.host_lib()
+    T = 3
+    upper = np.array([0, 1, 0], dtype=np.uint16)  # d(0,1)=0 d(0,2)=1 d(1,2)=0  ==  [[],[0],[1,0]]
+    p = L.phb_print_dist_mat(upper.ctypes.data, T)
+    s = ctypes.string_at(p).decode()
+    L.phb_free_buf(p)
+    assert s == orc.print_dist_mat(np.array([0, 1, 0]), 3)
+    assert s.splitlines()[2:5] == ["0", "0 0", "1 0 0"]
+
+
+def test_parse_errors_are_reported_not_fatal():
+    with pytest.raises(ValueError):
+        Forest.parse(["((a,b),c"])
+    with pytest.raises(ValueError):
+        orc.Forest(["((a,b),c"])
+
+
+def test_rf_library_exports_every_declared_symbol():
+    """include/phybin_rf.h <-> libphybin_rf.so: every declared entry point is exported."""
+    build.build_cuda()
+    hdr = open(os.path.join(ROOT, "include", "phybin_rf.h")).read()
+    declared = sorted(set(re.findall(r"PRF_API\s+[\w\s\*]+?\b(prf_\w+)\s*\(", hdr)))
+    assert declared == sorted(_native.RF_SYMBOLS)
+    lib = ctypes.CDLL(build.RF_SO)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+
+
+def test_rf_helpers_without_a_device():
+    L = _native.rf_lib()
+    T = 1000
+    assert L.prf_packed_index(T, 0, 1) == 0
+    assert L.prf_packed_index(T, 0, T - 1) == T - 2
+    assert L.prf_packed_index(T, T - 2, T - 1) == T * (T - 1) // 2 - 1
+    assert L.prf_packed_index(T, 5, 5) == 2**64 - 1
+    align = L.prf_shard_align()
+    P = 100000 * 99999 // 2
+    prev = 0
+    for r in range(8):
+        b, e = ctypes.c_uint64(), ctypes.c_uint64()
+        assert L.prf_shard_range(100000, r, 8, ctypes.byref(b), ctypes.byref(e)) == 0
+        assert b.value == prev and b.value % align == 0
+        prev = e.value
+    assert prev == P
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from phybin_b200.rfdistance import PhyBinRFError, RFContext
+    with pytest.raises(PhyBinRFError) as ei:
+        RFContext(0)
+    assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
