@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- RF tree-pairs/s on the headline workload (BASELINE.json: 100k trees x 200 taxa).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg3|cfg2|...]
+
+One "step" = one pass of the hot path over the whole batch: canonical bipartitions resident in HBM
+-> dedup -> incidence -> matrix kernel -> packed uint16 upper triangle resident in HBM.  With N > 1
+(torchrun, one rank per GPU) the trees are sharded across ranks, an NCCL all-gather rebuilds the full
+bipartition table on every rank, and each rank computes a contiguous, aligned slice of the packed
+triangle (fixed total work => "strong" scaling).  Rank 0 prints ONE JSON line.
+
+`e2e` is the same metric through the public host-buffer call prf_hashrf (pinned host input, H2D,
+compute, D2H of the whole matrix into pinned host memory).  `cpu_baseline` / `--impl reference` time
+the oracle's literal restatement of the reference algorithm (the Haskell binary cannot be built in
+this image: no GHC) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (T, n, seed, family, editdist, mode)
+    "cfg2": dict(T=10_000, n=100, seed=0x5EED0002, family=0, editdist=-1, mode="hashrf"),
+    "cfg3": dict(T=100_000, n=200, seed=0x5EED0003, family=0, editdist=-1, mode="hashrf"),
+    "cfg4": dict(T=50_000, n=500, seed=0x5EED0004, family=0, editdist=4, mode="hashrf"),
+    "cfg5": dict(T=20_000, n=150, seed=0x5EED0005, family=0, editdist=-1, mode="tolerant", p_missing=0.10),
+}
+METRIC = "rf_tree_pairs_per_sec"
+UNIT = "tree-pairs/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.lines = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU reference arm: the oracle's literal hashRF / naiveDistMatrix on a bounded sample
+# ---------------------------------------------------------------------------------------------------
+
+def cpu_sample(wl: dict, budget_trees: int):
+    """Times the oracle (literal restatement of RFDistance.hs:284-341 / :168-198) on the first
+    `budget_trees` trees of the workload.  Returns (pairs_per_s, seconds, sample description)."""
+    from oracle import oracle as orc
+    from phybin_b200.host import Forest
+    Ts = min(budget_trees, wl["T"])
+    f = Forest.synthetic(Ts, wl["n"], wl["seed"], wl["family"], 8, wl.get("p_missing", 0.0))
+    text = f.to_newick()
+    of = orc.Forest([text])
+    t0 = time.perf_counter()
+    if wl["mode"] == "tolerant":
+        of.naive()
+    else:
+        of.hashrf(wl["n"], "literal")
+    dt = time.perf_counter() - t0
+    pairs = Ts * (Ts - 1) // 2
+    return pairs / dt, dt, f"first {Ts} of {wl['T']} trees x {wl['n']} taxa, all {pairs} pairs, literal {wl['mode']} restatement (allBips + table + matrix)"
+
+
+def run_reference(args, wl, wl_name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sample_T = args.ref_trees or (2000 if wl["mode"] == "hashrf" else 150)
+    for _ in range(args.warmup):
+        cpu_sample(wl, max(100, sample_T // 8))
+    vals, secs, desc = [], [], ""
+    for _ in range(args.steps):
+        v, s, desc = cpu_sample(wl, sample_T)
+        vals.append(v); secs.append(s)
+    total_pairs = len(vals) * (min(sample_T, wl["T"]) * (min(sample_T, wl["T"]) - 1) // 2)
+    value = total_pairs / sum(secs)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64",
+        "data": "synthetic",
+        "config": {"workload": wl_name, "trees": wl["T"], "taxa": wl["n"], "mode": wl["mode"],
+                   "note": "reference arm = CPU oracle (C++ restatement of PhyBin's hashRF); GHC is absent so the Haskell binary cannot be built; the reference path is single-threaded (runST, RFDistance.hs:300-341)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc,
+                         "host_cores": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+
+def run_gpu(args, wl, wl_name):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from phybin_b200.host import Forest
+    from phybin_b200.rfdistance import MEM_DEVICE, RFContext, shard_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; phybin_b200 has no CPU path (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+
+    T, n, mode, editdist = wl["T"], wl["n"], wl["mode"], wl["editdist"]
+    P = T * (T - 1) // 2
+    ctx = RFContext(local_rank)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    # ---- synthetic input: every rank generates only its own shard of trees ----------------------
+    t_lo, t_hi = T * rank // world, T * (rank + 1) // world
+    f = Forest.synthetic(T, n, wl["seed"], wl["family"], 8, wl.get("p_missing", 0.0))
+    W = f.words
+    if mode == "hashrf":
+        bips_all, off_all = f.all_bips()
+        b0, b1 = int(off_all[t_lo]), int(off_all[t_hi])
+        my_bips = np.ascontiguousarray(bips_all[b0:b1])
+        counts = np.diff(off_all.astype(np.int64))
+    else:
+        clades_all, off_all, leaf_all = f.raw_clades()
+        b0, b1 = int(off_all[t_lo]), int(off_all[t_hi])
+        my_bips = np.ascontiguousarray(clades_all[b0:b1])
+        counts = np.diff(off_all.astype(np.int64))
+    nnz = int(off_all[-1])
+    del f
+
+    with torch.cuda.stream(ext):
+        d_my = torch.from_numpy(my_bips.view(np.int64)).to(dev)                  # this rank's tree shard, resident
+        d_off = torch.from_numpy(off_all.view(np.int64)).to(dev)                  # offsets are tiny and replicated
+        d_leaf = torch.from_numpy(leaf_all.view(np.int64)).to(dev) if mode == "tolerant" else None
+        shard_rows = [int(off_all[T * (r + 1) // world] - off_all[T * r // world]) for r in range(world)]
+        max_rows = max(shard_rows)
+        d_full = torch.empty((nnz, W), dtype=torch.int64, device=dev) if world > 1 else d_my
+        d_gather = torch.empty((world, max_rows, W), dtype=torch.int64, device=dev) if world > 1 else None
+        d_pad = torch.zeros((max_rows, W), dtype=torch.int64, device=dev) if world > 1 else None
+        p_begin, p_end = shard_range(T, rank, world)
+        d_out = torch.empty(max(p_end - p_begin, 8), dtype=torch.int16, device=dev)
+        d_mask = torch.empty(max((p_end - p_begin + 31) // 32, 1), dtype=torch.int32, device=dev) if editdist >= 0 else None
+    ext.synchronize()
+
+    matrix_ms = []
+
+    def step():
+        """dedup + incidence + matrix for this rank's slice; inputs and outputs stay in HBM."""
+        with torch.cuda.stream(ext):
+            if world > 1:
+                d_pad[: d_my.shape[0]].copy_(d_my)
+                dist.all_gather_into_tensor(d_gather.view(-1), d_pad.view(-1))     # NCCL over NVLink
+                pos = 0
+                for r in range(world):
+                    d_full[pos:pos + shard_rows[r]].copy_(d_gather[r, : shard_rows[r]])
+                    pos += shard_rows[r]
+        if mode == "hashrf":
+            ctx.hashrf_load(d_full.data_ptr(), d_off.data_ptr(), T, W, MEM_DEVICE)
+            st = ctx.hashrf_compute(p_begin, p_end, editdist, 0, d_out.data_ptr(),
+                                    d_mask.data_ptr() if d_mask is not None else 0)
+        else:
+            ctx.tolerant_load(d_full.data_ptr(), d_off.data_ptr(), d_leaf.data_ptr(), T, W, MEM_DEVICE)
+            st = ctx.tolerant_compute(p_begin, p_end, editdist, d_out.data_ptr(),
+                                      d_mask.data_ptr() if d_mask is not None else 0)
+        matrix_ms.append(st["ms_matrix"])
+        return st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        st = step()
+    barrier()
+    matrix_ms.clear()
+    launches0 = ctx.launches
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(ext)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st = step()
+    ev1.record(ext)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    dev_s = ev0.elapsed_time(ev1) / 1e3
+    launches = ctx.launches - launches0
+    tm = torch.tensor([dev_s, wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    dev_s, wall = float(tm[0]), float(tm[1])
+    # the step synchronises with the host a few times (scalar read-backs), so device-event time on the
+    # library's stream and wall time between the bracketing synchronisations agree; report the larger.
+    step_s = max(dev_s, wall) / args.steps
+    value = P / step_s
+
+    # ---- light self-check on the resident result (not timed): sampled pairs vs direct set intersection
+    if mode == "hashrf" and rank == 0:
+        rng = np.random.default_rng(1)
+        out_h = d_out[: min(p_end - p_begin, 1 << 20)].cpu().numpy().view(np.uint16)
+        pos = rng.integers(0, len(out_h), size=64)
+        for p in pos:
+            gp = p_begin + int(p)
+            a = int(np.searchsorted(np.array([r * T - r * (r + 1) // 2 for r in range(min(T, 4096))]), gp, side="right") - 1)
+            b = a + 1 + gp - (a * T - a * (a + 1) // 2)
+            sa = {tuple(x) for x in bips_all[int(off_all[a]):int(off_all[a + 1])].tolist()}
+            sb = {tuple(x) for x in bips_all[int(off_all[b]):int(off_all[b + 1])].tolist()}
+            assert int(out_h[p]) == len(sa ^ sb), f"self-check failed at pair ({a},{b})"
+
+    # ---- roofline of the dominant kernel (the matrix kernel), per launch ---------------------------
+    peaks, peak_src = load_peaks()
+    my_pairs = p_end - p_begin
+    alg_bytes = 2 * my_pairs + (my_pairs // 8 if editdist >= 0 else 0)
+    avg_ms = sum(matrix_ms) / max(len(matrix_ms), 1)
+    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                "kernel": "sparse_chunk_kernel" if mode == "hashrf" else "tolerant_kernel",
+                "kernel_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel_share_of_step": avg_ms * 1e-3 / step_s}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            with open(traffic_file) as fh:
+                roofline["traffic"] = json.load(fh).get(wl_name if world == 1 else "", None)
+        except Exception:
+            pass
+
+    # ---- e2e through the host-buffer C ABI call (rank-local slice of work: whole job at N=1) ------
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        e2e = run_e2e(ctx, wl, mode, bips_all if mode == "hashrf" else clades_all, off_all,
+                      None if mode == "hashrf" else leaf_all, P, editdist, max(1, min(args.steps, 2)))
+    elif world > 1:
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+               "note": "host-buffer e2e is measured at N=1 (single prf_ctx); multi-GPU ranks keep their slice in HBM"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, s, desc = cpu_sample(wl, args.ref_trees or (2000 if mode == "hashrf" else 150))
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc, "seconds": s,
+                        "host_cores": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u16" if mode == "hashrf" else "u64",
+            "data": "synthetic",
+            "config": {"workload": wl_name, "trees": T, "taxa": n, "mode": mode, "editdist": editdist,
+                       "pairs": P, "nnz": nnz, "words": W, "n_unique": st.get("n_unique"), "n_hits": st.get("n_hits"),
+                       "variant": {1: "sparse", 2: "dense"}.get(st.get("variant_used"), mode),
+                       "parallelism": f"packed-range shard x{world}" + (" + NCCL all-gather of bipartition keys" if world > 1 else ""),
+                       "l2": "output per step (>= 2 B/pair) far exceeds the 126 MB L2; no explicit flush"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks, "device_s": dev_s, "wall_s": wall,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(ctx, wl, mode, keys, off, leaf, P, editdist, steps):
+    """Host buffers in, host buffers out, through prf_hashrf / prf_tolerant; copies inside the timed region."""
+    import numpy as np
+    import torch
+    T = wl["T"]
+    W = keys.shape[1]
+    pin_in = torch.from_numpy(keys.view(np.int64)).pin_memory()
+    pin_out = torch.empty(P, dtype=torch.int16).pin_memory()
+    pin_mask = torch.empty((P + 31) // 32, dtype=torch.int32).pin_memory() if editdist >= 0 else None
+    L = ctx._L
+    import ctypes as C
+    from phybin_b200._native import prf_stats
+    st = prf_stats()
+    offc = np.ascontiguousarray(off, dtype=np.uint64)
+    leafc = np.ascontiguousarray(leaf, dtype=np.uint64) if leaf is not None else None
+
+    def call():
+        if mode == "hashrf":
+            rc = L.prf_hashrf(ctx._h, pin_in.data_ptr(), offc.ctypes.data, T, W, editdist, pin_out.data_ptr(),
+                              pin_mask.data_ptr() if pin_mask is not None else None, C.byref(st))
+        else:
+            rc = L.prf_tolerant(ctx._h, pin_in.data_ptr(), offc.ctypes.data, leafc.ctypes.data, T, W, editdist,
+                                pin_out.data_ptr(), pin_mask.data_ptr() if pin_mask is not None else None, C.byref(st))
+        ctx._ck(rc)
+
+    call()  # warm-up (allocations, page faults of the pinned buffers)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    h2d = int(keys.nbytes + offc.nbytes + (leafc.nbytes if leafc is not None else 0))
+    d2h = int(P * 2 + ((P + 31) // 32 * 4 if editdist >= 0 else 0))
+    return {"value": P / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_step": dt * 1e3, "steps": steps,
+            "phases_ms": {"h2d": st.ms_h2d, "dedup": st.ms_dedup, "incidence": st.ms_incidence,
+                          "matrix": st.ms_matrix, "d2h": st.ms_d2h}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--trees", type=int, default=0, help="override the number of trees (debug)")
+    ap.add_argument("--ref-trees", type=int, default=0, help="CPU sample size in trees")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    wl = dict(WORKLOADS[args.workload])
+    if args.trees:
+        wl["T"] = args.trees
+    if args.impl == "reference":
+        return run_reference(args, wl, args.workload)
+    return run_gpu(args, wl, args.workload)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
