@@ -1,10 +1,12 @@
 // prf_incidence.cuh -- the `build` phase of hashRF (RFDistance.hs:289-297) on the device:
 //   K1  global bipartition dedup: open-addressing hash table over the W-word bit sets with exact
-//       full-key verification (a 64-bit hash only routes; equality is always decided on the key);
-//   K2  trees x unique-bipartitions incidence in the two forms the matrix kernels want:
-//       inverted lists (bipartition -> ascending tree ids) for bipartitions present in >= 2 trees
-//       -- a bipartition seen in one tree can never be shared, it only counts in |B_t| -- and,
-//       per tree, the list suffixes "members after me" that the sparse kernel walks.
+//       full-key verification (a 64-bit hash only routes; equality is always decided on the key).
+//       A bit per slot records "seen by a second entry": bipartitions present in one tree only
+//       (~3/4 of them on random topologies) can never be shared, they only count in |B_t|.
+//   K2  trees x unique-bipartitions incidence in the form the matrix kernels want: the entries of
+//       shared bipartitions, stably radix-sorted by table slot, are the inverted lists
+//       (bipartition -> ascending tree ids); per tree, the list suffixes "members after me" are
+//       what the sparse kernel walks.
 // The reference's Map DenseLabelSet (IntSet of tree ids) (:289-297) is exactly this inverted index.
 #pragma once
 
@@ -30,20 +32,21 @@ __device__ __forceinline__ void load_key(const uint64_t* __restrict__ bips, uint
   }
 }
 
-// One warp per tree; lanes stride over the tree's entries.  Finds (or claims) the slot of every
-// key, records it, and counts the slot's multiplicity.
+// counters[0] = unique keys (claims), [1] = shared lists, [2] = duplicate (slot, tree) entries
+// One warp per tree; lanes stride over the tree's entries.  Finds (or claims) the slot of every key.
 //   slots[s]  = (tag << 32) | representative entry, kEmptySlot when free
-//   cnt[s]    = number of entries that landed in s
+//   shared[s/32] bit s%32 = some entry other than the representative landed in s
 template <int W>
 __global__ void __launch_bounds__(256) dedup_insert_kernel(const uint64_t* __restrict__ bips,
                                                            const uint64_t* __restrict__ tree_off,
                                                            uint32_t T, unsigned long long* slots,
-                                                           uint32_t* cnt, uint64_t cap_mask,
+                                                           uint32_t* shared_bits, uint64_t cap_mask,
                                                            uint32_t* __restrict__ ent_slot,
-                                                           uint32_t* __restrict__ ent_tree) {
+                                                           unsigned long long* counters) {
   const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= T) return;
   const uint64_t e0 = tree_off[t], e1 = tree_off[t + 1];
+  uint32_t claims = 0;
   for (uint64_t e = e0 + lane_id(); e < e1; e += 32) {
     uint64_t k[W];
     load_key<W>(bips, e, k);
@@ -57,7 +60,7 @@ __global__ void __launch_bounds__(256) dedup_insert_kernel(const uint64_t* __res
       unsigned long long cur = slots[s];
       if (cur == kEmptySlot) {
         cur = atomicCAS(&slots[s], (unsigned long long)kEmptySlot, mine);
-        if (cur == kEmptySlot) break;  // claimed: this entry is the representative
+        if (cur == kEmptySlot) { ++claims; break; }  // claimed: this entry is the representative
       }
       if ((cur >> 32) == tag) {  // same tag: decide on the full key
         uint64_t r[W];
@@ -65,105 +68,157 @@ __global__ void __launch_bounds__(256) dedup_insert_kernel(const uint64_t* __res
         bool eq = true;
 #pragma unroll
         for (int w = 0; w < W; ++w) eq &= (r[w] == k[w]);
-        if (eq) break;
+        if (eq) {
+          const uint32_t bit = 1u << (s & 31);
+          if (!(shared_bits[s >> 5] & bit)) atomicOr(&shared_bits[s >> 5], bit);
+          break;
+        }
       }
       s = (s + 1) & cap_mask;
     }
     ent_slot[e] = (uint32_t)s;
-    ent_tree[e] = t;
-    atomicAdd(&cnt[s], 1u);
-  }
-}
-
-struct SlotShared {  // 1 when the slot's bipartition occurs in >= 2 trees
-  const uint32_t* cnt;
-  __device__ uint32_t operator()(uint64_t i) const { return cnt[i] >= 2u; }
-};
-struct EntryShared {
-  const uint32_t* cnt;
-  const uint32_t* ent_slot;
-  __device__ uint32_t operator()(uint64_t e) const { return cnt[ent_slot[e]] >= 2u; }
-};
-
-// Table statistics: number of occupied slots (U), sum m(m-1)/2 (shared-split hits).
-__global__ void __launch_bounds__(256) slot_stats_kernel(const uint32_t* __restrict__ cnt, uint64_t cap,
-                                                         unsigned long long* out /* [2] */) {
-  unsigned long long u = 0, hits = 0;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap;
-       i += (uint64_t)gridDim.x * blockDim.x) {
-    uint64_t m = cnt[i];
-    u += m > 0;
-    hits += m * (m - (m > 0)) / 2;
   }
 #pragma unroll
-  for (int d = 16; d; d >>= 1) {
-    u += __shfl_xor_sync(0xffffffffu, u, d);
-    hits += __shfl_xor_sync(0xffffffffu, hits, d);
+  for (int d = 16; d; d >>= 1) claims += __shfl_xor_sync(0xffffffffu, claims, d);
+  if (lane_id() == 0 && claims) atomicAdd(&counters[0], (unsigned long long)claims);
+}
+
+// Per tree: number of entries whose bipartition is shared; also |B_t| before duplicate removal.
+__global__ void __launch_bounds__(256) count_shared_kernel(const uint64_t* __restrict__ tree_off, uint32_t T,
+                                                           const uint32_t* __restrict__ ent_slot,
+                                                           const uint32_t* __restrict__ shared_bits,
+                                                           uint32_t* __restrict__ sc, uint32_t* __restrict__ nb32) {
+  const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  const uint64_t e0 = tree_off[t], e1 = tree_off[t + 1];
+  uint32_t c = 0;
+  for (uint64_t e = e0 + lane_id(); e < e1; e += 32) {
+    const uint32_t s = ent_slot[e];
+    c += (shared_bits[s >> 5] >> (s & 31)) & 1u;
   }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
   if (lane_id() == 0) {
-    if (u) atomicAdd(&out[0], u);
-    if (hits) atomicAdd(&out[1], hits);
+    sc[t] = c;
+    nb32[t] = (uint32_t)(e1 - e0);
   }
 }
 
-// For shared slots: list_cnt[sid] = multiplicity.
-__global__ void __launch_bounds__(256) list_count_kernel(const uint32_t* __restrict__ cnt,
-                                                         const uint32_t* __restrict__ sid_of_slot,
-                                                         uint64_t cap, uint32_t* __restrict__ list_cnt) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < cap && cnt[i] >= 2u) list_cnt[sid_of_slot[i]] = cnt[i];
-}
-
-// Compacts the entries of shared bipartitions, keeping tree order: (sid, tree) pairs.
-__global__ void __launch_bounds__(256) gather_shared_kernel(const uint32_t* __restrict__ cnt,
+// Writes the (slot, tree) pairs of the shared entries in tree order (stable warp compaction).
+__global__ void __launch_bounds__(256) gather_shared_kernel(const uint64_t* __restrict__ tree_off, uint32_t T,
                                                             const uint32_t* __restrict__ ent_slot,
-                                                            const uint32_t* __restrict__ ent_tree,
-                                                            const uint32_t* __restrict__ ent_pos,
-                                                            const uint32_t* __restrict__ sid_of_slot,
-                                                            uint64_t nnz, uint32_t* __restrict__ sid,
-                                                            uint32_t* __restrict__ tree) {
-  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= nnz) return;
-  uint32_t s = ent_slot[e];
-  if (cnt[s] >= 2u) {
-    uint32_t k = ent_pos[e];
-    sid[k] = sid_of_slot[s];
-    tree[k] = ent_tree[e];
+                                                            const uint32_t* __restrict__ shared_bits,
+                                                            const uint32_t* __restrict__ soff,
+                                                            uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  const uint64_t e0 = tree_off[t], e1 = tree_off[t + 1];
+  uint32_t pos = soff[t];
+  const uint32_t lt = lanemask_lt();
+  for (uint64_t eb = e0; eb < e1; eb += 32) {
+    const uint64_t e = eb + lane_id();
+    uint32_t s = 0;
+    bool sh = false;
+    if (e < e1) {
+      s = ent_slot[e];
+      sh = (shared_bits[s >> 5] >> (s & 31)) & 1u;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, sh);
+    if (sh) {
+      const uint32_t o = pos + __popc(m & lt);
+      keys[o] = s;
+      vals[o] = t;
+    }
+    pos += __popc(m);
   }
 }
 
-// Flags sorted (sid, tree) pairs that repeat their predecessor: a bipartition listed twice in one
-// tree.  A tree's bipartitions are a set, so those are dropped.
+// Sorted (slot, tree) pairs: a list starts where the slot changes.
+struct HeadFlag {
+  const uint32_t* slot;
+  __device__ uint32_t operator()(uint64_t k) const { return k == 0 || slot[k] != slot[k - 1]; }
+};
+// A pair that repeats its predecessor is a bipartition listed twice by one tree.
 struct DupFlag {
-  const uint32_t* sid;
+  const uint32_t* slot;
   const uint32_t* tree;
   __device__ uint32_t operator()(uint64_t k) const {
-    return k > 0 && sid[k] == sid[k - 1] && tree[k] == tree[k - 1];
+    return k > 0 && slot[k] == slot[k - 1] && tree[k] == tree[k - 1];
   }
 };
-__global__ void __launch_bounds__(256) drop_dups_kernel(const uint32_t* __restrict__ sid,
-                                                        const uint32_t* __restrict__ tree,
-                                                        const uint32_t* __restrict__ dup_before,
-                                                        uint32_t n, uint32_t* __restrict__ sid_out,
-                                                        uint32_t* __restrict__ tree_out,
-                                                        uint32_t* list_cnt, uint32_t* nb32) {
-  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+
+// head_pos[l] = first sorted position of list l; head_pos[L] = n.  Also raises counters[2] when
+// a duplicate pair is seen.
+__global__ void __launch_bounds__(256) list_heads_kernel(const uint32_t* __restrict__ slot,
+                                                         const uint32_t* __restrict__ tree,
+                                                         const uint32_t* __restrict__ lid_ex, uint32_t n,
+                                                         uint32_t* __restrict__ head_pos,
+                                                         unsigned long long* counters) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  bool dup = k > 0 && sid[k] == sid[k - 1] && tree[k] == tree[k - 1];
-  if (dup) {
-    atomicSub(&list_cnt[sid[k]], 1u);
-    atomicSub(&nb32[tree[k]], 1u);
-  } else {
-    uint32_t o = k - dup_before[k];
-    sid_out[o] = sid[k];
-    tree_out[o] = tree[k];
+  const bool head = k == 0 || slot[k] != slot[k - 1];
+  if (head) head_pos[lid_ex[k]] = k;
+  else if (tree[k] == tree[k - 1]) atomicAdd(&counters[2], 1ull);
+  if (k == n - 1) head_pos[lid_ex[k] + (head ? 1 : 0)] = n;
+}
+
+// Position k holds tree a = tree[k] inside list l = [head_pos[l], head_pos[l+1]).  Its suffix
+// (k+1, end) lists the trees b > a sharing that bipartition.  Pass 1 counts the non-empty suffixes
+// per tree (and accumulates sum m(m-1)/2 at list heads), pass 2 stores them.
+__global__ void __launch_bounds__(256) range_count_kernel(const uint32_t* __restrict__ slot,
+                                                          const uint32_t* __restrict__ tree,
+                                                          const uint32_t* __restrict__ lid_ex,
+                                                          const uint32_t* __restrict__ head_pos, uint32_t n,
+                                                          uint32_t* rcount, unsigned long long* counters) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long hits = 0;
+  if (k < n) {
+    const bool head = k == 0 || slot[k] != slot[k - 1];
+    const uint32_t l = lid_ex[k] + (head ? 1 : 0) - 1;
+    const uint32_t end = head_pos[l + 1];
+    if (k + 1 < end) atomicAdd(&rcount[tree[k]], 1u);
+    if (head) {
+      const unsigned long long m = end - k;
+      hits = m * (m - 1) / 2;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, d);
+  if (lane_id() == 0 && hits) atomicAdd(&counters[3], hits);
+}
+__global__ void __launch_bounds__(256) range_fill_kernel(const uint32_t* __restrict__ slot,
+                                                         const uint32_t* __restrict__ tree,
+                                                         const uint32_t* __restrict__ lid_ex,
+                                                         const uint32_t* __restrict__ head_pos, uint32_t n,
+                                                         const uint32_t* __restrict__ roff, uint32_t* cursor,
+                                                         uint2* __restrict__ ranges) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const bool head = k == 0 || slot[k] != slot[k - 1];
+  const uint32_t l = lid_ex[k] + (head ? 1 : 0) - 1;
+  const uint32_t end = head_pos[l + 1];
+  if (k + 1 < end) {
+    const uint32_t a = tree[k];
+    ranges[roff[a] + atomicAdd(&cursor[a], 1u)] = make_uint2(k + 1, end);
   }
 }
 
-__global__ void __launch_bounds__(256) tree_counts_kernel(const uint64_t* __restrict__ tree_off, uint32_t T,
-                                                          uint32_t* __restrict__ nb32) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < T) nb32[t] = (uint32_t)(tree_off[t + 1] - tree_off[t]);
+// Slow path (a caller listed a bipartition twice in one tree): drop the repeats.
+__global__ void __launch_bounds__(256) drop_dups_kernel(const uint32_t* __restrict__ slot,
+                                                        const uint32_t* __restrict__ tree,
+                                                        const uint32_t* __restrict__ dup_before, uint32_t n,
+                                                        uint32_t* __restrict__ slot_out,
+                                                        uint32_t* __restrict__ tree_out, uint32_t* nb32) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const bool dup = k > 0 && slot[k] == slot[k - 1] && tree[k] == tree[k - 1];
+  if (dup) {
+    atomicSub(&nb32[tree[k]], 1u);
+  } else {
+    const uint32_t o = k - dup_before[k];
+    slot_out[o] = slot[k];
+    tree_out[o] = tree[k];
+  }
 }
 
 // nb32 -> uint16 + min/max.  mm[0] = min, mm[1] = max.
@@ -183,51 +238,19 @@ __global__ void __launch_bounds__(256) finish_nb_kernel(const uint32_t* __restri
   }
 }
 
-// Sorted position k holds tree a = members[k] inside list sid[k] = [list_off, list_off_next).
-// Its suffix (k+1, end) lists the trees b > a sharing that bipartition.  Pass 1 counts the
-// non-empty suffixes per tree, pass 2 stores them.
-__global__ void __launch_bounds__(256) range_count_kernel(const uint32_t* __restrict__ sid,
-                                                          const uint32_t* __restrict__ members,
-                                                          const uint32_t* __restrict__ list_off,
-                                                          uint32_t n, uint32_t* rcount) {
-  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  if (k + 1 < list_off[sid[k] + 1]) atomicAdd(&rcount[members[k]], 1u);
-}
-__global__ void __launch_bounds__(256) range_fill_kernel(const uint32_t* __restrict__ sid,
-                                                         const uint32_t* __restrict__ members,
-                                                         const uint32_t* __restrict__ list_off,
-                                                         uint32_t n, const uint32_t* __restrict__ roff,
-                                                         uint32_t* cursor, uint2* __restrict__ ranges) {
-  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  uint32_t end = list_off[sid[k] + 1];
-  if (k + 1 < end) {
-    uint32_t a = members[k];
-    uint32_t slot = roff[a] + atomicAdd(&cursor[a], 1u);
-    ranges[slot] = make_uint2(k + 1, end);
-  }
-}
-
-__global__ void fill_u64_kernel(unsigned long long* p, uint64_t n, unsigned long long v) {
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (uint64_t)gridDim.x * blockDim.x)
-    p[i] = v;
-}
-
 template <int W>
 static void launch_dedup(Ctx* ctx, const uint64_t* bips, const uint64_t* off, uint32_t T,
-                         unsigned long long* slots, uint32_t* cnt, uint64_t cap_mask,
-                         uint32_t* ent_slot, uint32_t* ent_tree) {
-  dedup_insert_kernel<W><<<(T + 7) / 8, 256, 0, ctx->stream>>>(bips, off, T, slots, cnt, cap_mask,
-                                                                ent_slot, ent_tree);
+                         unsigned long long* slots, uint32_t* shared_bits, uint64_t cap_mask,
+                         uint32_t* ent_slot, unsigned long long* counters) {
+  dedup_insert_kernel<W><<<(T + 7) / 8, 256, 0, ctx->stream>>>(bips, off, T, slots, shared_bits, cap_mask,
+                                                                ent_slot, counters);
 }
 
 static inline uint32_t grid_for(uint64_t n, uint32_t tpb = 256) { return (uint32_t)((n + tpb - 1) / tpb); }
 
-static inline int bits_for(uint32_t n_values) {  // bits needed to represent 0..n_values-1
+static inline int bits_for(uint64_t n_values) {  // bits needed to represent 0..n_values-1
   int b = 0;
-  while (b < 32 && (1ull << b) < n_values) ++b;
+  while (b < 63 && (1ull << b) < n_values) ++b;
   return b;
 }
 
@@ -243,27 +266,30 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
   H.P = (uint64_t)T * (T ? T - 1 : 0) / 2;
 
   uint64_t cap = 1024;
-  while (cap < 2 * nnz) cap <<= 1;
+  while (cap < nnz + nnz / 2) cap <<= 1;  // load factor <= 2/3 even if every key is distinct
 
-  DevBuf<unsigned long long> slots, acc;
-  DevBuf<uint32_t> cnt, ent_slot, ent_tree, nb32, scalars;
+  DevBuf<unsigned long long> slots, counters;
+  DevBuf<uint32_t> shared_bits, ent_slot, nb32, sc, soff, scalars;
   PRF_CK(ctx, slots.alloc(cap, s));
-  PRF_CK(ctx, cnt.alloc(cap, s));
+  PRF_CK(ctx, shared_bits.alloc(cap / 32, s));
   PRF_CK(ctx, ent_slot.alloc(nnz, s));
-  PRF_CK(ctx, ent_tree.alloc(nnz, s));
-  PRF_CK(ctx, nb32.alloc(T, s));
-  PRF_CK(ctx, acc.alloc(2, s));
+  PRF_CK(ctx, nb32.alloc((size_t)T + 1, s));
+  PRF_CK(ctx, sc.alloc((size_t)T + 1, s));
+  PRF_CK(ctx, soff.alloc((size_t)T + 1, s));
+  PRF_CK(ctx, counters.alloc(4, s));
   PRF_CK(ctx, scalars.alloc(8, s));
-  PRF_CK(ctx, cudaMemsetAsync(cnt.p, 0, cnt.bytes(), s));
-  PRF_CK(ctx, cudaMemsetAsync(acc.p, 0, acc.bytes(), s));
-  PRF_CK(ctx, cudaMemsetAsync(scalars.p, 0, scalars.bytes(), s));
+  PRF_CK(ctx, cudaMemsetAsync(shared_bits.p, 0, shared_bits.bytes(), s));
+  PRF_CK(ctx, cudaMemsetAsync(counters.p, 0, counters.bytes(), s));
+  PRF_CK(ctx, cudaMemsetAsync(sc.p, 0, sc.bytes(), s));
   PRF_CK(ctx, cudaMemsetAsync(slots.p, 0xff, slots.bytes(), s));
+  uint32_t mm_init[8] = {0, 0, 0, 0, 0xffffffffu, 0u, 0, 0};
+  PRF_CK(ctx, cudaMemcpyAsync(scalars.p, mm_init, sizeof mm_init, cudaMemcpyHostToDevice, s));
 
   PRF_CK(ctx, cudaEventRecord(ctx->ev[1], s));
   // ---- K1: dedup ----
   if (T) {
     switch (W) {
-#define PRF_W_CASE(w) case w: launch_dedup<w>(ctx, d_bips, d_off, T, slots.p, cnt.p, cap - 1, ent_slot.p, ent_tree.p); break;
+#define PRF_W_CASE(w) case w: launch_dedup<w>(ctx, d_bips, d_off, T, slots.p, shared_bits.p, cap - 1, ent_slot.p, counters.p); break;
       PRF_W_CASE(1) PRF_W_CASE(2) PRF_W_CASE(3) PRF_W_CASE(4) PRF_W_CASE(5) PRF_W_CASE(6) PRF_W_CASE(7)
       PRF_W_CASE(8) PRF_W_CASE(9) PRF_W_CASE(10) PRF_W_CASE(11) PRF_W_CASE(12) PRF_W_CASE(13)
       PRF_W_CASE(14) PRF_W_CASE(15) PRF_W_CASE(16)
@@ -271,122 +297,103 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
       default: return ctx->fail(PRF_E_UNSUPPORTED, "W=%u words per set; supported 1..%u", W, kMaxWords);
     }
     PRF_LAUNCHED(ctx);
-    tree_counts_kernel<<<grid_for(T), 256, 0, s>>>(d_off, T, nb32.p);
-    PRF_LAUNCHED(ctx);
   }
-  slot_stats_kernel<<<std::min<uint32_t>(grid_for(cap), 148 * 8), 256, 0, s>>>(cnt.p, cap, acc.p);
-  PRF_LAUNCHED(ctx);
   PRF_CK(ctx, cudaEventRecord(ctx->ev[2], s));
 
   // ---- K2: incidence ----
-  // shared slots -> dense ids
-  DevBuf<uint32_t> sid_of_slot, ent_pos;
-  PRF_CK(ctx, sid_of_slot.alloc(cap, s));
-  PRF_CK(ctx, ent_pos.alloc(nnz, s));
   int rc;
-  if ((rc = exclusive_scan(ctx, SlotShared{cnt.p}, cap, sid_of_slot.p, scalars.p + 0))) return rc;
-  if ((rc = exclusive_scan(ctx, EntryShared{cnt.p, ent_slot.p}, nnz, ent_pos.p, scalars.p + 1))) return rc;
-  uint32_t hs[8];
-  unsigned long long hacc[2];
-  PRF_CK(ctx, cudaMemcpyAsync(hs, scalars.p, sizeof hs, cudaMemcpyDeviceToHost, s));
-  PRF_CK(ctx, cudaMemcpyAsync(hacc, acc.p, sizeof hacc, cudaMemcpyDeviceToHost, s));
+  uint32_t n_sh_nnz = 0;
+  if (T) {
+    count_shared_kernel<<<(T + 7) / 8, 256, 0, s>>>(d_off, T, ent_slot.p, shared_bits.p, sc.p, nb32.p);
+    PRF_LAUNCHED(ctx);
+  }
+  if ((rc = exclusive_scan(ctx, LoadU32{sc.p}, (uint64_t)T + 1, soff.p, scalars.p + 0))) return rc;
+  PRF_CK(ctx, cudaMemcpyAsync(&n_sh_nnz, scalars.p + 0, 4, cudaMemcpyDeviceToHost, s));
   PRF_CK(ctx, cudaStreamSynchronize(s));
-  uint32_t n_shared = hs[0], n_sh_nnz = hs[1];
-  H.n_shared = n_shared;
   H.n_shared_nnz = n_sh_nnz;
 
-  DevBuf<uint32_t> list_cnt, list_off;
-  PRF_CK(ctx, list_cnt.alloc((size_t)n_shared + 1, s));
-  PRF_CK(ctx, list_off.alloc((size_t)n_shared + 1, s));
-  PRF_CK(ctx, cudaMemsetAsync(list_cnt.p, 0, list_cnt.bytes(), s));
-  PRF_CK(ctx, H.sh_sid.alloc(n_sh_nnz, s));
-  PRF_CK(ctx, H.sh_tree.alloc(n_sh_nnz, s));
-  DevBuf<uint32_t> sid_sorted;
-  PRF_CK(ctx, sid_sorted.alloc(n_sh_nnz, s));
+  DevBuf<uint32_t> slot_sorted, lid_ex, head_pos, rcount, cursor;
+  PRF_CK(ctx, slot_sorted.alloc(n_sh_nnz, s));
   PRF_CK(ctx, H.members.alloc(n_sh_nnz, s));
-  uint32_t n_sorted = n_sh_nnz;
-  if (n_sh_nnz) {
-    list_count_kernel<<<grid_for(cap), 256, 0, s>>>(cnt.p, sid_of_slot.p, cap, list_cnt.p);
-    PRF_LAUNCHED(ctx);
-    gather_shared_kernel<<<grid_for(nnz), 256, 0, s>>>(cnt.p, ent_slot.p, ent_tree.p, ent_pos.p,
-                                                       sid_of_slot.p, nnz, H.sh_sid.p, H.sh_tree.p);
-    PRF_LAUNCHED(ctx);
-    PRF_CK(ctx, cudaMemcpyAsync(sid_sorted.p, H.sh_sid.p, (size_t)n_sh_nnz * 4, cudaMemcpyDeviceToDevice, s));
-    PRF_CK(ctx, cudaMemcpyAsync(H.members.p, H.sh_tree.p, (size_t)n_sh_nnz * 4, cudaMemcpyDeviceToDevice, s));
-    // stable sort by bipartition id: inside a list the trees stay ascending
-    if ((rc = radix_sort_pairs(ctx, sid_sorted.p, H.members.p, n_sh_nnz, bits_for(n_shared)))) return rc;
-    // a bipartition listed twice by one tree counts once
-    DevBuf<uint32_t> dup_before;
-    PRF_CK(ctx, dup_before.alloc(n_sh_nnz, s));
-    if ((rc = exclusive_scan(ctx, DupFlag{sid_sorted.p, H.members.p}, n_sh_nnz, dup_before.p, scalars.p + 2)))
-      return rc;
-    uint32_t n_dups = 0;
-    PRF_CK(ctx, cudaMemcpyAsync(&n_dups, scalars.p + 2, 4, cudaMemcpyDeviceToHost, s));
-    PRF_CK(ctx, cudaStreamSynchronize(s));
-    if (n_dups) {
-      DevBuf<uint32_t> sid2, mem2;
-      PRF_CK(ctx, sid2.alloc(n_sh_nnz - n_dups, s));
-      PRF_CK(ctx, mem2.alloc(n_sh_nnz - n_dups, s));
-      drop_dups_kernel<<<grid_for(n_sh_nnz), 256, 0, s>>>(sid_sorted.p, H.members.p, dup_before.p, n_sh_nnz,
-                                                          sid2.p, mem2.p, list_cnt.p, nb32.p);
-      PRF_LAUNCHED(ctx);
-      sid_sorted = std::move(sid2);
-      H.members = std::move(mem2);
-      n_sorted = n_sh_nnz - n_dups;
-    }
-  }
-  if ((rc = exclusive_scan(ctx, LoadU32{list_cnt.p}, (uint64_t)n_shared + 1, list_off.p, nullptr))) return rc;
-
-  // per-tree suffix ranges
-  DevBuf<uint32_t> rcount, cursor;
+  PRF_CK(ctx, lid_ex.alloc(n_sh_nnz, s));
+  PRF_CK(ctx, head_pos.alloc((size_t)n_sh_nnz + 1, s));
   PRF_CK(ctx, rcount.alloc((size_t)T + 1, s));
   PRF_CK(ctx, cursor.alloc((size_t)T + 1, s));
   PRF_CK(ctx, H.roff.alloc((size_t)T + 1, s));
-  PRF_CK(ctx, cudaMemsetAsync(rcount.p, 0, rcount.bytes(), s));
-  PRF_CK(ctx, cudaMemsetAsync(cursor.p, 0, cursor.bytes(), s));
-  if (n_sorted) {
-    range_count_kernel<<<grid_for(n_sorted), 256, 0, s>>>(sid_sorted.p, H.members.p, list_off.p, n_sorted, rcount.p);
-    PRF_LAUNCHED(ctx);
-  }
-  if ((rc = exclusive_scan(ctx, LoadU32{rcount.p}, (uint64_t)T + 1, H.roff.p, scalars.p + 3))) return rc;
-  uint32_t n_ranges = 0;
-  PRF_CK(ctx, cudaMemcpyAsync(&n_ranges, scalars.p + 3, 4, cudaMemcpyDeviceToHost, s));
-  PRF_CK(ctx, cudaStreamSynchronize(s));
-  PRF_CK(ctx, H.ranges.alloc(n_ranges, s));
-  if (n_ranges) {
-    range_fill_kernel<<<grid_for(n_sorted), 256, 0, s>>>(sid_sorted.p, H.members.p, list_off.p, n_sorted,
-                                                         H.roff.p, cursor.p, H.ranges.p);
-    PRF_LAUNCHED(ctx);
-  }
-
-  // |B_t| as uint16 + min/max
+  PRF_CK(ctx, H.ranges.alloc(n_sh_nnz, s));  // upper bound: at most one suffix per shared entry
   PRF_CK(ctx, H.nb.alloc(T, s));
-  uint32_t mm_init[2] = {0xffffffffu, 0u};
-  PRF_CK(ctx, cudaMemcpyAsync(scalars.p + 4, mm_init, 8, cudaMemcpyHostToDevice, s));
-  if (T) {
-    finish_nb_kernel<<<grid_for(T), 256, 0, s>>>(nb32.p, T, H.nb.p, scalars.p + 4);
+  uint32_t n_sorted = n_sh_nnz;
+  if (n_sh_nnz) {
+    gather_shared_kernel<<<(T + 7) / 8, 256, 0, s>>>(d_off, T, ent_slot.p, shared_bits.p, soff.p, slot_sorted.p,
+                                                     H.members.p);
     PRF_LAUNCHED(ctx);
+    // stable sort by table slot: inside a list the trees stay ascending
+    if ((rc = radix_sort_pairs(ctx, slot_sorted.p, H.members.p, n_sh_nnz, bits_for(cap)))) return rc;
   }
-  uint32_t mm[2];
-  PRF_CK(ctx, cudaMemcpyAsync(mm, scalars.p + 4, 8, cudaMemcpyDeviceToHost, s));
-  PRF_CK(ctx, cudaEventRecord(ctx->ev[3], s));
-  PRF_CK(ctx, cudaStreamSynchronize(s));
+  unsigned long long hc[4] = {0, 0, 0, 0};
+  uint32_t hs[8] = {0};
+  for (int pass = 0; pass < 2; ++pass) {
+    PRF_CK(ctx, cudaMemsetAsync(rcount.p, 0, rcount.bytes(), s));
+    PRF_CK(ctx, cudaMemsetAsync(cursor.p, 0, cursor.bytes(), s));
+    PRF_CK(ctx, cudaMemsetAsync(counters.p + 2, 0, 16, s));
+    if (n_sorted) {
+      if ((rc = exclusive_scan(ctx, HeadFlag{slot_sorted.p}, n_sorted, lid_ex.p, scalars.p + 1))) return rc;
+      list_heads_kernel<<<grid_for(n_sorted), 256, 0, s>>>(slot_sorted.p, H.members.p, lid_ex.p, n_sorted,
+                                                           head_pos.p, counters.p);
+      PRF_LAUNCHED(ctx);
+      range_count_kernel<<<grid_for(n_sorted), 256, 0, s>>>(slot_sorted.p, H.members.p, lid_ex.p, head_pos.p,
+                                                            n_sorted, rcount.p, counters.p);
+      PRF_LAUNCHED(ctx);
+    }
+    if ((rc = exclusive_scan(ctx, LoadU32{rcount.p}, (uint64_t)T + 1, H.roff.p, nullptr))) return rc;
+    if (n_sorted) {
+      range_fill_kernel<<<grid_for(n_sorted), 256, 0, s>>>(slot_sorted.p, H.members.p, lid_ex.p, head_pos.p,
+                                                           n_sorted, H.roff.p, cursor.p, H.ranges.p);
+      PRF_LAUNCHED(ctx);
+    }
+    if (T) {
+      finish_nb_kernel<<<grid_for(T), 256, 0, s>>>(nb32.p, T, H.nb.p, scalars.p + 4);
+      PRF_LAUNCHED(ctx);
+    }
+    PRF_CK(ctx, cudaMemcpyAsync(hc, counters.p, sizeof hc, cudaMemcpyDeviceToHost, s));
+    PRF_CK(ctx, cudaMemcpyAsync(hs, scalars.p, sizeof hs, cudaMemcpyDeviceToHost, s));
+    PRF_CK(ctx, cudaEventRecord(ctx->ev[3], s));
+    PRF_CK(ctx, cudaStreamSynchronize(s));
+    if (hc[2] == 0 || pass == 1) break;
+    // a tree listed some bipartition more than once: its bipartitions are a set -- drop the repeats
+    // from the sorted pairs, fix |B_t|, and rebuild the lists once more
+    DevBuf<uint32_t> dup_before, slot2, mem2;
+    PRF_CK(ctx, dup_before.alloc(n_sorted, s));
+    PRF_CK(ctx, slot2.alloc(n_sorted, s));
+    PRF_CK(ctx, mem2.alloc(n_sorted, s));
+    if ((rc = exclusive_scan(ctx, DupFlag{slot_sorted.p, H.members.p}, n_sorted, dup_before.p, nullptr))) return rc;
+    drop_dups_kernel<<<grid_for(n_sorted), 256, 0, s>>>(slot_sorted.p, H.members.p, dup_before.p, n_sorted,
+                                                        slot2.p, mem2.p, nb32.p);
+    PRF_LAUNCHED(ctx);
+    slot_sorted = std::move(slot2);
+    H.members = std::move(mem2);
+    n_sorted -= (uint32_t)hc[2];
+    uint32_t mm_reset[2] = {0xffffffffu, 0u};
+    PRF_CK(ctx, cudaMemcpyAsync(scalars.p + 4, mm_reset, 8, cudaMemcpyHostToDevice, s));
+  }
+  uint32_t mm[2] = {hs[4], hs[5]};
   if (T == 0) mm[0] = mm[1] = 0;
   if (mm[1] > kMaxBipsPerTree)
     return ctx->fail(PRF_E_RANGE, "a tree has %u bipartitions; distances would overflow uint16 (max %u per tree)",
                      mm[1], kMaxBipsPerTree);
   H.uniform_nb = mm[0] == mm[1];
   H.nb_uniform = mm[0];
+  H.n_shared = n_sorted ? hs[1] : 0;
 
   prf_stats& st = H.stats;
   st = prf_stats{};
   st.n_trees = T;
   st.n_words = W;
   st.nnz = nnz;
-  st.n_unique = hacc[0];
-  st.n_shared = n_shared;
-  st.n_shared_nnz = n_sh_nnz;
-  st.n_hits = hacc[1];
+  st.n_unique = hc[0];
+  st.n_shared = H.n_shared;
+  st.n_shared_nnz = n_sorted;
+  st.n_hits = hc[3];
   st.n_pairs = H.P;
   st.max_bips = mm[1];
   st.min_bips = mm[0];

@@ -10,7 +10,10 @@
 //   1. fill the chunk in shared memory with |B_a| + |B_b|;
 //   2. for every tree a that has a segment in the chunk, walk the suffixes of its shared
 //      bipartitions' inverted lists ("trees b > a that also have it", ascending) and subtract 2 at
-//      column b with a shared-memory atomic -- no global atomics, every output byte is written once;
+//      column b with a shared-memory atomic -- no global atomics, every output byte is written once.
+//      Lists are entered at the chunk's first column: one thread per list estimates the position by
+//      interpolation (tree ids are close to uniform) and gallops back until it is provably at or
+//      before the lower bound, all lists in parallel, so the dependent-load chain is ~2 deep;
 //   3. optionally ballot the d <= editdist mask, then hand the finished chunk to the TMA engine
 //      (cp.async.bulk shared -> global): one 16-byte-aligned bulk store per chunk.
 #pragma once
@@ -25,15 +28,12 @@ __device__ __forceinline__ uint32_t smem_addr(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
 
-// All lanes pass the same [lo, hi): first index whose member is >= key.
-__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__ a, uint32_t lo,
-                                                    uint32_t hi, uint32_t key) {
-  while (lo < hi) {
-    uint32_t mid = lo + ((hi - lo) >> 1);
-    if (__ldg(a + mid) < key) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
+struct StagedRange {
+  uint32_t begin, end;  // walk members[begin, end)
+  int32_t base;         // tile index of column b is base + b
+  uint32_t b_lo;        // only columns in [b_lo, b_hi) belong to this chunk's segment of the row
+  uint32_t b_hi;
+};
 
 template <int kChunk>
 __global__ void __launch_bounds__(kSparseThreads) sparse_chunk_kernel(
@@ -42,59 +42,88 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_chunk_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ members, int32_t editdist,
     uint16_t* __restrict__ out, uint32_t* __restrict__ mask) {
   extern __shared__ __align__(128) uint16_t tile[];  // kChunk entries
+  __shared__ StagedRange staged[kSparseThreads];
   uint32_t* tile32 = reinterpret_cast<uint32_t*>(tile);
 
   const uint64_t p0 = p_begin + (uint64_t)blockIdx.x * kChunk;
   const uint32_t n = (uint32_t)min((uint64_t)kChunk, p_end - p0);
   const uint32_t a0 = row_of(p0, T), a1 = row_of(p0 + n - 1, T);
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t k0 = __ldg(roff + a0), k1 = __ldg(roff + a1 + 1);
+  const uint32_t b_first = a0 + 1 + (uint32_t)(p0 - row_start(a0, T));          // first column of row a0 in the chunk
+  const uint32_t b_last_excl = a1 + 1 + (uint32_t)(p0 + n - row_start(a1, T));  // one past the last column of row a1
 
-  // ---- 1. d = |B_a| + |B_b| ----
-  if (uniform_nb) {
-    const uint32_t v = 2u * nb_uniform;
-    const uint32_t vv = v | (v << 16);
-    uint4 q = make_uint4(vv, vv, vv, vv);
-    uint4* t4 = reinterpret_cast<uint4*>(tile);
-    for (uint32_t i = threadIdx.x; i < kChunk / 8; i += kSparseThreads) t4[i] = q;
-  } else {
-    for (uint32_t a = a0; a <= a1; ++a) {
-      const uint64_t rs = row_start(a, T);
-      const uint64_t lo = max(rs, p0), hi = min(rs + (T - 1 - a), p0 + n);
-      const uint32_t na = nb[a];
-      const uint32_t cnt = (uint32_t)(hi - lo);
-      const uint32_t toff = (uint32_t)(lo - p0);
-      const uint16_t* nbb = nb + (a + 1 + (lo - rs));  // column of position lo
-      for (uint32_t i = threadIdx.x; i < cnt; i += kSparseThreads)
-        tile[toff + i] = (uint16_t)(na + nbb[i]);
-    }
-  }
-  __syncthreads();
-
-  // ---- 2. subtract 2 per shared bipartition ----
-  {
-    const uint32_t k0 = roff[a0], k1 = roff[a1 + 1];
-    uint32_t a = a0;
-    uint32_t a_end = roff[a0 + 1];  // ranges of tree a are [roff[a], a_end)
-    const uint32_t b_first = a0 + 1 + (uint32_t)(p0 - row_start(a0, T));          // first column of row a0 in the chunk
-    const uint32_t b_last_excl = a1 + 1 + (uint32_t)(p0 + n - row_start(a1, T));  // one past the last column of row a1
-    for (uint32_t k = k0 + warp; k < k1; k += kSparseThreads / 32) {
-      while (k >= a_end) { ++a; a_end = roff[a + 1]; }
+  for (uint32_t kb = k0; kb < k1 || kb == k0; kb += kSparseThreads) {
+    // ---- 2a. stage up to 256 ranges: one thread each ----
+    const uint32_t k = kb + threadIdx.x;
+    if (k < k1) {
+      // the row that owns range k: largest a in [a0, a1] with roff[a] <= k
+      uint32_t lo = a0, hi = a1;
+      while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (__ldg(roff + mid) <= k) lo = mid; else hi = mid - 1;
+      }
+      const uint32_t a = lo;
       const uint2 r = ranges[k];
       const uint32_t b_lo = a == a0 ? b_first : a + 1;
       const uint32_t b_hi = a == a1 ? b_last_excl : T;
-      // tile index of column b: row_start(a) + (b - a - 1) - p0
-      const int64_t base = (int64_t)row_start(a, T) - (int64_t)p0 - (int64_t)a - 1;
-      uint32_t s = r.x;
-      if (b_lo > a + 1 && r.y - r.x > 64) s = lower_bound_u32(members, r.x, r.y, b_lo);
-      for (uint32_t m = s + lane; m < r.y; m += 32) {
+      uint32_t g = r.x;
+      if (b_lo > a + 1) {
+        // members of (a, T) are near-uniform: interpolate, then gallop back until members[g-1] < b_lo
+        const uint32_t len = r.y - r.x;
+        uint32_t est = r.x + (uint32_t)(((uint64_t)(b_lo - a - 1) * len) / (uint64_t)(T - a - 1));
+        g = est > r.x + 16 ? est - 16 : r.x;
+        uint32_t step = 32;
+        while (g > r.x && __ldg(members + g - 1) >= b_lo) {
+          g = g - r.x > step ? g - step : r.x;
+          step <<= 1;
+        }
+      }
+      StagedRange s;
+      s.begin = g;
+      s.end = r.y;
+      s.base = (int32_t)((int64_t)row_start(a, T) - (int64_t)p0 - (int64_t)a - 1);
+      s.b_lo = b_lo;
+      s.b_hi = b_hi;
+      staged[threadIdx.x] = s;
+    }
+    if (kb == k0) {
+      // ---- 1. d = |B_a| + |B_b| (first pass only; overlaps the staging loads of other warps) ----
+      if (uniform_nb) {
+        const uint32_t v = 2u * nb_uniform;
+        const uint32_t vv = v | (v << 16);
+        uint4 q = make_uint4(vv, vv, vv, vv);
+        uint4* t4 = reinterpret_cast<uint4*>(tile);
+#pragma unroll 4
+        for (uint32_t i = threadIdx.x; i < kChunk / 8; i += kSparseThreads) t4[i] = q;
+      } else {
+        for (uint32_t a = a0; a <= a1; ++a) {
+          const uint64_t rs = row_start(a, T);
+          const uint64_t lo = max(rs, p0), hi = min(rs + (T - 1 - a), p0 + n);
+          const uint32_t na = nb[a];
+          const uint32_t cnt = (uint32_t)(hi - lo);
+          const uint32_t toff = (uint32_t)(lo - p0);
+          const uint16_t* nbb = nb + (a + 1 + (lo - rs));  // column of position lo
+          for (uint32_t i = threadIdx.x; i < cnt; i += kSparseThreads)
+            tile[toff + i] = (uint16_t)(na + nbb[i]);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- 2b. subtract 2 per shared bipartition: one warp per staged range ----
+    const uint32_t nstaged = min((uint32_t)kSparseThreads, k1 - kb);
+    for (uint32_t i = warp; i < nstaged; i += kSparseThreads / 32) {
+      const StagedRange s = staged[i];
+      for (uint32_t m = s.begin + lane; m < s.end; m += 32) {
         const uint32_t b = __ldg(members + m);
-        if (b >= b_hi) break;
-        if (b >= b_lo) {
-          const uint32_t idx = (uint32_t)(base + (int64_t)b);
+        if (b >= s.b_hi) break;
+        if (b >= s.b_lo) {
+          const uint32_t idx = (uint32_t)(s.base + (int32_t)b);
           atomicSub(&tile32[idx >> 1], 2u << ((idx & 1u) * 16u));
         }
       }
     }
+    if (kb + kSparseThreads < k1) __syncthreads();  // staged[] is reused by the next batch
   }
   // make the generic-proxy writes visible to the async proxy before the bulk store reads them
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
