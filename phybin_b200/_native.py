@@ -112,6 +112,7 @@ def rf_lib():
         L.prf_launch_count.restype = C.c_uint64
         L.prf_launch_count.argtypes = [vp]
         # test-only entry points (not in phybin_rf.h)
+        L.prf_debug_small_tiles.argtypes = [vp, C.c_int]
         L.prf_debug_scan.argtypes = [vp, vp, C.c_uint64, vp, vp]
         L.prf_debug_sort.argtypes = [vp, vp, vp, C.c_uint32, C.c_int]
         _rf = L

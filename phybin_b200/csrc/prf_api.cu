@@ -130,6 +130,7 @@ PRF_API void prf_destroy(prf_ctx* h) {
   cudaSetDevice(c.device);
   c.h = HashRFState{};
   c.tol = TolerantState{};
+  c.plan = RowPlan{};
   c.out.release();
   c.mask.release();
   cudaStreamSynchronize(c.stream);
@@ -180,6 +181,7 @@ PRF_API int prf_hashrf_load(prf_ctx* h, const uint64_t* bips, const uint64_t* tr
   ctx->h.loaded = false;
   ctx->out_valid = ctx->mask_valid = false;
 
+  trace_mark("hashrf_load: enter");
   PRF_CK(ctx, cudaEventRecord(ctx->ev[0], s));
   // offsets first: nnz = tree_off[T]
   DevBuf<uint64_t> d_off_own, d_bips_own;
@@ -209,8 +211,10 @@ PRF_API int prf_hashrf_load(prf_ctx* h, const uint64_t* bips, const uint64_t* tr
   } else if (nnz && (reinterpret_cast<uintptr_t>(bips) & 15)) {
     return ctx->fail(PRF_E_INVALID, "device bips pointer must be 16-byte aligned");
   }
+  trace_mark("hashrf_load: uploads queued");
   int rc = hashrf_build(ctx, d_bips, d_off, T, W, nnz);
   if (rc) return rc;
+  trace_mark("hashrf_load: build done");
   prf_stats& st = ctx->h.stats;
   st.ms_h2d = ev_ms(ctx->ev[0], ctx->ev[1]);
   st.ms_dedup = ev_ms(ctx->ev[1], ctx->ev[2]);
@@ -236,20 +240,24 @@ PRF_API int prf_hashrf_compute(prf_ctx* h, uint64_t p_begin, uint64_t p_end, int
     return ctx->fail(PRF_E_INVALID, "unknown variant %d", variant);
   PRF_CK(ctx, cudaSetDevice(ctx->device));
   uint64_t launches0 = ctx->launches;
+  trace_mark("hashrf_compute: enter");
   if ((rc = own_output(ctx, p_begin, p_end, editdist >= 0, &d_out, &d_mask))) return rc;
   if (editdist < 0) d_mask = nullptr;
+  trace_mark("hashrf_compute: output ready");
 
   int use = variant == PRF_VARIANT_AUTO ? PRF_VARIANT_SPARSE : variant;
   if (use == PRF_VARIANT_DENSE)
     return ctx->fail(PRF_E_UNSUPPORTED, "dense (tcgen05) variant is not built into this library version");
   PRF_CK(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
   if (p_end > p_begin) {
-    if ((rc = launch_sparse<16384>(ctx, p_begin, p_end, editdist, d_out, d_mask))) return rc;
+    if ((rc = launch_sparse(ctx, p_begin, p_end, editdist, d_out, d_mask))) return rc;
   }
   PRF_CK(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
   H.stats.variant_used = use;
+  trace_mark("hashrf_compute: launched");
   if (stats) {
     PRF_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    trace_mark("hashrf_compute: synced");
     prf_stats st = H.stats;
     st.ms_matrix = ev_ms(ctx->ev[4], ctx->ev[5]);
     st.gpu_launches = (int32_t)(ctx->launches - launches0);
@@ -321,6 +329,7 @@ PRF_API int prf_hashrf(prf_ctx* h, const uint64_t* bips, const uint64_t* tree_of
   if (out_mask && editdist >= 0 && (rc = prf_fetch_mask(h, 0, P, out_mask))) return rc;
   PRF_CK(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
   PRF_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  trace_mark("hashrf: fetched");
   if (stats) {
     *stats = st2;
     stats->ms_h2d = st.ms_h2d;
@@ -451,6 +460,12 @@ PRF_API int prf_tolerant(prf_ctx* h, const uint64_t* clades, const uint64_t* tre
 // ---------------------------------------------------------------------------------------------
 // Debug entry points for tests of the primitives (not part of phybin_rf.h).
 // ---------------------------------------------------------------------------------------------
+
+PRF_API int prf_debug_small_tiles(prf_ctx* h, int on) {
+  if (!h) return PRF_E_INVALID;
+  h->c.debug_small_tiles = on != 0;
+  return PRF_OK;
+}
 
 PRF_API int prf_debug_scan(prf_ctx* h, const uint32_t* host_in, uint64_t n, uint32_t* host_out, uint32_t* total) {
   if (!h) return PRF_E_INVALID;

@@ -3,7 +3,9 @@
 
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -67,6 +69,23 @@ struct HashRFState {
   prf_stats stats{};
 };
 
+// Work item of the sparse matrix kernel (prf_sparse.cuh): one row a0 == a1 restricted to columns
+// [cb, ce), or the whole rows a0..a1 (a1 > a0) packed into one tile.
+struct RowItem {
+  uint32_t a0, a1, cb, ce;
+};
+
+// Cached cut of a packed range into RowItems (depends only on T and the range, not on the trees).
+struct RowPlan {
+  bool valid = false;
+  uint32_t T = 0, n_items = 0, tile = 0;
+  uint64_t p_begin = 0, p_end = 0;
+  int ctas_per_sm = 0;
+  DevBuf<RowItem> items;
+  DevBuf<uint32_t> counter;
+  DevBuf<uint2> cursor_ws;
+};
+
 struct TolerantState {
   bool loaded = false;
   uint32_t T = 0, W = 0, max_clades = 0;
@@ -86,6 +105,8 @@ struct Ctx {
   uint64_t launches = 0;
   HashRFState h;
   TolerantState tol;
+  RowPlan plan;
+  bool debug_small_tiles = false;
   // ctx-owned result of the last compute
   DevBuf<uint16_t> out;
   DevBuf<uint32_t> mask;
@@ -102,6 +123,19 @@ struct Ctx {
     return code;
   }
 };
+
+// PRF_TRACE=1 in the environment: host wall-clock marks on stderr (where does a call spend its time).
+inline bool trace_on() {
+  static const bool on = [] { const char* e = getenv("PRF_TRACE"); return e && *e && *e != '0'; }();
+  return on;
+}
+inline void trace_mark(const char* what) {
+  if (!trace_on()) return;
+  static std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+  auto now = std::chrono::steady_clock::now();
+  fprintf(stderr, "[prf] %-28s +%9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+  last = now;
+}
 
 #define PRF_CK(ctx, call)                                                                      \
   do {                                                                                         \

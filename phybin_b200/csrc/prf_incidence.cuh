@@ -285,6 +285,7 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
   uint32_t mm_init[8] = {0, 0, 0, 0, 0xffffffffu, 0u, 0, 0};
   PRF_CK(ctx, cudaMemcpyAsync(scalars.p, mm_init, sizeof mm_init, cudaMemcpyHostToDevice, s));
 
+  trace_mark("build: temporaries allocated");
   PRF_CK(ctx, cudaEventRecord(ctx->ev[1], s));
   // ---- K1: dedup ----
   if (T) {
@@ -310,6 +311,7 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
   if ((rc = exclusive_scan(ctx, LoadU32{sc.p}, (uint64_t)T + 1, soff.p, scalars.p + 0))) return rc;
   PRF_CK(ctx, cudaMemcpyAsync(&n_sh_nnz, scalars.p + 0, 4, cudaMemcpyDeviceToHost, s));
   PRF_CK(ctx, cudaStreamSynchronize(s));
+  trace_mark("build: dedup + count synced");
   H.n_shared_nnz = n_sh_nnz;
 
   DevBuf<uint32_t> slot_sorted, lid_ex, head_pos, rcount, cursor;
@@ -359,6 +361,7 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
     PRF_CK(ctx, cudaMemcpyAsync(hs, scalars.p, sizeof hs, cudaMemcpyDeviceToHost, s));
     PRF_CK(ctx, cudaEventRecord(ctx->ev[3], s));
     PRF_CK(ctx, cudaStreamSynchronize(s));
+    trace_mark("build: lists synced");
     if (hc[2] == 0 || pass == 1) break;
     // a tree listed some bipartition more than once: its bipartitions are a set -- drop the repeats
     // from the sorted pairs, fix |B_t|, and rebuild the lists once more

@@ -97,6 +97,10 @@ class RFContext:
         if rc != 0:
             raise PhyBinRFError(rc, self._L.prf_last_error(self._h).decode())
 
+    def debug_small_tiles(self, on: bool = True):
+        """Test hook: run the sparse matrix kernel with 256-entry tiles (prf_debug_small_tiles)."""
+        self._ck(self._L.prf_debug_small_tiles(self._h, 1 if on else 0))
+
     @property
     def launches(self) -> int:
         return int(self._L.prf_launch_count(self._h))

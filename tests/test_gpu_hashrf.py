@@ -17,9 +17,12 @@ from tests.util import oracle_packed, random_multifurcating_newicks
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=["default", "small_tiles"])
+def ctx(request):
+    """Every test runs twice: with the production tile size, and with the 256-entry debug tiles that
+    make even small inputs exercise multi-tile rows, cursor carry-over and the cursor spill area."""
     c = RFContext(0)
+    c.debug_small_tiles(request.param == "small_tiles")
     yield c
     c.close()
 
@@ -164,6 +167,49 @@ def test_editdist_mask_and_sharded_compute(ctx):
     ctx.hashrf_compute(0, P)
     rows = ctx.fetch_rows(10, 12)
     assert np.array_equal(rows, full[packed_index(T, 10, 11): packed_index(T, 12, 13)])
+
+
+def _numpy_incidence(bips, off):
+    """Independent restatement on the host: bipartition ids (exact, via np.unique on the raw words),
+    per-id multiplicity, and a CSR id -> trees."""
+    T = len(off) - 1
+    keys = np.ascontiguousarray(bips).view([("", bips.dtype)] * bips.shape[1]).ravel()
+    _, ids, counts = np.unique(keys, return_inverse=True, return_counts=True)
+    tree_of = np.repeat(np.arange(T, dtype=np.int64), np.diff(off.astype(np.int64)))
+    order = np.argsort(ids, kind="stable")
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    return ids, counts, tree_of[order], starts
+
+
+def test_large_T_multi_tile_rows_checksum_and_rows(ctx):
+    # rows longer than one production tile (16384 columns): T = 40 000.  Too big for the oracle, so
+    # check size-independent properties: the checksum identity
+    #     sum_{a<b} d(a,b) = sum_{a<b} (|B_a| + |B_b|) - 2 * sum_lists m(m-1)/2
+    # and complete rows recomputed on the host from an independent numpy incidence.
+    T, n = 40_000, 100
+    f = Forest.synthetic(T, n, seed=0x5EED0002)
+    bips, off = f.all_bips()
+    ids, counts, csr_trees, starts = _numpy_incidence(bips, off)
+    nb = np.diff(off.astype(np.int64))
+    st = ctx.hashrf_load(bips, off)
+    P = T * (T - 1) // 2
+    assert st["n_unique"] == len(counts)
+    hits = int((counts.astype(np.int64) * (counts.astype(np.int64) - 1) // 2).sum())
+    assert st["n_hits"] == hits
+    st = ctx.hashrf_compute(0, P, editdist=2 * (n - 3) - 2)
+    up = ctx.fetch(0, P)
+    total = int(up.astype(np.uint64).sum())
+    assert total == int(nb.sum()) * (T - 1) - 2 * hits
+    mask = np.unpackbits(ctx.fetch_mask(0, P).view(np.uint8), bitorder="little")[:P].astype(bool)
+    assert int(mask.sum()) == int((up <= 2 * (n - 3) - 2).sum())
+    for a in [0, 1, 7, 16383, 16384, 23617, T - 16386, T - 300, T - 2]:
+        shared = np.zeros(T, dtype=np.int64)
+        for i in ids[int(off[a]):int(off[a + 1])]:
+            np.add.at(shared, csr_trees[starts[i]:starts[i + 1]], 1)
+        want = (nb[a] + nb[a + 1:] - 2 * shared[a + 1:]).astype(np.uint16)
+        p0 = int(packed_index(T, a, a + 1))
+        assert np.array_equal(up[p0:p0 + T - 1 - a], want), f"row {a}"
+        assert np.array_equal(mask[p0:p0 + T - 1 - a], want <= 2 * (n - 3) - 2), f"mask row {a}"
 
 
 def test_error_codes_not_aborts(ctx):
