@@ -272,7 +272,7 @@ def run_gpu(args, wl, wl_name):
     value = P / step_s
 
     # ---- light self-check on the resident result (not timed): sampled pairs vs direct set intersection
-    if mode == "hashrf" and rank == 0:
+    if mode == "hashrf" and rank == 0 and not os.environ.get("PRF_DEBUG_NOWALK"):
         rng = np.random.default_rng(1)
         out_h = d_out[: min(p_end - p_begin, 1 << 20)].cpu().numpy().view(np.uint16)
         pos = rng.integers(0, len(out_h), size=64)

@@ -7,19 +7,28 @@
 //
 // Work is cut along ROWS of the packed upper triangle.  A work item is either one row a restricted
 // to columns [cb, ce) (long rows, and the partial first/last row of a shard), or a group of whole
-// short rows that fit one tile.  Persistent CTAs take items from an atomic counter (longest first).
-// A row is produced tile by tile (kTile consecutive columns) through a ring of three shared-memory
-// buffers:
-//   fill   d = |B_a| + |B_b| for the tile's columns (16-byte shared stores);
-//   walk   tree a's shared bipartitions each own a suffix of an inverted list ("trees b > a that also
-//          have it", ascending).  Every suffix keeps a cursor in shared memory that only moves forward
-//          from tile to tile, so each member is loaded exactly once per row and there is no search.
-//          One warp takes kWalkUnroll suffixes at a time, issues their loads together, and subtracts
-//          2 at column b with a shared-memory atomic -- no global atomics on the matrix;
-//   store  the finished tile goes out as ONE bulk asynchronous copy (cp.async.bulk shared -> global,
-//          the TMA engine; 16-byte aligned interior) while the CTA already walks the next tile.  The
-//          < 8 entries before/after the aligned interior are stored by a few threads.
-// Every output byte is written exactly once.  One __syncthreads per tile.
+// short rows that fit one tile.  Persistent CTAs take items round-robin (longest first).  A row is
+// produced tile by tile (kTile consecutive columns) through a ring of three shared-memory buffers.
+//
+// The CTA is warp-specialised and has no block-wide barrier in its main loop:
+//   service warp (warp 0)
+//     produce  fill d = |B_a| + |B_b| for the tile's columns (16-byte shared stores), publish the
+//              row's suffix cursors and a tile descriptor, arrive on the tile's `full` mbarrier;
+//     emit     once every walker has arrived on the tile's `done` mbarrier: optional d <= editdist
+//              mask, then the finished tile goes out as ONE bulk asynchronous copy (cp.async.bulk
+//              shared -> global, the TMA engine; 16-byte aligned interior; the < 8 entries before
+//              and after it are stored by a few lanes).
+//     Work-item metadata is prefetched three items ahead (item -> list offsets -> ranges, the ranges
+//     by cp.async straight into a 4-deep ring of cursor arrays), so no global latency sits on the
+//     service warp's path.
+//   walker warps (the other warps)
+//     tree a's shared bipartitions each own a suffix of an inverted list ("trees b > a that also have
+//     it", ascending).  Every suffix keeps a cursor that only moves forward from tile to tile, so each
+//     member is loaded once per row and there is no search.  A suffix always belongs to the same
+//     walker, so cursors need no synchronisation.  A walker issues the loads of kWalkUnroll suffixes
+//     together and subtracts 2 at column b with a shared-memory atomic -- no global atomics on the
+//     matrix.  Walkers run ahead of each other by up to two tiles.
+// Every output byte is written exactly once.
 #pragma once
 
 #include <algorithm>
@@ -28,15 +37,32 @@
 
 namespace prf {
 
-constexpr int kRowTile = 16384;   // entries per tile buffer (32 KB)
-constexpr int kRowThreads = 512;
 constexpr int kRowBufs = 3;
-constexpr int kRowCurCap = 1024;  // suffix cursors of one row kept in shared memory (more spill to global)
+constexpr int kCurRing = 4;       // cursor arrays in shared memory (see the safety argument at stage_prefetch)
 constexpr int kGroupRows = 256;   // most rows in a group item
 constexpr int kWalkUnroll = 4;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
 }
 
 struct RowParams {
@@ -53,9 +79,31 @@ struct RowParams {
   uint32_t* mask;
   const RowItem* items;
   uint32_t n_items;
-  uint32_t* counter;
-  uint2* cursor_ws;           // per-CTA spill area for rows with more than kCurCap suffixes
-  uint32_t cursor_ws_stride;  // entries per CTA
+  uint2* cursor_ws;           // 2 spill areas per CTA for rows with more suffixes than a shared cursor array
+  uint32_t cursor_ws_stride;  // entries per area
+  int debug_nowalk;           // calibration only: skip the walk (wrong results)
+};
+
+enum : uint32_t { kTileRow = 0, kTileGroup = 1, kTileExit = 2 };
+
+struct TileDesc {
+  uint32_t kind;     // kTileRow / kTileGroup / kTileExit
+  uint32_t a0;       // the row, or the group's first row
+  uint32_t nr;       // rows in the group
+  uint32_t k0;       // first range of the item
+  uint32_t R;        // ranges of the item
+  uint32_t c_hi;     // row tile: one past its last column
+  int32_t base;      // row tile: entry index of column b is base + b
+  uint32_t cur_sel;  // row tile: 0..kCurRing-1 = shared cursor array, kCurRing/kCurRing+1 = global spill area
+  uint64_t p_lo, p_hi;  // packed positions held by the tile; entry 0 is position p_lo & ~7
+};
+
+// What the service warp knows about an upcoming work item.
+struct Staged {
+  RowItem it;
+  uint32_t k0, R;  // first range / number of ranges of the item's rows
+  uint32_t arr;    // cursor array: < kCurRing shared, else global spill area (arr - kCurRing)
+  uint32_t valid;
 };
 
 // One warp, one suffix: consume members < c_hi starting with the already loaded b0/b1 (members
@@ -85,113 +133,49 @@ __device__ __forceinline__ uint32_t walk_suffix(const uint32_t* __restrict__ mem
   return cur;
 }
 
-template <int kTile, int kThreads, int kCurCap>
-__global__ void __launch_bounds__(kThreads, 2) sparse_rows_kernel(const RowParams prm) {
+template <int kTile, int kWalkers, int kCurCap>
+__global__ void __launch_bounds__(32 * (kWalkers + 1), (kTile > 16384 ? 1 : 2)) sparse_rows_kernel(const RowParams prm) {
   constexpr int kStride = kTile + 8;  // entries per buffer: a tile keeps the 16-byte phase of its global address
-  constexpr uint32_t kWarps = kThreads / 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint16_t* tiles = reinterpret_cast<uint16_t*>(smem_raw);
-  uint2* s_cur = reinterpret_cast<uint2*>(smem_raw + (size_t)kRowBufs * kStride * 2);
-  __shared__ uint32_t s_roff[kGroupRows + 1];
-  __shared__ uint32_t s_item[2];
+  uint2* s_cur = reinterpret_cast<uint2*>(smem_raw + (size_t)kRowBufs * kStride * 2);  // kCurRing x kCurCap
+  __shared__ TileDesc s_desc[kRowBufs];
+  __shared__ Staged s_st[4];
+  __shared__ __align__(8) uint64_t s_full[kRowBufs], s_done[kRowBufs];
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t T = prm.T;
   const uint32_t* __restrict__ members = prm.members;
-  const uint32_t vv = (2u * prm.nb_uniform) | ((2u * prm.nb_uniform) << 16);
 
-  // d = |B_a| + |B_b| for packed positions [p_lo, p_hi) of row a starting at column c_lo
-  auto fill_row = [&](uint16_t* tile, uint32_t a, uint32_t c_lo, uint64_t p_lo, uint64_t p_hi, uint64_t P0) {
-    if (prm.uniform_nb) {
-      const uint32_t cnt = (uint32_t)((p_hi - P0 + 7) >> 3);
-      uint4* t4 = reinterpret_cast<uint4*>(tile);
-      const uint4 q4 = make_uint4(vv, vv, vv, vv);
-      for (uint32_t i = tid; i < cnt; i += kThreads) t4[i] = q4;
-    } else {
-      const uint32_t na = prm.nb[a];
-      const uint32_t cnt = (uint32_t)(p_hi - p_lo), o = (uint32_t)(p_lo - P0);
-      const uint16_t* nbb = prm.nb + c_lo;
-      for (uint32_t i = tid; i < cnt; i += kThreads) tile[o + i] = (uint16_t)(na + nbb[i]);
+  if (tid == 0) {
+    for (int b = 0; b < kRowBufs; ++b) {
+      mbar_init(&s_full[b], 1);
+      mbar_init(&s_done[b], kWalkers);
     }
-  };
-
-  // mask bits, unaligned ends and the bulk store of a finished tile holding [p_lo, p_hi)
-  auto emit = [&](const uint16_t* tile, uint64_t p_lo, uint64_t p_hi, uint64_t P0) {
-    if (prm.editdist >= 0) {
-      const uint64_t w_lo = (p_lo - prm.p_begin) >> 5, w_hi = (p_hi - 1 - prm.p_begin) >> 5;
-      for (uint64_t w = w_lo + warp; w <= w_hi; w += kWarps) {
-        const uint64_t pw = prm.p_begin + (w << 5);
-        const uint64_t p = pw + lane;
-        const bool hit = p >= p_lo && p < p_hi && (int32_t)tile[p - P0] <= prm.editdist;
-        const uint32_t bits = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) {
-          if (pw >= p_lo && pw + 32 <= p_hi) prm.mask[w] = bits;
-          else if (bits) atomicOr(&prm.mask[w], bits);  // word shared with a neighbouring row (mask is pre-zeroed)
-        }
-      }
-    }
-    const uint64_t pa = (p_lo + 7) & ~7ull, pb = p_hi & ~7ull;
-    uint16_t* outp = prm.out - prm.p_begin;  // indexed by absolute packed position
-    if (pa >= p_hi) {
-      if (tid < 8 && p_lo + tid < p_hi) outp[p_lo + tid] = tile[p_lo + tid - P0];
-      return;
-    }
-    if (tid < 8 && p_lo + tid < pa) outp[p_lo + tid] = tile[p_lo + tid - P0];
-    if (tid >= 32 && tid < 40 && pb + (tid - 32) < p_hi) outp[pb + (tid - 32)] = tile[pb + (tid - 32) - P0];
-    if (tid == 0 && pb > pa) {
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(outp + pa),
-                   "r"(smem_addr(tile + (pa - P0))), "r"((uint32_t)((pb - pa) * 2))
-                   : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    }
-  };
-
-  uint32_t q = 0;  // tiles produced so far by this CTA; tile q lives in buffer q % kRowBufs
-  if (tid == 0) s_item[0] = blockIdx.x;
+  }
   __syncthreads();
-  uint32_t par = 0;
-  for (;;) {
-    const uint32_t it = s_item[par];
-    if (it >= prm.n_items) break;
-    uint32_t next = 0;
-    if (tid == 0) next = atomicAdd(prm.counter, 1u) + gridDim.x;  // latency hides behind this item
-    const RowItem item = prm.items[it];
 
-    if (item.a0 == item.a1) {
-      // ---------------- one row, columns [cb, ce) ----------------
-      const uint32_t a = item.a0, cb = item.cb, ce = item.ce;
-      const uint32_t k0 = __ldg(prm.roff + a), R = __ldg(prm.roff + a + 1) - k0;
-      const uint64_t p_row = row_start(a, T) + (cb - a - 1);
-      uint2* cur = R <= (uint32_t)kCurCap ? s_cur : prm.cursor_ws + (size_t)blockIdx.x * prm.cursor_ws_stride;
-      for (uint32_t k = tid; k < R; k += kThreads) {
-        uint2 r = prm.ranges[k0 + k];
-        if (cb > a + 1) {  // shard starts inside the row: first member >= cb
-          uint32_t lo = r.x, hi = r.y;
-          while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (__ldg(members + mid) < cb) lo = mid + 1; else hi = mid;
-          }
-          r.x = lo;
-        }
-        cur[k] = r;
-      }
-      const uint32_t len = ce - cb, nseg = (len + kTile - 1) / kTile;
-      {
-        const uint64_t p_hi = p_row + min(len, (uint32_t)kTile);
-        fill_row(tiles + (q % kRowBufs) * kStride, a, cb, p_row, p_hi, p_row & ~7ull);
-      }
-      __syncthreads();
-      for (uint32_t s = 0; s < nseg; ++s) {
-        const uint32_t c_lo = cb + s * kTile, c_hi = min(ce, c_lo + (uint32_t)kTile);
-        const uint64_t p_lo = p_row + (uint64_t)s * kTile, p_hi = p_lo + (c_hi - c_lo), P0 = p_lo & ~7ull;
-        uint16_t* tile = tiles + (q % kRowBufs) * kStride;
-        uint32_t* tile32 = reinterpret_cast<uint32_t*>(tile);
-        const int32_t base = (int32_t)(p_lo - P0) - (int32_t)c_lo;
-        for (uint32_t kb = warp * kWalkUnroll; kb < R; kb += kWarps * kWalkUnroll) {
+  if (warp != 0) {
+    // =========================== walkers ===========================
+    const uint32_t w = warp - 1;
+    for (uint32_t q = 0;; ++q) {
+      const uint32_t buf = q % kRowBufs;
+      mbar_wait(&s_full[buf], (q / kRowBufs) & 1u);
+      const TileDesc d = s_desc[buf];
+      if (d.kind == kTileExit) break;
+      uint32_t* tile32 = reinterpret_cast<uint32_t*>(tiles + buf * kStride);
+      if (d.kind == kTileRow) {
+        uint2* cur = d.cur_sel < (uint32_t)kCurRing
+                         ? s_cur + d.cur_sel * kCurCap
+                         : prm.cursor_ws + ((size_t)blockIdx.x * 2 + (d.cur_sel - kCurRing)) * prm.cursor_ws_stride;
+        for (uint32_t kb = w; kb < d.R; kb += kWalkers * kWalkUnroll) {
           uint2 c[kWalkUnroll];
           uint32_t b0[kWalkUnroll], b1[kWalkUnroll];
 #pragma unroll
-          for (int u = 0; u < kWalkUnroll; ++u) c[u] = kb + u < R ? cur[kb + u] : make_uint2(0u, 0u);
+          for (int u = 0; u < kWalkUnroll; ++u) {
+            const uint32_t k = kb + u * kWalkers;
+            c[u] = k < d.R ? cur[k] : make_uint2(0u, 0u);
+          }
 #pragma unroll
           for (int u = 0; u < kWalkUnroll; ++u) {
             const uint32_t m = c[u].x + lane;
@@ -201,85 +185,300 @@ __global__ void __launch_bounds__(kThreads, 2) sparse_rows_kernel(const RowParam
 #pragma unroll
           for (int u = 0; u < kWalkUnroll; ++u) {
             if (c[u].x < c[u].y) {
-              const uint32_t nc = walk_suffix(members, c[u].x, c[u].y, b0[u], b1[u], c_hi, base, tile32, lane);
-              if (lane == 0 && nc != c[u].x) cur[kb + u].x = nc;
+              const uint32_t nc = walk_suffix(members, c[u].x, c[u].y, b0[u], b1[u], d.c_hi, d.base, tile32, lane);
+              if (lane == 0 && nc != c[u].x) cur[kb + u * kWalkers].x = nc;
             }
           }
         }
-        if (s + 1 < nseg) {
-          const uint32_t n_lo = c_lo + kTile, n_hi = min(ce, n_lo + (uint32_t)kTile);
-          const uint64_t np_lo = p_lo + kTile;
-          fill_row(tiles + ((q + 1) % kRowBufs) * kStride, a, n_lo, np_lo, np_lo + (n_hi - n_lo), np_lo & ~7ull);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the bulk copy
-        if (tid == 0) {
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // tile q-1 has left shared memory
-          if (s + 1 == nseg) s_item[par ^ 1] = next;
-        }
-        __syncthreads();
-        emit(tile, p_lo, p_hi, P0);
-        ++q;
-      }
-    } else {
-      // ---------------- a group of whole short rows a0..a1 in one tile ----------------
-      const uint32_t a0 = item.a0, nr = item.a1 - item.a0 + 1;
-      const uint64_t p_lo = row_start(a0, T), p_hi = row_start((uint64_t)item.a1 + 1, T), P0 = p_lo & ~7ull;
-      uint16_t* tile = tiles + (q % kRowBufs) * kStride;
-      uint32_t* tile32 = reinterpret_cast<uint32_t*>(tile);
-      for (uint32_t i = tid; i <= nr; i += kThreads) s_roff[i] = __ldg(prm.roff + a0 + i);
-      if (prm.uniform_nb) {
-        fill_row(tile, a0, a0 + 1, p_lo, p_hi, P0);
       } else {
-        for (uint32_t r = 0; r < nr; ++r) {
-          const uint32_t a = a0 + r;
-          const uint64_t rs = row_start(a, T);
-          fill_row(tile, a, a + 1, rs, rs + (T - 1 - a), P0);
+        const uint64_t P0 = d.p_lo & ~7ull;
+        for (uint32_t kb = w; kb < d.R; kb += kWalkers * kWalkUnroll) {
+          uint2 c[kWalkUnroll];
+          uint32_t b0[kWalkUnroll], b1[kWalkUnroll];
+          int32_t base[kWalkUnroll];
+#pragma unroll
+          for (int u = 0; u < kWalkUnroll; ++u) {
+            c[u] = make_uint2(0u, 0u);
+            base[u] = 0;
+            const uint32_t kk = kb + u * kWalkers;
+            if (kk < d.R) {
+              const uint32_t k = d.k0 + kk;
+              c[u] = prm.ranges[k];
+              uint32_t lo = 0, hi = d.nr - 1;  // largest i with roff[a0 + i] <= k
+              while (lo < hi) {
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if (__ldg(prm.roff + d.a0 + mid) <= k) lo = mid; else hi = mid - 1;
+              }
+              const uint32_t a = d.a0 + lo;
+              base[u] = (int32_t)(row_start(a, T) - P0) - (int32_t)(a + 1);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kWalkUnroll; ++u) {
+            const uint32_t m = c[u].x + lane;
+            b0[u] = m < c[u].y ? __ldg(members + m) : 0xffffffffu;
+            b1[u] = m + 32 < c[u].y ? __ldg(members + m + 32) : 0xffffffffu;
+          }
+#pragma unroll
+          for (int u = 0; u < kWalkUnroll; ++u)
+            if (c[u].x < c[u].y) walk_suffix(members, c[u].x, c[u].y, b0[u], b1[u], T, base[u], tile32, lane);
         }
       }
-      __syncthreads();
-      const uint32_t k0 = s_roff[0], R = s_roff[nr] - k0;
-      for (uint32_t kb = warp * kWalkUnroll; kb < R; kb += kWarps * kWalkUnroll) {
-        uint2 c[kWalkUnroll];
-        uint32_t b0[kWalkUnroll], b1[kWalkUnroll];
-        int32_t base[kWalkUnroll];
-#pragma unroll
-        for (int u = 0; u < kWalkUnroll; ++u) {
-          c[u] = make_uint2(0u, 0u);
-          base[u] = 0;
-          if (kb + u < R) {
-            const uint32_t k = k0 + kb + u;
-            c[u] = prm.ranges[k];
-            uint32_t lo = 0, hi = nr - 1;  // largest i with s_roff[i] <= k
-            while (lo < hi) {
-              const uint32_t mid = (lo + hi + 1) >> 1;
-              if (s_roff[mid] <= k) lo = mid; else hi = mid - 1;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my shared writes -> visible to the bulk copy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_done[buf]);
+    }
+    return;
+  }
+
+  // =========================== service warp ===========================
+  const uint32_t vv = (2u * prm.nb_uniform) | ((2u * prm.nb_uniform) << 16);
+  const uint4 q4 = make_uint4(vv, vv, vv, vv);
+
+  // d = |B_a| + |B_b| for packed positions [p_lo, p_hi) of row a starting at column c_lo; entry 0 = P0
+  auto fill_row = [&](uint16_t* tile, uint32_t a, uint32_t c_lo, uint64_t p_lo, uint64_t p_hi, uint64_t P0) {
+    if (prm.uniform_nb) {
+      const uint32_t cnt = (uint32_t)((p_hi - P0 + 7) >> 3);
+      uint4* t4 = reinterpret_cast<uint4*>(tile);
+#pragma unroll 8
+      for (uint32_t i = lane; i < cnt; i += 32) t4[i] = q4;
+    } else {
+      const uint32_t na = prm.nb[a];
+      const uint32_t cnt = (uint32_t)(p_hi - p_lo), o = (uint32_t)(p_lo - P0);
+      const uint16_t* nbb = prm.nb + c_lo;
+#pragma unroll 4
+      for (uint32_t i = lane; i < cnt; i += 32) tile[o + i] = (uint16_t)(na + nbb[i]);
+    }
+  };
+
+  // ---- work-item pipeline.  With item j current: item j+1's ranges are in flight (cp.async into its
+  // cursor array), item j+2's list offsets and item j+3's RowItem are in flight in registers.  What
+  // has landed lives in the shared ring s_st[item % 4] (the service warp is its only user), so the
+  // pipeline costs six registers.  All values are warp-uniform; lane 0 writes shared memory.
+  uint32_t row_seq = 0;    // row items that took a shared cursor array so far
+  uint32_t spill_seq = 0;  // row items that took a spill area so far
+  auto item_index = [&](uint32_t n) { return (uint64_t)blockIdx.x + (uint64_t)n * gridDim.x; };
+  auto ld_item = [&](uint32_t n) {
+    const uint64_t idx = item_index(n);
+    return idx < prm.n_items ? __ldg(reinterpret_cast<const uint4*>(prm.items + idx)) : make_uint4(0u, 0u, 0u, 0u);
+  };
+  // Starts copying a row item's ranges into its cursor array.  Array choice: the s-th row item with
+  // R <= kCurCap takes shared array s % kCurRing.  This runs when the item BEFORE it becomes current,
+  // i.e. inside produce() of a tile t that follows done[t-2]; the array's previous user is kCurRing = 4
+  // row items back, whose tiles are all <= t-2.  Spilled rows alternate between two global areas that
+  // are written synchronously in produce() (previous user two row items back: tiles <= t-2 as well).
+  auto stage_prefetch = [&](Staged& st) {
+    if (!st.valid || st.it.a0 != st.it.a1) return;
+    if (st.R <= (uint32_t)kCurCap) {
+      st.arr = row_seq++ % kCurRing;
+      uint2* dst = s_cur + st.arr * kCurCap;
+      for (uint32_t k = lane; k < st.R; k += 32)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst + k)), "l"(prm.ranges + st.k0 + k)
+                     : "memory");
+    } else {
+      st.arr = kCurRing + (spill_seq++ & 1u);
+    }
+  };
+  auto make_staged = [&](uint32_t n, uint4 v) {
+    Staged st;
+    st.it = RowItem{v.x, v.y, v.z, v.w};
+    st.k0 = st.R = st.arr = 0;
+    st.valid = item_index(n) < prm.n_items;
+    return st;
+  };
+  auto ld_offsets = [&](const Staged& st, uint32_t& k0, uint32_t& k1) {
+    k0 = k1 = 0;
+    if (st.valid) {
+      k0 = __ldg(prm.roff + st.it.a0);
+      k1 = prm.debug_nowalk ? k0 : __ldg(prm.roff + st.it.a1 + 1);
+    }
+  };
+
+  uint32_t j = 0;   // current item (local sequence number)
+  uint32_t seg = 0; // next tile of the current item
+  bool exit_sent = false;
+  uint4 pend_item;          // RowItem of item j+3
+  uint32_t pend_k0, pend_k1;  // list offsets of item j+2
+  {
+    // prologue: items 0..2 complete enough, item 3 in flight
+    Staged s0 = make_staged(0, ld_item(0)), s1 = make_staged(1, ld_item(1)), s2 = make_staged(2, ld_item(2));
+    uint32_t a, b;
+    ld_offsets(s0, a, b); s0.k0 = a; s0.R = b - a;
+    ld_offsets(s1, a, b); s1.k0 = a; s1.R = b - a;
+    stage_prefetch(s0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    stage_prefetch(s1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    ld_offsets(s2, pend_k0, pend_k1);
+    pend_item = ld_item(3);
+    if (lane == 0) { s_st[0] = s0; s_st[1] = s1; s_st[2] = s2; }
+    __syncwarp();
+  }
+
+  auto advance_item = [&]() {
+    // (a) item j+3's RowItem and (b) item j+2's offsets have landed
+    Staged s3 = make_staged(j + 3, pend_item);
+    Staged s2 = s_st[(j + 2) & 3];
+    s2.k0 = pend_k0;
+    s2.R = pend_k1 - pend_k0;
+    // (c) ranges of item j+2, (d) offsets of item j+3, (e) RowItem of item j+4
+    stage_prefetch(s2);
+    asm volatile("cp.async.commit_group;" ::: "memory");  // one group per advance, possibly empty
+    ld_offsets(s3, pend_k0, pend_k1);
+    pend_item = ld_item(j + 4);
+    __syncwarp();  // every lane has read s_st[(j+2)&3]
+    if (lane == 0) { s_st[(j + 2) & 3] = s2; s_st[(j + 3) & 3] = s3; }
+    __syncwarp();
+    ++j;
+    seg = 0;
+  };
+
+  // Produces the next tile of this CTA's sequence into ring slot `slot` (or the exit marker).
+  auto produce = [&](uint32_t slot) {
+    if (exit_sent) return;
+    TileDesc* d = &s_desc[slot];
+    const Staged cs = s_st[j & 3];
+    if (!cs.valid) {
+      if (lane == 0) d->kind = kTileExit;
+      exit_sent = true;
+    } else {
+      uint16_t* tile = tiles + slot * kStride;
+      const RowItem it = cs.it;
+      if (it.a0 == it.a1) {
+        const uint32_t a = it.a0, cb = it.cb, ce = it.ce, R = cs.R, k0 = cs.k0;
+        const uint32_t len = ce - cb, nseg = (len + kTile - 1) / kTile;
+        if (seg == 0) {
+          // the row's suffix cursors: all cp.async groups but the newest (item j+1's) have landed
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+          __syncwarp();
+          const bool spilled = cs.arr >= (uint32_t)kCurRing;
+          uint2* cur = !spilled ? s_cur + cs.arr * kCurCap
+                                : prm.cursor_ws + ((size_t)blockIdx.x * 2 + (cs.arr - kCurRing)) * prm.cursor_ws_stride;
+          if (spilled || cb > a + 1) {
+            for (uint32_t k = lane; k < R; k += 32) {
+              uint2 r = spilled ? prm.ranges[k0 + k] : cur[k];
+              if (cb > a + 1) {  // shard starts inside the row: first member >= cb
+                uint32_t lo = r.x, hi = r.y;
+                while (lo < hi) {
+                  const uint32_t mid = (lo + hi) >> 1;
+                  if (__ldg(members + mid) < cb) lo = mid + 1; else hi = mid;
+                }
+                r.x = lo;
+              }
+              cur[k] = r;
             }
-            const uint32_t a = a0 + lo;
-            base[u] = (int32_t)(row_start(a, T) - P0) - (int32_t)(a + 1);
           }
         }
-#pragma unroll
-        for (int u = 0; u < kWalkUnroll; ++u) {
-          const uint32_t m = c[u].x + lane;
-          b0[u] = m < c[u].y ? __ldg(members + m) : 0xffffffffu;
-          b1[u] = m + 32 < c[u].y ? __ldg(members + m + 32) : 0xffffffffu;
+        const uint32_t c_lo = cb + seg * kTile, c_hi = min(ce, c_lo + (uint32_t)kTile);
+        const uint64_t p_lo = row_start(a, T) + (c_lo - a - 1), p_hi = p_lo + (c_hi - c_lo), P0 = p_lo & ~7ull;
+        fill_row(tile, a, c_lo, p_lo, p_hi, P0);
+        if (lane == 0) {
+          d->kind = kTileRow;
+          d->a0 = a;
+          d->nr = 1;
+          d->k0 = k0;
+          d->R = R;
+          d->c_hi = c_hi;
+          d->base = (int32_t)(p_lo - P0) - (int32_t)c_lo;
+          d->cur_sel = cs.arr;
+          d->p_lo = p_lo;
+          d->p_hi = p_hi;
         }
-#pragma unroll
-        for (int u = 0; u < kWalkUnroll; ++u)
-          if (c[u].x < c[u].y) walk_suffix(members, c[u].x, c[u].y, b0[u], b1[u], T, base[u], tile32, lane);
+        if (++seg == nseg) advance_item();
+      } else {
+        const uint32_t a0 = it.a0, nr = it.a1 - it.a0 + 1;
+        const uint64_t p_lo = row_start(a0, T), p_hi = row_start((uint64_t)it.a1 + 1, T), P0 = p_lo & ~7ull;
+        if (prm.uniform_nb) {
+          fill_row(tile, a0, a0 + 1, p_lo, p_hi, P0);
+        } else {
+          for (uint32_t r = 0; r < nr; ++r) {
+            const uint32_t a = a0 + r;
+            const uint64_t rs = row_start(a, T);
+            fill_row(tile, a, a + 1, rs, rs + (T - 1 - a), P0);
+          }
+        }
+        if (lane == 0) {
+          d->kind = kTileGroup;
+          d->a0 = a0;
+          d->nr = nr;
+          d->k0 = cs.k0;
+          d->R = cs.R;
+          d->c_hi = T;
+          d->base = 0;
+          d->cur_sel = 0;
+          d->p_lo = p_lo;
+          d->p_hi = p_hi;
+        }
+        advance_item();
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      if (tid == 0) {
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        s_item[par ^ 1] = next;
-      }
-      __syncthreads();
-      emit(tile, p_lo, p_hi, P0);
-      ++q;
     }
-    par ^= 1;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_full[slot]);
+  };
+
+  // mask bits, unaligned ends and the bulk store of the finished tile in ring slot `slot`
+  auto emit = [&](uint32_t slot) {
+    const uint16_t* tile = tiles + slot * kStride;
+    const uint64_t p_lo = s_desc[slot].p_lo, p_hi = s_desc[slot].p_hi, P0 = p_lo & ~7ull;
+    if (prm.editdist >= 0) {
+      // 8 entries (one aligned 16-byte group) per lane -> one mask byte
+      const uint32_t ngroups = (uint32_t)((p_hi - P0 + 7) >> 3);
+      const uint32_t thr = (uint32_t)prm.editdist;
+      uint8_t* mask8 = reinterpret_cast<uint8_t*>(prm.mask);
+      for (uint32_t g = lane; g < ngroups; g += 32) {
+        const uint4 v = reinterpret_cast<const uint4*>(tile)[g];
+        const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+        const uint64_t pg = P0 + 8ull * g;
+        uint32_t bits = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t e = (wds[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+          bits |= (e <= thr ? 1u : 0u) << i;
+        }
+        const uint64_t byte = (pg - prm.p_begin) >> 3;
+        if (pg >= p_lo && pg + 8 <= p_hi) {
+          mask8[byte] = (uint8_t)bits;
+        } else {  // group shared with a neighbouring row: keep only my positions, OR into the pre-zeroed word
+          uint32_t valid = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) valid |= ((pg + i >= p_lo && pg + i < p_hi) ? 1u : 0u) << i;
+          bits &= valid;
+          if (bits) atomicOr(&prm.mask[byte >> 2], bits << ((byte & 3) * 8));
+        }
+      }
+    }
+    const uint64_t pa = (p_lo + 7) & ~7ull, pb = p_hi & ~7ull;
+    uint16_t* outp = prm.out - prm.p_begin;  // indexed by absolute packed position
+    if (pa >= p_hi) {
+      if (lane < 8 && p_lo + lane < p_hi) outp[p_lo + lane] = tile[p_lo + lane - P0];
+    } else {
+      if (lane < 8 && p_lo + lane < pa) outp[p_lo + lane] = tile[p_lo + lane - P0];
+      if (lane >= 8 && lane < 16 && pb + (lane - 8) < p_hi) outp[pb + (lane - 8)] = tile[pb + (lane - 8) - P0];
+      if (lane == 0 && pb > pa) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(outp + pa),
+                     "r"(smem_addr(tile + (pa - P0))), "r"((uint32_t)((pb - pa) * 2))
+                     : "memory");
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");  // one group per tile, even if empty
+  };
+
+  for (uint32_t f = 0; f < kRowBufs - 1; ++f) produce(f);
+  for (uint32_t e = 0;; ++e) {
+    const uint32_t slot = e % kRowBufs;
+    if (s_desc[slot].kind == kTileExit) break;
+    mbar_wait(&s_done[slot], (e / kRowBufs) & 1u);
+    emit(slot);
+    // the slot to refill held tile e-1: its bulk copy (the group before the one just committed) must have
+    // finished reading shared memory
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncwarp();
+    produce((e + kRowBufs - 1) % kRowBufs);
   }
-  if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncwarp();
 }
 
 // Cuts packed positions [p_begin, p_end) into work items, longest first.
@@ -320,13 +519,14 @@ static void build_row_plan(uint32_t T, uint64_t p_begin, uint64_t p_end, uint32_
                    [](const RowItem& x, const RowItem& y) { return x.ce - x.cb > y.ce - y.cb; });
 }
 
-template <int kTile, int kThreads, int kCurCap>
+template <int kTile, int kWalkers, int kCurCap>
 static int launch_sparse_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out,
                            uint32_t* d_mask) {
   const HashRFState& H = ctx->h;
   cudaStream_t s = ctx->stream;
-  constexpr size_t smem = (size_t)kRowBufs * (kTile + 8) * 2 + (size_t)kCurCap * sizeof(uint2);
-  auto kern = sparse_rows_kernel<kTile, kThreads, kCurCap>;
+  constexpr int kThreads = 32 * (kWalkers + 1);
+  constexpr size_t smem = (size_t)kRowBufs * (kTile + 8) * 2 + (size_t)kCurRing * kCurCap * sizeof(uint2);
+  auto kern = sparse_rows_kernel<kTile, kWalkers, kCurCap>;
   RowPlan& plan = ctx->plan;
   if (!plan.valid || plan.T != H.T || plan.p_begin != p_begin || plan.p_end != p_end || plan.tile != kTile) {
     plan.valid = false;
@@ -342,14 +542,10 @@ static int launch_sparse_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t e
     plan.p_begin = p_begin;
     plan.p_end = p_end;
     plan.tile = kTile;
-    plan.ctas_per_sm = 0;
-    if (!plan.counter.p) PRF_CK(ctx, plan.counter.alloc(1, s));
-    if (plan.ctas_per_sm == 0) {
-      PRF_CK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      int nb = 0;
-      PRF_CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem));
-      plan.ctas_per_sm = nb > 0 ? nb : 1;
-    }
+    PRF_CK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    PRF_CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem));
+    plan.ctas_per_sm = nb > 0 ? nb : 1;
     plan.valid = true;
   }
   if (plan.n_items == 0) return PRF_OK;
@@ -368,14 +564,16 @@ static int launch_sparse_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t e
   prm.mask = d_mask;
   prm.items = plan.items.p;
   prm.n_items = plan.n_items;
-  prm.counter = plan.counter.p;
   if (H.stats.max_bips > (uint32_t)kCurCap) {
-    const size_t need = (size_t)grid * H.stats.max_bips;
+    const size_t need = (size_t)grid * 2 * H.stats.max_bips;
     if (plan.cursor_ws.n < need) PRF_CK(ctx, plan.cursor_ws.alloc(need, s));
     prm.cursor_ws = plan.cursor_ws.p;
     prm.cursor_ws_stride = H.stats.max_bips;
   }
-  PRF_CK(ctx, cudaMemsetAsync(plan.counter.p, 0, sizeof(uint32_t), s));
+  {
+    const char* e = getenv("PRF_DEBUG_NOWALK");
+    prm.debug_nowalk = e && *e == '1';
+  }
   if (d_mask) PRF_CK(ctx, cudaMemsetAsync(d_mask, 0, ((p_end - p_begin + 31) / 32) * sizeof(uint32_t), s));
   kern<<<grid, kThreads, smem, s>>>(prm);
   PRF_LAUNCHED(ctx);
@@ -385,8 +583,8 @@ static int launch_sparse_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t e
 static int launch_sparse(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out,
                          uint32_t* d_mask) {
   // the tiny-tile build exists so that small test inputs exercise multi-tile rows and cursor spill
-  if (ctx->debug_small_tiles) return launch_sparse_t<256, 128, 8>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-  return launch_sparse_t<kRowTile, kRowThreads, kRowCurCap>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  if (ctx->debug_small_tiles) return launch_sparse_t<256, 3, 8>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  return launch_sparse_t<16384, 15, 384>(ctx, p_begin, p_end, editdist, d_out, d_mask);
 }
 
 }  // namespace prf
