@@ -11,16 +11,17 @@
 // produced tile by tile (kTile consecutive columns) through a ring of three shared-memory buffers.
 //
 // The CTA is warp-specialised and has no block-wide barrier in its main loop:
-//   service warp (warp 0)
-//     produce  fill d = |B_a| + |B_b| for the tile's columns (16-byte shared stores), publish the
-//              row's suffix cursors and a tile descriptor, arrive on the tile's `full` mbarrier;
-//     emit     once every walker has arrived on the tile's `done` mbarrier: optional d <= editdist
-//              mask, then the finished tile goes out as ONE bulk asynchronous copy (cp.async.bulk
-//              shared -> global, the TMA engine; 16-byte aligned interior; the < 8 entries before
-//              and after it are stored by a few lanes).
-//     Work-item metadata is prefetched three items ahead (item -> list offsets -> ranges, the ranges
-//     by cp.async straight into a 4-deep ring of cursor arrays), so no global latency sits on the
-//     service warp's path.
+//   producer warp (warp 0)
+//     waits for the ring slot's `empty` mbarrier, fills d = |B_a| + |B_b| for the tile's columns
+//     (16-byte shared stores), publishes the row's suffix cursors and a tile descriptor, and arrives
+//     on the tile's `full` mbarrier.  Work-item metadata is prefetched three items ahead (item ->
+//     list offsets -> ranges, the ranges by cp.async straight into a 4-deep ring of cursor arrays),
+//     so no global latency sits on its path.
+//   emitter warp (warp 1)
+//     once every walker has arrived on the tile's `done` mbarrier: optional d <= editdist mask, then
+//     the finished tile goes out as ONE bulk asynchronous copy (cp.async.bulk shared -> global, the
+//     TMA engine; 16-byte aligned interior; the < 8 entries before and after it are stored by a few
+//     lanes).  When the copy has finished reading shared memory the slot's `empty` barrier is signalled.
 //   walker warps (the other warps)
 //     tree a's shared bipartitions each own a suffix of an inverted list ("trees b > a that also have
 //     it", ascending).  Every suffix keeps a cursor that only moves forward from tile to tile, so each
@@ -41,6 +42,7 @@ constexpr int kRowBufs = 3;
 constexpr int kCurRing = 4;       // cursor arrays in shared memory (see the safety argument at stage_prefetch)
 constexpr int kGroupRows = 256;   // most rows in a group item
 constexpr int kWalkUnroll = 4;
+constexpr int kSlots = 8;        // suffixes per walker kept in registers (cursor, end, look-ahead window)
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -56,12 +58,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
       "}" ::"r"(smem_addr(bar)),
-      "r"(parity)
+      "r"(parity), "r"(1000000u)  // suspend-time hint (ns): sleep in hardware instead of spinning on issue slots
       : "memory");
 }
 
@@ -95,6 +97,7 @@ struct TileDesc {
   uint32_t c_hi;     // row tile: one past its last column
   int32_t base;      // row tile: entry index of column b is base + b
   uint32_t cur_sel;  // row tile: 0..kCurRing-1 = shared cursor array, kCurRing/kCurRing+1 = global spill area
+  uint32_t flags;    // row tile: bit 0 = first tile of the row item, bit 1 = last
   uint64_t p_lo, p_hi;  // packed positions held by the tile; entry 0 is position p_lo & ~7
 };
 
@@ -134,14 +137,14 @@ __device__ __forceinline__ uint32_t walk_suffix(const uint32_t* __restrict__ mem
 }
 
 template <int kTile, int kWalkers, int kCurCap>
-__global__ void __launch_bounds__(32 * (kWalkers + 1), (kTile > 16384 ? 1 : 2)) sparse_rows_kernel(const RowParams prm) {
+__global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) sparse_rows_kernel(const RowParams prm) {
   constexpr int kStride = kTile + 8;  // entries per buffer: a tile keeps the 16-byte phase of its global address
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint16_t* tiles = reinterpret_cast<uint16_t*>(smem_raw);
   uint2* s_cur = reinterpret_cast<uint2*>(smem_raw + (size_t)kRowBufs * kStride * 2);  // kCurRing x kCurCap
   __shared__ TileDesc s_desc[kRowBufs];
   __shared__ Staged s_st[4];
-  __shared__ __align__(8) uint64_t s_full[kRowBufs], s_done[kRowBufs];
+  __shared__ __align__(8) uint64_t s_full[kRowBufs], s_done[kRowBufs], s_empty[kRowBufs];
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t T = prm.T;
@@ -151,13 +154,20 @@ __global__ void __launch_bounds__(32 * (kWalkers + 1), (kTile > 16384 ? 1 : 2)) 
     for (int b = 0; b < kRowBufs; ++b) {
       mbar_init(&s_full[b], 1);
       mbar_init(&s_done[b], kWalkers);
+      mbar_init(&s_empty[b], 1);
     }
   }
   __syncthreads();
 
-  if (warp != 0) {
+  if (warp >= 2) {
     // =========================== walkers ===========================
-    const uint32_t w = warp - 1;
+    const uint32_t w = warp - 2;
+    // Register-resident suffixes of the current row: slot u is range w + u * kWalkers.  win[u] is a
+    // look-ahead window, members[cx[u] + lane] (0xffffffff past the end), loaded as soon as the cursor
+    // moves -- i.e. before the next tile's `full` wait -- so its latency hides behind the barrier.
+    uint32_t cx[kSlots], ce[kSlots], win[kSlots];
+#pragma unroll
+    for (int u = 0; u < kSlots; ++u) cx[u] = ce[u] = 0u, win[u] = 0xffffffffu;
     for (uint32_t q = 0;; ++q) {
       const uint32_t buf = q % kRowBufs;
       mbar_wait(&s_full[buf], (q / kRowBufs) & 1u);
@@ -168,7 +178,47 @@ __global__ void __launch_bounds__(32 * (kWalkers + 1), (kTile > 16384 ? 1 : 2)) 
         uint2* cur = d.cur_sel < (uint32_t)kCurRing
                          ? s_cur + d.cur_sel * kCurCap
                          : prm.cursor_ws + ((size_t)blockIdx.x * 2 + (d.cur_sel - kCurRing)) * prm.cursor_ws_stride;
-        for (uint32_t kb = w; kb < d.R; kb += kWalkers * kWalkUnroll) {
+        const bool first = d.flags & 1u, last = d.flags & 2u;
+        if (first) {
+#pragma unroll
+          for (int u = 0; u < kSlots; ++u) {
+            const uint32_t k = w + u * kWalkers;
+            const uint2 r = k < d.R ? cur[k] : make_uint2(0u, 0u);
+            cx[u] = r.x;
+            ce[u] = r.y;
+          }
+#pragma unroll
+          for (int u = 0; u < kSlots; ++u) {
+            const uint32_t m = cx[u] + lane;
+            win[u] = m < ce[u] ? __ldg(members + m) : 0xffffffffu;
+          }
+        }
+        bool again;
+        do {
+          again = false;
+#pragma unroll
+          for (int u = 0; u < kSlots; ++u) {
+            const bool in = win[u] < d.c_hi;
+            const uint32_t bal = __ballot_sync(0xffffffffu, in);
+            if (bal) {
+              if (in) {
+                const uint32_t idx = (uint32_t)(d.base + (int32_t)win[u]);
+                atomicSub(&tile32[idx >> 1], 2u << ((idx & 1u) * 16u));
+              }
+              cx[u] += __popc(bal);
+              const bool full = bal == 0xffffffffu;
+              again |= full;
+              if (full || !last) {  // slide the window (more of this tile, or the next tile of the row)
+                const uint32_t m = cx[u] + lane;
+                win[u] = m < ce[u] ? __ldg(members + m) : 0xffffffffu;
+              } else {
+                win[u] = 0xffffffffu;  // consumed; the row ends here, nothing to look ahead to
+              }
+            }
+          }
+        } while (again);
+        // suffixes beyond the register slots (rows with more than kSlots * kWalkers shared bipartitions)
+        for (uint32_t kb = w + kSlots * kWalkers; kb < d.R; kb += kWalkers * kWalkUnroll) {
           uint2 c[kWalkUnroll];
           uint32_t b0[kWalkUnroll], b1[kWalkUnroll];
 #pragma unroll
@@ -231,17 +281,18 @@ __global__ void __launch_bounds__(32 * (kWalkers + 1), (kTile > 16384 ? 1 : 2)) 
     return;
   }
 
-  // =========================== service warp ===========================
+  // =========================== producer (warp 0) and emitter (warp 1) ===========================
   const uint32_t vv = (2u * prm.nb_uniform) | ((2u * prm.nb_uniform) << 16);
   const uint4 q4 = make_uint4(vv, vv, vv, vv);
 
   // d = |B_a| + |B_b| for packed positions [p_lo, p_hi) of row a starting at column c_lo; entry 0 = P0
   auto fill_row = [&](uint16_t* tile, uint32_t a, uint32_t c_lo, uint64_t p_lo, uint64_t p_hi, uint64_t P0) {
     if (prm.uniform_nb) {
-      const uint32_t cnt = (uint32_t)((p_hi - P0 + 7) >> 3);
-      uint4* t4 = reinterpret_cast<uint4*>(tile);
-#pragma unroll 8
-      for (uint32_t i = lane; i < cnt; i += 32) t4[i] = q4;
+      // the whole buffer, unconditionally: kTile/256 stores with immediate offsets
+      uint4* t4 = reinterpret_cast<uint4*>(tile) + lane;
+#pragma unroll
+      for (int i = 0; i < kTile / 256; ++i) t4[32 * i] = q4;
+      if (lane == 0) t4[kTile / 8] = q4;
     } else {
       const uint32_t na = prm.nb[a];
       const uint32_t cnt = (uint32_t)(p_hi - p_lo), o = (uint32_t)(p_lo - P0);
@@ -334,8 +385,10 @@ __global__ void __launch_bounds__(32 * (kWalkers + 1), (kTile > 16384 ? 1 : 2)) 
   };
 
   // Produces the next tile of this CTA's sequence into ring slot `slot` (or the exit marker).
-  auto produce = [&](uint32_t slot) {
+  auto produce = [&](uint32_t q) {
     if (exit_sent) return;
+    const uint32_t slot = q % kRowBufs;
+    if (q >= (uint32_t)kRowBufs) mbar_wait(&s_empty[slot], ((q / kRowBufs) & 1u) ^ 1u);  // tile q-3 has left the slot
     TileDesc* d = &s_desc[slot];
     const Staged cs = s_st[j & 3];
     if (!cs.valid) {
@@ -381,6 +434,7 @@ __global__ void __launch_bounds__(32 * (kWalkers + 1), (kTile > 16384 ? 1 : 2)) 
           d->c_hi = c_hi;
           d->base = (int32_t)(p_lo - P0) - (int32_t)c_lo;
           d->cur_sel = cs.arr;
+          d->flags = (seg == 0 ? 1u : 0u) | (seg + 1 == nseg ? 2u : 0u);
           d->p_lo = p_lo;
           d->p_hi = p_hi;
         }
@@ -406,6 +460,7 @@ __global__ void __launch_bounds__(32 * (kWalkers + 1), (kTile > 16384 ? 1 : 2)) 
           d->c_hi = T;
           d->base = 0;
           d->cur_sel = 0;
+          d->flags = 3u;
           d->p_lo = p_lo;
           d->p_hi = p_hi;
         }
@@ -448,36 +503,46 @@ __global__ void __launch_bounds__(32 * (kWalkers + 1), (kTile > 16384 ? 1 : 2)) 
         }
       }
     }
-    const uint64_t pa = (p_lo + 7) & ~7ull, pb = p_hi & ~7ull;
-    uint16_t* outp = prm.out - prm.p_begin;  // indexed by absolute packed position
-    if (pa >= p_hi) {
-      if (lane < 8 && p_lo + lane < p_hi) outp[p_lo + lane] = tile[p_lo + lane - P0];
-    } else {
-      if (lane < 8 && p_lo + lane < pa) outp[p_lo + lane] = tile[p_lo + lane - P0];
-      if (lane >= 8 && lane < 16 && pb + (lane - 8) < p_hi) outp[pb + (lane - 8)] = tile[pb + (lane - 8) - P0];
-      if (lane == 0 && pb > pa) {
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(outp + pa),
-                     "r"(smem_addr(tile + (pa - P0))), "r"((uint32_t)((pb - pa) * 2))
-                     : "memory");
-      }
+    // tile-index space: entry i is packed position P0 + i
+    const uint32_t o_lo = (uint32_t)(p_lo - P0), o_hi = (uint32_t)(p_hi - P0);
+    const uint32_t ia = (o_lo + 7) & ~7u, ib = o_hi & ~7u;
+    uint16_t* g = prm.out + (P0 - prm.p_begin);
+    if (lane < 8) {
+      const uint32_t i = o_lo + lane;
+      if (i < min(ia, o_hi)) g[i] = tile[i];
+    } else if (lane < 16) {
+      const uint32_t i = ib + (lane - 8);
+      if (ib >= ia && i < o_hi) g[i] = tile[i];
+    }
+    if (lane == 0 && ib > ia) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g + ia),
+                   "r"(smem_addr(tile + ia)), "r"((ib - ia) * 2u)
+                   : "memory");
     }
     if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");  // one group per tile, even if empty
   };
 
-  for (uint32_t f = 0; f < kRowBufs - 1; ++f) produce(f);
-  for (uint32_t e = 0;; ++e) {
-    const uint32_t slot = e % kRowBufs;
-    if (s_desc[slot].kind == kTileExit) break;
-    mbar_wait(&s_done[slot], (e / kRowBufs) & 1u);
-    emit(slot);
-    // the slot to refill held tile e-1: its bulk copy (the group before the one just committed) must have
-    // finished reading shared memory
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-    __syncwarp();
-    produce((e + kRowBufs - 1) % kRowBufs);
+  if (warp == 0) {
+    for (uint32_t q = 0; !exit_sent; ++q) produce(q);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else {
+    for (uint32_t e = 0;; ++e) {
+      const uint32_t slot = e % kRowBufs, par = (e / kRowBufs) & 1u;
+      mbar_wait(&s_full[slot], par);  // descriptor published
+      if (s_desc[slot].kind == kTileExit) break;
+      mbar_wait(&s_done[slot], par);
+      emit(slot);
+      if (e > 0) {
+        // tile e-1's bulk copy (the group before the one just committed) has finished reading its slot
+        __syncwarp();  // and so have this warp's own reads of it
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          mbar_arrive(&s_empty[(e - 1) % kRowBufs]);
+        }
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncwarp();
 }
 
@@ -524,7 +589,7 @@ static int launch_sparse_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t e
                            uint32_t* d_mask) {
   const HashRFState& H = ctx->h;
   cudaStream_t s = ctx->stream;
-  constexpr int kThreads = 32 * (kWalkers + 1);
+  constexpr int kThreads = 32 * (kWalkers + 2);
   constexpr size_t smem = (size_t)kRowBufs * (kTile + 8) * 2 + (size_t)kCurRing * kCurCap * sizeof(uint2);
   auto kern = sparse_rows_kernel<kTile, kWalkers, kCurCap>;
   RowPlan& plan = ctx->plan;
@@ -583,8 +648,11 @@ static int launch_sparse_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t e
 static int launch_sparse(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out,
                          uint32_t* d_mask) {
   // the tiny-tile build exists so that small test inputs exercise multi-tile rows and cursor spill
-  if (ctx->debug_small_tiles) return launch_sparse_t<256, 3, 8>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-  return launch_sparse_t<16384, 15, 384>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  if (ctx->debug_small_tiles) return launch_sparse_t<256, 2, 8>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  static const int cfg = [] { const char* e = getenv("PRF_SPARSE_CFG"); return e ? atoi(e) : 0; }();
+  if (cfg == 1) return launch_sparse_t<32768, 30, 512>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  if (cfg == 2) return launch_sparse_t<16384, 10, 384>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  return launch_sparse_t<16384, 14, 384>(ctx, p_begin, p_end, editdist, d_out, d_mask);
 }
 
 }  // namespace prf
