@@ -532,13 +532,12 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
       if (s_desc[slot].kind == kTileExit) break;
       mbar_wait(&s_done[slot], par);
       emit(slot);
-      if (e > 0) {
-        // tile e-1's bulk copy (the group before the one just committed) has finished reading its slot
-        __syncwarp();  // and so have this warp's own reads of it
-        if (lane == 0) {
-          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          mbar_arrive(&s_empty[(e - 1) % kRowBufs]);
-        }
+      // hand the slot back as soon as the bulk copy has read it (the emitter has nothing else to do):
+      // the producer can then refill it while the walkers are still busy with the next two tiles
+      __syncwarp();  // this warp's own reads of the tile are done
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(&s_empty[slot]);
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
