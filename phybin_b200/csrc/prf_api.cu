@@ -131,6 +131,7 @@ PRF_API void prf_destroy(prf_ctx* h) {
   c.h = HashRFState{};
   c.tol = TolerantState{};
   c.plan = RowPlan{};
+  c.timing.release();
   c.out.release();
   c.mask.release();
   cudaStreamSynchronize(c.stream);
@@ -464,6 +465,19 @@ PRF_API int prf_tolerant(prf_ctx* h, const uint64_t* clades, const uint64_t* tre
 PRF_API int prf_debug_small_tiles(prf_ctx* h, int on) {
   if (!h) return PRF_E_INVALID;
   h->c.debug_small_tiles = on != 0;
+  return PRF_OK;
+}
+
+// PRF_TIMING builds: copies the per-CTA cycle counters of the last sparse launch ([grid][64]).
+PRF_API int prf_debug_timing(prf_ctx* h, unsigned long long* dst, uint32_t cap, uint32_t* grid) {
+  if (!h) return PRF_E_INVALID;
+  Ctx* ctx = &h->c;
+  if (grid) *grid = ctx->timing_grid;
+  size_t n = std::min<size_t>((size_t)ctx->timing_grid * 64, cap);
+  if (n && ctx->timing.p) {
+    PRF_CK(ctx, cudaMemcpyAsync(dst, ctx->timing.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PRF_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   return PRF_OK;
 }
 

@@ -107,6 +107,8 @@ struct Ctx {
   TolerantState tol;
   RowPlan plan;
   bool debug_small_tiles = false;
+  DevBuf<unsigned long long> timing;  // PRF_TIMING builds only
+  uint32_t timing_grid = 0;
   // ctx-owned result of the last compute
   DevBuf<uint16_t> out;
   DevBuf<uint32_t> mask;

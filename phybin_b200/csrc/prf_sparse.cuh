@@ -42,7 +42,6 @@ constexpr int kRowBufs = 3;
 constexpr int kCurRing = 4;       // cursor arrays in shared memory (see the safety argument at stage_prefetch)
 constexpr int kGroupRows = 256;   // most rows in a group item
 constexpr int kWalkUnroll = 4;
-constexpr int kSlots = 8;        // suffixes per walker kept in registers (cursor, end, look-ahead window)
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -53,18 +52,24 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1, %2;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t"
-      "}" ::"r"(smem_addr(bar)),
-      "r"(parity), "r"(1000000u)  // suspend-time hint (ns): sleep in hardware instead of spinning on issue slots
+      "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_addr(bar)), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+// Waiting warps back off with nanosleep so that they leave the issue slots to the working warps.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t sleep_ns = 0) {
+  while (!mbar_try(bar, parity)) {
+    if (sleep_ns) __nanosleep(sleep_ns);
+  }
 }
 
 struct RowParams {
@@ -84,6 +89,8 @@ struct RowParams {
   uint2* cursor_ws;           // 2 spill areas per CTA for rows with more suffixes than a shared cursor array
   uint32_t cursor_ws_stride;  // entries per area
   int debug_nowalk;           // calibration only: skip the walk (wrong results)
+  uint32_t debug_sleep;       // ns of back-off between mbarrier polls (0 = spin)
+  unsigned long long* timing; // PRF_TIMING builds: per-CTA cycle counters [grid][16]
 };
 
 enum : uint32_t { kTileRow = 0, kTileGroup = 1, kTileExit = 2 };
@@ -136,7 +143,7 @@ __device__ __forceinline__ uint32_t walk_suffix(const uint32_t* __restrict__ mem
   return cur;
 }
 
-template <int kTile, int kWalkers, int kCurCap>
+template <int kTile, int kWalkers, int kCurCap, int kSlots>
 __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) sparse_rows_kernel(const RowParams prm) {
   constexpr int kStride = kTile + 8;  // entries per buffer: a tile keeps the 16-byte phase of its global address
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -162,6 +169,12 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
   if (warp >= 2) {
     // =========================== walkers ===========================
     const uint32_t w = warp - 2;
+#ifdef PRF_TIMING
+    long long t_wait = 0, t_work = 0, t0 = clock64(), t1;
+#define TICK(acc) do { t1 = clock64(); acc += t1 - t0; t0 = t1; } while (0)
+#else
+#define TICK(acc) do {} while (0)
+#endif
     // Register-resident suffixes of the current row: slot u is range w + u * kWalkers.  win[u] is a
     // look-ahead window, members[cx[u] + lane] (0xffffffff past the end), loaded as soon as the cursor
     // moves -- i.e. before the next tile's `full` wait -- so its latency hides behind the barrier.
@@ -170,7 +183,9 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
     for (int u = 0; u < kSlots; ++u) cx[u] = ce[u] = 0u, win[u] = 0xffffffffu;
     for (uint32_t q = 0;; ++q) {
       const uint32_t buf = q % kRowBufs;
-      mbar_wait(&s_full[buf], (q / kRowBufs) & 1u);
+      TICK(t_work);
+      mbar_wait(&s_full[buf], (q / kRowBufs) & 1u, prm.debug_sleep);
+      TICK(t_wait);
       const TileDesc d = s_desc[buf];
       if (d.kind == kTileExit) break;
       uint32_t* tile32 = reinterpret_cast<uint32_t*>(tiles + buf * kStride);
@@ -278,10 +293,19 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_done[buf]);
     }
+#ifdef PRF_TIMING
+    if (lane == 0 && prm.timing) {
+      prm.timing[(size_t)blockIdx.x * 64 + 2 * warp] = t_wait;
+      prm.timing[(size_t)blockIdx.x * 64 + 2 * warp + 1] = t_work;
+    }
+#endif
     return;
   }
 
   // =========================== producer (warp 0) and emitter (warp 1) ===========================
+#ifdef PRF_TIMING
+  long long t_wait = 0, t_work = 0, t_wait2 = 0, t0 = clock64(), t1;
+#endif
   const uint32_t vv = (2u * prm.nb_uniform) | ((2u * prm.nb_uniform) << 16);
   const uint4 q4 = make_uint4(vv, vv, vv, vv);
 
@@ -388,7 +412,9 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
   auto produce = [&](uint32_t q) {
     if (exit_sent) return;
     const uint32_t slot = q % kRowBufs;
-    if (q >= (uint32_t)kRowBufs) mbar_wait(&s_empty[slot], ((q / kRowBufs) & 1u) ^ 1u);  // tile q-3 has left the slot
+    TICK(t_work);
+    if (q >= (uint32_t)kRowBufs) mbar_wait(&s_empty[slot], ((q / kRowBufs) & 1u) ^ 1u, prm.debug_sleep);  // tile q-3 has left the slot
+    TICK(t_wait);
     TileDesc* d = &s_desc[slot];
     const Staged cs = s_st[j & 3];
     if (!cs.valid) {
@@ -528,21 +554,33 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
   } else {
     for (uint32_t e = 0;; ++e) {
       const uint32_t slot = e % kRowBufs, par = (e / kRowBufs) & 1u;
+      TICK(t_work);
       mbar_wait(&s_full[slot], par);  // descriptor published
       if (s_desc[slot].kind == kTileExit) break;
-      mbar_wait(&s_done[slot], par);
+      mbar_wait(&s_done[slot], par, prm.debug_sleep);
+      TICK(t_wait);
       emit(slot);
       // hand the slot back as soon as the bulk copy has read it (the emitter has nothing else to do):
       // the producer can then refill it while the walkers are still busy with the next two tiles
       __syncwarp();  // this warp's own reads of the tile are done
+      TICK(t_work);
       if (lane == 0) {
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         mbar_arrive(&s_empty[slot]);
       }
+      __syncwarp();
+      TICK(t_wait2);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
   __syncwarp();
+#ifdef PRF_TIMING
+  if (lane == 0 && prm.timing) {
+    prm.timing[(size_t)blockIdx.x * 64 + 2 * warp] = t_wait;
+    prm.timing[(size_t)blockIdx.x * 64 + 2 * warp + 1] = t_work;
+    if (warp == 1) prm.timing[(size_t)blockIdx.x * 64 + 63] = t_wait2;
+  }
+#endif
 }
 
 // Cuts packed positions [p_begin, p_end) into work items, longest first.
@@ -583,14 +621,14 @@ static void build_row_plan(uint32_t T, uint64_t p_begin, uint64_t p_end, uint32_
                    [](const RowItem& x, const RowItem& y) { return x.ce - x.cb > y.ce - y.cb; });
 }
 
-template <int kTile, int kWalkers, int kCurCap>
+template <int kTile, int kWalkers, int kCurCap, int kSlots>
 static int launch_sparse_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out,
                            uint32_t* d_mask) {
   const HashRFState& H = ctx->h;
   cudaStream_t s = ctx->stream;
   constexpr int kThreads = 32 * (kWalkers + 2);
   constexpr size_t smem = (size_t)kRowBufs * (kTile + 8) * 2 + (size_t)kCurRing * kCurCap * sizeof(uint2);
-  auto kern = sparse_rows_kernel<kTile, kWalkers, kCurCap>;
+  auto kern = sparse_rows_kernel<kTile, kWalkers, kCurCap, kSlots>;
   RowPlan& plan = ctx->plan;
   if (!plan.valid || plan.T != H.T || plan.p_begin != p_begin || plan.p_end != p_end || plan.tile != kTile) {
     plan.valid = false;
@@ -637,7 +675,15 @@ static int launch_sparse_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t e
   {
     const char* e = getenv("PRF_DEBUG_NOWALK");
     prm.debug_nowalk = e && *e == '1';
+    const char* z = getenv("PRF_SPARSE_SLEEP");
+    prm.debug_sleep = z ? (uint32_t)atoi(z) : 0u;
   }
+#ifdef PRF_TIMING
+  if (ctx->timing.n < (size_t)grid * 64) PRF_CK(ctx, ctx->timing.alloc((size_t)grid * 64, s));
+  PRF_CK(ctx, cudaMemsetAsync(ctx->timing.p, 0, ctx->timing.bytes(), s));
+  prm.timing = ctx->timing.p;
+  ctx->timing_grid = grid;
+#endif
   if (d_mask) PRF_CK(ctx, cudaMemsetAsync(d_mask, 0, ((p_end - p_begin + 31) / 32) * sizeof(uint32_t), s));
   kern<<<grid, kThreads, smem, s>>>(prm);
   PRF_LAUNCHED(ctx);
@@ -647,11 +693,10 @@ static int launch_sparse_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t e
 static int launch_sparse(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out,
                          uint32_t* d_mask) {
   // the tiny-tile build exists so that small test inputs exercise multi-tile rows and cursor spill
-  if (ctx->debug_small_tiles) return launch_sparse_t<256, 2, 8>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  if (ctx->debug_small_tiles) return launch_sparse_t<256, 2, 8, 8>(ctx, p_begin, p_end, editdist, d_out, d_mask);
   static const int cfg = [] { const char* e = getenv("PRF_SPARSE_CFG"); return e ? atoi(e) : 0; }();
-  if (cfg == 1) return launch_sparse_t<32768, 30, 512>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-  if (cfg == 2) return launch_sparse_t<16384, 10, 384>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-  return launch_sparse_t<16384, 14, 384>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  if (cfg == 1) return launch_sparse_t<8192, 14, 384, 8>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  return launch_sparse_t<16384, 14, 384, 8>(ctx, p_begin, p_end, editdist, d_out, d_mask);
 }
 
 }  // namespace prf
