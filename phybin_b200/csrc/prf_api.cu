@@ -10,6 +10,7 @@
 #include "prf_primitives.cuh"
 #include "prf_incidence.cuh"
 #include "prf_sparse.cuh"
+#include "prf_dense.cuh"
 #include "prf_tolerant.cuh"
 
 using namespace prf;
@@ -246,12 +247,23 @@ PRF_API int prf_hashrf_compute(prf_ctx* h, uint64_t p_begin, uint64_t p_end, int
   if (editdist < 0) d_mask = nullptr;
   trace_mark("hashrf_compute: output ready");
 
-  int use = variant == PRF_VARIANT_AUTO ? PRF_VARIANT_SPARSE : variant;
-  if (use == PRF_VARIANT_DENSE)
-    return ctx->fail(PRF_E_UNSUPPORTED, "dense (tcgen05) variant is not built into this library version");
+  int use = variant;
+  if (use == PRF_VARIANT_AUTO) {
+    // Measured split density decides.  Cost models from this round's B200 runs: the
+    // sparse join pays ~1.9 ps per shared (pair, bipartition) incidence, the tensor-core Gram
+    // 2 * Kpad int8 ops per pair at ~2 Pop/s sustained; both write the same 2 B per pair.
+    const double pairs = (double)(p_end - p_begin);
+    const double hits = (double)H.stats.n_hits * (H.P ? pairs / (double)H.P : 0.0);
+    const double kpad = (double)((H.n_shared + kDK - 1) / kDK * kDK);
+    const double t_sparse = hits * 1.9e-12, t_dense = pairs * kpad * 2.0 / 2.0e15;
+    const double operand = (double)((H.T + kDN - 1) / kDN * kDN) * kpad;
+    use = (H.n_shared > 0 && operand < 32e9 && t_dense < t_sparse) ? PRF_VARIANT_DENSE : PRF_VARIANT_SPARSE;
+  }
   PRF_CK(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
   if (p_end > p_begin) {
-    if ((rc = launch_sparse(ctx, p_begin, p_end, editdist, d_out, d_mask))) return rc;
+    if (use == PRF_VARIANT_DENSE) rc = launch_dense(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    else rc = launch_sparse(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    if (rc) return rc;
   }
   PRF_CK(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
   H.stats.variant_used = use;

@@ -64,8 +64,12 @@ struct HashRFState {
   // tree-major incidence over shared bipartition ids (dense variant input)
   uint32_t n_shared = 0;
   uint64_t n_shared_nnz = 0;
-  DevBuf<uint32_t> sh_tree;      // [n_shared_nnz] tree of the k-th shared entry (tree order)
-  DevBuf<uint32_t> sh_sid;       // [n_shared_nnz] its shared bipartition id
+  DevBuf<uint32_t> lid;          // [n_shared_nnz] dense id (0..n_shared-1) of the list each member entry belongs to
+  // dense variant: tiled uint8 operand, built lazily by the first dense compute (prf_dense.cuh)
+  bool dense_ready = false;
+  uint32_t dense_Tpad = 0, dense_Kpad = 0;
+  DevBuf<uint8_t> dense_At;
+  DevBuf<uint2> dense_tiles;
   prf_stats stats{};
 };
 

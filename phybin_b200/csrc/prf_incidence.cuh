@@ -169,12 +169,14 @@ __global__ void __launch_bounds__(256) range_count_kernel(const uint32_t* __rest
                                                           const uint32_t* __restrict__ tree,
                                                           const uint32_t* __restrict__ lid_ex,
                                                           const uint32_t* __restrict__ head_pos, uint32_t n,
-                                                          uint32_t* rcount, unsigned long long* counters) {
+                                                          uint32_t* rcount, unsigned long long* counters,
+                                                          uint32_t* __restrict__ lid_out) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long hits = 0;
   if (k < n) {
     const bool head = k == 0 || slot[k] != slot[k - 1];
     const uint32_t l = lid_ex[k] + (head ? 1 : 0) - 1;
+    lid_out[k] = l;
     const uint32_t end = head_pos[l + 1];
     if (k + 1 < end) atomicAdd(&rcount[tree[k]], 1u);
     if (head) {
@@ -317,6 +319,7 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
   DevBuf<uint32_t> slot_sorted, lid_ex, head_pos, rcount, cursor;
   PRF_CK(ctx, slot_sorted.alloc(n_sh_nnz, s));
   PRF_CK(ctx, H.members.alloc(n_sh_nnz, s));
+  PRF_CK(ctx, H.lid.alloc(n_sh_nnz, s));
   PRF_CK(ctx, lid_ex.alloc(n_sh_nnz, s));
   PRF_CK(ctx, head_pos.alloc((size_t)n_sh_nnz + 1, s));
   PRF_CK(ctx, rcount.alloc((size_t)T + 1, s));
@@ -344,7 +347,7 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
                                                            head_pos.p, counters.p);
       PRF_LAUNCHED(ctx);
       range_count_kernel<<<grid_for(n_sorted), 256, 0, s>>>(slot_sorted.p, H.members.p, lid_ex.p, head_pos.p,
-                                                            n_sorted, rcount.p, counters.p);
+                                                            n_sorted, rcount.p, counters.p, H.lid.p);
       PRF_LAUNCHED(ctx);
     }
     if ((rc = exclusive_scan(ctx, LoadU32{rcount.p}, (uint64_t)T + 1, H.roff.p, nullptr))) return rc;

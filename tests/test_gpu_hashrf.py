@@ -262,3 +262,60 @@ def test_tolerant_equals_hashrf_on_complete_taxa(ctx):
     a = hashRF(24, f, ctx)
     b, _ = naiveDistMatrix(f, ctx)
     assert np.array_equal(a.upper, b.upper)
+
+
+# ---- dense (tcgen05 int8 Gram) variant ---------------------------------------------------------
+
+def run_variant(ctx, bips, off, variant, editdist=-1, p_begin=0, p_end=None):
+    ctx.hashrf_load(bips, off)
+    p_end = ctx.P if p_end is None else p_end
+    st = ctx.hashrf_compute(p_begin, p_end, editdist=editdist, variant=variant)
+    up = ctx.fetch(p_begin, p_end)
+    mask = ctx.fetch_mask(p_begin, p_end) if editdist >= 0 else None
+    return up, mask, st
+
+
+@pytest.mark.parametrize("T,n,family,nni", [(300, 30, NNI_FAMILY, 4), (700, 64, NNI_FAMILY, 8), (1000, 100, NNI_FAMILY, 8),
+                                            (513, 20, 0, 0), (2, 6, 0, 0), (257, 12, NNI_FAMILY, 2)])
+def test_dense_variant_vs_literal_oracle(ctx, T, n, family, nni):
+    f = Forest.synthetic(T, n, seed=0xD0 + T, family=family, nni_max=nni)
+    o = orc.Forest([f.to_newick()])
+    bips, off = f.all_bips()
+    up, _, st = run_variant(ctx, bips, off, 2)
+    assert st["variant_used"] == 2
+    assert np.array_equal(up.astype(np.int64), oracle_packed(o, "hashrf", "literal"))
+
+
+def test_dense_variant_multifurcating_mask_and_shards(ctx):
+    rng = random.Random(21)
+    text = [random_multifurcating_newicks(rng, 900, 24)]
+    f, o = Forest.parse(text), orc.Forest(text)
+    bips, off = f.all_bips()
+    want = oracle_packed(o, "hashrf", "literal")
+    T = len(f)
+    P = T * (T - 1) // 2
+    thr = int(np.median(want))
+    up, mask, st = run_variant(ctx, bips, off, 2, editdist=thr)
+    assert st["min_bips"] < st["max_bips"]
+    assert np.array_equal(up.astype(np.int64), want)
+    bits = np.unpackbits(mask.view(np.uint8), bitorder="little")[:P].astype(bool)
+    assert np.array_equal(bits, want <= thr) and bits.any() and not bits.all()
+    for r in range(3):
+        b, e = shard_range(T, r, 3)
+        got, m, _ = run_variant(ctx, bips, off, 2, editdist=thr, p_begin=b, p_end=e)
+        assert np.array_equal(got.astype(np.int64), want[b:e])
+        mb = np.unpackbits(m.view(np.uint8), bitorder="little")[: e - b].astype(bool)
+        assert np.array_equal(mb, want[b:e] <= thr)
+
+
+def test_auto_picks_dense_for_similar_trees_and_sparse_for_random(ctx):
+    f = Forest.synthetic(3000, 100, seed=5, family=NNI_FAMILY, nni_max=8)
+    bips, off = f.all_bips()
+    dense, _, st = run_variant(ctx, bips, off, 0)
+    assert st["variant_used"] == 2
+    sparse, _, st2 = run_variant(ctx, bips, off, 1)
+    assert st2["variant_used"] == 1 and np.array_equal(dense, sparse)
+    f = Forest.synthetic(3000, 100, seed=6)
+    bips, off = f.all_bips()
+    _, _, st = run_variant(ctx, bips, off, 0)
+    assert st["variant_used"] == 1
