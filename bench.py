@@ -32,6 +32,9 @@ WORKLOADS = {
     # name: (T, n, seed, family, editdist, mode)
     "cfg2": dict(T=10_000, n=100, seed=0x5EED0002, family=0, editdist=-1, mode="hashrf"),
     "cfg3": dict(T=100_000, n=200, seed=0x5EED0003, family=0, editdist=-1, mode="hashrf"),
+    # the "dense-universe" family of SURVEY 8d: one base tree + r ~ U{0..8} NNI moves per tree (tensor-core variant)
+    "cfg2_nni": dict(T=10_000, n=100, seed=0x5EED0002, family=1, editdist=-1, mode="hashrf"),
+    "cfg3_nni": dict(T=100_000, n=200, seed=0x5EED0003, family=1, editdist=-1, mode="hashrf"),
     "cfg4": dict(T=50_000, n=500, seed=0x5EED0004, family=0, editdist=4, mode="hashrf"),
     "cfg5": dict(T=20_000, n=150, seed=0x5EED0005, family=0, editdist=-1, mode="tolerant", p_missing=0.10),
 }
@@ -158,6 +161,7 @@ def run_gpu(args, wl, wl_name):
     import torch.distributed as dist
     from phybin_b200.host import Forest
     from phybin_b200.rfdistance import MEM_DEVICE, RFContext, shard_range
+    from phybin_b200.distributed import KeyGather, shard_rows as key_shard_rows, tree_shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -177,7 +181,7 @@ def run_gpu(args, wl, wl_name):
     ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
     # ---- synthetic input: every rank generates only its own shard of trees ----------------------
-    t_lo, t_hi = T * rank // world, T * (rank + 1) // world
+    t_lo, t_hi = tree_shard(T, rank, world)
     f = Forest.synthetic(T, n, wl["seed"], wl["family"], 8, wl.get("p_missing", 0.0))
     W = f.words
     if mode == "hashrf":
@@ -197,11 +201,7 @@ def run_gpu(args, wl, wl_name):
         d_my = torch.from_numpy(my_bips.view(np.int64)).to(dev)                  # this rank's tree shard, resident
         d_off = torch.from_numpy(off_all.view(np.int64)).to(dev)                  # offsets are tiny and replicated
         d_leaf = torch.from_numpy(leaf_all.view(np.int64)).to(dev) if mode == "tolerant" else None
-        shard_rows = [int(off_all[T * (r + 1) // world] - off_all[T * r // world]) for r in range(world)]
-        max_rows = max(shard_rows)
-        d_full = torch.empty((nnz, W), dtype=torch.int64, device=dev) if world > 1 else d_my
-        d_gather = torch.empty((world, max_rows, W), dtype=torch.int64, device=dev) if world > 1 else None
-        d_pad = torch.zeros((max_rows, W), dtype=torch.int64, device=dev) if world > 1 else None
+        gather = KeyGather(key_shard_rows(off_all, T, world), W, dev)
         p_begin, p_end = shard_range(T, rank, world)
         d_out = torch.empty(max(p_end - p_begin, 8), dtype=torch.int16, device=dev)
         d_mask = torch.empty(max((p_end - p_begin + 31) // 32, 1), dtype=torch.int32, device=dev) if editdist >= 0 else None
@@ -212,13 +212,7 @@ def run_gpu(args, wl, wl_name):
     def step():
         """dedup + incidence + matrix for this rank's slice; inputs and outputs stay in HBM."""
         with torch.cuda.stream(ext):
-            if world > 1:
-                d_pad[: d_my.shape[0]].copy_(d_my)
-                dist.all_gather_into_tensor(d_gather.view(-1), d_pad.view(-1))     # NCCL over NVLink
-                pos = 0
-                for r in range(world):
-                    d_full[pos:pos + shard_rows[r]].copy_(d_gather[r, : shard_rows[r]])
-                    pos += shard_rows[r]
+            d_full = gather(d_my)     # NCCL all-gather over NVLink when world > 1
         if mode == "hashrf":
             ctx.hashrf_load(d_full.data_ptr(), d_off.data_ptr(), T, W, MEM_DEVICE)
             st = ctx.hashrf_compute(p_begin, p_end, editdist, 0, d_out.data_ptr(),
@@ -251,8 +245,13 @@ def run_gpu(args, wl, wl_name):
     wall = time.perf_counter() - t0
     dev_s = ev0.elapsed_time(ev1) / 1e3
     launches = ctx.launches - launches0
+    tm = torch.tensor([dev_s, wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    dev_s, wall = float(tm[0]), float(tm[1])
     # the timed region can be shorter than nvidia-smi's sampling period: keep the GPU under the same load
-    # (identical, untimed steps) until the sampler has seen it for >= 1.5 s, all ranks in lock-step
+    # (identical, untimed steps) until the sampler has seen it for >= 1.5 s.  The count comes from the
+    # all-reduced time, so every rank runs the same number of (collective) steps.
     probe_steps = 0
     if wall < 1.5:
         probe_steps = int(min(2000, max(1, (1.5 - wall) / max(wall / args.steps, 1e-4))))
@@ -262,10 +261,6 @@ def run_gpu(args, wl, wl_name):
     clocks = sampler.stop() if sampler else None
     if clocks is not None:
         clocks["sampled_over"] = f"timed region + {probe_steps} identical untimed steps (sampler period 50 ms)"
-    tm = torch.tensor([dev_s, wall], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    dev_s, wall = float(tm[0]), float(tm[1])
     # the step synchronises with the host a few times (scalar read-backs), so device-event time on the
     # library's stream and wall time between the bracketing synchronisations agree; report the larger.
     step_s = max(dev_s, wall) / args.steps
@@ -296,6 +291,17 @@ def run_gpu(args, wl, wl_name):
                 "kernel": "sparse_rows_kernel" if mode == "hashrf" else "tolerant_kernel",
                 "kernel_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_share_of_step": avg_ms * 1e-3 / step_s}
+    if mode == "hashrf" and st.get("variant_used") == 2:
+        # tensor-core variant: 2 * Kpad int8 ops per pair (Kpad = shared bipartitions padded to the 128-column k-block)
+        kpad = (int(st["n_shared"]) + 127) // 128 * 128
+        ops = 2.0 * kpad * my_pairs
+        tops = ops / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
+        peak_i8 = 2.0 * peaks["bf16_tflops"]
+        roofline = {"bound": "tensor", "achieved": tops, "peak": peak_i8, "unit": "TFLOP/s", "frac": tops / peak_i8,
+                    "traffic": None, "peak_source": peak_src + " bf16 x2 (int8 dense peak is not in MEASURED_PEAKS.json; nominal ratio)",
+                    "kernel": "dense_gram_kernel", "kernel_ms": avg_ms, "algorithmic_ops_per_launch": ops,
+                    "k_columns": kpad, "output_gbs": alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0,
+                    "kernel_share_of_step": avg_ms * 1e-3 / step_s}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
@@ -327,7 +333,7 @@ def run_gpu(args, wl, wl_name):
             "data": "synthetic",
             "config": {"workload": wl_name, "trees": T, "taxa": n, "mode": mode, "editdist": editdist,
                        "pairs": P, "nnz": nnz, "words": W, "n_unique": st.get("n_unique"), "n_hits": st.get("n_hits"),
-                       "variant": {1: "sparse", 2: "dense"}.get(st.get("variant_used"), mode),
+                       "variant": {1: "sparse", 2: "dense"}.get(st.get("variant_used"), mode), "n_shared": st.get("n_shared"),
                        "parallelism": f"packed-range shard x{world}" + (" + NCCL all-gather of bipartition keys" if world > 1 else ""),
                        "l2": "output per step (>= 2 B/pair) far exceeds the 126 MB L2; no explicit flush"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,

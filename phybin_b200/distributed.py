@@ -1,0 +1,48 @@
+"""Multi-GPU plumbing of the hashRF path (one process per GPU, torch.distributed).
+
+The matrix shards with no data-path collective: every output entry depends only on
+the two trees' rows of the incidence, so rank r computes the aligned slice prf_shard_range(T, r, world)
+of the packed triangle from the WHOLE bipartition table.  The only exchange is before the build:
+ranks hold disjoint tree shards (the host extracted their bipartitions) and all-gather the keys
+(NCCL over NVLink on GPUs; gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def tree_shard(T: int, rank: int, world: int) -> Tuple[int, int]:
+    """Trees [lo, hi) owned by `rank`: contiguous, balanced to within one tree."""
+    return T * rank // world, T * (rank + 1) // world
+
+
+def shard_rows(tree_off: np.ndarray, T: int, world: int) -> List[int]:
+    """Number of bipartition entries each rank contributes (tree_off is the global T+1 offset array)."""
+    return [int(tree_off[tree_shard(T, r, world)[1]] - tree_off[tree_shard(T, r, world)[0]]) for r in range(world)]
+
+
+class KeyGather:
+    """All-gathers per-rank [rows_r, W] int64 key blocks into one [nnz, W] table (rows_r may differ:
+    blocks are padded to the longest).  Buffers are allocated once and reused every step."""
+
+    def __init__(self, rows: List[int], W: int, device: torch.device):
+        self.rows, self.W, self.world = rows, W, len(rows)
+        self.max_rows = max(rows) if rows else 0
+        self.full = torch.empty((sum(rows), W), dtype=torch.int64, device=device)
+        self.gathered = torch.empty((self.world, self.max_rows, W), dtype=torch.int64, device=device)
+        self.pad = torch.zeros((self.max_rows, W), dtype=torch.int64, device=device)
+
+    def __call__(self, mine: torch.Tensor) -> torch.Tensor:
+        if self.world == 1:
+            return mine
+        self.pad[: mine.shape[0]].copy_(mine)
+        dist.all_gather_into_tensor(self.gathered.view(-1), self.pad.view(-1))
+        pos = 0
+        for r in range(self.world):
+            self.full[pos:pos + self.rows[r]].copy_(self.gathered[r, : self.rows[r]])
+            pos += self.rows[r]
+        return self.full
