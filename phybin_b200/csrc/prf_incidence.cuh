@@ -390,6 +390,7 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
   H.uniform_nb = mm[0] == mm[1];
   H.nb_uniform = mm[0];
   H.n_shared = n_sorted ? hs[1] : 0;
+  H.n_shared_nnz = n_sorted;  // after duplicate removal
 
   prf_stats& st = H.stats;
   st = prf_stats{};

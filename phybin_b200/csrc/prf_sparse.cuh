@@ -507,16 +507,15 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
       const uint32_t ngroups = (uint32_t)((p_hi - P0 + 7) >> 3);
       const uint32_t thr = (uint32_t)prm.editdist;
       uint8_t* mask8 = reinterpret_cast<uint8_t*>(prm.mask);
+      const uint32_t thr2 = thr | (thr << 16);
       for (uint32_t g = lane; g < ngroups; g += 32) {
         const uint4 v = reinterpret_cast<const uint4*>(tile)[g];
-        const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
         const uint64_t pg = P0 + 8ull * g;
-        uint32_t bits = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t e = (wds[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
-          bits |= (e <= thr ? 1u : 0u) << i;
-        }
+        // per-halfword (entry <= thr) -> 1: two entries per SIMD compare, then squeeze bit 16 down to bit 1
+        const uint32_t r0 = __vsetleu2(v.x, thr2), r1 = __vsetleu2(v.y, thr2), r2 = __vsetleu2(v.z, thr2),
+                       r3 = __vsetleu2(v.w, thr2);
+        uint32_t bits = ((r0 | (r0 >> 15)) & 3u) | (((r1 | (r1 >> 15)) & 3u) << 2) | (((r2 | (r2 >> 15)) & 3u) << 4) |
+                        (((r3 | (r3 >> 15)) & 3u) << 6);
         const uint64_t byte = (pg - prm.p_begin) >> 3;
         if (pg >= p_lo && pg + 8 <= p_hi) {
           mask8[byte] = (uint8_t)bits;

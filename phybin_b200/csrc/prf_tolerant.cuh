@@ -14,7 +14,9 @@
 //
 // One warp per pair.  Lanes normalise the clades of both trees and insert them into a small
 // per-warp open-addressing table in shared memory (hash routes, equality is decided on the full
-// key); each slot accumulates "seen in a" / "seen in b" flags; d = number of slots with exactly one.
+// key, rebuilt on demand from the key's number so that the table is 4 bytes per slot and ~32 warps
+// fit on an SM); each slot accumulates "seen in a" / "seen in b" flags; d = number of slots with
+// exactly one.
 #pragma once
 
 #include "prf_common.cuh"
@@ -82,9 +84,56 @@ __device__ __forceinline__ uint32_t hash_set(const BitSet<W>& s) {
   return (uint32_t)h;
 }
 
-// slot word: [31:30] flags (1 = in a, 2 = in b), [29:11] tag, [10:0] key index + 1; 0 = empty
+// Everything a lane needs to (re)build the canonical set of any clade of the pair.
 template <int W>
-__device__ __forceinline__ void table_insert(uint32_t* table, uint32_t tmask, uint64_t* keys, uint32_t idx,
+struct PairCtx {
+  const uint64_t* clades;
+  uint64_t oa, ob;   // first clade of tree a / tree b
+  uint32_t na, nb;   // clade counts
+  BitSet<W> S, R;    // shared taxa; normBip's universe {0..k-1}
+  uint32_t k, half;
+  bool fullA, fullB; // the tree's taxon set equals S: the reference uses its cached, un-pruned bips
+};
+
+// Key number idx of the pair: idx < na -> clade idx of tree a; idx < na+nb -> clade idx-na of tree b;
+// beyond -> the (idx-na-nb)-th taxon of S as a singleton (only reachable when k <= 3).
+// Returns false when the reference would not keep this set (empty, the whole of S after pruning, or
+// size <= 1 after normalisation).
+template <int W>
+__device__ __forceinline__ bool make_key(const PairCtx<W>& P, uint32_t idx, BitSet<W>& key) {
+  BitSet<W> m;
+  uint32_t pc;
+  if (idx < P.na + P.nb) {
+    const bool isb = idx >= P.na;
+    const uint64_t* src = P.clades + (isb ? P.ob + (idx - P.na) : P.oa + idx) * W;
+#pragma unroll
+    for (int i = 0; i < W; ++i) m.w[i] = src[i] & P.S.w[i];
+    pc = popc_set<W>(m);
+    // drop the empty set, and the full set unless the cached (unpruned) bips are used
+    if (pc == 0 || (pc == P.k && !(isb ? P.fullB : P.fullA))) return false;
+  } else {
+    uint32_t j = idx - P.na - P.nb, seen = 0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      m.w[i] = 0;
+      uint64_t word = P.S.w[i];
+      while (word) {
+        const uint64_t low = word & (0 - word);
+        if (seen == j) m.w[i] = low;
+        ++seen;
+        word ^= low;
+      }
+    }
+    pc = 1;
+  }
+  return norm_bip<W>(m, pc, P.R, P.half, key) > 1;
+}
+
+// slot word: [31:30] flags (1 = in a, 2 = in b), [29:11] tag, [10:0] key number + 1; 0 = empty.
+// The table holds no keys: on a tag match the other key is rebuilt from its number (its raw clade is
+// an L1/L2 hit), so a warp needs only 4 bytes of shared memory per slot and many warps fit on an SM.
+template <int W>
+__device__ __forceinline__ void table_insert(uint32_t* table, uint32_t tmask, const PairCtx<W>& P, uint32_t idx,
                                              const BitSet<W>& key, uint32_t flag) {
   const uint32_t h = hash_set<W>(key);
   const uint32_t tag = (h >> 13) & 0x7ffffu;
@@ -97,10 +146,11 @@ __device__ __forceinline__ void table_insert(uint32_t* table, uint32_t tmask, ui
       if (cur == 0) return;
     }
     if (((cur >> 11) & 0x7ffffu) == tag) {
-      const uint64_t* other = keys + (size_t)((cur & 0x7ffu) - 1) * W;
+      BitSet<W> other;
+      make_key<W>(P, (cur & 0x7ffu) - 1, other);  // it was inserted, so it is a kept key
       bool eq = true;
 #pragma unroll
-      for (int i = 0; i < W; ++i) eq &= (other[i] == key.w[i]);
+      for (int i = 0; i < W; ++i) eq &= (other.w[i] == key.w[i]);
       if (eq) {
         atomicOr(&table[s], flag << 30);
         return;
@@ -111,21 +161,18 @@ __device__ __forceinline__ void table_insert(uint32_t* table, uint32_t tmask, ui
 }
 
 template <int W>
-__global__ void __launch_bounds__(256) tolerant_kernel(uint32_t T, uint64_t p_begin, uint64_t p_end,
+__global__ void __launch_bounds__(512) tolerant_kernel(uint32_t T, uint64_t p_begin, uint64_t p_end,
                                                        const uint64_t* __restrict__ clades,
                                                        const uint64_t* __restrict__ off,
                                                        const uint64_t* __restrict__ leafsets, uint32_t tsize,
-                                                       uint32_t key_cap, int32_t editdist,
-                                                       uint16_t* __restrict__ out, uint32_t* __restrict__ mask) {
+                                                       int32_t editdist, uint16_t* __restrict__ out,
+                                                       uint32_t* __restrict__ mask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t warps = blockDim.x >> 5;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // layout: per-warp key areas (uint64), then per-warp tables (uint32), then the CTA's results
-  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw) + (size_t)warp * key_cap * W;
-  uint32_t* table = reinterpret_cast<uint32_t*>(reinterpret_cast<uint64_t*>(smem_raw) + (size_t)warps * key_cap * W) +
-                    (size_t)warp * tsize;
-  uint16_t* res = reinterpret_cast<uint16_t*>(reinterpret_cast<uint32_t*>(
-      reinterpret_cast<uint64_t*>(smem_raw) + (size_t)warps * key_cap * W) + (size_t)warps * tsize);
+  // layout: per-warp tables (uint32), then the CTA's results
+  uint32_t* table = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * tsize;
+  uint16_t* res = reinterpret_cast<uint16_t*>(reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warps * tsize);
   const uint32_t tmask = tsize - 1;
   for (uint32_t s = lane; s < tsize; s += 32) table[s] = 0;
   __syncwarp();
@@ -140,87 +187,40 @@ __global__ void __launch_bounds__(256) tolerant_kernel(uint32_t T, uint64_t p_be
       if (p >= p_end) break;
       const uint32_t a = row_of(p, T);
       const uint32_t b = a + 1 + (uint32_t)(p - row_start(a, T));
-      BitSet<W> La, Lb, S, R;
+      PairCtx<W> P;
+      P.clades = clades;
+      P.fullA = P.fullB = true;
 #pragma unroll
       for (int i = 0; i < W; ++i) {
-        La.w[i] = leafsets[(size_t)a * W + i];
-        Lb.w[i] = leafsets[(size_t)b * W + i];
-        S.w[i] = La.w[i] & Lb.w[i];
+        const uint64_t la = leafsets[(size_t)a * W + i], lb = leafsets[(size_t)b * W + i];
+        P.S.w[i] = la & lb;
+        P.fullA &= la == P.S.w[i];
+        P.fullB &= lb == P.S.w[i];
       }
-      const uint32_t k = popc_set<W>(S);
+      P.k = popc_set<W>(P.S);
       uint32_t d = 0;
-      if (k != 0) {  // inBoth empty -> 0 (RFDistance.hs:195-196)
-        const uint32_t half = k >> 1;
-        bool fullA = true, fullB = true;
+      if (P.k != 0) {  // inBoth empty -> 0 (RFDistance.hs:195-196)
+        P.half = P.k >> 1;
 #pragma unroll
         for (int i = 0; i < W; ++i) {
-          fullA &= La.w[i] == S.w[i];
-          fullB &= Lb.w[i] == S.w[i];
-          int64_t rem = (int64_t)k - 64 * i;
-          R.w[i] = rem >= 64 ? ~0ull : (rem <= 0 ? 0ull : ((1ull << rem) - 1));
+          const int64_t rem = (int64_t)P.k - 64 * i;
+          P.R.w[i] = rem >= 64 ? ~0ull : (rem <= 0 ? 0ull : ((1ull << rem) - 1));
         }
-        const uint64_t oa = off[a], na = off[a + 1] - oa, ob = off[b], nbb = off[b + 1] - ob;
-        // both trees, one pass each: tree index 0 -> a (flag 1), 1 -> b (flag 2)
-#pragma unroll 1
-        for (int t = 0; t < 2; ++t) {
-          const uint64_t o = t ? ob : oa;
-          const uint32_t cnt = (uint32_t)(t ? nbb : na);
-          const bool full = t ? fullB : fullA;
-          const uint32_t idx0 = t ? (uint32_t)na : 0u;
-          for (uint32_t c0 = 0; c0 < cnt; c0 += 32) {
-            const uint32_t c = c0 + lane;
-            bool have = false;
-            BitSet<W> key;
-            if (c < cnt) {
-              BitSet<W> m;
-              const uint64_t* src = clades + (o + c) * W;
-#pragma unroll
-              for (int i = 0; i < W; ++i) m.w[i] = src[i] & S.w[i];
-              const uint32_t pc = popc_set<W>(m);
-              // drop the empty set, and the full set unless the cached (unpruned) bips are used
-              if (pc != 0 && (pc != k || full)) have = norm_bip<W>(m, pc, R, half, key) > 1;
-              if (have) {
-                uint64_t* dst = keys + (size_t)(idx0 + c) * W;
-#pragma unroll
-                for (int i = 0; i < W; ++i) dst[i] = key.w[i];
-              }
-            }
-            __syncwarp();
-            if (have) table_insert<W>(table, tmask, keys, idx0 + c, key, t ? 2u : 1u);
-            __syncwarp();
-          }
+        P.oa = off[a];
+        P.na = (uint32_t)(off[a + 1] - P.oa);
+        P.ob = off[b];
+        P.nb = (uint32_t)(off[b + 1] - P.ob);
+        // every key of the pair: the clades of a (flag 1), of b (flag 2) and, when k <= 3, the
+        // singletons of S (both pruned trees have every leaf of S: flag 3; they still matter because
+        // another clade may normalise to the same set)
+        const uint32_t n_keys = P.na + P.nb + (P.k <= 3 ? P.k : 0u);
+        for (uint32_t c0 = 0; c0 < n_keys; c0 += 32) {
+          const uint32_t idx = c0 + lane;
+          BitSet<W> key;
+          const bool have = idx < n_keys && make_key<W>(P, idx, key);
+          if (have) table_insert<W>(table, tmask, P, idx, key, idx < P.na ? 1u : (idx < P.na + P.nb ? 2u : 3u));
         }
-        if (k <= 3) {
-          // singleton leaf sets survive the `> 1` filter only here; both pruned trees have every
-          // leaf of S, so they enter with both flags (they still matter: another clade of one tree
-          // may normalise to the same set).
-          const uint32_t idx0 = (uint32_t)(na + nbb);
-          uint32_t seen = 0;
-          bool have = false;
-          BitSet<W> key, m;
-#pragma unroll
-          for (int i = 0; i < W; ++i) {
-            m.w[i] = 0;
-            uint64_t word = S.w[i];
-            while (word) {
-              uint64_t low = word & (0 - word);
-              if (seen == lane) m.w[i] = low;
-              ++seen;
-              word ^= low;
-            }
-          }
-          if (lane < k) {
-            have = norm_bip<W>(m, 1, R, half, key) > 1;
-            if (have) {
-              uint64_t* dst = keys + (size_t)(idx0 + lane) * W;
-#pragma unroll
-              for (int i = 0; i < W; ++i) dst[i] = key.w[i];
-            }
-          }
-          __syncwarp();
-          if (have) table_insert<W>(table, tmask, keys, idx0 + lane, key, 3u);
-          __syncwarp();
-        }
+        __syncwarp();
         // count slots seen in exactly one tree, and clear the table for the next pair
         for (uint32_t s = lane; s < tsize; s += 32) {
           const uint32_t fl = table[s] >> 30;
@@ -257,23 +257,19 @@ static int launch_tolerant_w(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t
   const uint32_t key_cap = 2 * S.max_clades + 4;
   uint32_t tsize = 64;
   while (tsize < key_cap + key_cap / 2) tsize <<= 1;  // load factor <= 2/3 even if no key repeats
-  const size_t per_warp = (size_t)key_cap * W * 8 + (size_t)tsize * 4;
-  uint32_t warps = 8;
-  while (warps > 1 && warps * per_warp + warps * kTolPairsPerWarp * 2 > 100 * 1024) warps >>= 1;
   // pairs per CTA must be a multiple of 32 so mask words never straddle CTAs: 8 pairs/warp -> warps % 4 == 0
-  if (warps < 4) {
-    warps = 4;
-    if (warps * per_warp + warps * kTolPairsPerWarp * 2 > 220 * 1024)
-      return ctx->fail(PRF_E_UNSUPPORTED, "tolerant mode: %u clades x %d words per tree needs too much shared memory",
-                       S.max_clades, W);
-  }
-  const size_t smem = warps * per_warp + warps * kTolPairsPerWarp * 2;
+  uint32_t warps = 16;
+  while (warps > 4 && (size_t)warps * tsize * 4 + warps * kTolPairsPerWarp * 2 > 64 * 1024) warps -= 4;
+  const size_t smem = (size_t)warps * tsize * 4 + warps * kTolPairsPerWarp * 2;
   PRF_CK(ctx, cudaFuncSetAttribute(tolerant_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int ctas = 0;
+  PRF_CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, tolerant_kernel<W>, (int)(warps * 32), smem));
+  if (ctas < 1) ctas = 1;
   const uint32_t per_cta = warps * kTolPairsPerWarp;
   const uint64_t n_blocks = (p_end - p_begin + per_cta - 1) / per_cta;
-  const uint32_t grid = (uint32_t)std::min<uint64_t>(n_blocks, (uint64_t)ctx->sm_count * 64);
-  tolerant_kernel<W><<<grid, warps * 32, smem, ctx->stream>>>(S.T, p_begin, p_end, S.clades.p, S.off.p,
-                                                             S.leafsets.p, tsize, key_cap, editdist, d_out, d_mask);
+  const uint32_t grid = (uint32_t)std::min<uint64_t>(n_blocks, (uint64_t)ctx->sm_count * ctas * 8);
+  tolerant_kernel<W><<<grid, warps * 32, smem, ctx->stream>>>(S.T, p_begin, p_end, S.clades.p, S.off.p, S.leafsets.p,
+                                                             tsize, editdist, d_out, d_mask);
   PRF_LAUNCHED(ctx);
   return PRF_OK;
 }
