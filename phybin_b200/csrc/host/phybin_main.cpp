@@ -1,0 +1,185 @@
+// phybin -- command-line host for the B200 RF distance-matrix path.
+//
+// Flag-compatible with the in-scope subset of the reference CLI (Main.hs:79-176) and mirroring the
+// driver's flow for that path (PhyBin.hs:84-243, doCluster :343-364): read Newick files, build the
+// global label table, (HashRF) keep trees with numLeaves == #taxa, compute the matrix ON THE GPU
+// through libphybin_rf.so, print the reference's log lines, write DIR/distance_matrix.txt in
+// printDistMat format (RFDistance.hs:352-361) and, with --rfdist, the same text on stdout.
+// Everything else of the reference CLI (binning, graphviz, consensus, --prune, ...) stays with the
+// Haskell program and is rejected here with a message.  There is no CPU path: without a B200 the
+// program exits with the library's error.
+#include <sys/stat.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <numeric>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "phybin_host.h"
+#include "phybin_rf.h"
+
+namespace {
+
+struct Options {
+  bool tolerant = false, rfdist = false, single = false;
+  int editdist = -1, name_prefix = -1, variant = PRF_VARIANT_AUTO;
+  std::string out_dir = "phybin_out";
+  std::vector<std::string> files;
+};
+
+[[noreturn]] void die(const std::string& m) {
+  std::fprintf(stderr, "phybin: %s\n", m.c_str());
+  std::exit(1);
+}
+
+bool starts(const char* a, const char* pfx, const char** rest) {
+  size_t n = std::strlen(pfx);
+  if (std::strncmp(a, pfx, n)) return false;
+  *rest = a + n;
+  return true;
+}
+
+Options parse_args(int argc, char** argv) {
+  Options o;
+  for (int i = 1; i < argc; ++i) {
+    const char* a = argv[i];
+    const char* v = nullptr;
+    auto need = [&](const char* what) -> const char* {
+      if (i + 1 >= argc) die(std::string("option ") + what + " needs an argument");
+      return argv[++i];
+    };
+    if (!std::strcmp(a, "--hashrf")) o.tolerant = false;
+    else if (!std::strcmp(a, "--tolerant")) o.tolerant = true;
+    else if (!std::strcmp(a, "--rfdist")) o.rfdist = true;
+    else if (!std::strcmp(a, "--single")) o.single = true;
+    else if (!std::strcmp(a, "--complete") || !std::strcmp(a, "--UPGMA")) o.single = false;
+    else if (starts(a, "--editdist=", &v)) o.editdist = std::atoi(v);
+    else if (!std::strcmp(a, "--editdist")) o.editdist = std::atoi(need(a));
+    else if (starts(a, "--output=", &v)) o.out_dir = v;
+    else if (!std::strcmp(a, "-o") || !std::strcmp(a, "--output")) o.out_dir = need(a);
+    else if (starts(a, "--nameprefix=", &v)) o.name_prefix = std::atoi(v);
+    else if (!std::strcmp(a, "-p") || !std::strcmp(a, "--nameprefix")) o.name_prefix = std::atoi(need(a));
+    else if (!std::strcmp(a, "--sparse")) o.variant = PRF_VARIANT_SPARSE;   // not in the reference: force a kernel variant
+    else if (!std::strcmp(a, "--dense")) o.variant = PRF_VARIANT_DENSE;
+    else if (!std::strcmp(a, "-V") || !std::strcmp(a, "--version")) {
+      std::printf("phybin (B200 RF path) -- %s\n", prf_version());
+      std::exit(0);
+    } else if (a[0] == '-' && a[1])
+      die(std::string("option ") + a + " belongs to the part of PhyBin that stays in the Haskell host (see DESIGN.md)");
+    else o.files.push_back(a);
+  }
+  if (o.files.empty()) die("no input files");
+  return o;
+}
+
+std::string slurp(const std::string& path) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) die("cannot read " + path);
+  std::ostringstream ss;
+  ss << f.rdbuf();
+  return ss.str();
+}
+
+uint32_t find(std::vector<uint32_t>& p, uint32_t x) {
+  while (p[x] != x) x = p[x] = p[p[x]];
+  return x;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  Options opt = parse_args(argc, argv);
+  std::vector<std::string> texts;
+  for (auto& f : opt.files) texts.push_back(slurp(f));
+  std::vector<const char*> ptrs;
+  for (auto& t : texts) ptrs.push_back(t.c_str());
+  phb_forest* forest = phb_parse((int)ptrs.size(), ptrs.data(), opt.name_prefix);
+  if (const char* e = phb_error(forest)) die(e);
+  const uint32_t n_taxa = phb_num_labels(forest);
+  std::printf("Parsed %u trees, %u taxa.\n", phb_num_trees(forest), n_taxa);
+  if (!opt.tolerant) {  // HashRF keeps only trees with every taxon (PhyBin.hs:187-194)
+    const uint32_t before = phb_num_trees(forest), kept = phb_filter_num_leaves(forest, n_taxa);
+    if (kept != before) std::printf("WARNING: dropped %u trees whose leaf count differs from %u\n", before - kept, n_taxa);
+  } else if (phb_has_duplicate_leaves(forest)) {
+    die("--tolerant on the device needs distinct leaf labels within each tree");
+  }
+  const uint32_t T = phb_num_trees(forest), W = phb_words(forest);
+  const uint64_t P = (uint64_t)T * (T ? T - 1 : 0) / 2;
+
+  prf_ctx* ctx = prf_create(0);
+  if (!ctx) die(std::string("cannot use the GPU: ") + prf_last_error(nullptr));
+  std::vector<uint16_t> upper(P ? P : 1);
+  std::vector<uint32_t> mask(opt.editdist >= 0 ? (P + 31) / 32 + 1 : 1);
+  prf_stats st{};
+  const auto t0 = std::chrono::steady_clock::now();
+  int rc;
+  if (!opt.tolerant) {
+    std::printf(" Using HashRF-style algorithm...\n");  // PhyBin.hs:346
+    uint64_t *bips = nullptr, *off = nullptr, nnz = 0;
+    if (phb_allbips(forest, W, 0, &bips, &off, &nnz)) die("bipartition extraction failed");
+    rc = prf_hashrf_load(ctx, bips, off, T, W, PRF_MEM_HOST, &st);
+    if (!rc) rc = prf_hashrf_compute(ctx, 0, P, opt.editdist, opt.variant, nullptr, nullptr, &st);
+    phb_free_buf(bips);
+    phb_free_buf(off);
+  } else {
+    uint64_t *clades = nullptr, *off = nullptr, *leaf = nullptr, nnz = 0;
+    if (phb_raw_clades(forest, W, 0, &clades, &off, &leaf, &nnz)) die("clade extraction failed");
+    rc = prf_tolerant_load(ctx, clades, off, leaf, T, W, PRF_MEM_HOST, &st);
+    if (!rc) rc = prf_tolerant_compute(ctx, 0, P, opt.editdist, nullptr, nullptr, &st);
+    phb_free_buf(clades);
+    phb_free_buf(off);
+    phb_free_buf(leaf);
+  }
+  if (!rc && P) rc = prf_fetch(ctx, 0, P, upper.data());
+  if (!rc && P && opt.editdist >= 0) rc = prf_fetch_mask(ctx, 0, P, mask.data());
+  if (rc) die(std::string("phybin_rf error: ") + prf_last_error(ctx));
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  std::printf(" Built matrix for dim %u\n", T);  // RFDistance.hs:314
+  std::printf("Time to compute distance matrix: %.6fs (%s kernel %.3f ms, %llu unique bipartitions)\n", secs,
+              st.variant_used == PRF_VARIANT_DENSE ? "dense tcgen05" : (opt.tolerant ? "tolerant" : "sparse"), st.ms_matrix,
+              (unsigned long long)st.n_unique);
+
+  mkdir(opt.out_dir.c_str(), 0777);
+  if (T <= 20000) {
+    const std::string path = opt.out_dir + "/distance_matrix.txt";
+    if (phb_write_dist_mat(path.c_str(), upper.data(), T)) die("cannot write " + path);
+    std::printf("Wrote %s\n", path.c_str());
+  } else {
+    std::printf("distance_matrix.txt skipped: %u trees would be a %.1f GB text file (use the C ABI's prf_fetch_rows)\n", T,
+                (double)P * 4 / 1e9);
+  }
+  if (opt.rfdist && T <= 20000) {
+    char* txt = phb_print_dist_mat(upper.data(), T);
+    std::fputs(txt, stdout);
+    phb_free_buf(txt);
+  }
+  if (opt.editdist >= 0) {
+    // flat clusters at distance <= D from the fused threshold mask.  For single linkage these ARE the
+    // reference's sliceDendro clusters (PhyBin.hs:415-422); for complete/UPGMA they are the connected
+    // components every such cluster is contained in.
+    std::vector<uint32_t> parent(T);
+    std::iota(parent.begin(), parent.end(), 0u);
+    uint64_t p = 0, close = 0;
+    for (uint32_t a = 0; a + 1 < T; ++a)
+      for (uint32_t b = a + 1; b < T; ++b, ++p)
+        if ((mask[p >> 5] >> (p & 31)) & 1u) {
+          ++close;
+          parent[find(parent, a)] = find(parent, b);
+        }
+    uint32_t comps = 0;
+    for (uint32_t t = 0; t < T; ++t) comps += find(parent, t) == t;
+    std::printf("%llu of %llu pairs within edit distance %d; %u %s at that threshold\n", (unsigned long long)close,
+                (unsigned long long)P, opt.editdist, comps,
+                opt.single ? "single-linkage clusters" : "connected components (supersets of the complete/UPGMA clusters)");
+    std::ofstream cf(opt.out_dir + "/components.txt");
+    for (uint32_t t = 0; t < T; ++t) cf << t << ' ' << find(parent, t) << '\n';
+  }
+  prf_destroy(ctx);
+  phb_free(forest);
+  return 0;
+}

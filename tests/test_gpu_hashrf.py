@@ -319,3 +319,25 @@ def test_auto_picks_dense_for_similar_trees_and_sparse_for_random(ctx):
     bips, off = f.all_bips()
     _, _, st = run_variant(ctx, bips, off, 0)
     assert st["variant_used"] == 1
+
+
+# ---- the command-line host ----------------------------------------------------------------------
+
+def test_cli_matches_reference_output_format(golden, tmp_path):
+    import subprocess
+    from phybin_b200 import build
+    cli = build.build_cli()
+    c = golden["t30_file"]
+    tr = tmp_path / "mismatched.tr"
+    tr.write_text(c["texts"][0])
+    out = tmp_path / "out"
+    r = subprocess.run([cli, "--tolerant", "--rfdist", "-o", str(out), str(tr)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert " Built matrix for dim 3" in r.stdout
+    want = "Robinson-Foulds distance (matrix format):\n" + "-" * 41 + "\n0\n0 0\n1 0 0\n" + "-" * 41 + "\n"
+    assert want in r.stdout and (out / "distance_matrix.txt").read_text() == want
+    # default mode is --hashrf: the 9-taxon tree is filtered out (PhyBin.hs:187-194), 2 trees remain
+    r = subprocess.run([cli, "--editdist=0", "--single", "-o", str(out), str(tr)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert " Using HashRF-style algorithm..." in r.stdout and " Built matrix for dim 2" in r.stdout
+    assert (out / "distance_matrix.txt").read_text().splitlines()[2:4] == ["0", "1 0"]
