@@ -161,7 +161,7 @@ def run_gpu(args, wl, wl_name):
     import torch.distributed as dist
     from phybin_b200.host import Forest
     from phybin_b200.rfdistance import MEM_DEVICE, RFContext, shard_range
-    from phybin_b200.distributed import KeyGather, shard_rows as key_shard_rows, tree_shard
+    from phybin_b200.distributed import KeyGather, shard_rows as key_shard_rows, sharded_load, tree_shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -202,6 +202,11 @@ def run_gpu(args, wl, wl_name):
         d_off = torch.from_numpy(off_all.view(np.int64)).to(dev)                  # offsets are tiny and replicated
         d_leaf = torch.from_numpy(leaf_all.view(np.int64)).to(dev) if mode == "tolerant" else None
         gather = KeyGather(key_shard_rows(off_all, T, world), W, dev)
+        d_off_my = torch.from_numpy((off_all[t_lo:t_hi + 1] - off_all[t_lo]).astype(np.int64)).to(dev)
+    # N = 2: all-gathering the keys and building twice is cheaper than the partitioned build's fixed latencies
+    build = args.build if args.build != "auto" else ("sharded" if world >= 4 else "replicated")
+    sharded = world > 1 and mode == "hashrf" and build == "sharded"
+    with torch.cuda.stream(ext):
         p_begin, p_end = shard_range(T, rank, world)
         d_out = torch.empty(max(p_end - p_begin, 8), dtype=torch.int16, device=dev)
         d_mask = torch.empty(max((p_end - p_begin + 31) // 32, 1), dtype=torch.int32, device=dev) if editdist >= 0 else None
@@ -211,9 +216,16 @@ def run_gpu(args, wl, wl_name):
 
     def step():
         """dedup + incidence + matrix for this rank's slice; inputs and outputs stay in HBM."""
-        with torch.cuda.stream(ext):
-            d_full = gather(d_my)     # NCCL all-gather over NVLink when world > 1
-        if mode == "hashrf":
+        if sharded:
+            # hash-partitioned build: all-to-all of keys, per-class dedup, all-gather + merge of the structures
+            sharded_load(ctx, d_my, d_off_my, T, stream=ext)
+        else:
+            with torch.cuda.stream(ext):
+                d_full = gather(d_my)     # NCCL all-gather over NVLink when world > 1
+        if sharded:
+            st = ctx.hashrf_compute(p_begin, p_end, editdist, 0, d_out.data_ptr(),
+                                    d_mask.data_ptr() if d_mask is not None else 0)
+        elif mode == "hashrf":
             ctx.hashrf_load(d_full.data_ptr(), d_off.data_ptr(), T, W, MEM_DEVICE)
             st = ctx.hashrf_compute(p_begin, p_end, editdist, 0, d_out.data_ptr(),
                                     d_mask.data_ptr() if d_mask is not None else 0)
@@ -315,9 +327,40 @@ def run_gpu(args, wl, wl_name):
     if world == 1 and not args.no_e2e:
         e2e = run_e2e(ctx, wl, mode, bips_all if mode == "hashrf" else clades_all, off_all,
                       None if mode == "hashrf" else leaf_all, P, editdist, max(1, min(args.steps, 2)))
-    elif world > 1:
-        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
-               "note": "host-buffer e2e is measured at N=1 (single prf_ctx); multi-GPU ranks keep their slice in HBM"}
+    elif world > 1 and not args.no_e2e:
+        # every rank: its tree shard from pinned host memory -> HBM, all-gather, build, its slice of the matrix,
+        # slice -> pinned host memory.  Each GPU uses its own PCIe link, so the copies run in parallel.
+        pin_in = torch.from_numpy(my_bips.view(np.int64)).pin_memory()
+        pin_out = torch.empty(max(p_end - p_begin, 8), dtype=torch.int16).pin_memory()
+        pin_mask = torch.empty(max((p_end - p_begin + 31) // 32, 1), dtype=torch.int32).pin_memory() if editdist >= 0 else None
+        n_e2e = max(1, min(args.steps, 2))
+
+        def e2e_step():
+            with torch.cuda.stream(ext):
+                d_my.copy_(pin_in, non_blocking=True)
+            step()
+            with torch.cuda.stream(ext):
+                pin_out[: p_end - p_begin].copy_(d_out[: p_end - p_begin], non_blocking=True)
+                if pin_mask is not None:
+                    pin_mask.copy_(d_mask, non_blocking=True)
+            ext.synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        nbytes = torch.tensor([float(my_bips.nbytes), float((p_end - p_begin) * 2 + (pin_mask.numel() * 4 if pin_mask is not None else 0))],
+                              dtype=torch.float64, device=dev)
+        dist.all_reduce(nbytes, op=dist.ReduceOp.SUM)
+        del pin_in, pin_out, pin_mask  # before the library's stream goes away (the host allocator records events on it)
+        e2e = {"value": P / float(dt[0]), "unit": UNIT, "h2d_bytes_per_step": int(nbytes[0]), "d2h_bytes_per_step": int(nbytes[1]),
+               "ms_per_step": float(dt[0]) * 1e3, "steps": n_e2e,
+               "note": "per rank: pinned tree shard -> HBM, NCCL all-gather of keys, build, own slice, slice -> pinned host; bytes summed over ranks"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -334,12 +377,13 @@ def run_gpu(args, wl, wl_name):
             "config": {"workload": wl_name, "trees": T, "taxa": n, "mode": mode, "editdist": editdist,
                        "pairs": P, "nnz": nnz, "words": W, "n_unique": st.get("n_unique"), "n_hits": st.get("n_hits"),
                        "variant": {1: "sparse", 2: "dense"}.get(st.get("variant_used"), mode), "n_shared": st.get("n_shared"),
-                       "parallelism": f"packed-range shard x{world}" + (" + NCCL all-gather of bipartition keys" if world > 1 else ""),
+                       "parallelism": f"packed-range shard x{world}" + ((" + hash-partitioned build (NCCL all-to-all of keys, all-gather of the per-class structures)" if sharded else " + NCCL all-gather of bipartition keys") if world > 1 else ""),
                        "l2": "output per step (>= 2 B/pair) far exceeds the 126 MB L2; no explicit flush"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "device_s": dev_s, "wall_s": wall,
         }
         print(json.dumps(line), flush=True)
+    torch.cuda.synchronize(dev)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -396,6 +440,8 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--trees", type=int, default=0, help="override the number of trees (debug)")
     ap.add_argument("--ref-trees", type=int, default=0, help="CPU sample size in trees")
+    ap.add_argument("--build", default="auto", choices=["auto", "sharded", "replicated"],
+                    help="N > 1: hash-partitioned build, or all-gather of the keys + replicated build (auto: sharded from 4 GPUs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

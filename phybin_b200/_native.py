@@ -16,6 +16,14 @@ u32p = C.POINTER(C.c_uint32)
 u16p = C.POINTER(C.c_uint16)
 
 
+class prf_part(C.Structure):
+    _fields_ = [
+        ("n_trees", C.c_uint64), ("n_ranges", C.c_uint64), ("n_members", C.c_uint64), ("n_lists", C.c_uint64),
+        ("nnz", C.c_uint64), ("n_unique", C.c_uint64), ("n_hits", C.c_uint64),
+        ("nb", C.c_void_p), ("roff", C.c_void_p), ("ranges", C.c_void_p), ("members", C.c_void_p), ("lid", C.c_void_p),
+    ]
+
+
 class prf_stats(C.Structure):
     _fields_ = [
         ("n_trees", C.c_uint64), ("n_words", C.c_uint64), ("nnz", C.c_uint64),
@@ -104,6 +112,9 @@ def rf_lib():
         L.prf_tolerant.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int32, vp, vp, st]
         L.prf_tolerant_load.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int, st]
         L.prf_tolerant_compute.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int32, vp, vp, st]
+        L.prf_hashrf_partition.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, u64p]
+        L.prf_hashrf_export.argtypes = [vp, C.POINTER(prf_part)]
+        L.prf_hashrf_merge.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(prf_part), st]
         L.prf_packed_index.restype = C.c_uint64
         L.prf_packed_index.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
         L.prf_shard_align.restype = C.c_uint64
@@ -122,7 +133,7 @@ def rf_lib():
 # Every symbol include/phybin_rf.h declares (tests check the built library exports them all).
 RF_SYMBOLS = [
     "prf_create", "prf_destroy", "prf_last_error", "prf_version", "prf_stream", "prf_hashrf",
-    "prf_hashrf_load", "prf_hashrf_compute", "prf_fetch", "prf_fetch_mask", "prf_fetch_rows",
+    "prf_hashrf_load", "prf_hashrf_compute", "prf_hashrf_partition", "prf_hashrf_export", "prf_hashrf_merge", "prf_fetch", "prf_fetch_mask", "prf_fetch_rows",
     "prf_tolerant", "prf_tolerant_load", "prf_tolerant_compute", "prf_packed_index",
     "prf_shard_align", "prf_shard_range", "prf_limits", "prf_launch_count",
 ]

@@ -11,6 +11,7 @@
 #include "prf_incidence.cuh"
 #include "prf_sparse.cuh"
 #include "prf_dense.cuh"
+#include "prf_shard.cuh"
 #include "prf_tolerant.cuh"
 
 using namespace prf;
@@ -352,6 +353,180 @@ PRF_API int prf_hashrf(prf_ctx* h, const uint64_t* bips, const uint64_t* tree_of
     stats->ms_total = ev_ms(ctx->ev[0], ctx->ev[7]);
     stats->gpu_launches = st.gpu_launches + st2.gpu_launches;
   }
+  return PRF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// hashRF: multi-GPU build
+// ---------------------------------------------------------------------------------------------
+
+PRF_API int prf_hashrf_partition(prf_ctx* h, const uint64_t* d_bips, const uint64_t* d_off, uint32_t T_local, uint32_t W,
+                                 uint32_t world, uint64_t* d_send_keys, uint32_t* d_send_counts, uint64_t* h_first) {
+  if (!h) return PRF_E_INVALID;
+  Ctx* ctx = &h->c;
+  ctx->err.clear();
+  if (!d_off || !d_send_counts || !h_first) return ctx->fail(PRF_E_INVALID, "null pointer");
+  if (W == 0 || W > kMaxWords) return ctx->fail(PRF_E_UNSUPPORTED, "W=%u words per set; supported 1..%u", W, kMaxWords);
+  if (world == 0 || world > 16) return ctx->fail(PRF_E_UNSUPPORTED, "world=%u; supported 1..16", world);
+  PRF_CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  uint64_t nnz = 0;
+  PRF_CK(ctx, cudaMemcpyAsync(&nnz, d_off + T_local, 8, cudaMemcpyDeviceToHost, s));
+  PRF_CK(ctx, cudaStreamSynchronize(s));
+  if (nnz >= 0xffffffffull) return ctx->fail(PRF_E_UNSUPPORTED, "nnz=%llu entries; supported < 2^32 - 1", (unsigned long long)nnz);
+  if (nnz && (!d_bips || !d_send_keys)) return ctx->fail(PRF_E_INVALID, "null key buffer");
+  DevBuf<uint32_t> owner, idx;
+  DevBuf<unsigned long long> first;
+  PRF_CK(ctx, owner.alloc(nnz, s));
+  PRF_CK(ctx, idx.alloc(nnz, s));
+  PRF_CK(ctx, first.alloc((size_t)world + 1, s));
+  if (T_local) {
+    switch (W) {
+#define PRF_W_CASE(w) case w: part_owner_kernel<w><<<(T_local + 7) / 8, 256, 0, s>>>(d_bips, d_off, T_local, world, owner.p, idx.p, d_send_counts); break;
+      PRF_W_CASE(1) PRF_W_CASE(2) PRF_W_CASE(3) PRF_W_CASE(4) PRF_W_CASE(5) PRF_W_CASE(6) PRF_W_CASE(7) PRF_W_CASE(8)
+      PRF_W_CASE(9) PRF_W_CASE(10) PRF_W_CASE(11) PRF_W_CASE(12) PRF_W_CASE(13) PRF_W_CASE(14) PRF_W_CASE(15) PRF_W_CASE(16)
+#undef PRF_W_CASE
+    }
+    PRF_LAUNCHED(ctx);
+  }
+  int rc = radix_sort_pairs(ctx, owner.p, idx.p, (uint32_t)nnz, std::max(1, bits_for(world)));  // stable: tree order kept per class
+  if (rc) return rc;
+  class_bounds_kernel<<<1, 32, 0, s>>>(owner.p, (uint32_t)nnz, world, first.p);
+  PRF_LAUNCHED(ctx);
+  if (nnz) {
+    gather_keys_kernel<<<grid_for(nnz * W), 256, 0, s>>>(d_bips, idx.p, nnz * W, W, d_send_keys);
+    PRF_LAUNCHED(ctx);
+  }
+  unsigned long long hf[17];
+  PRF_CK(ctx, cudaMemcpyAsync(hf, first.p, ((size_t)world + 1) * 8, cudaMemcpyDeviceToHost, s));
+  PRF_CK(ctx, cudaStreamSynchronize(s));
+  for (uint32_t c = 0; c <= world; ++c) h_first[c] = hf[c];
+  return PRF_OK;
+}
+
+PRF_API int prf_hashrf_export(prf_ctx* h, prf_part* out) {
+  if (!h || !out) return PRF_E_INVALID;
+  Ctx* ctx = &h->c;
+  ctx->err.clear();
+  HashRFState& H = ctx->h;
+  if (!H.loaded) return ctx->fail(PRF_E_STATE, "prf_hashrf_export before a successful prf_hashrf_load");
+  out->n_trees = H.T;
+  out->n_ranges = H.n_ranges;
+  out->n_members = H.n_shared_nnz;
+  out->n_lists = H.n_shared;
+  out->nnz = H.stats.nnz;
+  out->n_unique = H.stats.n_unique;
+  out->n_hits = H.stats.n_hits;
+  out->nb = H.nb.p;
+  out->roff = H.roff.p;
+  out->ranges = H.ranges.p;
+  out->members = H.members.p;
+  out->lid = H.lid.p;
+  return PRF_OK;
+}
+
+PRF_API int prf_hashrf_merge(prf_ctx* h, uint32_t T, uint32_t W, uint32_t world, const prf_part* parts, prf_stats* stats) {
+  if (!h || !parts) return PRF_E_INVALID;
+  Ctx* ctx = &h->c;
+  ctx->err.clear();
+  if (world == 0 || world > 16) return ctx->fail(PRF_E_UNSUPPORTED, "world=%u; supported 1..16", world);
+  PRF_CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  uint64_t launches0 = ctx->launches;
+  MergeParts P{};
+  P.world = world;
+  uint64_t n_members = 0, n_lists = 0, n_ranges = 0, nnz = 0, n_unique = 0, n_hits = 0;
+  for (uint32_t r = 0; r < world; ++r) {
+    const prf_part& q = parts[r];
+    if (q.n_trees != T) return ctx->fail(PRF_E_INVALID, "part %u covers %llu trees, expected %u", r, (unsigned long long)q.n_trees, T);
+    P.nb[r] = q.nb;
+    P.roff[r] = q.roff;
+    P.ranges[r] = static_cast<const uint2*>(q.ranges);
+    P.members[r] = q.members;
+    P.lid[r] = q.lid;
+    P.member_base[r] = (uint32_t)n_members;
+    P.list_base[r] = (uint32_t)n_lists;
+    P.n_members[r] = (uint32_t)q.n_members;
+    n_members += q.n_members;
+    n_lists += q.n_lists;
+    n_ranges += q.n_ranges;
+    nnz += q.nnz;
+    n_unique += q.n_unique;
+    n_hits += q.n_hits;
+  }
+  if (n_members >= 0xffffffffull) return ctx->fail(PRF_E_UNSUPPORTED, "merged member count does not fit 32 bits");
+  PRF_CK(ctx, cudaEventRecord(ctx->ev[2], s));
+  // build into fresh buffers: a part may alias the context's current structure
+  DevBuf<uint16_t> nb;
+  DevBuf<uint32_t> roff, members, lid, nb32, cnt, mm;
+  DevBuf<uint2> ranges;
+  PRF_CK(ctx, nb.alloc(T, s));
+  PRF_CK(ctx, roff.alloc((size_t)T + 1, s));
+  PRF_CK(ctx, members.alloc(n_members, s));
+  PRF_CK(ctx, lid.alloc(n_members, s));
+  PRF_CK(ctx, ranges.alloc(n_ranges, s));
+  PRF_CK(ctx, nb32.alloc((size_t)T + 1, s));
+  PRF_CK(ctx, cnt.alloc((size_t)T + 1, s));
+  PRF_CK(ctx, mm.alloc(2, s));
+  const uint32_t mm_init[2] = {0xffffffffu, 0u};
+  PRF_CK(ctx, cudaMemcpyAsync(mm.p, mm_init, 8, cudaMemcpyHostToDevice, s));
+  merge_count_kernel<<<grid_for((uint64_t)T + 1), 256, 0, s>>>(P, T, nb32.p, cnt.p);
+  PRF_LAUNCHED(ctx);
+  int rc = exclusive_scan(ctx, LoadU32{cnt.p}, (uint64_t)T + 1, roff.p, nullptr);
+  if (rc) return rc;
+  if (T) {
+    merge_ranges_kernel<<<grid_for((uint64_t)world * T), 256, 0, s>>>(P, T, roff.p, ranges.p);
+    PRF_LAUNCHED(ctx);
+    finish_nb_kernel<<<grid_for(T), 256, 0, s>>>(nb32.p, T, nb.p, mm.p);
+    PRF_LAUNCHED(ctx);
+  }
+  for (uint32_t r = 0; r < world; ++r)
+    if (P.n_members[r]) {
+      merge_members_kernel<<<grid_for(P.n_members[r]), 256, 0, s>>>(P, r, members.p, lid.p);
+      PRF_LAUNCHED(ctx);
+    }
+  uint32_t hmm[2] = {0, 0};
+  PRF_CK(ctx, cudaMemcpyAsync(hmm, mm.p, 8, cudaMemcpyDeviceToHost, s));
+  PRF_CK(ctx, cudaEventRecord(ctx->ev[3], s));
+  PRF_CK(ctx, cudaStreamSynchronize(s));
+  if (T == 0) hmm[0] = hmm[1] = 0;
+  if (hmm[1] > kMaxBipsPerTree)
+    return ctx->fail(PRF_E_RANGE, "a tree has %u bipartitions; distances would overflow uint16 (max %u per tree)", hmm[1],
+                     kMaxBipsPerTree);
+  HashRFState& H = ctx->h;
+  H = HashRFState{};  // frees the previous structure (stream-ordered, after the kernels above)
+  H.T = T;
+  H.W = W;
+  H.nnz = nnz;
+  H.P = (uint64_t)T * (T ? T - 1 : 0) / 2;
+  H.uniform_nb = hmm[0] == hmm[1];
+  H.nb_uniform = hmm[0];
+  H.nb = std::move(nb);
+  H.roff = std::move(roff);
+  H.ranges = std::move(ranges);
+  H.members = std::move(members);
+  H.lid = std::move(lid);
+  H.n_shared = (uint32_t)n_lists;
+  H.n_shared_nnz = n_members;
+  H.n_ranges = n_ranges;
+  prf_stats& st = H.stats;
+  st = prf_stats{};
+  st.n_trees = T;
+  st.n_words = W;
+  st.nnz = nnz;
+  st.n_unique = n_unique;
+  st.n_shared = n_lists;
+  st.n_shared_nnz = n_members;
+  st.n_hits = n_hits;
+  st.n_pairs = H.P;
+  st.max_bips = hmm[1];
+  st.min_bips = hmm[0];
+  st.ms_incidence = ev_ms(ctx->ev[2], ctx->ev[3]);
+  st.gpu_launches = (int32_t)(ctx->launches - launches0);
+  H.loaded = true;
+  ctx->tol.loaded = false;
+  ctx->out_valid = ctx->mask_valid = false;
+  if (stats) *stats = st;
   return PRF_OK;
 }
 

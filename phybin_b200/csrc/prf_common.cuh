@@ -64,6 +64,7 @@ struct HashRFState {
   // tree-major incidence over shared bipartition ids (dense variant input)
   uint32_t n_shared = 0;
   uint64_t n_shared_nnz = 0;
+  uint64_t n_ranges = 0;         // roff[T]
   DevBuf<uint32_t> lid;          // [n_shared_nnz] dense id (0..n_shared-1) of the list each member entry belongs to
   // dense variant: tiled uint8 operand, built lazily by the first dense compute (prf_dense.cuh)
   bool dense_ready = false;

@@ -337,6 +337,7 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
   }
   unsigned long long hc[4] = {0, 0, 0, 0};
   uint32_t hs[8] = {0};
+  uint32_t h_nranges = 0;
   for (int pass = 0; pass < 2; ++pass) {
     PRF_CK(ctx, cudaMemsetAsync(rcount.p, 0, rcount.bytes(), s));
     PRF_CK(ctx, cudaMemsetAsync(cursor.p, 0, cursor.bytes(), s));
@@ -362,6 +363,7 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
     }
     PRF_CK(ctx, cudaMemcpyAsync(hc, counters.p, sizeof hc, cudaMemcpyDeviceToHost, s));
     PRF_CK(ctx, cudaMemcpyAsync(hs, scalars.p, sizeof hs, cudaMemcpyDeviceToHost, s));
+    PRF_CK(ctx, cudaMemcpyAsync(&h_nranges, H.roff.p + T, 4, cudaMemcpyDeviceToHost, s));
     PRF_CK(ctx, cudaEventRecord(ctx->ev[3], s));
     PRF_CK(ctx, cudaStreamSynchronize(s));
     trace_mark("build: lists synced");
@@ -391,6 +393,7 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
   H.nb_uniform = mm[0];
   H.n_shared = n_sorted ? hs[1] : 0;
   H.n_shared_nnz = n_sorted;  // after duplicate removal
+  H.n_ranges = h_nranges;
 
   prf_stats& st = H.stats;
   st = prf_stats{};

@@ -341,3 +341,49 @@ def test_cli_matches_reference_output_format(golden, tmp_path):
     assert r.returncode == 0, r.stderr
     assert " Using HashRF-style algorithm..." in r.stdout and " Built matrix for dim 2" in r.stdout
     assert (out / "distance_matrix.txt").read_text().splitlines()[2:4] == ["0", "1 0"]
+
+
+# ---- multi-GPU build (hash-partitioned dedup), emulated on one GPU ---------------------------------
+
+@pytest.mark.parametrize("world,T,n,family", [(2, 300, 30, 0), (3, 700, 64, 0), (4, 513, 40, NNI_FAMILY), (8, 1000, 100, 0)])
+def test_sharded_build_loopback_matches_single_gpu_and_oracle(world, T, n, family):
+    from phybin_b200.distributed import sharded_load_loopback
+    f = Forest.synthetic(T, n, seed=0x51 + T, family=family, nni_max=6)
+    bips, off = f.all_bips()
+    o = orc.Forest([f.to_newick()])
+    want = oracle_packed(o, "hashrf", "literal")
+    ctxs = [RFContext(0) for _ in range(world)]
+    try:
+        stats = sharded_load_loopback(ctxs, bips, off)
+        ost = {}
+        o.hashrf(n, "closed", ost)
+        assert stats[0]["n_unique"] == ost["n_unique"] and stats[0]["nnz"] == len(bips)
+        P = T * (T - 1) // 2
+        for r in (0, world - 1):
+            ctxs[r].hashrf_compute(0, P, variant=1)
+            assert np.array_equal(ctxs[r].fetch(0, P).astype(np.int64), want)
+        # the dense variant runs on the merged structure as well
+        ctxs[0].hashrf_compute(0, P, variant=2)
+        assert np.array_equal(ctxs[0].fetch(0, P).astype(np.int64), want)
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_sharded_build_loopback_nonuniform_and_duplicates():
+    from phybin_b200.distributed import sharded_load_loopback
+    rng = random.Random(33)
+    text = [random_multifurcating_newicks(rng, 400, 30)]
+    f, o = Forest.parse(text), orc.Forest(text)
+    bips, off = f.all_bips()
+    want = oracle_packed(o, "hashrf", "literal")
+    rep, off2 = np.repeat(bips, 2, axis=0), off * 2   # a tree's bipartitions are a set: duplicates count once
+    ctxs = [RFContext(0) for _ in range(3)]
+    try:
+        sharded_load_loopback(ctxs, rep, off2)
+        T = len(f)
+        ctxs[1].hashrf_compute(0, T * (T - 1) // 2)
+        assert np.array_equal(ctxs[1].fetch().astype(np.int64), want)
+    finally:
+        for c in ctxs:
+            c.close()
