@@ -229,49 +229,65 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_gram_kernel(const DensePar
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_tempty[acc]);
       // ---- write-out: one row (tree a) at a time, the whole warp on its run of the packed triangle ----
-      for (uint32_t r = 0; r < 32; ++r) {
-        const uint32_t ar = m0 + 32 * q + r;
-        if (ar + 1 >= T) break;
-        const uint32_t b_lo = max(n0, ar + 1), b_hi = min(n0 + (uint32_t)kDN, T);
-        if (b_lo >= b_hi) continue;
-        const uint64_t e0 = row_start(ar, T) + (b_lo - ar - 1);
-        const uint64_t e_lo = max(e0, prm.p_begin), e_hi = min(e0 + (b_hi - b_lo), prm.p_end);
-        if (e_lo >= e_hi) continue;
-        const uint32_t s0 = (b_lo - n0) + (uint32_t)(e_lo - e0);  // staging entry of position e_lo
+      // lane r prepares row r's run once (64-bit index math); the row loop only shuffles it around
+      uint64_t my_e_lo = 0;
+      uint32_t my_cnt = 0, my_s0 = 0;
+      {
+        const uint32_t ar = m0 + 32 * q + lane;
+        if (ar + 1 < T) {
+          const uint32_t b_lo = max(n0, ar + 1), b_hi = min(n0 + (uint32_t)kDN, T);
+          if (b_lo < b_hi) {
+            const uint64_t e0 = row_start(ar, T) + (b_lo - ar - 1);
+            const uint64_t e_lo = max(e0, prm.p_begin), e_hi = min(e0 + (b_hi - b_lo), prm.p_end);
+            if (e_lo < e_hi) {
+              my_e_lo = e_lo;
+              my_cnt = (uint32_t)(e_hi - e_lo);
+              my_s0 = (b_lo - n0) + (uint32_t)(e_lo - e0);  // staging entry of position e_lo
+            }
+          }
+        }
+      }
+      const uint32_t rows_mask = __ballot_sync(0xffffffffu, my_cnt != 0);
+      for (uint32_t rm = rows_mask; rm; rm &= rm - 1) {
+        const uint32_t r = __ffs(rm) - 1;
+        const uint64_t e_lo = __shfl_sync(0xffffffffu, my_e_lo, r);
+        const uint32_t cnt = __shfl_sync(0xffffffffu, my_cnt, r), s0 = __shfl_sync(0xffffffffu, my_s0, r);
         const uint32_t* row = my_stage + (size_t)r * kDRowWords;
         const uint16_t* row16 = reinterpret_cast<const uint16_t*>(row);
-        for (uint64_t G = (e_lo & ~7ull) + 8ull * lane; G < e_hi; G += 256) {
-          if (G >= e_lo && G + 8 <= e_hi) {
-            const uint32_t idx = s0 + (uint32_t)(G - e_lo);
+        uint16_t* gout = prm.out + ((e_lo & ~7ull) - prm.p_begin);  // 16-byte aligned; entry i is position (e_lo & ~7) + i
+        const uint32_t o_lo = (uint32_t)(e_lo & 7ull), o_hi = o_lo + cnt;
+        for (uint32_t g = 8 * lane; g < o_hi; g += 256) {  // group of 8 entries at [g, g + 8)
+          const int32_t idx = (int32_t)(s0 + g) - (int32_t)o_lo;  // staging entry of the group's first position
+          if (g >= o_lo && g + 8 <= o_hi) {
             const uint32_t* wp = row + (idx >> 1);
-            const uint32_t sh = (idx & 1u) * 16u;
+            const uint32_t sh = ((uint32_t)idx & 1u) * 16u;
             const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
             uint4 o;
             o.x = __funnelshift_r(w0, w1, sh);
             o.y = __funnelshift_r(w1, w2, sh);
             o.z = __funnelshift_r(w2, w3, sh);
             o.w = __funnelshift_r(w3, w4, sh);
-            *reinterpret_cast<uint4*>(prm.out + (G - prm.p_begin)) = o;
+            *reinterpret_cast<uint4*>(gout + g) = o;
             if (prm.editdist >= 0) {
-              const uint32_t thr = (uint32_t)prm.editdist;
-              const uint32_t ws[4] = {o.x, o.y, o.z, o.w};
-              uint32_t bits = 0;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) bits |= (((ws[i >> 1] >> ((i & 1) * 16)) & 0xffffu) <= thr ? 1u : 0u) << i;
-              reinterpret_cast<uint8_t*>(prm.mask)[(G - prm.p_begin) >> 3] = (uint8_t)bits;
+              const uint32_t thr = (uint32_t)prm.editdist, thr2 = thr | (thr << 16);
+              const uint32_t r0 = __vsetleu2(o.x, thr2), r1 = __vsetleu2(o.y, thr2), r2 = __vsetleu2(o.z, thr2),
+                             r3 = __vsetleu2(o.w, thr2);
+              const uint32_t bits = ((r0 | (r0 >> 15)) & 3u) | (((r1 | (r1 >> 15)) & 3u) << 2) |
+                                    (((r2 | (r2 >> 15)) & 3u) << 4) | (((r3 | (r3 >> 15)) & 3u) << 6);
+              reinterpret_cast<uint8_t*>(prm.mask)[((e_lo & ~7ull) - prm.p_begin + g) >> 3] = (uint8_t)bits;
             }
           } else {
             uint32_t bits = 0;
-            for (int i = 0; i < 8; ++i) {
-              const uint64_t e = G + i;
-              if (e >= e_lo && e < e_hi) {
-                const uint16_t dv = row16[s0 + (uint32_t)(e - e_lo)];
-                prm.out[e - prm.p_begin] = dv;
+            for (uint32_t i = 0; i < 8; ++i) {
+              const uint32_t e = g + i;
+              if (e >= o_lo && e < o_hi) {
+                const uint16_t dv = row16[idx + (int32_t)i];
+                gout[e] = dv;
                 if (prm.editdist >= 0 && (int32_t)dv <= prm.editdist) bits |= 1u << i;
               }
             }
             if (bits) {
-              const uint64_t byte = (G - prm.p_begin) >> 3;
+              const uint64_t byte = ((e_lo & ~7ull) - prm.p_begin + g) >> 3;
               atomicOr(&prm.mask[byte >> 2], bits << ((byte & 3) * 8));  // group shared with another row/tile (mask pre-zeroed)
             }
           }
@@ -323,9 +339,13 @@ static int launch_dense(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t edit
   const uint32_t a_first = row_of(p_begin, H.T), a_last = row_of(p_end - 1, H.T);
   std::vector<uint2> tiles;
   const uint32_t n_cb = H.dense_Tpad / kDN;
-  for (uint32_t mi = a_first / kDM; mi <= a_last / kDM; ++mi)
+  // order: groups of 8 row blocks, column block by column block, so that the ~148 tiles in flight share
+  // a few operand tiles (8 row-block operands, ~18 column-block operands: L2-resident working set)
+  constexpr uint32_t kGroup = 8;
+  for (uint32_t mg = a_first / kDM; mg <= a_last / kDM; mg += kGroup)
     for (uint32_t nj = 0; nj < n_cb; ++nj)
-      if ((uint64_t)nj * kDN + kDN - 1 > (uint64_t)mi * kDM) tiles.push_back(make_uint2(mi, nj));  // some b > some a
+      for (uint32_t mi = mg; mi < mg + kGroup && mi <= a_last / kDM; ++mi)
+        if ((uint64_t)nj * kDN + kDN - 1 > (uint64_t)mi * kDM) tiles.push_back(make_uint2(mi, nj));  // some b > some a
   if (tiles.empty()) return PRF_OK;
   PRF_CK(ctx, H.dense_tiles.alloc(tiles.size(), s));
   PRF_CK(ctx, cudaMemcpyAsync(H.dense_tiles.p, tiles.data(), tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice, s));
