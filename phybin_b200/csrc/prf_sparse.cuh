@@ -38,8 +38,6 @@
 
 namespace prf {
 
-constexpr int kRowBufs = 3;
-constexpr int kCurRing = 4;       // cursor arrays in shared memory (see the safety argument at stage_prefetch)
 constexpr int kGroupRows = 256;   // most rows in a group item
 constexpr int kWalkUnroll = 4;
 
@@ -86,7 +84,7 @@ struct RowParams {
   uint32_t* mask;
   const RowItem* items;
   uint32_t n_items;
-  uint2* cursor_ws;           // 2 spill areas per CTA for rows with more suffixes than a shared cursor array
+  uint2* cursor_ws;           // kRowBufs + 2 spill areas per CTA for rows with more suffixes than a shared cursor array
   uint32_t cursor_ws_stride;  // entries per area
   int debug_nowalk;           // calibration only: skip the walk (wrong results)
   uint32_t debug_sleep;       // ns of back-off between mbarrier polls (0 = spin)
@@ -143,9 +141,10 @@ __device__ __forceinline__ uint32_t walk_suffix(const uint32_t* __restrict__ mem
   return cur;
 }
 
-template <int kTile, int kWalkers, int kCurCap, int kSlots>
+template <int kTile, int kWalkers, int kCurCap, int kSlots, int kRowBufs>
 __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) sparse_rows_kernel(const RowParams prm) {
   constexpr int kStride = kTile + 8;  // entries per buffer: a tile keeps the 16-byte phase of its global address
+  constexpr int kCurRing = kRowBufs + 2;  // cursor arrays in shared memory (see the safety argument at stage_prefetch)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint16_t* tiles = reinterpret_cast<uint16_t*>(smem_raw);
   uint2* s_cur = reinterpret_cast<uint2*>(smem_raw + (size_t)kRowBufs * kStride * 2);  // kCurRing x kCurCap
@@ -192,7 +191,7 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
       if (d.kind == kTileRow) {
         uint2* cur = d.cur_sel < (uint32_t)kCurRing
                          ? s_cur + d.cur_sel * kCurCap
-                         : prm.cursor_ws + ((size_t)blockIdx.x * 2 + (d.cur_sel - kCurRing)) * prm.cursor_ws_stride;
+                         : prm.cursor_ws + ((size_t)blockIdx.x * kCurRing + (d.cur_sel - kCurRing)) * prm.cursor_ws_stride;
         const bool first = d.flags & 1u, last = d.flags & 2u;
         if (first) {
 #pragma unroll
@@ -338,10 +337,12 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
     return idx < prm.n_items ? __ldg(reinterpret_cast<const uint4*>(prm.items + idx)) : make_uint4(0u, 0u, 0u, 0u);
   };
   // Starts copying a row item's ranges into its cursor array.  Array choice: the s-th row item with
-  // R <= kCurCap takes shared array s % kCurRing.  This runs when the item BEFORE it becomes current,
-  // i.e. inside produce() of a tile t that follows done[t-2]; the array's previous user is kCurRing = 4
-  // row items back, whose tiles are all <= t-2.  Spilled rows alternate between two global areas that
-  // are written synchronously in produce() (previous user two row items back: tiles <= t-2 as well).
+  // R <= kCurCap takes shared array s % kCurRing.  This runs when the item before-before it is being
+  // finished, inside produce() of a tile t, which follows empty[t-kRowBufs] (hence done[t-kRowBufs]).
+  // The array's previous user is kCurRing = kRowBufs + 2 row items back; the two row items in between
+  // and it each own at least one tile, so its tiles are all <= t-kRowBufs: every walker is through with
+  // it.  Spilled rows (R > kCurCap) rotate over kCurRing global areas, written synchronously in
+  // produce() of the row's first tile (same argument with distance kCurRing >= kRowBufs).
   auto stage_prefetch = [&](Staged& st) {
     if (!st.valid || st.it.a0 != st.it.a1) return;
     if (st.R <= (uint32_t)kCurCap) {
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst + k)), "l"(prm.ranges + st.k0 + k)
                      : "memory");
     } else {
-      st.arr = kCurRing + (spill_seq++ & 1u);
+      st.arr = kCurRing + (spill_seq++ % kCurRing);
     }
   };
   auto make_staged = [&](uint32_t n, uint4 v) {
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
           __syncwarp();
           const bool spilled = cs.arr >= (uint32_t)kCurRing;
           uint2* cur = !spilled ? s_cur + cs.arr * kCurCap
-                                : prm.cursor_ws + ((size_t)blockIdx.x * 2 + (cs.arr - kCurRing)) * prm.cursor_ws_stride;
+                                : prm.cursor_ws + ((size_t)blockIdx.x * kCurRing + (cs.arr - kCurRing)) * prm.cursor_ws_stride;
           if (spilled || cb > a + 1) {
             for (uint32_t k = lane; k < R; k += 32) {
               uint2 r = spilled ? prm.ranges[k0 + k] : cur[k];
@@ -620,14 +621,14 @@ static void build_row_plan(uint32_t T, uint64_t p_begin, uint64_t p_end, uint32_
                    [](const RowItem& x, const RowItem& y) { return x.ce - x.cb > y.ce - y.cb; });
 }
 
-template <int kTile, int kWalkers, int kCurCap, int kSlots>
+template <int kTile, int kWalkers, int kCurCap, int kSlots, int kRowBufs>
 static int launch_sparse_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out,
                            uint32_t* d_mask) {
   const HashRFState& H = ctx->h;
   cudaStream_t s = ctx->stream;
   constexpr int kThreads = 32 * (kWalkers + 2);
-  constexpr size_t smem = (size_t)kRowBufs * (kTile + 8) * 2 + (size_t)kCurRing * kCurCap * sizeof(uint2);
-  auto kern = sparse_rows_kernel<kTile, kWalkers, kCurCap, kSlots>;
+  constexpr size_t smem = (size_t)kRowBufs * (kTile + 8) * 2 + (size_t)(kRowBufs + 2) * kCurCap * sizeof(uint2);
+  auto kern = sparse_rows_kernel<kTile, kWalkers, kCurCap, kSlots, kRowBufs>;
   RowPlan& plan = ctx->plan;
   if (!plan.valid || plan.T != H.T || plan.p_begin != p_begin || plan.p_end != p_end || plan.tile != kTile) {
     plan.valid = false;
@@ -666,7 +667,7 @@ static int launch_sparse_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t e
   prm.items = plan.items.p;
   prm.n_items = plan.n_items;
   if (H.stats.max_bips > (uint32_t)kCurCap) {
-    const size_t need = (size_t)grid * 2 * H.stats.max_bips;
+    const size_t need = (size_t)grid * (kRowBufs + 2) * H.stats.max_bips;
     if (plan.cursor_ws.n < need) PRF_CK(ctx, plan.cursor_ws.alloc(need, s));
     prm.cursor_ws = plan.cursor_ws.p;
     prm.cursor_ws_stride = H.stats.max_bips;
@@ -692,10 +693,12 @@ static int launch_sparse_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t e
 static int launch_sparse(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out,
                          uint32_t* d_mask) {
   // the tiny-tile build exists so that small test inputs exercise multi-tile rows and cursor spill
-  if (ctx->debug_small_tiles) return launch_sparse_t<256, 2, 8, 8>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  if (ctx->debug_small_tiles) return launch_sparse_t<256, 2, 8, 8, 3>(ctx, p_begin, p_end, editdist, d_out, d_mask);
   static const int cfg = [] { const char* e = getenv("PRF_SPARSE_CFG"); return e ? atoi(e) : 0; }();
-  if (cfg == 1) return launch_sparse_t<8192, 14, 384, 8>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-  return launch_sparse_t<16384, 14, 384, 8>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  if (cfg == 1) return launch_sparse_t<12288, 14, 288, 8, 4>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  if (cfg == 2) return launch_sparse_t<8192, 14, 256, 8, 6>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  if (cfg == 3) return launch_sparse_t<16384, 14, 256, 8, 3>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  return launch_sparse_t<16384, 14, 320, 8, 3>(ctx, p_begin, p_end, editdist, d_out, d_mask);
 }
 
 }  // namespace prf
