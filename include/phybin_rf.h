@@ -85,6 +85,9 @@ typedef struct prf_stats {
   int32_t variant_used;  /* prf_variant actually run by the last compute */
   int32_t gpu_launches;  /* kernels launched by the last call */
   float ms_h2d, ms_dedup, ms_incidence, ms_matrix, ms_d2h, ms_total;
+  uint32_t n_flipped;    /* bipartitions held by > T/2 trees, stored as the list of trees LACKING them (n_hits,
+                            n_shared_nnz and min/max_bips then describe the flipped sets D_t = B_t xor majority) */
+  uint32_t reserved;
 } prf_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------- */

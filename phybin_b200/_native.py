@@ -33,6 +33,7 @@ class prf_stats(C.Structure):
         ("variant_used", C.c_int32), ("gpu_launches", C.c_int32),
         ("ms_h2d", C.c_float), ("ms_dedup", C.c_float), ("ms_incidence", C.c_float),
         ("ms_matrix", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float),
+        ("n_flipped", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
     def as_dict(self):
@@ -124,6 +125,7 @@ def rf_lib():
         L.prf_launch_count.argtypes = [vp]
         # test-only entry points (not in phybin_rf.h)
         L.prf_debug_small_tiles.argtypes = [vp, C.c_int]
+        L.prf_debug_no_flip.argtypes = [vp, C.c_int]
         L.prf_debug_scan.argtypes = [vp, vp, C.c_uint64, vp, vp]
         L.prf_debug_sort.argtypes = [vp, vp, vp, C.c_uint32, C.c_int]
         _rf = L

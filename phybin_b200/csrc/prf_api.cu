@@ -460,7 +460,8 @@ PRF_API int prf_hashrf_merge(prf_ctx* h, uint32_t T, uint32_t W, uint32_t world,
   DevBuf<uint16_t> nb;
   DevBuf<uint32_t> roff, members, lid, nb32, cnt, mm;
   DevBuf<uint2> ranges;
-  PRF_CK(ctx, nb.alloc(T, s));
+  PRF_CK(ctx, nb.alloc((size_t)T + 16, s));
+  PRF_CK(ctx, cudaMemsetAsync(nb.p, 0, nb.bytes(), s));
   PRF_CK(ctx, roff.alloc((size_t)T + 1, s));
   PRF_CK(ctx, members.alloc(n_members, s));
   PRF_CK(ctx, lid.alloc(n_members, s));
@@ -648,6 +649,12 @@ PRF_API int prf_tolerant(prf_ctx* h, const uint64_t* clades, const uint64_t* tre
 // ---------------------------------------------------------------------------------------------
 // Debug entry points for tests of the primitives (not part of phybin_rf.h).
 // ---------------------------------------------------------------------------------------------
+
+PRF_API int prf_debug_no_flip(prf_ctx* h, int on) {
+  if (!h) return PRF_E_INVALID;
+  h->c.debug_no_flip = on != 0;
+  return PRF_OK;
+}
 
 PRF_API int prf_debug_small_tiles(prf_ctx* h, int on) {
   if (!h) return PRF_E_INVALID;

@@ -153,10 +153,11 @@ __global__ void __launch_bounds__(256) list_heads_kernel(const uint32_t* __restr
                                                          const uint32_t* __restrict__ tree,
                                                          const uint32_t* __restrict__ lid_ex, uint32_t n,
                                                          uint32_t* __restrict__ head_pos,
-                                                         unsigned long long* counters) {
+                                                         unsigned long long* counters, uint32_t* __restrict__ lid_out) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const bool head = k == 0 || slot[k] != slot[k - 1];
+  lid_out[k] = lid_ex[k] + (head ? 1 : 0) - 1;
   if (head) head_pos[lid_ex[k]] = k;
   else if (tree[k] == tree[k - 1]) atomicAdd(&counters[2], 1ull);
   if (k == n - 1) head_pos[lid_ex[k] + (head ? 1 : 0)] = n;
@@ -165,44 +166,106 @@ __global__ void __launch_bounds__(256) list_heads_kernel(const uint32_t* __restr
 // Position k holds tree a = tree[k] inside list l = [head_pos[l], head_pos[l+1]).  Its suffix
 // (k+1, end) lists the trees b > a sharing that bipartition.  Pass 1 counts the non-empty suffixes
 // per tree (and accumulates sum m(m-1)/2 at list heads), pass 2 stores them.
-__global__ void __launch_bounds__(256) range_count_kernel(const uint32_t* __restrict__ slot,
+__global__ void __launch_bounds__(256) range_count_kernel(const uint32_t* __restrict__ lid,
                                                           const uint32_t* __restrict__ tree,
-                                                          const uint32_t* __restrict__ lid_ex,
                                                           const uint32_t* __restrict__ head_pos, uint32_t n,
-                                                          uint32_t* rcount, unsigned long long* counters,
-                                                          uint32_t* __restrict__ lid_out) {
+                                                          uint32_t* rcount, unsigned long long* counters) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long hits = 0;
+  unsigned long long hits = 0, longest = 0;
   if (k < n) {
-    const bool head = k == 0 || slot[k] != slot[k - 1];
-    const uint32_t l = lid_ex[k] + (head ? 1 : 0) - 1;
-    lid_out[k] = l;
+    const uint32_t l = lid[k];
     const uint32_t end = head_pos[l + 1];
     if (k + 1 < end) atomicAdd(&rcount[tree[k]], 1u);
-    if (head) {
+    if (k == head_pos[l]) {
       const unsigned long long m = end - k;
       hits = m * (m - 1) / 2;
+      longest = m;
     }
   }
 #pragma unroll
-  for (int d = 16; d; d >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, d);
+  for (int d = 16; d; d >>= 1) {
+    hits += __shfl_xor_sync(0xffffffffu, hits, d);
+    longest = max(longest, __shfl_xor_sync(0xffffffffu, longest, d));
+  }
   if (lane_id() == 0 && hits) atomicAdd(&counters[3], hits);
+  if (lane_id() == 0 && longest > *((volatile unsigned long long*)&counters[4])) atomicMax(&counters[4], longest);
 }
-__global__ void __launch_bounds__(256) range_fill_kernel(const uint32_t* __restrict__ slot,
+__global__ void __launch_bounds__(256) range_fill_kernel(const uint32_t* __restrict__ lid,
                                                          const uint32_t* __restrict__ tree,
-                                                         const uint32_t* __restrict__ lid_ex,
                                                          const uint32_t* __restrict__ head_pos, uint32_t n,
                                                          const uint32_t* __restrict__ roff, uint32_t* cursor,
                                                          uint2* __restrict__ ranges) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const bool head = k == 0 || slot[k] != slot[k - 1];
-  const uint32_t l = lid_ex[k] + (head ? 1 : 0) - 1;
-  const uint32_t end = head_pos[l + 1];
+  const uint32_t end = head_pos[lid[k] + 1];
   if (k + 1 < end) {
     const uint32_t a = tree[k];
     ranges[roff[a] + atomicAdd(&cursor[a], 1u)] = make_uint2(k + 1, end);
   }
+}
+
+// ---- majority flip -----------------------------------------------------------------------------------
+// [u in B_a] xor [u in B_b] is unchanged when membership of bipartition u is complemented for EVERY
+// tree, so a list held by more than half of the trees can be replaced by the (shorter) list of trees
+// that lack it: d(a,b) = |D_a| + |D_b| - 2 |D_a n D_b| with D_t = B_t xor {majority bipartitions}.
+// Similar trees (few differences from a common backbone) become a sparse problem again.
+struct FlipLen {
+  const uint32_t* head_pos;
+  uint32_t T, n_lists;
+  __device__ uint32_t operator()(uint64_t l) const {
+    if (l >= n_lists) return 0;
+    const uint32_t m = head_pos[l + 1] - head_pos[l];
+    return 2ull * m > T ? T - m : m;
+  }
+};
+// light lists are copied (one thread per entry); members of heavy lists are only counted per tree
+__global__ void __launch_bounds__(256) flip_copy_kernel(const uint32_t* __restrict__ lid,
+                                                        const uint32_t* __restrict__ tree,
+                                                        const uint32_t* __restrict__ head_pos,
+                                                        const uint32_t* __restrict__ head2, uint32_t n, uint32_t T,
+                                                        uint32_t* __restrict__ tree2, uint32_t* __restrict__ lid2,
+                                                        uint32_t* hcnt) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t l = lid[k], h = head_pos[l], m = head_pos[l + 1] - h;
+  if (2ull * m > T) {
+    atomicAdd(&hcnt[tree[k]], 1u);
+  } else {
+    const uint32_t o = head2[l] + (k - h);
+    tree2[o] = tree[k];
+    lid2[o] = l;
+  }
+}
+// heavy lists: one thread per gap between consecutive members writes the trees of the gap
+__global__ void __launch_bounds__(256) flip_complement_kernel(const uint32_t* __restrict__ lid,
+                                                              const uint32_t* __restrict__ tree,
+                                                              const uint32_t* __restrict__ head_pos,
+                                                              const uint32_t* __restrict__ head2, uint32_t n, uint32_t T,
+                                                              uint32_t* __restrict__ tree2, uint32_t* __restrict__ lid2,
+                                                              unsigned long long* counters) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t l = lid[k], h = head_pos[l], e = head_pos[l + 1], m = e - h;
+  if (2ull * m <= T) return;
+  if (k == h) atomicAdd(&counters[5], 1ull);  // number of heavy lists
+  const uint32_t i = k - h;                   // members before me in the list
+  const uint32_t base = head2[l];
+  // gap before member i: trees (previous member, this member)
+  const uint32_t lo = i ? tree[k - 1] + 1 : 0u, hi = tree[k];
+  for (uint32_t t = lo; t < hi; ++t) {
+    tree2[base + t - i] = t;
+    lid2[base + t - i] = l;
+  }
+  if (k + 1 == e)  // gap after the last member
+    for (uint32_t t = tree[k] + 1; t < T; ++t) {
+      tree2[base + t - (i + 1)] = t;
+      lid2[base + t - (i + 1)] = l;
+    }
+}
+__global__ void __launch_bounds__(256) flip_nb_kernel(uint32_t* nb32, const uint32_t* __restrict__ hcnt, uint32_t T,
+                                                      const unsigned long long* counters) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < T) nb32[t] = nb32[t] + (uint32_t)counters[5] - 2u * hcnt[t];
 }
 
 // Slow path (a caller listed a bipartition twice in one tree): drop the repeats.
@@ -278,7 +341,7 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
   PRF_CK(ctx, nb32.alloc((size_t)T + 1, s));
   PRF_CK(ctx, sc.alloc((size_t)T + 1, s));
   PRF_CK(ctx, soff.alloc((size_t)T + 1, s));
-  PRF_CK(ctx, counters.alloc(4, s));
+  PRF_CK(ctx, counters.alloc(6, s));
   PRF_CK(ctx, scalars.alloc(8, s));
   PRF_CK(ctx, cudaMemsetAsync(shared_bits.p, 0, shared_bits.bytes(), s));
   PRF_CK(ctx, cudaMemsetAsync(counters.p, 0, counters.bytes(), s));
@@ -326,7 +389,8 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
   PRF_CK(ctx, cursor.alloc((size_t)T + 1, s));
   PRF_CK(ctx, H.roff.alloc((size_t)T + 1, s));
   PRF_CK(ctx, H.ranges.alloc(n_sh_nnz, s));  // upper bound: at most one suffix per shared entry
-  PRF_CK(ctx, H.nb.alloc(T, s));
+  PRF_CK(ctx, H.nb.alloc((size_t)T + 16, s));  // slack: the matrix kernel reads |B| in aligned 32-bit pairs
+  PRF_CK(ctx, cudaMemsetAsync(H.nb.p, 0, H.nb.bytes(), s));
   uint32_t n_sorted = n_sh_nnz;
   if (n_sh_nnz) {
     gather_shared_kernel<<<(T + 7) / 8, 256, 0, s>>>(d_off, T, ent_slot.p, shared_bits.p, soff.p, slot_sorted.p,
@@ -335,26 +399,26 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
     // stable sort by table slot: inside a list the trees stay ascending
     if ((rc = radix_sort_pairs(ctx, slot_sorted.p, H.members.p, n_sh_nnz, bits_for(cap)))) return rc;
   }
-  unsigned long long hc[4] = {0, 0, 0, 0};
+  unsigned long long hc[6] = {0, 0, 0, 0, 0, 0};
   uint32_t hs[8] = {0};
   uint32_t h_nranges = 0;
   for (int pass = 0; pass < 2; ++pass) {
     PRF_CK(ctx, cudaMemsetAsync(rcount.p, 0, rcount.bytes(), s));
     PRF_CK(ctx, cudaMemsetAsync(cursor.p, 0, cursor.bytes(), s));
-    PRF_CK(ctx, cudaMemsetAsync(counters.p + 2, 0, 16, s));
+    PRF_CK(ctx, cudaMemsetAsync(counters.p + 2, 0, 32, s));
     if (n_sorted) {
       if ((rc = exclusive_scan(ctx, HeadFlag{slot_sorted.p}, n_sorted, lid_ex.p, scalars.p + 1))) return rc;
       list_heads_kernel<<<grid_for(n_sorted), 256, 0, s>>>(slot_sorted.p, H.members.p, lid_ex.p, n_sorted,
-                                                           head_pos.p, counters.p);
+                                                           head_pos.p, counters.p, H.lid.p);
       PRF_LAUNCHED(ctx);
-      range_count_kernel<<<grid_for(n_sorted), 256, 0, s>>>(slot_sorted.p, H.members.p, lid_ex.p, head_pos.p,
-                                                            n_sorted, rcount.p, counters.p, H.lid.p);
+      range_count_kernel<<<grid_for(n_sorted), 256, 0, s>>>(H.lid.p, H.members.p, head_pos.p, n_sorted, rcount.p,
+                                                            counters.p);
       PRF_LAUNCHED(ctx);
     }
     if ((rc = exclusive_scan(ctx, LoadU32{rcount.p}, (uint64_t)T + 1, H.roff.p, nullptr))) return rc;
     if (n_sorted) {
-      range_fill_kernel<<<grid_for(n_sorted), 256, 0, s>>>(slot_sorted.p, H.members.p, lid_ex.p, head_pos.p,
-                                                           n_sorted, H.roff.p, cursor.p, H.ranges.p);
+      range_fill_kernel<<<grid_for(n_sorted), 256, 0, s>>>(H.lid.p, H.members.p, head_pos.p, n_sorted, H.roff.p,
+                                                           cursor.p, H.ranges.p);
       PRF_LAUNCHED(ctx);
     }
     if (T) {
@@ -384,6 +448,58 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
     uint32_t mm_reset[2] = {0xffffffffu, 0u};
     PRF_CK(ctx, cudaMemcpyAsync(scalars.p + 4, mm_reset, 8, cudaMemcpyHostToDevice, s));
   }
+  // ---- majority flip (only when some bipartition is held by more than half of the trees) ----
+  uint32_t n_lists = n_sorted ? hs[1] : 0;
+  if (n_sorted && 2ull * hc[4] > T && !ctx->debug_no_flip) {
+    DevBuf<uint32_t> head2, mem2, lid2, hcnt;
+    PRF_CK(ctx, head2.alloc((size_t)n_lists + 1, s));
+    PRF_CK(ctx, hcnt.alloc((size_t)T + 1, s));
+    PRF_CK(ctx, cudaMemsetAsync(hcnt.p, 0, hcnt.bytes(), s));
+    if ((rc = exclusive_scan(ctx, FlipLen{head_pos.p, T, n_lists}, (uint64_t)n_lists + 1, head2.p, scalars.p + 2))) return rc;
+    uint32_t n2 = 0;
+    PRF_CK(ctx, cudaMemcpyAsync(&n2, scalars.p + 2, 4, cudaMemcpyDeviceToHost, s));
+    PRF_CK(ctx, cudaStreamSynchronize(s));
+    PRF_CK(ctx, mem2.alloc(n2, s));
+    PRF_CK(ctx, lid2.alloc(n2, s));
+    flip_copy_kernel<<<grid_for(n_sorted), 256, 0, s>>>(H.lid.p, H.members.p, head_pos.p, head2.p, n_sorted, T, mem2.p,
+                                                        lid2.p, hcnt.p);
+    PRF_LAUNCHED(ctx);
+    flip_complement_kernel<<<grid_for(n_sorted), 256, 0, s>>>(H.lid.p, H.members.p, head_pos.p, head2.p, n_sorted, T,
+                                                              mem2.p, lid2.p, counters.p);
+    PRF_LAUNCHED(ctx);
+    flip_nb_kernel<<<grid_for(T), 256, 0, s>>>(nb32.p, hcnt.p, T, counters.p);
+    PRF_LAUNCHED(ctx);
+    H.members = std::move(mem2);
+    H.lid = std::move(lid2);
+    n_sorted = n2;
+    // ranges, hits and |D_t| statistics over the flipped lists
+    PRF_CK(ctx, H.ranges.alloc(n_sorted, s));
+    PRF_CK(ctx, cudaMemsetAsync(rcount.p, 0, rcount.bytes(), s));
+    PRF_CK(ctx, cudaMemsetAsync(cursor.p, 0, cursor.bytes(), s));
+    PRF_CK(ctx, cudaMemsetAsync(counters.p + 3, 0, 16, s));
+    const uint32_t mm_reset[2] = {0xffffffffu, 0u};
+    PRF_CK(ctx, cudaMemcpyAsync(scalars.p + 4, mm_reset, 8, cudaMemcpyHostToDevice, s));
+    if (n_sorted) {
+      range_count_kernel<<<grid_for(n_sorted), 256, 0, s>>>(H.lid.p, H.members.p, head2.p, n_sorted, rcount.p, counters.p);
+      PRF_LAUNCHED(ctx);
+    }
+    if ((rc = exclusive_scan(ctx, LoadU32{rcount.p}, (uint64_t)T + 1, H.roff.p, nullptr))) return rc;
+    if (n_sorted) {
+      range_fill_kernel<<<grid_for(n_sorted), 256, 0, s>>>(H.lid.p, H.members.p, head2.p, n_sorted, H.roff.p, cursor.p,
+                                                           H.ranges.p);
+      PRF_LAUNCHED(ctx);
+    }
+    finish_nb_kernel<<<grid_for(T), 256, 0, s>>>(nb32.p, T, H.nb.p, scalars.p + 4);
+    PRF_LAUNCHED(ctx);
+    unsigned long long hc2[6];
+    PRF_CK(ctx, cudaMemcpyAsync(hc2, counters.p, sizeof hc2, cudaMemcpyDeviceToHost, s));
+    PRF_CK(ctx, cudaMemcpyAsync(hs, scalars.p, sizeof hs, cudaMemcpyDeviceToHost, s));
+    PRF_CK(ctx, cudaMemcpyAsync(&h_nranges, H.roff.p + T, 4, cudaMemcpyDeviceToHost, s));
+    PRF_CK(ctx, cudaEventRecord(ctx->ev[3], s));
+    PRF_CK(ctx, cudaStreamSynchronize(s));
+    hc[3] = hc2[3];
+    H.n_flipped = (uint32_t)hc2[5];
+  }
   uint32_t mm[2] = {hs[4], hs[5]};
   if (T == 0) mm[0] = mm[1] = 0;
   if (mm[1] > kMaxBipsPerTree)
@@ -391,7 +507,7 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
                      mm[1], kMaxBipsPerTree);
   H.uniform_nb = mm[0] == mm[1];
   H.nb_uniform = mm[0];
-  H.n_shared = n_sorted ? hs[1] : 0;
+  H.n_shared = n_lists;
   H.n_shared_nnz = n_sorted;  // after duplicate removal
   H.n_ranges = h_nranges;
 
@@ -407,6 +523,7 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
   st.n_pairs = H.P;
   st.max_bips = mm[1];
   st.min_bips = mm[0];
+  st.n_flipped = H.n_flipped;
   H.loaded = true;
   return PRF_OK;
 }

@@ -317,11 +317,32 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
       for (int i = 0; i < kTile / 256; ++i) t4[32 * i] = q4;
       if (lane == 0) t4[kTile / 8] = q4;
     } else {
+      // tile entries [o, o + cnt) <- na + nb[c_lo ..).  One aligned 16-byte group of the tile per lane and
+      // iteration: 5 aligned 32-bit loads of nb (its element offset is arbitrary), funnel-shifted into
+      // place, two entries per SIMD add.
       const uint32_t na = prm.nb[a];
+      const uint32_t na2 = na | (na << 16);
       const uint32_t cnt = (uint32_t)(p_hi - p_lo), o = (uint32_t)(p_lo - P0);
-      const uint16_t* nbb = prm.nb + c_lo;
-#pragma unroll 4
-      for (uint32_t i = lane; i < cnt; i += 32) tile[o + i] = (uint16_t)(na + nbb[i]);
+      const uint32_t* nb32 = reinterpret_cast<const uint32_t*>(prm.nb);  // nb is allocated with 16 entries of slack
+      uint4* t4 = reinterpret_cast<uint4*>(tile);
+      const uint32_t g_lo = (o + 7) >> 3, g_hi = (o + cnt) >> 3;  // fully covered groups [g_lo, g_hi)
+      for (uint32_t g = g_lo + lane; g < g_hi; g += 32) {
+        const uint32_t src = c_lo + 8 * g - o;  // nb index of the group's first entry
+        const uint32_t* wp = nb32 + (src >> 1);
+        const uint32_t sh = (src & 1u) * 16u;
+        const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3), w4 = __ldg(wp + 4);
+        uint4 v;
+        v.x = __vadd2(__funnelshift_r(w0, w1, sh), na2);
+        v.y = __vadd2(__funnelshift_r(w1, w2, sh), na2);
+        v.z = __vadd2(__funnelshift_r(w2, w3, sh), na2);
+        v.w = __vadd2(__funnelshift_r(w3, w4, sh), na2);
+        t4[g] = v;
+      }
+      // the < 8 entries before the first / after the last full group (adjacent rows of a group tile own the rest)
+      const uint32_t head_end = min(8 * g_lo, o + cnt), tail_beg = max(8 * g_hi, head_end);
+      if (lane < 8 && o + lane < head_end) tile[o + lane] = (uint16_t)(na + prm.nb[c_lo + lane]);
+      if (lane >= 8 && lane < 16 && tail_beg + (lane - 8) < o + cnt)
+        tile[tail_beg + (lane - 8)] = (uint16_t)(na + prm.nb[c_lo + (tail_beg + (lane - 8) - o)]);
     }
   };
 

@@ -308,13 +308,39 @@ def test_dense_variant_multifurcating_mask_and_shards(ctx):
         assert np.array_equal(mb, want[b:e] <= thr)
 
 
-def test_auto_picks_dense_for_similar_trees_and_sparse_for_random(ctx):
+def test_majority_flip_keeps_distances_and_shrinks_the_join(ctx):
+    # similar trees: the backbone's bipartitions are held by most trees and get stored as complement lists
+    f = Forest.synthetic(1500, 60, seed=77, family=NNI_FAMILY, nni_max=3)
+    o = orc.Forest([f.to_newick()])
+    want = oracle_packed(o, "hashrf", "literal")
+    bips, off = f.all_bips()
+    flipped, _, st = run_variant(ctx, bips, off, 1)
+    assert st["n_flipped"] > 0 and np.array_equal(flipped.astype(np.int64), want)
+    ctx._ck(ctx._L.prf_debug_no_flip(ctx._h, 1))
+    try:
+        plain, _, st0 = run_variant(ctx, bips, off, 1)
+    finally:
+        ctx._ck(ctx._L.prf_debug_no_flip(ctx._h, 0))
+    assert st0["n_flipped"] == 0 and np.array_equal(plain, flipped)
+    assert st["n_hits"] * 4 < st0["n_hits"] and st["n_unique"] == st0["n_unique"]
+
+
+def test_auto_variant_choice_follows_measured_density(ctx):
     f = Forest.synthetic(3000, 100, seed=5, family=NNI_FAMILY, nni_max=8)
     bips, off = f.all_bips()
-    dense, _, st = run_variant(ctx, bips, off, 0)
-    assert st["variant_used"] == 2
+    auto, _, st = run_variant(ctx, bips, off, 0)
+    assert st["variant_used"] in (1, 2)   # decided by the cost model on the (flipped) incidence
+    dense, _, st1 = run_variant(ctx, bips, off, 2)
     sparse, _, st2 = run_variant(ctx, bips, off, 1)
-    assert st2["variant_used"] == 1 and np.array_equal(dense, sparse)
+    assert st1["variant_used"] == 2 and st2["variant_used"] == 1
+    assert np.array_equal(dense, sparse) and np.array_equal(auto, sparse)
+    # with the majority flip switched off the same trees are a dense problem and AUTO takes the tensor cores
+    ctx._ck(ctx._L.prf_debug_no_flip(ctx._h, 1))
+    try:
+        noflip, _, st3 = run_variant(ctx, bips, off, 0)
+    finally:
+        ctx._ck(ctx._L.prf_debug_no_flip(ctx._h, 0))
+    assert st3["variant_used"] == 2 and np.array_equal(noflip, sparse)
     f = Forest.synthetic(3000, 100, seed=6)
     bips, off = f.all_bips()
     _, _, st = run_variant(ctx, bips, off, 0)
