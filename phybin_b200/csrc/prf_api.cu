@@ -250,13 +250,14 @@ PRF_API int prf_hashrf_compute(prf_ctx* h, uint64_t p_begin, uint64_t p_end, int
 
   int use = variant;
   if (use == PRF_VARIANT_AUTO) {
-    // Measured split density decides.  Cost models from this round's B200 runs: the
-    // sparse join pays ~1.9 ps per shared (pair, bipartition) incidence, the tensor-core Gram
-    // 2 * Kpad int8 ops per pair at ~2 Pop/s sustained; both write the same 2 B per pair.
+    // Measured split density decides.  Cost models from this round's B200 runs, per pair
+    // of trees: the sparse join pays ~1.9 ps per shared (pair, bipartition) incidence of the (majority-
+    // flipped) lists plus ~0.9 ps when |B_t| is not uniform (per-column fill); the tensor-core Gram pays
+    // 2 * Kpad int8 ops at the ~0.9 Pop/s the operand traffic allows.  Both write the same 2 B per pair.
     const double pairs = (double)(p_end - p_begin);
     const double hits = (double)H.stats.n_hits * (H.P ? pairs / (double)H.P : 0.0);
     const double kpad = (double)((H.n_shared + kDK - 1) / kDK * kDK);
-    const double t_sparse = hits * 1.9e-12, t_dense = pairs * kpad * 2.0 / 2.0e15;
+    const double t_sparse = hits * 1.9e-12 + (H.uniform_nb ? 0.0 : pairs * 0.9e-12), t_dense = pairs * kpad * 2.0 / 0.9e15;
     const double operand = (double)((H.T + kDN - 1) / kDN * kDN) * kpad;
     use = (H.n_shared > 0 && operand < 32e9 && t_dense < t_sparse) ? PRF_VARIANT_DENSE : PRF_VARIANT_SPARSE;
   }

@@ -187,8 +187,21 @@ __global__ void __launch_bounds__(256) range_count_kernel(const uint32_t* __rest
     hits += __shfl_xor_sync(0xffffffffu, hits, d);
     longest = max(longest, __shfl_xor_sync(0xffffffffu, longest, d));
   }
-  if (lane_id() == 0 && hits) atomicAdd(&counters[3], hits);
-  if (lane_id() == 0 && longest > *((volatile unsigned long long*)&counters[4])) atomicMax(&counters[4], longest);
+  // one pair of global atomics per block, not per warp: both targets are single hot addresses
+  __shared__ unsigned long long s_hits[8], s_long[8];
+  if (lane_id() == 0) {
+    s_hits[threadIdx.x >> 5] = hits;
+    s_long[threadIdx.x >> 5] = longest;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      hits += s_hits[w];
+      longest = max(longest, s_long[w]);
+    }
+    if (hits) atomicAdd(&counters[3], hits);
+    if (longest) atomicMax(&counters[4], longest);
+  }
 }
 __global__ void __launch_bounds__(256) range_fill_kernel(const uint32_t* __restrict__ lid,
                                                          const uint32_t* __restrict__ tree,
