@@ -104,12 +104,23 @@ __global__ void __launch_bounds__(256) count_shared_kernel(const uint64_t* __res
   }
 }
 
-// Writes the (slot, tree) pairs of the shared entries in tree order (stable warp compaction).
+// Number of shared slots in one 32-slot word of the bitmap (scanned into per-word ranks).
+struct PopcWord {
+  const uint32_t* bits;
+  __device__ uint32_t operator()(uint64_t w) const { return __popc(bits[w]); }
+};
+
+// Writes the (list id, tree) pairs of the shared entries in tree order (stable warp compaction).  The
+// list id is the rank of the entry's slot among the shared slots (per-word rank + popcount below the
+// slot's bit): dense ids in slot order, so two 10-bit radix passes sort them and the sorted key array
+// IS the per-entry list id.  lsize[id] counts the list's entries.
 __global__ void __launch_bounds__(256) gather_shared_kernel(const uint64_t* __restrict__ tree_off, uint32_t T,
                                                             const uint32_t* __restrict__ ent_slot,
                                                             const uint32_t* __restrict__ shared_bits,
+                                                            const uint32_t* __restrict__ wrank,
                                                             const uint32_t* __restrict__ soff,
-                                                            uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                                            uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                            uint32_t* lsize) {
   const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= T) return;
   const uint64_t e0 = tree_off[t], e1 = tree_off[t + 1];
@@ -117,17 +128,20 @@ __global__ void __launch_bounds__(256) gather_shared_kernel(const uint64_t* __re
   const uint32_t lt = lanemask_lt();
   for (uint64_t eb = e0; eb < e1; eb += 32) {
     const uint64_t e = eb + lane_id();
-    uint32_t s = 0;
+    uint32_t id = 0;
     bool sh = false;
     if (e < e1) {
-      s = ent_slot[e];
-      sh = (shared_bits[s >> 5] >> (s & 31)) & 1u;
+      const uint32_t s = ent_slot[e];
+      const uint32_t word = shared_bits[s >> 5];
+      sh = (word >> (s & 31)) & 1u;
+      id = wrank[s >> 5] + __popc(word & ((1u << (s & 31)) - 1u));
     }
     const uint32_t m = __ballot_sync(0xffffffffu, sh);
     if (sh) {
       const uint32_t o = pos + __popc(m & lt);
-      keys[o] = s;
+      keys[o] = id;
       vals[o] = t;
+      atomicAdd(&lsize[id], 1u);
     }
     pos += __popc(m);
   }
@@ -159,7 +173,6 @@ __global__ void __launch_bounds__(256) list_heads_kernel(const uint32_t* __restr
   const bool head = k == 0 || slot[k] != slot[k - 1];
   lid_out[k] = lid_ex[k] + (head ? 1 : 0) - 1;
   if (head) head_pos[lid_ex[k]] = k;
-  else if (tree[k] == tree[k - 1]) atomicAdd(&counters[2], 1ull);
   if (k == n - 1) head_pos[lid_ex[k] + (head ? 1 : 0)] = n;
 }
 
@@ -176,6 +189,7 @@ __global__ void __launch_bounds__(256) range_count_kernel(const uint32_t* __rest
     const uint32_t l = lid[k];
     const uint32_t end = head_pos[l + 1];
     if (k + 1 < end) atomicAdd(&rcount[tree[k]], 1u);
+    if (k > 0 && lid[k - 1] == l && tree[k - 1] == tree[k]) atomicAdd(&counters[2], 1ull);  // listed twice by one tree (rare)
     if (k == head_pos[l]) {
       const unsigned long long m = end - k;
       hits = m * (m - 1) / 2;
@@ -387,17 +401,24 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
     PRF_LAUNCHED(ctx);
   }
   if ((rc = exclusive_scan(ctx, LoadU32{sc.p}, (uint64_t)T + 1, soff.p, scalars.p + 0))) return rc;
-  PRF_CK(ctx, cudaMemcpyAsync(&n_sh_nnz, scalars.p + 0, 4, cudaMemcpyDeviceToHost, s));
+  // rank of every shared slot = dense list id (in slot order); scalars[1] = number of lists
+  DevBuf<uint32_t> wrank;
+  PRF_CK(ctx, wrank.alloc(cap / 32, s));
+  if ((rc = exclusive_scan(ctx, PopcWord{shared_bits.p}, cap / 32, wrank.p, scalars.p + 1))) return rc;
+  uint32_t h01[2] = {0, 0};
+  PRF_CK(ctx, cudaMemcpyAsync(h01, scalars.p + 0, 8, cudaMemcpyDeviceToHost, s));
   PRF_CK(ctx, cudaStreamSynchronize(s));
   trace_mark("build: dedup + count synced");
+  n_sh_nnz = h01[0];
+  const uint32_t n_lists0 = h01[1];
   H.n_shared_nnz = n_sh_nnz;
 
-  DevBuf<uint32_t> slot_sorted, lid_ex, head_pos, rcount, cursor;
+  DevBuf<uint32_t> slot_sorted, lid_ex, head_pos, rcount, cursor, lsize;
   PRF_CK(ctx, slot_sorted.alloc(n_sh_nnz, s));
   PRF_CK(ctx, H.members.alloc(n_sh_nnz, s));
-  PRF_CK(ctx, H.lid.alloc(n_sh_nnz, s));
-  PRF_CK(ctx, lid_ex.alloc(n_sh_nnz, s));
   PRF_CK(ctx, head_pos.alloc((size_t)n_sh_nnz + 1, s));
+  PRF_CK(ctx, lsize.alloc((size_t)n_lists0 + 1, s));
+  PRF_CK(ctx, cudaMemsetAsync(lsize.p, 0, lsize.bytes(), s));
   PRF_CK(ctx, rcount.alloc((size_t)T + 1, s));
   PRF_CK(ctx, cursor.alloc((size_t)T + 1, s));
   PRF_CK(ctx, H.roff.alloc((size_t)T + 1, s));
@@ -406,12 +427,13 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
   PRF_CK(ctx, cudaMemsetAsync(H.nb.p, 0, H.nb.bytes(), s));
   uint32_t n_sorted = n_sh_nnz;
   if (n_sh_nnz) {
-    gather_shared_kernel<<<(T + 7) / 8, 256, 0, s>>>(d_off, T, ent_slot.p, shared_bits.p, soff.p, slot_sorted.p,
-                                                     H.members.p);
+    gather_shared_kernel<<<(T + 7) / 8, 256, 0, s>>>(d_off, T, ent_slot.p, shared_bits.p, wrank.p, soff.p, slot_sorted.p,
+                                                     H.members.p, lsize.p);
     PRF_LAUNCHED(ctx);
-    // stable sort by table slot: inside a list the trees stay ascending
-    if ((rc = radix_sort_pairs(ctx, slot_sorted.p, H.members.p, n_sh_nnz, bits_for(cap)))) return rc;
+    // stable sort by list id: inside a list the trees stay ascending
+    if ((rc = radix_sort_pairs(ctx, slot_sorted.p, H.members.p, n_sh_nnz, bits_for(n_lists0)))) return rc;
   }
+  bool ids_are_keys = true;  // until duplicates force the generic path, the sorted keys are the list ids
   unsigned long long hc[6] = {0, 0, 0, 0, 0, 0};
   uint32_t hs[8] = {0};
   uint32_t h_nranges = 0;
@@ -419,19 +441,26 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
     PRF_CK(ctx, cudaMemsetAsync(rcount.p, 0, rcount.bytes(), s));
     PRF_CK(ctx, cudaMemsetAsync(cursor.p, 0, cursor.bytes(), s));
     PRF_CK(ctx, cudaMemsetAsync(counters.p + 2, 0, 32, s));
+    const uint32_t* lid_p = slot_sorted.p;
     if (n_sorted) {
-      if ((rc = exclusive_scan(ctx, HeadFlag{slot_sorted.p}, n_sorted, lid_ex.p, scalars.p + 1))) return rc;
-      list_heads_kernel<<<grid_for(n_sorted), 256, 0, s>>>(slot_sorted.p, H.members.p, lid_ex.p, n_sorted,
-                                                           head_pos.p, counters.p, H.lid.p);
-      PRF_LAUNCHED(ctx);
-      range_count_kernel<<<grid_for(n_sorted), 256, 0, s>>>(H.lid.p, H.members.p, head_pos.p, n_sorted, rcount.p,
-                                                            counters.p);
+      if (ids_are_keys) {
+        if ((rc = exclusive_scan(ctx, LoadU32{lsize.p}, (uint64_t)n_lists0 + 1, head_pos.p, nullptr))) return rc;
+      } else {
+        if (!lid_ex.p) PRF_CK(ctx, lid_ex.alloc(n_sh_nnz, s));
+        if (!H.lid.p) PRF_CK(ctx, H.lid.alloc(n_sh_nnz, s));
+        if ((rc = exclusive_scan(ctx, HeadFlag{slot_sorted.p}, n_sorted, lid_ex.p, scalars.p + 1))) return rc;
+        list_heads_kernel<<<grid_for(n_sorted), 256, 0, s>>>(slot_sorted.p, H.members.p, lid_ex.p, n_sorted,
+                                                             head_pos.p, counters.p, H.lid.p);
+        PRF_LAUNCHED(ctx);
+        lid_p = H.lid.p;
+      }
+      range_count_kernel<<<grid_for(n_sorted), 256, 0, s>>>(lid_p, H.members.p, head_pos.p, n_sorted, rcount.p, counters.p);
       PRF_LAUNCHED(ctx);
     }
     if ((rc = exclusive_scan(ctx, LoadU32{rcount.p}, (uint64_t)T + 1, H.roff.p, nullptr))) return rc;
     if (n_sorted) {
-      range_fill_kernel<<<grid_for(n_sorted), 256, 0, s>>>(H.lid.p, H.members.p, head_pos.p, n_sorted, H.roff.p,
-                                                           cursor.p, H.ranges.p);
+      range_fill_kernel<<<grid_for(n_sorted), 256, 0, s>>>(lid_p, H.members.p, head_pos.p, n_sorted, H.roff.p, cursor.p,
+                                                           H.ranges.p);
       PRF_LAUNCHED(ctx);
     }
     if (T) {
@@ -457,10 +486,12 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
     PRF_LAUNCHED(ctx);
     slot_sorted = std::move(slot2);
     H.members = std::move(mem2);
+    ids_are_keys = false;
     n_sorted -= (uint32_t)hc[2];
     uint32_t mm_reset[2] = {0xffffffffu, 0u};
     PRF_CK(ctx, cudaMemcpyAsync(scalars.p + 4, mm_reset, 8, cudaMemcpyHostToDevice, s));
   }
+  if (ids_are_keys) H.lid = std::move(slot_sorted);
   // ---- majority flip (only when some bipartition is held by more than half of the trees) ----
   uint32_t n_lists = n_sorted ? hs[1] : 0;
   if (n_sorted && 2ull * hc[4] > T && !ctx->debug_no_flip) {

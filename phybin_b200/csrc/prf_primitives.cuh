@@ -126,30 +126,34 @@ constexpr int kSortThreads = 256;
 constexpr int kSortItems = 16;  // per thread
 constexpr int kSortTile = kSortThreads * kSortItems;  // 4096: 8 warps x 16 rounds x 32 lanes
 
+template <int kBits>
 __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const uint32_t* __restrict__ keys,
                                                                   uint32_t n, int shift,
                                                                   uint32_t* __restrict__ hist,
                                                                   uint32_t tiles) {
-  __shared__ uint32_t h[256];
-  h[threadIdx.x] = 0;
+  constexpr uint32_t kBins = 1u << kBits;
+  __shared__ uint32_t h[kBins];
+  for (uint32_t d = threadIdx.x; d < kBins; d += kSortThreads) h[d] = 0;
   __syncthreads();
   const uint32_t base = blockIdx.x * kSortTile;
 #pragma unroll
   for (int k = 0; k < kSortItems; ++k) {
     uint32_t i = base + k * kSortThreads + threadIdx.x;
-    if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    if (i < n) atomicAdd(&h[(keys[i] >> shift) & (kBins - 1)], 1u);
   }
   __syncthreads();
-  hist[(uint32_t)threadIdx.x * tiles + blockIdx.x] = h[threadIdx.x];  // digit-major
+  for (uint32_t d = threadIdx.x; d < kBins; d += kSortThreads) hist[d * tiles + blockIdx.x] = h[d];  // digit-major
 }
 
+template <int kBits>
 __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t n,
     int shift, const uint32_t* __restrict__ hist_scanned, uint32_t tiles,
     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
-  __shared__ uint32_t whist[kSortThreads / 32][256];
+  constexpr uint32_t kBins = 1u << kBits;
+  __shared__ uint32_t whist[kSortThreads / 32][kBins];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < (kSortThreads / 32) * 256; i += kSortThreads) (&whist[0][0])[i] = 0;
+  for (uint32_t i = threadIdx.x; i < (kSortThreads / 32) * kBins; i += kSortThreads) (&whist[0][0])[i] = 0;
   __syncthreads();
   // warp w owns the contiguous sub-tile [base + w*512, base + (w+1)*512), 16 rounds of 32
   const uint32_t wbase = blockIdx.x * kSortTile + warp * (kSortItems * 32);
@@ -163,15 +167,15 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(
     v[r] = valid ? vals_in[i] : 0;
     uint32_t act = __ballot_sync(0xffffffffu, valid);
     if (valid) {
-      uint32_t d = (k[r] >> shift) & 255u;
+      uint32_t d = (k[r] >> shift) & (kBins - 1);
       uint32_t peers = __match_any_sync(act, d);
       if ((peers & lt) == 0) whist[warp][d] += __popc(peers);  // lowest lane of the group
     }
     __syncwarp();
   }
   __syncthreads();
-  {  // thread d: turn per-warp counts of digit d into global start offsets
-    uint32_t d = threadIdx.x;
+  // thread d: turn per-warp counts of digit d into global start offsets
+  for (uint32_t d = threadIdx.x; d < kBins; d += kSortThreads) {
     uint32_t run = hist_scanned[d * tiles + blockIdx.x];
 #pragma unroll
     for (int w = 0; w < kSortThreads / 32; ++w) {
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(
     uint32_t act = __ballot_sync(0xffffffffu, valid);
     uint32_t d = 0, peers = 0;
     if (valid) {
-      d = (k[r] >> shift) & 255u;
+      d = (k[r] >> shift) & (kBins - 1);
       peers = __match_any_sync(act, d);
       uint32_t pos = whist[warp][d] + __popc(peers & lt);
       keys_out[pos] = k[r];
@@ -200,27 +204,39 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(
   }
 }
 
-// Sorts in place (result ends in keys/vals); tmp buffers of the same size are allocated inside.
-inline int radix_sort_pairs(Ctx* ctx, uint32_t* keys, uint32_t* vals, uint32_t n, int nbits) {
-  if (n < 2 || nbits <= 0) return PRF_OK;
+template <int kBits>
+inline int radix_sort_passes(Ctx* ctx, uint32_t*& ki, uint32_t*& vi, uint32_t*& ko, uint32_t*& vo, uint32_t n, int nbits,
+                             uint32_t* hist, uint32_t tiles) {
   cudaStream_t s = ctx->stream;
-  uint32_t tiles = (n + kSortTile - 1) / kSortTile;
-  DevBuf<uint32_t> k2, v2, hist;
-  PRF_CK(ctx, k2.alloc(n, s));
-  PRF_CK(ctx, v2.alloc(n, s));
-  PRF_CK(ctx, hist.alloc((size_t)256 * tiles, s));
-  uint32_t *ki = keys, *vi = vals, *ko = k2.p, *vo = v2.p;
-  for (int shift = 0; shift < nbits; shift += 8) {
-    sort_hist_kernel<<<tiles, kSortThreads, 0, s>>>(ki, n, shift, hist.p, tiles);
+  for (int shift = 0; shift < nbits; shift += kBits) {
+    sort_hist_kernel<kBits><<<tiles, kSortThreads, 0, s>>>(ki, n, shift, hist, tiles);
     PRF_LAUNCHED(ctx);
-    int rc = exclusive_scan(ctx, LoadU32{hist.p}, (uint64_t)256 * tiles, hist.p, nullptr);
+    int rc = exclusive_scan(ctx, LoadU32{hist}, (uint64_t)(1u << kBits) * tiles, hist, nullptr);
     if (rc) return rc;
-    sort_scatter_kernel<<<tiles, kSortThreads, 0, s>>>(ki, vi, n, shift, hist.p, tiles, ko, vo);
+    sort_scatter_kernel<kBits><<<tiles, kSortThreads, 0, s>>>(ki, vi, n, shift, hist, tiles, ko, vo);
     PRF_LAUNCHED(ctx);
     uint32_t* t;
     t = ki; ki = ko; ko = t;
     t = vi; vi = vo; vo = t;
   }
+  return PRF_OK;
+}
+
+// Sorts in place (result ends in keys/vals); tmp buffers of the same size are allocated inside.
+// 8-bit digits for short keys, 10-bit digits (1024 shared-memory bins per warp) when that saves a pass.
+inline int radix_sort_pairs(Ctx* ctx, uint32_t* keys, uint32_t* vals, uint32_t n, int nbits) {
+  if (n < 2 || nbits <= 0) return PRF_OK;
+  cudaStream_t s = ctx->stream;
+  uint32_t tiles = (n + kSortTile - 1) / kSortTile;
+  const bool wide = (nbits + 9) / 10 < (nbits + 7) / 8;
+  DevBuf<uint32_t> k2, v2, hist;
+  PRF_CK(ctx, k2.alloc(n, s));
+  PRF_CK(ctx, v2.alloc(n, s));
+  PRF_CK(ctx, hist.alloc((size_t)(wide ? 1024 : 256) * tiles, s));
+  uint32_t *ki = keys, *vi = vals, *ko = k2.p, *vo = v2.p;
+  int rc = wide ? radix_sort_passes<10>(ctx, ki, vi, ko, vo, n, nbits, hist.p, tiles)
+                : radix_sort_passes<8>(ctx, ki, vi, ko, vo, n, nbits, hist.p, tiles);
+  if (rc) return rc;
   if (ki != keys) {
     PRF_CK(ctx, cudaMemcpyAsync(keys, ki, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
     PRF_CK(ctx, cudaMemcpyAsync(vals, vi, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
