@@ -187,6 +187,16 @@ PRF_API int prf_tolerant_load(prf_ctx* ctx, const uint64_t* clades, const uint64
 PRF_API int prf_tolerant_compute(prf_ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist,
                                  uint16_t* d_out, uint32_t* d_mask, prf_stats* stats);
 
+/* ---- first consumer of the matrix: flat clusters at the --editdist threshold -------------------- */
+
+/* Connected components of the graph { (a,b) : d(a,b) <= editdist } read from a threshold mask that
+ * covers the whole triangle [0, P): d_mask = a device mask written by *_compute, or NULL for the
+ * context-owned mask of the last compute.  labels (host, T entries) receives the smallest tree id of
+ * every tree's component.  Single linkage: these are the reference's flat clusters (sliceDendro,
+ * PhyBin.hs:415-422); complete linkage / UPGMA clusters are subsets of them. */
+PRF_API int prf_mask_components(prf_ctx* ctx, const uint32_t* d_mask, uint32_t T, uint32_t* labels,
+                                uint32_t* n_components);
+
 /* ---- helpers -------------------------------------------------------------------------------- */
 
 /* p(a,b) for a < b < T (see layout above); UINT64_MAX on bad arguments. */

@@ -116,6 +116,7 @@ def rf_lib():
         L.prf_hashrf_partition.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, u64p]
         L.prf_hashrf_export.argtypes = [vp, C.POINTER(prf_part)]
         L.prf_hashrf_merge.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(prf_part), st]
+        L.prf_mask_components.argtypes = [vp, vp, C.c_uint32, vp, u32p]
         L.prf_packed_index.restype = C.c_uint64
         L.prf_packed_index.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
         L.prf_shard_align.restype = C.c_uint64
@@ -136,6 +137,6 @@ def rf_lib():
 RF_SYMBOLS = [
     "prf_create", "prf_destroy", "prf_last_error", "prf_version", "prf_stream", "prf_hashrf",
     "prf_hashrf_load", "prf_hashrf_compute", "prf_hashrf_partition", "prf_hashrf_export", "prf_hashrf_merge", "prf_fetch", "prf_fetch_mask", "prf_fetch_rows",
-    "prf_tolerant", "prf_tolerant_load", "prf_tolerant_compute", "prf_packed_index",
+    "prf_tolerant", "prf_tolerant_load", "prf_tolerant_compute", "prf_mask_components", "prf_packed_index",
     "prf_shard_align", "prf_shard_range", "prf_limits", "prf_launch_count",
 ]

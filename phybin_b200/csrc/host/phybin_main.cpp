@@ -15,7 +15,6 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
-#include <numeric>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -83,11 +82,6 @@ std::string slurp(const std::string& path) {
   std::ostringstream ss;
   ss << f.rdbuf();
   return ss.str();
-}
-
-uint32_t find(std::vector<uint32_t>& p, uint32_t x) {
-  while (p[x] != x) x = p[x] = p[p[x]];
-  return x;
 }
 
 }  // namespace
@@ -162,22 +156,17 @@ int main(int argc, char** argv) {
     // flat clusters at distance <= D from the fused threshold mask.  For single linkage these ARE the
     // reference's sliceDendro clusters (PhyBin.hs:415-422); for complete/UPGMA they are the connected
     // components every such cluster is contained in.
-    std::vector<uint32_t> parent(T);
-    std::iota(parent.begin(), parent.end(), 0u);
-    uint64_t p = 0, close = 0;
-    for (uint32_t a = 0; a + 1 < T; ++a)
-      for (uint32_t b = a + 1; b < T; ++b, ++p)
-        if ((mask[p >> 5] >> (p & 31)) & 1u) {
-          ++close;
-          parent[find(parent, a)] = find(parent, b);
-        }
+    std::vector<uint32_t> label(T ? T : 1);
     uint32_t comps = 0;
-    for (uint32_t t = 0; t < T; ++t) comps += find(parent, t) == t;
+    if ((rc = prf_mask_components(ctx, nullptr, T, label.data(), &comps)))  // union-find over the mask, on the GPU
+      die(std::string("phybin_rf error: ") + prf_last_error(ctx));
+    uint64_t close = 0;
+    for (uint64_t w = 0; w < (P + 31) / 32; ++w) close += (uint64_t)__builtin_popcount(mask[w]);
     std::printf("%llu of %llu pairs within edit distance %d; %u %s at that threshold\n", (unsigned long long)close,
                 (unsigned long long)P, opt.editdist, comps,
                 opt.single ? "single-linkage clusters" : "connected components (supersets of the complete/UPGMA clusters)");
     std::ofstream cf(opt.out_dir + "/components.txt");
-    for (uint32_t t = 0; t < T; ++t) cf << t << ' ' << find(parent, t) << '\n';
+    for (uint32_t t = 0; t < T; ++t) cf << t << ' ' << label[t] << '\n';
   }
   prf_destroy(ctx);
   phb_free(forest);

@@ -12,6 +12,7 @@
 #include "prf_sparse.cuh"
 #include "prf_dense.cuh"
 #include "prf_shard.cuh"
+#include "prf_cluster.cuh"
 #include "prf_tolerant.cuh"
 
 using namespace prf;
@@ -644,6 +645,48 @@ PRF_API int prf_tolerant(prf_ctx* h, const uint64_t* clades, const uint64_t* tre
     stats->ms_total = ev_ms(ctx->ev[0], ctx->ev[7]);
     stats->gpu_launches = st.gpu_launches + st2.gpu_launches;
   }
+  return PRF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// flat clusters from the threshold mask
+// ---------------------------------------------------------------------------------------------
+
+PRF_API int prf_mask_components(prf_ctx* h, const uint32_t* d_mask, uint32_t T, uint32_t* labels, uint32_t* n_components) {
+  if (!h) return PRF_E_INVALID;
+  Ctx* ctx = &h->c;
+  ctx->err.clear();
+  if (!labels && T) return ctx->fail(PRF_E_INVALID, "labels is NULL");
+  const uint64_t P = (uint64_t)T * (T ? T - 1 : 0) / 2;
+  if (!d_mask) {
+    if (!ctx->mask_valid || ctx->mask_begin != 0 || ctx->mask_end != P)
+      return ctx->fail(PRF_E_STATE, "no context-owned mask covering the whole triangle (compute with editdist >= 0 first)");
+    d_mask = ctx->mask.p;
+  }
+  PRF_CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  DevBuf<uint32_t> parent, label, roots;
+  PRF_CK(ctx, parent.alloc(T, s));
+  PRF_CK(ctx, label.alloc(T, s));
+  PRF_CK(ctx, roots.alloc(1, s));
+  PRF_CK(ctx, cudaMemsetAsync(roots.p, 0, 4, s));
+  uint32_t hroots = 0;
+  if (T) {
+    cc_init_kernel<<<grid_for(T), 256, 0, s>>>(parent.p, T);
+    PRF_LAUNCHED(ctx);
+    const uint64_t n_words = (P + 31) / 32;
+    if (n_words) {
+      if (n_words > 0x7fffffffull * 256) return ctx->fail(PRF_E_UNSUPPORTED, "mask too large for one launch");
+      cc_hook_kernel<<<(uint32_t)((n_words + 255) / 256), 256, 0, s>>>(d_mask, n_words, 0, P, T, parent.p);
+      PRF_LAUNCHED(ctx);
+    }
+    cc_flatten_kernel<<<grid_for(T), 256, 0, s>>>(parent.p, T, label.p, roots.p);
+    PRF_LAUNCHED(ctx);
+    PRF_CK(ctx, cudaMemcpyAsync(labels, label.p, (size_t)T * 4, cudaMemcpyDeviceToHost, s));
+  }
+  PRF_CK(ctx, cudaMemcpyAsync(&hroots, roots.p, 4, cudaMemcpyDeviceToHost, s));
+  PRF_CK(ctx, cudaStreamSynchronize(s));
+  if (n_components) *n_components = hroots;
   return PRF_OK;
 }
 

@@ -195,6 +195,15 @@ class RFContext:
                                               C.byref(st) if want_stats else None))
         return st.as_dict() if want_stats else None
 
+    # ---- flat clusters --------------------------------------------------------------------------
+    def mask_components(self, d_mask: int = 0) -> Tuple[np.ndarray, int]:
+        """prf_mask_components on the context-owned mask of the last compute (or a device mask pointer):
+        (labels[T] = smallest tree id of each tree's component of {d <= editdist}, number of components)."""
+        labels = np.empty(self.T, dtype=np.uint32)
+        n = C.c_uint32(0)
+        self._ck(self._L.prf_mask_components(self._h, d_mask or None, self.T, labels.ctypes.data, C.byref(n)))
+        return labels, n.value
+
     # ---- results -----------------------------------------------------------------------------
     def fetch(self, p_begin: int = 0, p_end: Optional[int] = None) -> np.ndarray:
         p_end = self.P if p_end is None else p_end

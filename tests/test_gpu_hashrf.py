@@ -413,3 +413,56 @@ def test_sharded_build_loopback_nonuniform_and_duplicates():
     finally:
         for c in ctxs:
             c.close()
+
+
+# ---- wide bit sets (cfg4 shape: 500 taxa = 8 words) and many suffixes per row -----------------------
+
+def test_config4_shape_wide_sets_mask_vs_oracle(ctx):
+    # BASELINE config 4 family (500 taxa, W = 8, --editdist mask) at an oracle-sized T.  A row has more
+    # shared bipartitions than a walker keeps in registers, so the shared-memory cursor path runs too.
+    T, n = 600, 500
+    f = Forest.synthetic(T, n, seed=0x5EED0004)
+    assert f.words == 8
+    o = orc.Forest([f.to_newick()])
+    bips, off = f.all_bips()
+    want = oracle_packed(o, "hashrf", "closed")
+    small = orc.Forest([f.to_newick(0, 60)])
+    assert np.array_equal(small.hashrf(n, "closed"), small.hashrf(n, "literal"))
+    thr = 2 * (n - 3) - 4
+    for variant in (1, 2):
+        up, mask, st = run_variant(ctx, bips, off, variant, editdist=thr)
+        assert np.array_equal(up.astype(np.int64), want)
+        bits = np.unpackbits(mask.view(np.uint8), bitorder="little")[: len(want)].astype(bool)
+        assert np.array_equal(bits, want <= thr)
+
+
+def test_tolerant_wide_sets_vs_oracle(ctx):
+    # 300 taxa with missing taxa: W = 5 words in the tolerant kernel
+    T, n = 40, 300
+    f = Forest.synthetic(T, n, seed=0x7015, p_missing=0.08)
+    o = orc.Forest([f.to_newick()])
+    clades, off, leaf = f.raw_clades()
+    assert leaf.shape[1] == 5
+    up, _, _ = ctx.tolerant(clades, off, leaf)
+    assert np.array_equal(up.astype(np.int64), oracle_packed(o, "naive"))
+
+
+# ---- flat clusters from the fused threshold mask --------------------------------------
+
+@pytest.mark.parametrize("T,n,nni,thr", [(1200, 40, 3, 4), (700, 30, 6, 8), (300, 12, 0, 2), (5, 8, 1, 0)])
+def test_mask_components_match_host_union_find(ctx, T, n, nni, thr):
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    f = Forest.synthetic(T, n, seed=0xCC + T, family=NNI_FAMILY if nni else 0, nni_max=max(nni, 1))
+    bips, off = f.all_bips()
+    up, _, _ = run_variant(ctx, bips, off, 0, editdist=thr)
+    labels, ncomp = ctx.mask_components()
+    ii, jj = np.triu_indices(T, 1)              # row-major upper triangle == packed order
+    close = up <= thr
+    g = coo_matrix((np.ones(int(close.sum()), dtype=np.int8), (ii[close], jj[close])), shape=(T, T))
+    want_n, want = connected_components(g, directed=False)
+    assert ncomp == want_n
+    # same partition, and every label is the smallest member of its component
+    smallest = np.full(want_n, T, dtype=np.int64)
+    np.minimum.at(smallest, want, np.arange(T))
+    assert np.array_equal(labels.astype(np.int64), smallest[want])
