@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
   uint2* s_cur = reinterpret_cast<uint2*>(smem_raw + (size_t)kRowBufs * kStride * 2);  // kCurRing x kCurCap
   __shared__ TileDesc s_desc[kRowBufs];
   __shared__ Staged s_st[4];
+  __shared__ uint32_t s_end[kSlots > 8 ? kWalkers * kSlots : 1];  // list ends of the walkers' slots (kSlots > 8)
   __shared__ __align__(8) uint64_t s_full[kRowBufs], s_done[kRowBufs], s_empty[kRowBufs];
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -177,9 +178,22 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
     // Register-resident suffixes of the current row: slot u is range w + u * kWalkers.  win[u] is a
     // look-ahead window, members[cx[u] + lane] (0xffffffff past the end), loaded as soon as the cursor
     // moves -- i.e. before the next tile's `full` wait -- so its latency hides behind the barrier.
-    uint32_t cx[kSlots], ce[kSlots], win[kSlots];
+    // With more than 8 slots the list ends move to shared memory (one broadcast load per window slide)
+    // so that a slot costs two registers: rows with many shared bipartitions (500 taxa) stay off the
+    // slower shared-memory cursor path.
+    constexpr bool kEndInSmem = kSlots > 8;
+    uint32_t cx[kSlots], ce[kEndInSmem ? 1 : kSlots], win[kSlots];
+    uint32_t* my_end = &s_end[kEndInSmem ? w * kSlots : 0];
 #pragma unroll
-    for (int u = 0; u < kSlots; ++u) cx[u] = ce[u] = 0u, win[u] = 0xffffffffu;
+    for (int u = 0; u < kSlots; ++u) cx[u] = 0u, win[u] = 0xffffffffu;
+    if constexpr (!kEndInSmem) {
+#pragma unroll
+      for (int u = 0; u < kSlots; ++u) ce[u] = 0u;
+    }
+    auto slot_end = [&](int u) -> uint32_t {
+      if constexpr (kEndInSmem) return my_end[u];
+      else return ce[u];
+    };
     for (uint32_t q = 0;; ++q) {
       const uint32_t buf = q % kRowBufs;
       TICK(t_work);
@@ -199,12 +213,17 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
             const uint32_t k = w + u * kWalkers;
             const uint2 r = k < d.R ? cur[k] : make_uint2(0u, 0u);
             cx[u] = r.x;
-            ce[u] = r.y;
+            if constexpr (kEndInSmem) {
+              if (lane == 0) my_end[u] = r.y;
+            } else {
+              ce[u] = r.y;
+            }
           }
+          if constexpr (kEndInSmem) __syncwarp();
 #pragma unroll
           for (int u = 0; u < kSlots; ++u) {
             const uint32_t m = cx[u] + lane;
-            win[u] = m < ce[u] ? __ldg(members + m) : 0xffffffffu;
+            win[u] = m < slot_end(u) ? __ldg(members + m) : 0xffffffffu;
           }
         }
         bool again;
@@ -224,7 +243,7 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
               again |= full;
               if (full || !last) {  // slide the window (more of this tile, or the next tile of the row)
                 const uint32_t m = cx[u] + lane;
-                win[u] = m < ce[u] ? __ldg(members + m) : 0xffffffffu;
+                win[u] = m < slot_end(u) ? __ldg(members + m) : 0xffffffffu;
               } else {
                 win[u] = 0xffffffffu;  // consumed; the row ends here, nothing to look ahead to
               }
@@ -650,6 +669,7 @@ static int launch_sparse_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t e
   constexpr int kThreads = 32 * (kWalkers + 2);
   constexpr size_t smem = (size_t)kRowBufs * (kTile + 8) * 2 + (size_t)(kRowBufs + 2) * kCurCap * sizeof(uint2);
   auto kern = sparse_rows_kernel<kTile, kWalkers, kCurCap, kSlots, kRowBufs>;
+  PRF_CK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per instantiation
   RowPlan& plan = ctx->plan;
   if (!plan.valid || plan.T != H.T || plan.p_begin != p_begin || plan.p_end != p_end || plan.tile != kTile) {
     plan.valid = false;
@@ -665,7 +685,6 @@ static int launch_sparse_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t e
     plan.p_begin = p_begin;
     plan.p_end = p_end;
     plan.tile = kTile;
-    PRF_CK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
     PRF_CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem));
     plan.ctas_per_sm = nb > 0 ? nb : 1;
@@ -719,6 +738,9 @@ static int launch_sparse(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t edi
   if (cfg == 1) return launch_sparse_t<12288, 14, 288, 8, 4>(ctx, p_begin, p_end, editdist, d_out, d_mask);
   if (cfg == 2) return launch_sparse_t<8192, 14, 256, 8, 6>(ctx, p_begin, p_end, editdist, d_out, d_mask);
   if (cfg == 3) return launch_sparse_t<16384, 14, 256, 8, 3>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  // rows with more shared bipartitions than 14 walkers x 8 register slots: 12 slots, list ends in shared memory
+  if (cfg == 4 || (cfg == 0 && ctx->h.stats.max_bips > 14 * 8 + 16))
+    return launch_sparse_t<16384, 14, 320, 12, 3>(ctx, p_begin, p_end, editdist, d_out, d_mask);
   return launch_sparse_t<16384, 14, 320, 8, 3>(ctx, p_begin, p_end, editdist, d_out, d_mask);
 }
 
