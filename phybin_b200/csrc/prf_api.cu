@@ -460,7 +460,7 @@ PRF_API int prf_hashrf_merge(prf_ctx* h, uint32_t T, uint32_t W, uint32_t world,
   PRF_CK(ctx, cudaEventRecord(ctx->ev[2], s));
   // build into fresh buffers: a part may alias the context's current structure
   DevBuf<uint16_t> nb;
-  DevBuf<uint32_t> roff, members, lid, nb32, cnt, mm;
+  DevBuf<uint32_t> roff, members, lid, nb32, cnt, mm;  // mm: min |B|, max |B|, max ranges per tree
   DevBuf<uint2> ranges;
   PRF_CK(ctx, nb.alloc((size_t)T + 16, s));
   PRF_CK(ctx, cudaMemsetAsync(nb.p, 0, nb.bytes(), s));
@@ -470,9 +470,9 @@ PRF_API int prf_hashrf_merge(prf_ctx* h, uint32_t T, uint32_t W, uint32_t world,
   PRF_CK(ctx, ranges.alloc(n_ranges, s));
   PRF_CK(ctx, nb32.alloc((size_t)T + 1, s));
   PRF_CK(ctx, cnt.alloc((size_t)T + 1, s));
-  PRF_CK(ctx, mm.alloc(2, s));
-  const uint32_t mm_init[2] = {0xffffffffu, 0u};
-  PRF_CK(ctx, cudaMemcpyAsync(mm.p, mm_init, 8, cudaMemcpyHostToDevice, s));
+  PRF_CK(ctx, mm.alloc(3, s));
+  const uint32_t mm_init[3] = {0xffffffffu, 0u, 0u};
+  PRF_CK(ctx, cudaMemcpyAsync(mm.p, mm_init, 12, cudaMemcpyHostToDevice, s));
   merge_count_kernel<<<grid_for((uint64_t)T + 1), 256, 0, s>>>(P, T, nb32.p, cnt.p);
   PRF_LAUNCHED(ctx);
   int rc = exclusive_scan(ctx, LoadU32{cnt.p}, (uint64_t)T + 1, roff.p, nullptr);
@@ -480,7 +480,7 @@ PRF_API int prf_hashrf_merge(prf_ctx* h, uint32_t T, uint32_t W, uint32_t world,
   if (T) {
     merge_ranges_kernel<<<grid_for((uint64_t)world * T), 256, 0, s>>>(P, T, roff.p, ranges.p);
     PRF_LAUNCHED(ctx);
-    finish_nb_kernel<<<grid_for(T), 256, 0, s>>>(nb32.p, T, nb.p, mm.p);
+    finish_nb_kernel<<<grid_for(T), 256, 0, s>>>(nb32.p, T, nb.p, mm.p, roff.p);
     PRF_LAUNCHED(ctx);
   }
   for (uint32_t r = 0; r < world; ++r)
@@ -488,8 +488,8 @@ PRF_API int prf_hashrf_merge(prf_ctx* h, uint32_t T, uint32_t W, uint32_t world,
       merge_members_kernel<<<grid_for(P.n_members[r]), 256, 0, s>>>(P, r, members.p, lid.p);
       PRF_LAUNCHED(ctx);
     }
-  uint32_t hmm[2] = {0, 0};
-  PRF_CK(ctx, cudaMemcpyAsync(hmm, mm.p, 8, cudaMemcpyDeviceToHost, s));
+  uint32_t hmm[3] = {0, 0, 0};
+  PRF_CK(ctx, cudaMemcpyAsync(hmm, mm.p, 12, cudaMemcpyDeviceToHost, s));
   PRF_CK(ctx, cudaEventRecord(ctx->ev[3], s));
   PRF_CK(ctx, cudaStreamSynchronize(s));
   if (T == 0) hmm[0] = hmm[1] = 0;
@@ -512,6 +512,7 @@ PRF_API int prf_hashrf_merge(prf_ctx* h, uint32_t T, uint32_t W, uint32_t world,
   H.n_shared = (uint32_t)n_lists;
   H.n_shared_nnz = n_members;
   H.n_ranges = n_ranges;
+  H.max_ranges = hmm[2];
   prf_stats& st = H.stats;
   st = prf_stats{};
   st.n_trees = T;
@@ -693,6 +694,12 @@ PRF_API int prf_mask_components(prf_ctx* h, const uint32_t* d_mask, uint32_t T, 
 // ---------------------------------------------------------------------------------------------
 // Debug entry points for tests of the primitives (not part of phybin_rf.h).
 // ---------------------------------------------------------------------------------------------
+
+PRF_API int prf_debug_wide_slots(prf_ctx* h, int on) {
+  if (!h) return PRF_E_INVALID;
+  h->c.debug_wide_slots = on != 0;
+  return PRF_OK;
+}
 
 PRF_API int prf_debug_no_flip(prf_ctx* h, int on) {
   if (!h) return PRF_E_INVALID;

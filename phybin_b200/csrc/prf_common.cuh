@@ -65,6 +65,7 @@ struct HashRFState {
   uint32_t n_shared = 0;
   uint64_t n_shared_nnz = 0;
   uint64_t n_ranges = 0;         // roff[T]
+  uint32_t max_ranges = 0;       // most suffix ranges of one tree
   uint32_t n_flipped = 0;        // bipartitions held by > T/2 trees, stored as the list of trees lacking them
   DevBuf<uint32_t> lid;          // [n_shared_nnz] dense id (0..n_shared-1) of the list each member entry belongs to
   // dense variant: tiled uint8 operand, built lazily by the first dense compute (prf_dense.cuh)
@@ -114,6 +115,7 @@ struct Ctx {
   RowPlan plan;
   bool debug_small_tiles = false;
   bool debug_no_flip = false;         // tests: keep majority lists as they are
+  bool debug_wide_slots = false;      // tests: force the 8-byte-slot dedup table
   DevBuf<unsigned long long> timing;  // PRF_TIMING builds only
   uint32_t timing_grid = 0;
   // ctx-owned result of the last compute

@@ -83,6 +83,63 @@ __global__ void __launch_bounds__(256) dedup_insert_kernel(const uint64_t* __res
   if (lane_id() == 0 && claims) atomicAdd(&counters[0], (unsigned long long)claims);
 }
 
+// Compact variant for nnz < 2^25 - 1 entries: 4-byte slots ( tag:7 | representative entry + 1 : 25, 0 = free )
+// and a table of 1.25 * nnz slots addressed by multiply-shift instead of a power-of-two mask.  At the
+// headline shape the table is 98 MB instead of 268 MB: it stays in the 126 MB L2 (the key stream is
+// loaded with an evict-first policy), so the random probes and CAS are L2 hits instead of DRAM sectors.
+template <int W>
+__global__ void __launch_bounds__(256) dedup_insert32_kernel(const uint64_t* __restrict__ bips,
+                                                             const uint64_t* __restrict__ tree_off, uint32_t T,
+                                                             uint32_t* slots, uint32_t* shared_bits, uint32_t cap,
+                                                             uint32_t* __restrict__ ent_slot,
+                                                             unsigned long long* counters) {
+  const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  const uint64_t e0 = tree_off[t], e1 = tree_off[t + 1];
+  uint32_t claims = 0;
+  for (uint64_t e = e0 + lane_id(); e < e1; e += 32) {
+    uint64_t k[W];
+    {
+      const uint64_t* p = bips + e * W;
+#pragma unroll
+      for (int w = 0; w < W; ++w)
+        asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(k[w]) : "l"(p + w), "l"(policy));
+    }
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+#pragma unroll
+    for (int w = 0; w < W; ++w) h = mix64(h ^ (k[w] + 0x632BE59BD9B4E019ull * (w + 1)));
+    const uint32_t tag = (uint32_t)(h >> 57);  // 7 bits, independent of the slot bits below
+    const uint32_t mine = (tag << 25) | ((uint32_t)e + 1u);
+    uint32_t s = (uint32_t)(((h & 0xffffffffull) * (uint64_t)cap) >> 32);
+    for (;;) {
+      uint32_t cur = slots[s];
+      if (cur == 0u) {
+        cur = atomicCAS(&slots[s], 0u, mine);
+        if (cur == 0u) { ++claims; break; }  // claimed: this entry is the representative
+      }
+      if ((cur >> 25) == tag) {  // same tag: decide on the full key
+        uint64_t r[W];
+        load_key<W>(bips, (cur & 0x1ffffffu) - 1u, r);
+        bool eq = true;
+#pragma unroll
+        for (int w = 0; w < W; ++w) eq &= (r[w] == k[w]);
+        if (eq) {
+          const uint32_t bit = 1u << (s & 31);
+          if (!(shared_bits[s >> 5] & bit)) atomicOr(&shared_bits[s >> 5], bit);
+          break;
+        }
+      }
+      s = s + 1 == cap ? 0u : s + 1;
+    }
+    ent_slot[e] = s;
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) claims += __shfl_xor_sync(0xffffffffu, claims, d);
+  if (lane_id() == 0 && claims) atomicAdd(&counters[0], (unsigned long long)claims);
+}
+
 // Per tree: number of entries whose bipartition is shared; also |B_t| before duplicate removal.
 __global__ void __launch_bounds__(256) count_shared_kernel(const uint64_t* __restrict__ tree_off, uint32_t T,
                                                            const uint32_t* __restrict__ ent_slot,
@@ -314,19 +371,24 @@ __global__ void __launch_bounds__(256) drop_dups_kernel(const uint32_t* __restri
 }
 
 // nb32 -> uint16 + min/max.  mm[0] = min, mm[1] = max.
+// Also mm[2] = most suffix ranges of one tree (roff is the exclusive scan of the per-tree counts).
 __global__ void __launch_bounds__(256) finish_nb_kernel(const uint32_t* __restrict__ nb32, uint32_t T,
-                                                        uint16_t* __restrict__ nb16, uint32_t* mm) {
+                                                        uint16_t* __restrict__ nb16, uint32_t* mm,
+                                                        const uint32_t* __restrict__ roff) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t v = t < T ? nb32[t] : 0, lo = t < T ? v : 0xffffffffu, hi = v;
+  uint32_t rmax = t < T ? roff[t + 1] - roff[t] : 0;
   if (t < T) nb16[t] = (uint16_t)(v > 0xffffu ? 0xffffu : v);
 #pragma unroll
   for (int d = 16; d; d >>= 1) {
     lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
     hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    rmax = max(rmax, __shfl_xor_sync(0xffffffffu, rmax, d));
   }
   if (lane_id() == 0) {
     atomicMin(&mm[0], lo);
     atomicMax(&mm[1], hi);
+    atomicMax(&mm[2], rmax);
   }
 }
 
@@ -357,12 +419,20 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
   H.nnz = nnz;
   H.P = (uint64_t)T * (T ? T - 1 : 0) / 2;
 
+  // compact 4-byte slots whenever the entry index fits 25 bits (see dedup_insert32_kernel)
+  const bool compact = nnz < (1ull << 25) - 1 && !ctx->debug_wide_slots;
   uint64_t cap = 1024;
-  while (cap < nnz + nnz / 2) cap <<= 1;  // load factor <= 2/3 even if every key is distinct
+  if (compact) {
+    cap = std::max<uint64_t>(1024, (nnz + nnz / 4 + 31) / 32 * 32);  // load factor <= 0.8, multiple of the bitmap word
+  } else {
+    while (cap < nnz + nnz / 2) cap <<= 1;  // load factor <= 2/3 even if every key is distinct
+  }
 
   DevBuf<unsigned long long> slots, counters;
+  DevBuf<uint32_t> slots32;
   DevBuf<uint32_t> shared_bits, ent_slot, nb32, sc, soff, scalars;
-  PRF_CK(ctx, slots.alloc(cap, s));
+  if (compact) PRF_CK(ctx, slots32.alloc(cap, s));
+  else PRF_CK(ctx, slots.alloc(cap, s));
   PRF_CK(ctx, shared_bits.alloc(cap / 32, s));
   PRF_CK(ctx, ent_slot.alloc(nnz, s));
   PRF_CK(ctx, nb32.alloc((size_t)T + 1, s));
@@ -373,7 +443,8 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
   PRF_CK(ctx, cudaMemsetAsync(shared_bits.p, 0, shared_bits.bytes(), s));
   PRF_CK(ctx, cudaMemsetAsync(counters.p, 0, counters.bytes(), s));
   PRF_CK(ctx, cudaMemsetAsync(sc.p, 0, sc.bytes(), s));
-  PRF_CK(ctx, cudaMemsetAsync(slots.p, 0xff, slots.bytes(), s));
+  if (compact) PRF_CK(ctx, cudaMemsetAsync(slots32.p, 0, slots32.bytes(), s));
+  else PRF_CK(ctx, cudaMemsetAsync(slots.p, 0xff, slots.bytes(), s));
   uint32_t mm_init[8] = {0, 0, 0, 0, 0xffffffffu, 0u, 0, 0};
   PRF_CK(ctx, cudaMemcpyAsync(scalars.p, mm_init, sizeof mm_init, cudaMemcpyHostToDevice, s));
 
@@ -382,7 +453,14 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
   // ---- K1: dedup ----
   if (T) {
     switch (W) {
-#define PRF_W_CASE(w) case w: launch_dedup<w>(ctx, d_bips, d_off, T, slots.p, shared_bits.p, cap - 1, ent_slot.p, counters.p); break;
+#define PRF_W_CASE(w)                                                                                                  \
+  case w:                                                                                                              \
+    if (compact)                                                                                                       \
+      dedup_insert32_kernel<w><<<(T + 7) / 8, 256, 0, s>>>(d_bips, d_off, T, slots32.p, shared_bits.p, (uint32_t)cap,   \
+                                                           ent_slot.p, counters.p);                                    \
+    else                                                                                                               \
+      launch_dedup<w>(ctx, d_bips, d_off, T, slots.p, shared_bits.p, cap - 1, ent_slot.p, counters.p);                 \
+    break;
       PRF_W_CASE(1) PRF_W_CASE(2) PRF_W_CASE(3) PRF_W_CASE(4) PRF_W_CASE(5) PRF_W_CASE(6) PRF_W_CASE(7)
       PRF_W_CASE(8) PRF_W_CASE(9) PRF_W_CASE(10) PRF_W_CASE(11) PRF_W_CASE(12) PRF_W_CASE(13)
       PRF_W_CASE(14) PRF_W_CASE(15) PRF_W_CASE(16)
@@ -464,7 +542,7 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
       PRF_LAUNCHED(ctx);
     }
     if (T) {
-      finish_nb_kernel<<<grid_for(T), 256, 0, s>>>(nb32.p, T, H.nb.p, scalars.p + 4);
+      finish_nb_kernel<<<grid_for(T), 256, 0, s>>>(nb32.p, T, H.nb.p, scalars.p + 4, H.roff.p);
       PRF_LAUNCHED(ctx);
     }
     PRF_CK(ctx, cudaMemcpyAsync(hc, counters.p, sizeof hc, cudaMemcpyDeviceToHost, s));
@@ -488,8 +566,8 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
     H.members = std::move(mem2);
     ids_are_keys = false;
     n_sorted -= (uint32_t)hc[2];
-    uint32_t mm_reset[2] = {0xffffffffu, 0u};
-    PRF_CK(ctx, cudaMemcpyAsync(scalars.p + 4, mm_reset, 8, cudaMemcpyHostToDevice, s));
+    uint32_t mm_reset[3] = {0xffffffffu, 0u, 0u};
+    PRF_CK(ctx, cudaMemcpyAsync(scalars.p + 4, mm_reset, 12, cudaMemcpyHostToDevice, s));
   }
   if (ids_are_keys) H.lid = std::move(slot_sorted);
   // ---- majority flip (only when some bipartition is held by more than half of the trees) ----
@@ -521,8 +599,8 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
     PRF_CK(ctx, cudaMemsetAsync(rcount.p, 0, rcount.bytes(), s));
     PRF_CK(ctx, cudaMemsetAsync(cursor.p, 0, cursor.bytes(), s));
     PRF_CK(ctx, cudaMemsetAsync(counters.p + 3, 0, 16, s));
-    const uint32_t mm_reset[2] = {0xffffffffu, 0u};
-    PRF_CK(ctx, cudaMemcpyAsync(scalars.p + 4, mm_reset, 8, cudaMemcpyHostToDevice, s));
+    const uint32_t mm_reset[3] = {0xffffffffu, 0u, 0u};
+    PRF_CK(ctx, cudaMemcpyAsync(scalars.p + 4, mm_reset, 12, cudaMemcpyHostToDevice, s));
     if (n_sorted) {
       range_count_kernel<<<grid_for(n_sorted), 256, 0, s>>>(H.lid.p, H.members.p, head2.p, n_sorted, rcount.p, counters.p);
       PRF_LAUNCHED(ctx);
@@ -533,7 +611,7 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
                                                            H.ranges.p);
       PRF_LAUNCHED(ctx);
     }
-    finish_nb_kernel<<<grid_for(T), 256, 0, s>>>(nb32.p, T, H.nb.p, scalars.p + 4);
+    finish_nb_kernel<<<grid_for(T), 256, 0, s>>>(nb32.p, T, H.nb.p, scalars.p + 4, H.roff.p);
     PRF_LAUNCHED(ctx);
     unsigned long long hc2[6];
     PRF_CK(ctx, cudaMemcpyAsync(hc2, counters.p, sizeof hc2, cudaMemcpyDeviceToHost, s));
@@ -554,6 +632,7 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
   H.n_shared = n_lists;
   H.n_shared_nnz = n_sorted;  // after duplicate removal
   H.n_ranges = h_nranges;
+  H.max_ranges = hs[6];
 
   prf_stats& st = H.stats;
   st = prf_stats{};

@@ -706,11 +706,11 @@ static int launch_sparse_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t e
   prm.mask = d_mask;
   prm.items = plan.items.p;
   prm.n_items = plan.n_items;
-  if (H.stats.max_bips > (uint32_t)kCurCap) {
-    const size_t need = (size_t)grid * (kRowBufs + 2) * H.stats.max_bips;
+  if (H.max_ranges > (uint32_t)kCurCap) {
+    const size_t need = (size_t)grid * (kRowBufs + 2) * H.max_ranges;
     if (plan.cursor_ws.n < need) PRF_CK(ctx, plan.cursor_ws.alloc(need, s));
     prm.cursor_ws = plan.cursor_ws.p;
-    prm.cursor_ws_stride = H.stats.max_bips;
+    prm.cursor_ws_stride = H.max_ranges;
   }
   {
     const char* e = getenv("PRF_DEBUG_NOWALK");
@@ -738,8 +738,8 @@ static int launch_sparse(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t edi
   if (cfg == 1) return launch_sparse_t<12288, 14, 288, 8, 4>(ctx, p_begin, p_end, editdist, d_out, d_mask);
   if (cfg == 2) return launch_sparse_t<8192, 14, 256, 8, 6>(ctx, p_begin, p_end, editdist, d_out, d_mask);
   if (cfg == 3) return launch_sparse_t<16384, 14, 256, 8, 3>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-  // rows with more shared bipartitions than 14 walkers x 8 register slots: 12 slots, list ends in shared memory
-  if (cfg == 4 || (cfg == 0 && ctx->h.stats.max_bips > 14 * 8 + 16))
+  // trees with clearly more suffix ranges than 14 walkers x 8 register slots: 12 slots, list ends in shared memory
+  if (cfg == 4 || (cfg == 0 && ctx->h.max_ranges > 14 * 8 + 16))
     return launch_sparse_t<16384, 14, 320, 12, 3>(ctx, p_begin, p_end, editdist, d_out, d_mask);
   return launch_sparse_t<16384, 14, 320, 8, 3>(ctx, p_begin, p_end, editdist, d_out, d_mask);
 }

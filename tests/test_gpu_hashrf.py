@@ -466,3 +466,19 @@ def test_mask_components_match_host_union_find(ctx, T, n, nni, thr):
     smallest = np.full(want_n, T, dtype=np.int64)
     np.minimum.at(smallest, want, np.arange(T))
     assert np.array_equal(labels.astype(np.int64), smallest[want])
+
+
+def test_dedup_table_variants_agree(ctx):
+    # the compact 4-byte-slot table (default below 2^25 entries) and the 8-byte-slot table give the same matrix
+    f = Forest.synthetic(800, 70, seed=0xDED)
+    o = orc.Forest([f.to_newick()])
+    want = oracle_packed(o, "hashrf", "literal")
+    bips, off = f.all_bips()
+    a, _, st_a = run_variant(ctx, bips, off, 1)
+    ctx._ck(ctx._L.prf_debug_wide_slots(ctx._h, 1))
+    try:
+        b, _, st_b = run_variant(ctx, bips, off, 1)
+    finally:
+        ctx._ck(ctx._L.prf_debug_wide_slots(ctx._h, 0))
+    assert np.array_equal(a.astype(np.int64), want) and np.array_equal(a, b)
+    assert st_a["n_unique"] == st_b["n_unique"] and st_a["n_hits"] == st_b["n_hits"]
