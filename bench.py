@@ -241,6 +241,9 @@ def run_gpu(args, wl, wl_name):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    for _ in range(2):   # setup, not warm-up: lets the stream-ordered memory pool reach its steady size
+        step()
+    barrier()
     for _ in range(args.warmup):
         st = step()
     barrier()

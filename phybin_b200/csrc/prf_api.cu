@@ -527,6 +527,7 @@ PRF_API int prf_hashrf_merge(prf_ctx* h, uint32_t T, uint32_t W, uint32_t world,
   st.min_bips = hmm[0];
   st.ms_incidence = ev_ms(ctx->ev[2], ctx->ev[3]);
   st.gpu_launches = (int32_t)(ctx->launches - launches0);
+  if ((rc = build_nb_shift(ctx))) return rc;
   H.loaded = true;
   ctx->tol.loaded = false;
   ctx->out_valid = ctx->mask_valid = false;

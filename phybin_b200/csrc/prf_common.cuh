@@ -58,6 +58,9 @@ struct HashRFState {
   bool uniform_nb = false;       // every tree has the same |B|
   uint32_t nb_uniform = 0;
   DevBuf<uint16_t> nb;           // [T]   |B_t| (distinct bipartitions)
+  DevBuf<uint16_t> nb_shift;     // 8 copies of nb shifted by 0..7 entries (only when |B_t| is not uniform): any run
+                                 // nb[c..] is then a 16-byte aligned bulk copy away from a 16-byte aligned tile
+  uint32_t nb_shift_stride = 0;
   DevBuf<uint32_t> roff;         // [T+1] per-tree offsets into `ranges`
   DevBuf<uint2> ranges;          // member-list suffixes (begin, end) into `members`, tree-major
   DevBuf<uint32_t> members;      // inverted lists of the shared bipartitions, ascending tree ids

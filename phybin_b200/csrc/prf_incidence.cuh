@@ -392,6 +392,15 @@ __global__ void __launch_bounds__(256) finish_nb_kernel(const uint32_t* __restri
   }
 }
 
+// nb_shift[k * stride + j] = nb[j + k] (0 past the end), k = 0..7
+__global__ void __launch_bounds__(256) nb_shift_kernel(const uint16_t* __restrict__ nb, uint32_t T, uint32_t stride,
+                                                       uint16_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 8 * stride) return;
+  const uint32_t k = i / stride, j = i - k * stride;
+  out[i] = j + k < T ? nb[j + k] : (uint16_t)0;
+}
+
 template <int W>
 static void launch_dedup(Ctx* ctx, const uint64_t* bips, const uint64_t* off, uint32_t T,
                          unsigned long long* slots, uint32_t* shared_bits, uint64_t cap_mask,
@@ -401,6 +410,18 @@ static void launch_dedup(Ctx* ctx, const uint64_t* bips, const uint64_t* off, ui
 }
 
 static inline uint32_t grid_for(uint64_t n, uint32_t tpb = 256) { return (uint32_t)((n + tpb - 1) / tpb); }
+
+// The shifted copies of |B_t| the sparse kernel's producer bulk-loads (non-uniform |B_t| only).
+static int build_nb_shift(Ctx* ctx) {
+  HashRFState& H = ctx->h;
+  if (H.uniform_nb || H.T == 0) return PRF_OK;
+  const uint32_t stride = (H.T + 16 + 7) / 8 * 8 + 8;
+  PRF_CK(ctx, H.nb_shift.alloc((size_t)8 * stride, ctx->stream));
+  nb_shift_kernel<<<(8 * stride + 255) / 256, 256, 0, ctx->stream>>>(H.nb.p, H.T, stride, H.nb_shift.p);
+  PRF_LAUNCHED(ctx);
+  H.nb_shift_stride = stride;
+  return PRF_OK;
+}
 
 static inline int bits_for(uint64_t n_values) {  // bits needed to represent 0..n_values-1
   int b = 0;
@@ -647,6 +668,7 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
   st.max_bips = mm[1];
   st.min_bips = mm[0];
   st.n_flipped = H.n_flipped;
+  if ((rc = build_nb_shift(ctx))) return rc;
   H.loaded = true;
   return PRF_OK;
 }

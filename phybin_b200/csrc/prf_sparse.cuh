@@ -74,6 +74,8 @@ struct RowParams {
   uint32_t T;
   uint64_t p_begin;
   const uint16_t* nb;
+  const uint16_t* nb_shift;   // 8 shifted copies of nb (non-uniform |B_t|), see HashRFState
+  uint32_t nb_shift_stride;
   int uniform_nb;
   uint32_t nb_uniform;
   const uint32_t* roff;
@@ -150,6 +152,7 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
   uint2* s_cur = reinterpret_cast<uint2*>(smem_raw + (size_t)kRowBufs * kStride * 2);  // kCurRing x kCurCap
   __shared__ TileDesc s_desc[kRowBufs];
   __shared__ Staged s_st[4];
+  __shared__ __align__(8) uint64_t s_fill;  // completion of the producer's bulk load of |B| (non-uniform rows)
   __shared__ uint32_t s_end[kSlots > 8 ? kWalkers * kSlots : 1];  // list ends of the walkers' slots (kSlots > 8)
   __shared__ __align__(8) uint64_t s_full[kRowBufs], s_done[kRowBufs], s_empty[kRowBufs];
 
@@ -163,6 +166,8 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
       mbar_init(&s_done[b], kWalkers);
       mbar_init(&s_empty[b], 1);
     }
+    mbar_init(&s_fill, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
@@ -328,7 +333,9 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
   const uint4 q4 = make_uint4(vv, vv, vv, vv);
 
   // d = |B_a| + |B_b| for packed positions [p_lo, p_hi) of row a starting at column c_lo; entry 0 = P0
-  auto fill_row = [&](uint16_t* tile, uint32_t a, uint32_t c_lo, uint64_t p_lo, uint64_t p_hi, uint64_t P0) {
+  uint32_t fill_phase = 0;
+  auto fill_row = [&](uint16_t* tile, uint32_t a, uint32_t c_lo, uint64_t p_lo, uint64_t p_hi, uint64_t P0,
+                      bool bulk_ok = false) {
     if (prm.uniform_nb) {
       // the whole buffer, unconditionally: kTile/256 stores with immediate offsets
       uint4* t4 = reinterpret_cast<uint4*>(tile) + lane;
@@ -336,26 +343,67 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
       for (int i = 0; i < kTile / 256; ++i) t4[32 * i] = q4;
       if (lane == 0) t4[kTile / 8] = q4;
     } else {
-      // tile entries [o, o + cnt) <- na + nb[c_lo ..).  One aligned 16-byte group of the tile per lane and
-      // iteration: 5 aligned 32-bit loads of nb (its element offset is arbitrary), funnel-shifted into
-      // place, two entries per SIMD add.
       const uint32_t na = prm.nb[a];
       const uint32_t na2 = na | (na << 16);
       const uint32_t cnt = (uint32_t)(p_hi - p_lo), o = (uint32_t)(p_lo - P0);
-      const uint32_t* nb32 = reinterpret_cast<const uint32_t*>(prm.nb);  // nb is allocated with 16 entries of slack
       uint4* t4 = reinterpret_cast<uint4*>(tile);
+      if (bulk_ok && c_lo >= o) {
+        // the run nb[c_lo - o ..) lands on tile entry 0: pick the copy of nb whose shift makes the source
+        // 16-byte aligned and let the bulk-copy engine bring it in, then add |B_a| two entries at a time.
+        // (Entries of the first/last group outside [o, o + cnt) get values that are never stored.)
+        const uint32_t d0 = c_lo - o, k = d0 & 7u, groups = (o + cnt + 7) >> 3;
+        const uint16_t* src = prm.nb_shift + (size_t)k * prm.nb_shift_stride + (d0 - k);
+        if (lane == 0) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&s_fill)), "r"(groups * 16u)
+                       : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           smem_addr(tile)),
+                       "l"(src), "r"(groups * 16u), "r"(smem_addr(&s_fill))
+                       : "memory");
+        }
+        mbar_wait(&s_fill, fill_phase);
+        fill_phase ^= 1u;
+#pragma unroll 4
+        for (uint32_t g = lane; g < groups; g += 32) {
+          uint4 v = t4[g];
+          v.x = __vadd2(v.x, na2);
+          v.y = __vadd2(v.y, na2);
+          v.z = __vadd2(v.z, na2);
+          v.w = __vadd2(v.w, na2);
+          t4[g] = v;
+        }
+        return;
+      }
+      // generic path (group tiles, the first rows): one aligned 16-byte group of the tile per lane:
+      // 5 aligned 32-bit loads of nb (its element offset is arbitrary), funnel-shifted into place.
+      const uint32_t* nb32 = reinterpret_cast<const uint32_t*>(prm.nb);  // nb is allocated with 16 entries of slack
       const uint32_t g_lo = (o + 7) >> 3, g_hi = (o + cnt) >> 3;  // fully covered groups [g_lo, g_hi)
-      for (uint32_t g = g_lo + lane; g < g_hi; g += 32) {
-        const uint32_t src = c_lo + 8 * g - o;  // nb index of the group's first entry
-        const uint32_t* wp = nb32 + (src >> 1);
-        const uint32_t sh = (src & 1u) * 16u;
-        const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3), w4 = __ldg(wp + 4);
-        uint4 v;
-        v.x = __vadd2(__funnelshift_r(w0, w1, sh), na2);
-        v.y = __vadd2(__funnelshift_r(w1, w2, sh), na2);
-        v.z = __vadd2(__funnelshift_r(w2, w3, sh), na2);
-        v.w = __vadd2(__funnelshift_r(w3, w4, sh), na2);
-        t4[g] = v;
+      // four groups per lane and round: 20 independent loads in flight (one warp fills the whole tile, so
+      // a load-use round trip per group would make the producer the bottleneck)
+      constexpr int kU = 4;
+      for (uint32_t gb = g_lo + lane; gb < g_hi; gb += 32 * kU) {
+        uint32_t wv[kU][5];
+#pragma unroll
+        for (int j = 0; j < kU; ++j) {
+          const uint32_t g = gb + 32 * j;
+          const uint32_t src = c_lo + 8 * g - o;  // nb index of the group's first entry
+          const uint32_t* wp = nb32 + (src >> 1);
+#pragma unroll
+          for (int i = 0; i < 5; ++i) wv[j][i] = g < g_hi ? __ldg(wp + i) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < kU; ++j) {
+          const uint32_t g = gb + 32 * j;
+          if (g < g_hi) {
+            const uint32_t sh = ((c_lo + 8 * g - o) & 1u) * 16u;
+            uint4 v;
+            v.x = __vadd2(__funnelshift_r(wv[j][0], wv[j][1], sh), na2);
+            v.y = __vadd2(__funnelshift_r(wv[j][1], wv[j][2], sh), na2);
+            v.z = __vadd2(__funnelshift_r(wv[j][2], wv[j][3], sh), na2);
+            v.w = __vadd2(__funnelshift_r(wv[j][3], wv[j][4], sh), na2);
+            t4[g] = v;
+          }
+        }
       }
       // the < 8 entries before the first / after the last full group (adjacent rows of a group tile own the rest)
       const uint32_t head_end = min(8 * g_lo, o + cnt), tail_beg = max(8 * g_hi, head_end);
@@ -491,7 +539,7 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
         }
         const uint32_t c_lo = cb + seg * kTile, c_hi = min(ce, c_lo + (uint32_t)kTile);
         const uint64_t p_lo = row_start(a, T) + (c_lo - a - 1), p_hi = p_lo + (c_hi - c_lo), P0 = p_lo & ~7ull;
-        fill_row(tile, a, c_lo, p_lo, p_hi, P0);
+        fill_row(tile, a, c_lo, p_lo, p_hi, P0, prm.nb_shift != nullptr);
         if (lane == 0) {
           d->kind = kTileRow;
           d->a0 = a;
@@ -696,6 +744,8 @@ static int launch_sparse_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t e
   prm.T = H.T;
   prm.p_begin = p_begin;
   prm.nb = H.nb.p;
+  prm.nb_shift = H.nb_shift.p;
+  prm.nb_shift_stride = H.nb_shift_stride;
   prm.uniform_nb = H.uniform_nb ? 1 : 0;
   prm.nb_uniform = H.nb_uniform;
   prm.roff = H.roff.p;

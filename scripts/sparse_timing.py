@@ -8,7 +8,7 @@ build.RF_SO = os.path.join(build.LIBDIR, "libphybin_rf_timing.so")
 from phybin_b200.host import Forest
 from phybin_b200.rfdistance import RFContext
 T, n = (int(sys.argv[1]) if len(sys.argv) > 1 else 100000), 200
-f = Forest.synthetic(T, n, 0x5EED0003)
+f = Forest.synthetic(T, n, 0x5EED0003, int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 bips, off = f.all_bips()
 ctx = RFContext(0)
 L = ctx._L
