@@ -281,18 +281,30 @@ def run_gpu(args, wl, wl_name):
     step_s = max(dev_s, wall) / args.steps
     value = P / step_s
 
-    # ---- light self-check on the resident result (not timed): sampled pairs vs direct set intersection
-    if mode == "hashrf" and rank == 0 and not os.environ.get("PRF_DEBUG_NOWALK"):
-        rng = np.random.default_rng(1)
-        out_h = d_out[: min(p_end - p_begin, 1 << 20)].cpu().numpy().view(np.uint16)
-        pos = rng.integers(0, len(out_h), size=64)
-        for p in pos:
+    # ---- self-check on the resident result (not timed) --------------------------------------------------
+    # (1) 256 pairs sampled over this rank's whole slice against a direct set symmetric difference;
+    # (2) the checksum identity  sum d = (T-1) * sum_t |B_t| - 2 * sum_lists m(m-1)/2  at N = 1 (when no
+    #     majority flip re-centred the sets: n_hits then counts exactly the shared incidences).
+    selfcheck = None
+    if mode == "hashrf" and not os.environ.get("PRF_DEBUG_NOWALK"):
+        rng = np.random.default_rng(1 + rank)
+        n_slice = p_end - p_begin
+        pos = np.sort(rng.integers(0, n_slice, size=256)) if n_slice else np.zeros(0, dtype=np.int64)
+        vals = d_out[torch.from_numpy(pos).to(dev)].cpu().numpy().view(np.uint16) if n_slice else []
+        row_starts = np.array([r * T - r * (r + 1) // 2 for r in range(T)], dtype=np.int64)
+        for p, v in zip(pos, vals):
             gp = p_begin + int(p)
-            a = int(np.searchsorted(np.array([r * T - r * (r + 1) // 2 for r in range(min(T, 4096))]), gp, side="right") - 1)
-            b = a + 1 + gp - (a * T - a * (a + 1) // 2)
+            a = int(np.searchsorted(row_starts, gp, side="right") - 1)
+            b = a + 1 + gp - int(row_starts[a])
             sa = {tuple(x) for x in bips_all[int(off_all[a]):int(off_all[a + 1])].tolist()}
             sb = {tuple(x) for x in bips_all[int(off_all[b]):int(off_all[b + 1])].tolist()}
-            assert int(out_h[p]) == len(sa ^ sb), f"self-check failed at pair ({a},{b})"
+            assert int(v) == len(sa ^ sb), f"self-check failed at pair ({a},{b}): {int(v)} != {len(sa ^ sb)}"
+        selfcheck = {"sampled_pairs": int(len(pos))}
+        if world == 1 and not st.get("n_flipped"):
+            total = int(d_out[:P].view(torch.int16).to(torch.int64).bitwise_and(0xFFFF).sum().item()) if P else 0
+            want = (T - 1) * int(counts.sum()) - 2 * int(st["n_hits"])
+            assert total == want, f"checksum identity failed: {total} != {want}"
+            selfcheck["checksum"] = total
 
     # ---- roofline of the dominant kernel (the matrix kernel), per launch ---------------------------
     peaks, peak_src = load_peaks()
@@ -383,7 +395,7 @@ def run_gpu(args, wl, wl_name):
                        "parallelism": f"packed-range shard x{world}" + ((" + hash-partitioned build (NCCL all-to-all of keys, all-gather of the per-class structures)" if sharded else " + NCCL all-gather of bipartition keys") if world > 1 else ""),
                        "l2": "output per step (>= 2 B/pair) far exceeds the 126 MB L2; no explicit flush"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks, "device_s": dev_s, "wall_s": wall,
+            "clocks": clocks, "device_s": dev_s, "wall_s": wall, "selfcheck": selfcheck,
         }
         print(json.dumps(line), flush=True)
     torch.cuda.synchronize(dev)
