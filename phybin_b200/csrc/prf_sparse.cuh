@@ -784,10 +784,7 @@ static int launch_sparse(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t edi
                          uint32_t* d_mask) {
   // the tiny-tile build exists so that small test inputs exercise multi-tile rows and cursor spill
   if (ctx->debug_small_tiles) return launch_sparse_t<256, 2, 8, 8, 3>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-  static const int cfg = [] { const char* e = getenv("PRF_SPARSE_CFG"); return e ? atoi(e) : 0; }();
-  if (cfg == 1) return launch_sparse_t<12288, 14, 288, 8, 4>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-  if (cfg == 2) return launch_sparse_t<8192, 14, 256, 8, 6>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-  if (cfg == 3) return launch_sparse_t<16384, 14, 256, 8, 3>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  static const int cfg = [] { const char* e = getenv("PRF_SPARSE_CFG"); return e ? atoi(e) : 0; }();  // 4: force 12 slots
   // trees with clearly more suffix ranges than 14 walkers x 8 register slots: 12 slots, list ends in shared memory
   if (cfg == 4 || (cfg == 0 && ctx->h.max_ranges > 14 * 8 + 16))
     return launch_sparse_t<16384, 14, 320, 12, 3>(ctx, p_begin, p_end, editdist, d_out, d_mask);
