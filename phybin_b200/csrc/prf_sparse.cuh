@@ -15,8 +15,9 @@
 //     waits for the ring slot's `empty` mbarrier, fills d = |B_a| + |B_b| for the tile's columns
 //     (16-byte shared stores), publishes the row's suffix cursors and a tile descriptor, and arrives
 //     on the tile's `full` mbarrier.  Work-item metadata is prefetched three items ahead (item ->
-//     list offsets -> ranges, the ranges by cp.async straight into a 4-deep ring of cursor arrays),
-//     so no global latency sits on its path.
+//     list offsets -> ranges, the ranges by cp.async straight into a ring of kRowBufs + 2 cursor
+//     arrays), so no global latency sits on its path.  Rows whose |B_t| differ are filled by a bulk
+//     copy of |B|[c_lo..] from one of 8 pre-shifted copies plus a SIMD add of |B_a|.
 //   emitter warp (warp 1)
 //     once every walker has arrived on the tile's `done` mbarrier: optional d <= editdist mask, then
 //     the finished tile goes out as ONE bulk asynchronous copy (cp.async.bulk shared -> global, the
@@ -26,9 +27,11 @@
 //     tree a's shared bipartitions each own a suffix of an inverted list ("trees b > a that also have
 //     it", ascending).  Every suffix keeps a cursor that only moves forward from tile to tile, so each
 //     member is loaded once per row and there is no search.  A suffix always belongs to the same
-//     walker, so cursors need no synchronisation.  A walker issues the loads of kWalkUnroll suffixes
-//     together and subtracts 2 at column b with a shared-memory atomic -- no global atomics on the
-//     matrix.  Walkers run ahead of each other by up to two tiles.
+//     walker, so cursors need no synchronisation: a walker keeps kSlots suffixes in registers (cursor,
+//     end, and a 32-member look-ahead window that is reloaded as soon as the cursor moves, i.e. before
+//     the next tile's `full` wait) and subtracts 2 at column b with a shared-memory reduction -- no
+//     global atomics on the matrix.  Suffixes beyond the register slots use shared-memory cursors.
+//     Walkers run ahead of each other by up to two tiles.
 // Every output byte is written exactly once.
 #pragma once
 
