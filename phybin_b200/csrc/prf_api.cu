@@ -696,6 +696,23 @@ PRF_API int prf_mask_components(prf_ctx* h, const uint32_t* d_mask, uint32_t T, 
 // Debug entry points for tests of the primitives (not part of phybin_rf.h).
 // ---------------------------------------------------------------------------------------------
 
+// Host-only: the work items launch_sparse would cut [p_begin, p_end) into (tests of the plan builder;
+// needs no device).  items: cap x 4 uint32 (a0, a1, cb, ce).  Returns the number of items or -1.
+PRF_API long long prf_debug_row_plan(uint32_t T, uint64_t p_begin, uint64_t p_end, uint32_t tile, uint32_t* items,
+                                     uint64_t cap) {
+  std::vector<RowItem> rows, groups;
+  build_row_plan(T, p_begin, p_end, tile, rows, groups);
+  rows.insert(rows.end(), groups.begin(), groups.end());
+  if (rows.size() > cap) return -1;
+  for (size_t i = 0; i < rows.size(); ++i) {
+    items[4 * i] = rows[i].a0;
+    items[4 * i + 1] = rows[i].a1;
+    items[4 * i + 2] = rows[i].cb;
+    items[4 * i + 3] = rows[i].ce;
+  }
+  return (long long)rows.size();
+}
+
 PRF_API int prf_debug_wide_slots(prf_ctx* h, int on) {
   if (!h) return PRF_E_INVALID;
   h->c.debug_wide_slots = on != 0;

@@ -156,3 +156,61 @@ def test_no_cpu_fallback_without_cuda():
     with pytest.raises(PhyBinRFError) as ei:
         RFContext(0)
     assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+@pytest.mark.parametrize("T,tile", [(2, 256), (3, 256), (50, 256), (700, 256), (5000, 16384), (100000, 16384)])
+def test_sparse_kernel_work_plan_tiles_every_shard_exactly(T, tile):
+    """Host logic of the matrix kernel: the work items (long rows / groups of short rows) of every shard
+    of every world size cover the shard's packed range exactly once."""
+    L = _native.rf_lib()
+    P = T * (T - 1) // 2
+    row_start = lambda a: a * T - a * (a + 1) // 2  # noqa: E731
+    buf = np.zeros((T + 8, 4), dtype=np.uint32)
+    for world in (1, 3, 8):
+        for rank in range(world):
+            b, e = ctypes.c_uint64(), ctypes.c_uint64()
+            assert L.prf_shard_range(T, rank, world, ctypes.byref(b), ctypes.byref(e)) == 0
+            n = L.prf_debug_row_plan(T, b.value, e.value, tile, buf.ctypes.data, len(buf))
+            assert n >= 0
+            spans = []
+            for a0, a1, cb, ce in buf[:n].tolist():
+                if a0 == a1:      # one row, columns [cb, ce)
+                    assert a0 + 1 <= cb < ce <= T
+                    spans.append((row_start(a0) + cb - a0 - 1, row_start(a0) + ce - a0 - 1))
+                else:             # whole rows a0..a1 in one tile
+                    lo, hi = row_start(a0), row_start(a1 + 1)
+                    assert a1 > a0 and hi - lo <= tile and a1 - a0 + 1 <= 256
+                    spans.append((lo, hi))
+            spans.sort()
+            pos = b.value
+            for lo, hi in spans:
+                assert lo == pos and hi > lo
+                pos = hi
+            assert pos == e.value
+    assert P == row_start(T - 1)
+
+
+def test_host_library_exports_every_declared_symbol():
+    """include/phybin_host.h <-> libphybin_host.so."""
+    build.build_host()
+    hdr = open(os.path.join(ROOT, "include", "phybin_host.h")).read()
+    declared = sorted(set(re.findall(r"PHB_API\s+[\w\s\*]+?\b(phb_\w+)\s*\(", hdr)))
+    assert len(declared) >= 15
+    lib = ctypes.CDLL(build.HOST_SO)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+
+
+def test_print_dist_mat_streams_the_same_text_to_a_file(tmp_path):
+    L = _native.host_lib()
+    rng = np.random.default_rng(5)
+    T = 37
+    upper = rng.integers(0, 70, size=T * (T - 1) // 2, dtype=np.uint16)
+    p = L.phb_print_dist_mat(upper.ctypes.data, T)
+    text = ctypes.string_at(p).decode()
+    L.phb_free_buf(p)
+    path = tmp_path / "distance_matrix.txt"
+    assert L.phb_write_dist_mat(str(path).encode(), upper.ctypes.data, T) == 0
+    ii, jj = np.tril_indices(T, -1)  # the reference's layout: row i holds d(i, 0..i-1)
+    lower = upper[(jj * T - jj * (jj + 1) // 2 + (ii - jj - 1))].astype(np.int64)
+    assert path.read_text() == text == orc.print_dist_mat(lower, T)
