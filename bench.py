@@ -63,7 +63,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
         except Exception:
@@ -72,6 +72,10 @@ class ClockSampler:
     def _pump(self):
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
+
+    def mark(self):
+        """Samples taken before this call are ignored by stop()."""
+        self.first = len(self.lines)
 
     def stop(self) -> dict:
         if not self.proc:
@@ -83,7 +87,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
-        for ln in self.lines:
+        for ln in self.lines[getattr(self, "first", 0):]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -241,6 +245,10 @@ def run_gpu(args, wl, wl_name):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # nvidia-smi is started BEFORE the warm-up: its start-up (NVML initialisation takes driver locks) can stall
+    # kernel launches for milliseconds and must not fall into the timed region; only samples taken after
+    # sampler.mark() below are used.
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(2):   # setup, not warm-up: lets the stream-ordered memory pool reach its steady size
         step()
     barrier()
@@ -249,7 +257,8 @@ def run_gpu(args, wl, wl_name):
     barrier()
     matrix_ms.clear()
     launches0 = ctx.launches
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(ext)
     t0 = time.perf_counter()
@@ -275,7 +284,7 @@ def run_gpu(args, wl, wl_name):
         barrier()
     clocks = sampler.stop() if sampler else None
     if clocks is not None:
-        clocks["sampled_over"] = f"timed region + {probe_steps} identical untimed steps (sampler period 50 ms)"
+        clocks["sampled_over"] = f"timed region + {probe_steps} identical untimed steps (sampler period 200 ms)"
     # the step synchronises with the host a few times (scalar read-backs), so device-event time on the
     # library's stream and wall time between the bracketing synchronisations agree; report the larger.
     step_s = max(dev_s, wall) / args.steps

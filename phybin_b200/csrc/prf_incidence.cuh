@@ -170,14 +170,13 @@ struct PopcWord {
 // Writes the (list id, tree) pairs of the shared entries in tree order (stable warp compaction).  The
 // list id is the rank of the entry's slot among the shared slots (per-word rank + popcount below the
 // slot's bit): dense ids in slot order, so two 10-bit radix passes sort them and the sorted key array
-// IS the per-entry list id.  lsize[id] counts the list's entries.
+// IS the per-entry list id.
 __global__ void __launch_bounds__(256) gather_shared_kernel(const uint64_t* __restrict__ tree_off, uint32_t T,
                                                             const uint32_t* __restrict__ ent_slot,
                                                             const uint32_t* __restrict__ shared_bits,
                                                             const uint32_t* __restrict__ wrank,
                                                             const uint32_t* __restrict__ soff,
-                                                            uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                            uint32_t* lsize) {
+                                                            uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= T) return;
   const uint64_t e0 = tree_off[t], e1 = tree_off[t + 1];
@@ -198,10 +197,18 @@ __global__ void __launch_bounds__(256) gather_shared_kernel(const uint64_t* __re
       const uint32_t o = pos + __popc(m & lt);
       keys[o] = id;
       vals[o] = t;
-      atomicAdd(&lsize[id], 1u);
     }
     pos += __popc(m);
   }
+}
+
+// Sorted dense ids (every id 0..L-1 occurs): head_pos[l] = first position of list l, head_pos[L] = n.
+__global__ void __launch_bounds__(256) id_heads_kernel(const uint32_t* __restrict__ lid, uint32_t n, uint32_t n_lists,
+                                                       uint32_t* __restrict__ head_pos) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  if (k == 0 || lid[k] != lid[k - 1]) head_pos[lid[k]] = k;
+  if (k == n - 1) head_pos[n_lists] = n;
 }
 
 // Sorted (slot, tree) pairs: a list starts where the slot changes.
@@ -444,7 +451,8 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
   const bool compact = nnz < (1ull << 25) - 1 && !ctx->debug_wide_slots;
   uint64_t cap = 1024;
   if (compact) {
-    cap = std::max<uint64_t>(1024, (nnz + nnz / 4 + 31) / 32 * 32);  // load factor <= 0.8, multiple of the bitmap word
+    static const double factor = [] { const char* e = getenv("PRF_DEDUP_FACTOR"); return e ? atof(e) : 1.25; }();
+    cap = std::max<uint64_t>(1024, ((uint64_t)(nnz * factor) + 31) / 32 * 32);  // load factor <= 0.8, multiple of the bitmap word
   } else {
     while (cap < nnz + nnz / 2) cap <<= 1;  // load factor <= 2/3 even if every key is distinct
   }
@@ -512,12 +520,10 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
   const uint32_t n_lists0 = h01[1];
   H.n_shared_nnz = n_sh_nnz;
 
-  DevBuf<uint32_t> slot_sorted, lid_ex, head_pos, rcount, cursor, lsize;
+  DevBuf<uint32_t> slot_sorted, lid_ex, head_pos, rcount, cursor;
   PRF_CK(ctx, slot_sorted.alloc(n_sh_nnz, s));
   PRF_CK(ctx, H.members.alloc(n_sh_nnz, s));
   PRF_CK(ctx, head_pos.alloc((size_t)n_sh_nnz + 1, s));
-  PRF_CK(ctx, lsize.alloc((size_t)n_lists0 + 1, s));
-  PRF_CK(ctx, cudaMemsetAsync(lsize.p, 0, lsize.bytes(), s));
   PRF_CK(ctx, rcount.alloc((size_t)T + 1, s));
   PRF_CK(ctx, cursor.alloc((size_t)T + 1, s));
   PRF_CK(ctx, H.roff.alloc((size_t)T + 1, s));
@@ -527,7 +533,7 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
   uint32_t n_sorted = n_sh_nnz;
   if (n_sh_nnz) {
     gather_shared_kernel<<<(T + 7) / 8, 256, 0, s>>>(d_off, T, ent_slot.p, shared_bits.p, wrank.p, soff.p, slot_sorted.p,
-                                                     H.members.p, lsize.p);
+                                                     H.members.p);
     PRF_LAUNCHED(ctx);
     // stable sort by list id: inside a list the trees stay ascending
     if ((rc = radix_sort_pairs(ctx, slot_sorted.p, H.members.p, n_sh_nnz, bits_for(n_lists0)))) return rc;
@@ -543,7 +549,8 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
     const uint32_t* lid_p = slot_sorted.p;
     if (n_sorted) {
       if (ids_are_keys) {
-        if ((rc = exclusive_scan(ctx, LoadU32{lsize.p}, (uint64_t)n_lists0 + 1, head_pos.p, nullptr))) return rc;
+        id_heads_kernel<<<grid_for(n_sorted), 256, 0, s>>>(slot_sorted.p, n_sorted, n_lists0, head_pos.p);
+        PRF_LAUNCHED(ctx);
       } else {
         if (!lid_ex.p) PRF_CK(ctx, lid_ex.alloc(n_sh_nnz, s));
         if (!H.lid.p) PRF_CK(ctx, H.lid.alloc(n_sh_nnz, s));
