@@ -146,8 +146,8 @@ __device__ __forceinline__ uint32_t walk_suffix(const uint32_t* __restrict__ mem
   return cur;
 }
 
-template <int kTile, int kWalkers, int kCurCap, int kSlots, int kRowBufs>
-__global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) sparse_rows_kernel(const RowParams prm) {
+template <int kTile, int kWalkers, int kCurCap, int kSlots, int kRowBufs, int kHelper>
+__global__ void __launch_bounds__(32 * (kWalkers + 2 + kHelper), (kTile > 16384 ? 1 : 2)) sparse_rows_kernel(const RowParams prm) {
   constexpr int kStride = kTile + 8;  // entries per buffer: a tile keeps the 16-byte phase of its global address
   constexpr int kCurRing = kRowBufs + 2;  // cursor arrays in shared memory (see the safety argument at stage_prefetch)
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -167,16 +167,16 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
     for (int b = 0; b < kRowBufs; ++b) {
       mbar_init(&s_full[b], 1);
       mbar_init(&s_done[b], kWalkers);
-      mbar_init(&s_empty[b], 1);
+      mbar_init(&s_empty[b], 1 + kHelper);
     }
     mbar_init(&s_fill, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  if (warp >= 2) {
+  if (warp >= 2 + kHelper) {
     // =========================== walkers ===========================
-    const uint32_t w = warp - 2;
+    const uint32_t w = warp - 2 - kHelper;
 #ifdef PRF_TIMING
     long long t_wait = 0, t_work = 0, t0 = clock64(), t1;
 #define TICK(acc) do { t1 = clock64(); acc += t1 - t0; t0 = t1; } while (0)
@@ -591,35 +591,57 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
   };
 
   // mask bits, unaligned ends and the bulk store of the finished tile in ring slot `slot`
-  auto emit = [&](uint32_t slot) {
+  // part / nparts: the mask's interior groups are shared between the emitter (part 0, which also does the
+  // partial groups and the stores) and, in the kHelper build, the helper warp (part 1, mask only)
+  auto emit = [&](uint32_t slot, uint32_t part, uint32_t nparts) {
     const uint16_t* tile = tiles + slot * kStride;
     const uint64_t p_lo = s_desc[slot].p_lo, p_hi = s_desc[slot].p_hi, P0 = p_lo & ~7ull;
     if (prm.editdist >= 0) {
-      // 8 entries (one aligned 16-byte group) per lane -> one mask byte
-      const uint32_t ngroups = (uint32_t)((p_hi - P0 + 7) >> 3);
-      const uint32_t thr = (uint32_t)prm.editdist;
-      uint8_t* mask8 = reinterpret_cast<uint8_t*>(prm.mask);
-      const uint32_t thr2 = thr | (thr << 16);
-      for (uint32_t g = lane; g < ngroups; g += 32) {
-        const uint4 v = reinterpret_cast<const uint4*>(tile)[g];
-        const uint64_t pg = P0 + 8ull * g;
-        // per-halfword (entry <= thr) -> 1: two entries per SIMD compare, then squeeze bit 16 down to bit 1
-        const uint32_t r0 = __vsetleu2(v.x, thr2), r1 = __vsetleu2(v.y, thr2), r2 = __vsetleu2(v.z, thr2),
-                       r3 = __vsetleu2(v.w, thr2);
-        uint32_t bits = ((r0 | (r0 >> 15)) & 3u) | (((r1 | (r1 >> 15)) & 3u) << 2) | (((r2 | (r2 >> 15)) & 3u) << 4) |
-                        (((r3 | (r3 >> 15)) & 3u) << 6);
-        const uint64_t byte = (pg - prm.p_begin) >> 3;
-        if (pg >= p_lo && pg + 8 <= p_hi) {
-          mask8[byte] = (uint8_t)bits;
-        } else {  // group shared with a neighbouring row: keep only my positions, OR into the pre-zeroed word
-          uint32_t valid = 0;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) valid |= ((pg + i >= p_lo && pg + i < p_hi) ? 1u : 0u) << i;
-          bits &= valid;
-          if (bits) atomicOr(&prm.mask[byte >> 2], bits << ((byte & 3) * 8));
+      // 8 entries (one aligned 16-byte group of the tile) per lane -> one mask byte: 1 shared load, 4 SIMD
+      // compares and a handful of bit operations (the emitter warp is alone on this and has to keep up with
+      // 14 walkers).  Bytes whose 32-bit mask word lies wholly inside the tile are plain stores; the few
+      // groups in a word shared with a neighbouring tile are OR-ed into the pre-zeroed mask, so every word
+      // is written either by one tile's stores or by atomics only.
+      const uint32_t thr = (uint32_t)prm.editdist, thr2 = thr | (thr << 16);
+      const uint32_t m_lo = (uint32_t)(p_lo - P0), m_hi = (uint32_t)(p_hi - P0);  // entries [m_lo, m_hi) of the tile
+      const uint32_t g_lo = (m_lo + 7) >> 3, g_hi = m_hi >> 3;                     // fully covered groups [g_lo, g_hi)
+      const uint64_t gb0 = (P0 - prm.p_begin) >> 3;                                // mask byte of group 0
+      const uint32_t ph = (uint32_t)gb0 & 3u;
+      const uint32_t gi_lo = g_lo + ((4u - ((ph + g_lo) & 3u)) & 3u);              // first group on a word boundary
+      const uint32_t gi_hi = g_hi - ((ph + g_hi) & 3u);                            // interior = [gi_lo, gi_hi) if gi_lo < gi_hi
+      uint8_t* mb = reinterpret_cast<uint8_t*>(prm.mask) + gb0;
+      const uint4* t4 = reinterpret_cast<const uint4*>(tile);
+      auto group_bits = [&](uint32_t g) {
+        const uint4 v = t4[g];
+        // per-halfword (entry <= thr) -> 1 at bits 0 and 16; interleave the four words, fold the high halves down
+        const uint32_t t = __vsetleu2(v.x, thr2) | (__vsetleu2(v.y, thr2) << 2) | (__vsetleu2(v.z, thr2) << 4) |
+                           (__vsetleu2(v.w, thr2) << 6);
+        return (t & 0x55u) | ((t >> 15) & 0xaau);
+      };
+      auto or_byte = [&](uint32_t g, uint32_t bits) {
+        const uint64_t byte = gb0 + g;
+        if (bits) atomicOr(&prm.mask[byte >> 2], bits << ((byte & 3) * 8));
+      };
+#pragma unroll 2
+      for (uint32_t g = g_lo + lane + 32 * part; g < g_hi; g += 32 * nparts) {
+        const uint32_t bits = group_bits(g);
+        if (g >= gi_lo && g < gi_hi) mb[g] = (uint8_t)bits;
+        else or_byte(g, bits);
+      }
+      if (lane < 2 && part == 0) {
+        // lane 0: the group holding the first entries (if it is partial); lane 1: the one holding the last
+        const bool head = lane == 0;
+        const bool have = head ? (m_lo & 7u) != 0 : ((m_hi & 7u) != 0 && (g_hi >= g_lo || (m_lo & 7u) == 0));
+        if (have) {
+          const uint32_t g = head ? m_lo >> 3 : g_hi;
+          uint32_t valid = 0xffu;
+          if ((m_lo >> 3) == g) valid &= 0xffu << (m_lo & 7u);
+          if ((m_hi >> 3) == g) valid &= (1u << (m_hi & 7u)) - 1u;
+          or_byte(g, group_bits(g) & valid);
         }
       }
     }
+    if (part != 0) return;
     // tile-index space: entry i is packed position P0 + i
     const uint32_t o_lo = (uint32_t)(p_lo - P0), o_hi = (uint32_t)(p_hi - P0);
     const uint32_t ia = (o_lo + 7) & ~7u, ib = o_hi & ~7u;
@@ -642,7 +664,8 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
   if (warp == 0) {
     for (uint32_t q = 0; !exit_sent; ++q) produce(q);
     asm volatile("cp.async.wait_all;" ::: "memory");
-  } else {
+  } else if (warp == 1) {
+    const uint32_t nparts = (kHelper && prm.editdist >= 0) ? 2u : 1u;
     for (uint32_t e = 0;; ++e) {
       const uint32_t slot = e % kRowBufs, par = (e / kRowBufs) & 1u;
       TICK(t_work);
@@ -650,7 +673,7 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
       if (s_desc[slot].kind == kTileExit) break;
       mbar_wait(&s_done[slot], par, prm.debug_sleep);
       TICK(t_wait);
-      emit(slot);
+      emit(slot, 0, nparts);
       // hand the slot back as soon as the bulk copy has read it (the emitter has nothing else to do):
       // the producer can then refill it while the walkers are still busy with the next two tiles
       __syncwarp();  // this warp's own reads of the tile are done
@@ -663,6 +686,17 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2), (kTile > 16384 ? 1 : 2)) 
       TICK(t_wait2);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  } else {
+    // helper warp (kHelper builds): the other half of the threshold mask of every tile
+    for (uint32_t e = 0;; ++e) {
+      const uint32_t slot = e % kRowBufs, par = (e / kRowBufs) & 1u;
+      mbar_wait(&s_full[slot], par);
+      if (s_desc[slot].kind == kTileExit) break;
+      mbar_wait(&s_done[slot], par, prm.debug_sleep);
+      if (prm.editdist >= 0) emit(slot, 1, 2);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[slot]);
+    }
   }
   __syncwarp();
 #ifdef PRF_TIMING
@@ -712,17 +746,17 @@ static void build_row_plan(uint32_t T, uint64_t p_begin, uint64_t p_end, uint32_
                    [](const RowItem& x, const RowItem& y) { return x.ce - x.cb > y.ce - y.cb; });
 }
 
-template <int kTile, int kWalkers, int kCurCap, int kSlots, int kRowBufs>
+template <int kTile, int kWalkers, int kCurCap, int kSlots, int kRowBufs, int kHelper>
 static int launch_sparse_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out,
                            uint32_t* d_mask) {
   const HashRFState& H = ctx->h;
   cudaStream_t s = ctx->stream;
-  constexpr int kThreads = 32 * (kWalkers + 2);
+  constexpr int kThreads = 32 * (kWalkers + 2 + kHelper);
   constexpr size_t smem = (size_t)kRowBufs * (kTile + 8) * 2 + (size_t)(kRowBufs + 2) * kCurCap * sizeof(uint2);
-  auto kern = sparse_rows_kernel<kTile, kWalkers, kCurCap, kSlots, kRowBufs>;
+  auto kern = sparse_rows_kernel<kTile, kWalkers, kCurCap, kSlots, kRowBufs, kHelper>;
   PRF_CK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per instantiation
   RowPlan& plan = ctx->plan;
-  if (!plan.valid || plan.T != H.T || plan.p_begin != p_begin || plan.p_end != p_end || plan.tile != kTile) {
+  if (!plan.valid || plan.T != H.T || plan.p_begin != p_begin || plan.p_end != p_end || plan.tile != kTile) {  // (occupancy is the same for every instantiation of a tile size)
     plan.valid = false;
     std::vector<RowItem> rows, groups;
     build_row_plan(H.T, p_begin, p_end, kTile, rows, groups);
@@ -786,12 +820,20 @@ static int launch_sparse_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t e
 static int launch_sparse(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out,
                          uint32_t* d_mask) {
   // the tiny-tile build exists so that small test inputs exercise multi-tile rows and cursor spill
-  if (ctx->debug_small_tiles) return launch_sparse_t<256, 2, 8, 8, 3>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  // With a threshold mask the emitter would be the bottleneck (one warp, 16 K compares per tile): one of
+  // the walker warps becomes a helper that builds half of the mask.
+  const bool mask = d_mask != nullptr;
+  if (ctx->debug_small_tiles)
+    return mask ? launch_sparse_t<256, 2, 8, 8, 3, 1>(ctx, p_begin, p_end, editdist, d_out, d_mask)
+                : launch_sparse_t<256, 2, 8, 8, 3, 0>(ctx, p_begin, p_end, editdist, d_out, d_mask);
   static const int cfg = [] { const char* e = getenv("PRF_SPARSE_CFG"); return e ? atoi(e) : 0; }();  // 4: force 12 slots
   // trees with clearly more suffix ranges than 14 walkers x 8 register slots: 12 slots, list ends in shared memory
-  if (cfg == 4 || (cfg == 0 && ctx->h.max_ranges > 14 * 8 + 16))
-    return launch_sparse_t<16384, 14, 320, 12, 3>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-  return launch_sparse_t<16384, 14, 320, 8, 3>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  const bool many = cfg == 4 || (cfg == 0 && ctx->h.max_ranges > 14 * 8 + 16);
+  if (mask)
+    return many ? launch_sparse_t<16384, 13, 320, 12, 3, 1>(ctx, p_begin, p_end, editdist, d_out, d_mask)
+                : launch_sparse_t<16384, 13, 320, 8, 3, 1>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  return many ? launch_sparse_t<16384, 14, 320, 12, 3, 0>(ctx, p_begin, p_end, editdist, d_out, d_mask)
+              : launch_sparse_t<16384, 14, 320, 8, 3, 0>(ctx, p_begin, p_end, editdist, d_out, d_mask);
 }
 
 }  // namespace prf

@@ -7,14 +7,16 @@ from phybin_b200 import _native, build
 build.RF_SO = os.path.join(build.LIBDIR, "libphybin_rf_timing.so")
 from phybin_b200.host import Forest
 from phybin_b200.rfdistance import RFContext
-T, n = (int(sys.argv[1]) if len(sys.argv) > 1 else 100000), 200
+T = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 200
+editdist = int(sys.argv[4]) if len(sys.argv) > 4 else -1
 f = Forest.synthetic(T, n, 0x5EED0003, int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 bips, off = f.all_bips()
 ctx = RFContext(0)
 L = ctx._L
 ctx.hashrf_load(bips, off)
 for it in range(3):
-    st = ctx.hashrf_compute(0, ctx.P)
+    st = ctx.hashrf_compute(0, ctx.P, editdist=editdist)
 grid = C.c_uint32(0)
 buf = np.zeros(1024 * 64, dtype=np.uint64)
 L.prf_debug_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
