@@ -75,6 +75,13 @@ PHB_API int phb_allbips(const phb_forest* f, uint32_t W, int threads, uint64_t**
 PHB_API int phb_raw_clades(const phb_forest* f, uint32_t W, int threads, uint64_t** clades,
                            uint64_t** tree_off, uint64_t** leafsets, uint64_t* nnz);
 
+/* The trees as the flat pre-order arrays prf_allbips (phybin_rf.h) takes: BORROWED pointers into the
+ * forest, valid until it is modified or freed.  node_label[v] >= 0: leaf label, -1: interior node;
+ * node_parent[v]: index of the parent (undefined for a tree's first node, its root); the nodes of tree
+ * t are tree_begin[t] .. tree_begin[t+1]-1; num_leaves[t] = numLeaves.  Any out pointer may be NULL. */
+PHB_API int phb_tree_arrays(const phb_forest* f, const int32_t** node_label, const uint32_t** node_parent,
+                            const uint64_t** tree_begin, const uint32_t** num_leaves, uint64_t* n_nodes);
+
 /* printDistMat text of a packed uint16 upper triangle; free with phb_free_buf. */
 PHB_API char* phb_print_dist_mat(const uint16_t* upper, uint32_t T);
 /* Streams the same text to a file; returns 0 on success. */

@@ -187,6 +187,47 @@ PRF_API int prf_tolerant_load(prf_ctx* ctx, const uint64_t* clades, const uint64
 PRF_API int prf_tolerant_compute(prf_ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist,
                                  uint16_t* d_out, uint32_t* d_mask, prf_stats* stats);
 
+/* ---- bipartition extraction on the device (replaces allBips, RFDistance.hs:207-248) ------------ */
+
+typedef enum prf_extract_mode {
+  PRF_EXTRACT_BIPS = 0,   /* allBips: normalised bipartitions of > 1 taxa (prf_hashrf_load's input)        */
+  PRF_EXTRACT_CLADES = 1  /* un-normalised clades of the non-root interior nodes + the trees' taxon sets  */
+                          /* (prf_tolerant_load's input)                                                   */
+} prf_extract_mode;
+
+typedef struct prf_extract_info {
+  uint64_t nnz;        /* sets produced */
+  uint32_t max_nodes;  /* largest tree, in nodes */
+  int32_t gpu_launches;
+  float ms_h2d, ms_kernels;
+} prf_extract_info;
+
+/* Trees as flat arrays, the nodes of tree t being tree_begin[t] .. tree_begin[t+1]-1 in PRE-ORDER (a
+ * parent precedes its children; the first node is the root):
+ *   node_label   >= 0: a leaf carrying that taxon label (Label, CoreTypes.hs:139); < 0: interior node
+ *   node_parent  index of the parent in the same arrays; ignored for a tree's first node
+ *   tree_begin   T+1 ascending offsets, tree_begin[0] = 0
+ *   num_leaves   numLeaves of every tree (CoreTypes.hs:289-291; duplicate labels count twice) -- the
+ *                `size` normBip works with (RFDistance.hs:215,229-239)
+ * `kind` says where the four arrays live.  The result stays on the device until the next extraction on
+ * this context; it is, per tree, the sorted SET (word-lexicographic order, word 0 first) of
+ *   mode BIPS:   normBip size c for every non-root node's leaf set c, kept when it has > 1 members
+ *                (labelBips :207-221, normBip :229-239 with its [0,size) complement universe and odd-size
+ *                tie rule, allBips' filter :248);
+ *   mode CLADES: the leaf set of every non-root interior node, plus leafsets[t] = the root's set.
+ * PRF_E_UNSUPPORTED when one tree's clade sets do not fit a CTA's shared memory
+ * (max_nodes * (8 W + 2) + 2 * pow2(max_nodes) bytes must stay under 200 KB). */
+PRF_API int prf_allbips(prf_ctx* ctx, const int32_t* node_label, const uint32_t* node_parent,
+                        const uint64_t* tree_begin, const uint32_t* num_leaves, uint32_t T, uint32_t W,
+                        int kind /* prf_memkind */, int mode /* prf_extract_mode */, prf_extract_info* info);
+/* Device pointers of the last extraction: keys (nnz*W words), tree_off (T+1), leafsets (T*W words, NULL in
+ * mode BIPS) -- pass them to prf_hashrf_load / prf_tolerant_load with PRF_MEM_DEVICE.  Any out pointer may
+ * be NULL. */
+PRF_API int prf_allbips_result(prf_ctx* ctx, const uint64_t** d_keys, const uint64_t** d_tree_off,
+                               const uint64_t** d_leafsets, uint64_t* nnz);
+/* Copies the last extraction to host memory (each destination may be NULL). */
+PRF_API int prf_allbips_fetch(prf_ctx* ctx, uint64_t* keys, uint64_t* tree_off, uint64_t* leafsets);
+
 /* ---- first consumer of the matrix: flat clusters at the --editdist threshold -------------------- */
 
 /* Connected components of the graph { (a,b) : d(a,b) <= editdist } read from a threshold mask that

@@ -24,6 +24,14 @@ class prf_part(C.Structure):
     ]
 
 
+class prf_extract_info(C.Structure):
+    _fields_ = [("nnz", C.c_uint64), ("max_nodes", C.c_uint32), ("gpu_launches", C.c_int32),
+                ("ms_h2d", C.c_float), ("ms_kernels", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 class prf_stats(C.Structure):
     _fields_ = [
         ("n_trees", C.c_uint64), ("n_words", C.c_uint64), ("nnz", C.c_uint64),
@@ -76,6 +84,7 @@ def host_lib():
         L.phb_allbips.argtypes = [vp, C.c_uint32, C.c_int, C.POINTER(u64p), C.POINTER(u64p), u64p]
         L.phb_raw_clades.argtypes = [vp, C.c_uint32, C.c_int, C.POINTER(u64p), C.POINTER(u64p),
                                      C.POINTER(u64p), u64p]
+        L.phb_tree_arrays.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), u64p]
         L.phb_print_dist_mat.restype = vp
         L.phb_print_dist_mat.argtypes = [vp, C.c_uint32]
         L.phb_write_dist_mat.argtypes = [C.c_char_p, vp, C.c_uint32]
@@ -116,6 +125,10 @@ def rf_lib():
         L.prf_hashrf_partition.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, u64p]
         L.prf_hashrf_export.argtypes = [vp, C.POINTER(prf_part)]
         L.prf_hashrf_merge.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(prf_part), st]
+        L.prf_allbips.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+                                  C.POINTER(prf_extract_info)]
+        L.prf_allbips_result.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), u64p]
+        L.prf_allbips_fetch.argtypes = [vp, vp, vp, vp]
         L.prf_mask_components.argtypes = [vp, vp, C.c_uint32, vp, u32p]
         L.prf_packed_index.restype = C.c_uint64
         L.prf_packed_index.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
@@ -140,6 +153,7 @@ def rf_lib():
 RF_SYMBOLS = [
     "prf_create", "prf_destroy", "prf_last_error", "prf_version", "prf_stream", "prf_hashrf",
     "prf_hashrf_load", "prf_hashrf_compute", "prf_hashrf_partition", "prf_hashrf_export", "prf_hashrf_merge", "prf_fetch", "prf_fetch_mask", "prf_fetch_rows",
-    "prf_tolerant", "prf_tolerant_load", "prf_tolerant_compute", "prf_mask_components", "prf_packed_index",
+    "prf_tolerant", "prf_tolerant_load", "prf_tolerant_compute", "prf_allbips", "prf_allbips_result", "prf_allbips_fetch",
+    "prf_mask_components", "prf_packed_index",
     "prf_shard_align", "prf_shard_range", "prf_limits", "prf_launch_count",
 ]

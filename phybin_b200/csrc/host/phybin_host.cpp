@@ -671,6 +671,19 @@ int phb_raw_clades(const phb_forest* h, uint32_t W, int threads, uint64_t** clad
   return 0;
 }
 
+int phb_tree_arrays(const phb_forest* h, const int32_t** node_label, const uint32_t** node_parent,
+                    const uint64_t** tree_begin, const uint32_t** num_leaves, uint64_t* n_nodes) {
+  if (!h) return -1;
+  const Forest& f = h->f;
+  if (f.tree_begin.size() != (size_t)f.T() + 1) return -1;
+  if (node_label) *node_label = f.label.data();
+  if (node_parent) *node_parent = f.parent.data();
+  if (tree_begin) *tree_begin = f.tree_begin.data();
+  if (num_leaves) *num_leaves = f.num_leaves.data();
+  if (n_nodes) *n_nodes = f.label.size();
+  return 0;
+}
+
 static void append_uint(std::string& o, unsigned x) {
   char buf[12];
   int n = 0;

@@ -25,7 +25,7 @@
 namespace {
 
 struct Options {
-  bool tolerant = false, rfdist = false, single = false;
+  bool tolerant = false, rfdist = false, single = false, host_bips = false;
   int editdist = -1, name_prefix = -1, variant = PRF_VARIANT_AUTO;
   std::string out_dir = "phybin_out";
   std::vector<std::string> files;
@@ -65,6 +65,7 @@ Options parse_args(int argc, char** argv) {
     else if (!std::strcmp(a, "-p") || !std::strcmp(a, "--nameprefix")) o.name_prefix = std::atoi(need(a));
     else if (!std::strcmp(a, "--sparse")) o.variant = PRF_VARIANT_SPARSE;   // not in the reference: force a kernel variant
     else if (!std::strcmp(a, "--dense")) o.variant = PRF_VARIANT_DENSE;
+    else if (!std::strcmp(a, "--host-bips")) o.host_bips = true;  // not in the reference: allBips in the C++ host code
     else if (!std::strcmp(a, "-V") || !std::strcmp(a, "--version")) {
       std::printf("phybin (B200 RF path) -- %s\n", prf_version());
       std::exit(0);
@@ -82,6 +83,19 @@ std::string slurp(const std::string& path) {
   std::ostringstream ss;
   ss << f.rdbuf();
   return ss.str();
+}
+
+// prf_allbips on the forest's own arrays.  PRF_E_UNSUPPORTED (a tree too large for one CTA's shared memory)
+// is reported with the way out; nothing silently changes path.
+int extract_on_device(prf_ctx* ctx, const phb_forest* forest, uint32_t T, uint32_t W, int mode) {
+  const int32_t* label = nullptr;
+  const uint32_t *parent = nullptr, *leaves = nullptr;
+  const uint64_t* begin = nullptr;
+  if (phb_tree_arrays(forest, &label, &parent, &begin, &leaves, nullptr)) die("cannot read the parsed trees");
+  const int rc = prf_allbips(ctx, label, parent, begin, leaves, T, W, PRF_MEM_HOST, mode, nullptr);
+  if (rc == PRF_E_UNSUPPORTED)
+    die(std::string(prf_last_error(ctx)) + " -- rerun with --host-bips to extract the bipartitions on the host");
+  return rc;
 }
 
 }  // namespace
@@ -114,20 +128,34 @@ int main(int argc, char** argv) {
   int rc;
   if (!opt.tolerant) {
     std::printf(" Using HashRF-style algorithm...\n");  // PhyBin.hs:346
-    uint64_t *bips = nullptr, *off = nullptr, nnz = 0;
-    if (phb_allbips(forest, W, 0, &bips, &off, &nnz)) die("bipartition extraction failed");
-    rc = prf_hashrf_load(ctx, bips, off, T, W, PRF_MEM_HOST, &st);
+    if (opt.host_bips) {
+      uint64_t *bips = nullptr, *off = nullptr, nnz = 0;
+      if (phb_allbips(forest, W, 0, &bips, &off, &nnz)) die("bipartition extraction failed");
+      rc = prf_hashrf_load(ctx, bips, off, T, W, PRF_MEM_HOST, &st);
+      phb_free_buf(bips);
+      phb_free_buf(off);
+    } else {  // allBips on the device from the parsed trees' flat arrays
+      const uint64_t *d_keys = nullptr, *d_off = nullptr;
+      rc = extract_on_device(ctx, forest, T, W, PRF_EXTRACT_BIPS);
+      if (!rc) rc = prf_allbips_result(ctx, &d_keys, &d_off, nullptr, nullptr);
+      if (!rc) rc = prf_hashrf_load(ctx, d_keys, d_off, T, W, PRF_MEM_DEVICE, &st);
+    }
     if (!rc) rc = prf_hashrf_compute(ctx, 0, P, opt.editdist, opt.variant, nullptr, nullptr, &st);
-    phb_free_buf(bips);
-    phb_free_buf(off);
   } else {
-    uint64_t *clades = nullptr, *off = nullptr, *leaf = nullptr, nnz = 0;
-    if (phb_raw_clades(forest, W, 0, &clades, &off, &leaf, &nnz)) die("clade extraction failed");
-    rc = prf_tolerant_load(ctx, clades, off, leaf, T, W, PRF_MEM_HOST, &st);
+    if (opt.host_bips) {
+      uint64_t *clades = nullptr, *off = nullptr, *leaf = nullptr, nnz = 0;
+      if (phb_raw_clades(forest, W, 0, &clades, &off, &leaf, &nnz)) die("clade extraction failed");
+      rc = prf_tolerant_load(ctx, clades, off, leaf, T, W, PRF_MEM_HOST, &st);
+      phb_free_buf(clades);
+      phb_free_buf(off);
+      phb_free_buf(leaf);
+    } else {
+      const uint64_t *d_keys = nullptr, *d_off = nullptr, *d_leaf = nullptr;
+      rc = extract_on_device(ctx, forest, T, W, PRF_EXTRACT_CLADES);
+      if (!rc) rc = prf_allbips_result(ctx, &d_keys, &d_off, &d_leaf, nullptr);
+      if (!rc) rc = prf_tolerant_load(ctx, d_keys, d_off, d_leaf, T, W, PRF_MEM_DEVICE, &st);
+    }
     if (!rc) rc = prf_tolerant_compute(ctx, 0, P, opt.editdist, nullptr, nullptr, &st);
-    phb_free_buf(clades);
-    phb_free_buf(off);
-    phb_free_buf(leaf);
   }
   if (!rc && P) rc = prf_fetch(ctx, 0, P, upper.data());
   if (!rc && P && opt.editdist >= 0) rc = prf_fetch_mask(ctx, 0, P, mask.data());

@@ -106,6 +106,17 @@ struct TolerantState {
   prf_stats stats{};
 };
 
+// Result of the last device-side extraction (prf_extract.cuh).
+struct ExtractState {
+  bool valid = false;
+  int mode = 0;
+  uint32_t T = 0, W = 0;
+  uint64_t nnz = 0;
+  DevBuf<uint64_t> keys;      // [nnz * W]
+  DevBuf<uint64_t> off;       // [T + 1]
+  DevBuf<uint64_t> leafsets;  // [T * W]  (mode PRF_EXTRACT_CLADES only)
+};
+
 struct Ctx {
   int device = 0;
   int sm_count = 148;
@@ -115,6 +126,7 @@ struct Ctx {
   uint64_t launches = 0;
   HashRFState h;
   TolerantState tol;
+  ExtractState ext;
   RowPlan plan;
   bool debug_small_tiles = false;
   bool debug_no_flip = false;         // tests: keep majority lists as they are

@@ -92,6 +92,25 @@ class Forest:
         return host_lib().phb_words(self._h)
 
     # -- device inputs ------------------------------------------------------------------------
+    def tree_arrays(self):
+        """(node_label int32[N], node_parent uint32[N], tree_begin uint64[T+1], num_leaves uint32[T]): the trees as
+        the flat pre-order arrays prf_allbips takes (phb_tree_arrays).  Views into the forest: keep it alive and
+        unmodified while they are in use."""
+        L = host_lib()
+        lp, pp, bp, nl = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n = C.c_uint64(0)
+        if L.phb_tree_arrays(self._h, C.byref(lp), C.byref(pp), C.byref(bp), C.byref(nl), C.byref(n)):
+            raise RuntimeError("phb_tree_arrays failed")
+        T, N = len(self), n.value
+
+        def view(ptr, count, ctype, dtype):
+            if not count:
+                return np.zeros(0, dtype=dtype)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,))
+
+        return (view(lp, N, C.c_int32, np.int32), view(pp, N, C.c_uint32, np.uint32),
+                view(bp, T + 1, C.c_uint64, np.uint64), view(nl, T, C.c_uint32, np.uint32))
+
     def all_bips(self, W: Optional[int] = None, threads: int = 0) -> Tuple[np.ndarray, np.ndarray]:
         """(bips[nnz, W] uint64, tree_off[T+1] uint64): allBips of every tree, bit-packed."""
         W = W or self.words

@@ -16,11 +16,12 @@ from typing import IO, List, Optional, Tuple
 import numpy as np
 
 from . import _native
-from ._native import prf_stats, rf_lib, host_lib
+from ._native import prf_extract_info, prf_stats, rf_lib, host_lib
 from .host import Forest, bits_to_labels
 
 VARIANT_AUTO, VARIANT_SPARSE, VARIANT_DENSE = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
+EXTRACT_BIPS, EXTRACT_CLADES = 0, 1
 
 
 class PhyBinRFError(RuntimeError):
@@ -195,6 +196,53 @@ class RFContext:
                                               C.byref(st) if want_stats else None))
         return st.as_dict() if want_stats else None
 
+    # ---- bipartition extraction on the device ------------------------------------------------------
+    def allbips(self, trees: Forest, mode: int = EXTRACT_BIPS, W: Optional[int] = None) -> dict:
+        """prf_allbips on a Forest's flat arrays: allBips (mode EXTRACT_BIPS) or the tolerant path's raw clades
+        (EXTRACT_CLADES) of every tree, left on the device.  Returns the prf_extract_info fields."""
+        label, parent, begin, leaves = trees.tree_arrays()
+        W = W or trees.words
+        info = prf_extract_info()
+        self._ck(self._L.prf_allbips(self._h, label.ctypes.data if label.size else None,
+                                     parent.ctypes.data if parent.size else None, begin.ctypes.data,
+                                     leaves.ctypes.data if leaves.size else None, len(trees), W, MEM_HOST, mode,
+                                     C.byref(info)))
+        self._ext = (len(trees), W, mode, info.nnz)
+        return info.as_dict()
+
+    def allbips_result(self) -> Tuple[int, int, int, int]:
+        """(d_keys, d_tree_off, d_leafsets, nnz): device pointers of the last extraction (prf_allbips_result)."""
+        k, o, l = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n = C.c_uint64(0)
+        self._ck(self._L.prf_allbips_result(self._h, C.byref(k), C.byref(o), C.byref(l), C.byref(n)))
+        return k.value or 0, o.value or 0, l.value or 0, n.value
+
+    def allbips_fetch(self):
+        """Host copies of the last extraction: (keys[nnz, W], tree_off[T+1]) or, in mode EXTRACT_CLADES,
+        (clades[nnz, W], tree_off[T+1], leafsets[T, W])."""
+        T, W, mode, nnz = self._ext
+        keys = np.empty((nnz, W), dtype=np.uint64)
+        off = np.empty(T + 1, dtype=np.uint64)
+        leaf = np.empty((T, W), dtype=np.uint64) if mode == EXTRACT_CLADES else None
+        self._ck(self._L.prf_allbips_fetch(self._h, keys.ctypes.data, off.ctypes.data,
+                                           leaf.ctypes.data if leaf is not None else None))
+        return (keys, off) if leaf is None else (keys, off, leaf)
+
+    def hashrf_load_trees(self, trees: Forest, W: Optional[int] = None) -> dict:
+        """allBips on the device, then the hashRF build on its device-resident output (no host bipartitions)."""
+        info = self.allbips(trees, EXTRACT_BIPS, W)
+        k, o, _, _ = self.allbips_result()
+        st = self.hashrf_load(k, o, T=len(trees), W=self._ext[1], kind=MEM_DEVICE)
+        st["extract"] = info
+        return st
+
+    def tolerant_load_trees(self, trees: Forest, W: Optional[int] = None) -> dict:
+        info = self.allbips(trees, EXTRACT_CLADES, W)
+        k, o, l, _ = self.allbips_result()
+        st = self.tolerant_load(k, o, l, T=len(trees), W=self._ext[1], kind=MEM_DEVICE)
+        st["extract"] = info
+        return st
+
     # ---- flat clusters --------------------------------------------------------------------------
     def mask_components(self, d_mask: int = 0) -> Tuple[np.ndarray, int]:
         """prf_mask_components on the context-owned mask of the last compute (or a device mask pointer):
@@ -246,15 +294,20 @@ def shard_range(T: int, rank: int, world: int) -> Tuple[int, int]:
 
 # ---- the reference's names ---------------------------------------------------------------------
 
-def hashRF(num_taxa: int, trees: Forest, ctx: Optional[RFContext] = None) -> DistanceMatrix:
+def hashRF(num_taxa: int, trees: Forest, ctx: Optional[RFContext] = None, extract: str = "device") -> DistanceMatrix:
     """hashRF num_taxa trees (RFDistance.hs:284).  `num_taxa` is accepted and ignored exactly as in
     the reference's IntSet build (it only reaches mkSingleDense, :295/:119).  The caller is
     expected to have applied the numLeaves filter (PhyBin.hs:187-194; Forest.filter_num_leaves)."""
     del num_taxa
     ctx = ctx or default_context()
-    bips, off = trees.all_bips()
-    upper, _, _ = ctx.hashrf(bips, off)
-    return DistanceMatrix(upper, len(trees))
+    if extract == "device":  # allBips runs on the device too (prf_allbips)
+        ctx.hashrf_load_trees(trees)
+    elif extract == "host":  # the C++ host extraction (phb_allbips), e.g. for trees too large for prf_allbips
+        ctx.hashrf_load(*trees.all_bips())
+    else:
+        raise ValueError("extract must be 'device' or 'host'")
+    ctx.hashrf_compute(want_stats=False)
+    return DistanceMatrix(ctx.fetch(), len(trees))
 
 
 def naiveDistMatrix(trees: Forest, ctx: Optional[RFContext] = None):
@@ -262,9 +315,11 @@ def naiveDistMatrix(trees: Forest, ctx: Optional[RFContext] = None):
     if trees.has_duplicate_leaves():
         raise PhyBinRFError(-6, "tolerant mode on the device needs distinct leaf labels within a tree")
     ctx = ctx or default_context()
-    clades, off, leafsets = trees.raw_clades()
-    upper, _, _ = ctx.tolerant(clades, off, leafsets)
-    bips, boff = trees.all_bips()
+    ctx.allbips(trees, EXTRACT_BIPS)  # the second component of the result: every tree's allBips
+    bips, boff = ctx.allbips_fetch()
+    ctx.tolerant_load_trees(trees)
+    ctx.tolerant_compute(want_stats=False)
+    upper = ctx.fetch()
     eachbips = [frozenset(bits_to_labels(b) for b in bips[int(boff[t]):int(boff[t + 1])])
                 for t in range(len(trees))]
     return DistanceMatrix(upper, len(trees)), eachbips

@@ -9,8 +9,8 @@ import pytest
 
 from oracle import oracle as orc
 from phybin_b200 import _native
-from phybin_b200.host import Forest, NNI_FAMILY
-from phybin_b200.rfdistance import (DistanceMatrix, PhyBinRFError, RFContext, hashRF, naiveDistMatrix,
+from phybin_b200.host import Forest, NNI_FAMILY, bits_to_labels
+from phybin_b200.rfdistance import (EXTRACT_BIPS, EXTRACT_CLADES, DistanceMatrix, PhyBinRFError, RFContext, hashRF, naiveDistMatrix,
                                     packed_index, printDistMat, shard_range)
 from tests.util import oracle_packed, random_multifurcating_newicks
 
@@ -482,3 +482,89 @@ def test_dedup_table_variants_agree(ctx):
         ctx._ck(ctx._L.prf_debug_wide_slots(ctx._h, 0))
     assert np.array_equal(a.astype(np.int64), want) and np.array_equal(a, b)
     assert st_a["n_unique"] == st_b["n_unique"] and st_a["n_hits"] == st_b["n_hits"]
+
+
+# ---- allBips / raw clades extracted on the device -----------------------------------
+
+def _assert_extraction_matches_host(ctx, f: Forest, W=None):
+    W = W or f.words
+    hb, ho = f.all_bips(W)
+    info = ctx.allbips(f, EXTRACT_BIPS, W)
+    db, do = ctx.allbips_fetch()
+    assert info["nnz"] == len(hb) and np.array_equal(do, ho) and np.array_equal(db, hb)
+    hc, hco, hl = f.raw_clades(W)
+    info = ctx.allbips(f, EXTRACT_CLADES, W)
+    dc, dco, dl = ctx.allbips_fetch()
+    assert info["nnz"] == len(hc) and np.array_equal(dco, hco) and np.array_equal(dc, hc) and np.array_equal(dl, hl)
+
+
+@pytest.mark.parametrize("T,n,family,p_missing", [(100, 10, 0, 0.0), (300, 64, 0, 0.0), (300, 65, 0, 0.0), (500, 100, 0, 0.0),
+                                                  (400, 200, 0, 0.0), (257, 150, 0, 0.1), (300, 100, NNI_FAMILY, 0.0),
+                                                  (64, 500, 0, 0.0), (33, 700, 0, 0.05), (1, 5, 0, 0.0)])
+def test_device_allbips_equals_host_extraction(ctx, T, n, family, p_missing):
+    f = Forest.synthetic(T, n, 0xA11B1 + T + n, family=family, p_missing=p_missing)
+    _assert_extraction_matches_host(ctx, f)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_device_allbips_odd_shapes_and_quirks(ctx, seed):
+    """Multifurcations, unary chains, missing taxa (non-dense labels: Q2), odd sizes (Q1), trees of 1-3 leaves
+    (where leaf singletons take part), wider-than-needed W."""
+    rng = random.Random(1234 + seed)
+    text = random_multifurcating_newicks(rng, 120, rng.choice([3, 4, 7, 13, 40, 70]), p_missing=0.3, unary=0.2)
+    f = Forest.parse([text + "(x0);" + "x1;" + "((x0,x1));" + "((x2),(x0,x1),x3);"])
+    _assert_extraction_matches_host(ctx, f)
+    _assert_extraction_matches_host(ctx, f, W=f.words + 2)
+    # and against the oracle's own allBips
+    o = orc.Forest([text])
+    g = Forest.parse([text])
+    ctx.allbips(g, EXTRACT_BIPS)
+    keys, off = ctx.allbips_fetch()
+    for t in range(len(g)):
+        dev = sorted(bits_to_labels(k) for k in keys[int(off[t]):int(off[t + 1])])
+        assert dev == sorted(tuple(sorted(b)) for b in o.all_bips(t))
+
+
+def test_device_allbips_feeds_the_matrix_without_host_bipartitions(ctx):
+    f = Forest.synthetic(900, 64, 77)
+    st = ctx.hashrf_load_trees(f)
+    assert st["extract"]["gpu_launches"] >= 2 and st["nnz"] == st["extract"]["nnz"]
+    ctx.hashrf_compute(editdist=3)
+    got = ctx.fetch()
+    bips, off = f.all_bips()
+    want, _, _ = ctx.hashrf(bips, off)
+    assert np.array_equal(got, want)
+    g = Forest.synthetic(300, 40, 78, p_missing=0.15)
+    ctx.tolerant_load_trees(g)
+    ctx.tolerant_compute()
+    got = ctx.fetch()
+    want, _, _ = ctx.tolerant(*g.raw_clades())
+    assert np.array_equal(got, want)
+    assert np.array_equal(got, oracle_packed(orc.Forest([g.to_newick()]), "naive"))
+
+
+def test_device_allbips_rejects_bad_input_with_codes(ctx):
+    f = Forest.synthetic(10, 8, 5)
+    label, parent, begin, leaves = (a.copy() for a in f.tree_arrays())
+    L = _native.rf_lib()
+    info = _native.prf_extract_info()
+
+    def call(label, parent, begin, leaves, T, W, mode=0):
+        return L.prf_allbips(ctx._h, label.ctypes.data, parent.ctypes.data, begin.ctypes.data, leaves.ctypes.data, T, W, 0,
+                             mode, C.byref(info))
+
+    assert call(label, parent, begin, leaves, 10, 1) == 0 and info.nnz == 50
+    bad = parent.copy()
+    bad[3] = 7  # a parent behind its child
+    assert call(label, bad, begin, leaves, 10, 1) == -1 and b"pre-order" in L.prf_last_error(ctx._h)
+    big = label.copy()
+    big[label >= 0] += 64
+    assert call(big, parent, begin, leaves, 10, 1) == -1
+    assert call(label, parent, begin, leaves, 10, 0) == -6 and call(label, parent, begin, leaves, 10, 1, mode=7) == -1
+    with pytest.raises(PhyBinRFError):  # a failed extraction leaves no result behind
+        ctx.allbips_result()
+    wide = Forest.synthetic(2, 1000, 1)  # 1998 nodes x 16 words do not fit one CTA's shared memory
+    with pytest.raises(PhyBinRFError) as e:
+        ctx.allbips(wide, EXTRACT_BIPS)
+    assert e.value.code == -6
+    assert hashRF(1000, wide, ctx, extract="host").rows() == DistanceMatrix(ctx.hashrf(*wide.all_bips())[0], 2).rows()
