@@ -51,6 +51,8 @@ PHB_API uint32_t phb_num_trees(const phb_forest* f);
 PHB_API uint32_t phb_num_labels(const phb_forest* f);
 PHB_API const char* phb_label_name(const phb_forest* f, uint32_t label);
 PHB_API uint32_t phb_tree_num_leaves(const phb_forest* f, uint32_t t);
+/* Trees parsed from the i-th text handed to phb_parse (as parsed: filters do not update it). */
+PHB_API uint32_t phb_file_num_trees(const phb_forest* f, uint32_t i);
 /* Drops trees whose numLeaves != expected (PhyBin.hs:187-194); returns the number kept. */
 PHB_API uint32_t phb_filter_num_leaves(phb_forest* f, uint32_t expected);
 /* Keeps only trees [t0, t1). */
@@ -81,6 +83,30 @@ PHB_API int phb_raw_clades(const phb_forest* f, uint32_t W, int threads, uint64_
  * t are tree_begin[t] .. tree_begin[t+1]-1; num_leaves[t] = numLeaves.  Any out pointer may be NULL. */
 PHB_API int phb_tree_arrays(const phb_forest* f, const int32_t** node_label, const uint32_t** node_parent,
                             const uint64_t** tree_begin, const uint32_t** num_leaves, uint64_t* n_nodes);
+
+/* bipsToTree num_taxa bips (RFDistance.hs:410-445) followed by displayStrippedTree (CoreTypes.hs:127-132) on one
+ * line: the tree whose bipartitions are the k given W-word sets (e.g. a consensus set from prf_consensus), with
+ * the forest's label names, as "(a, (b, c), d);".  Same subtree order as the reference: bipartitions by increasing
+ * size (ties in IntSet order), matching subtrees glommed in list order, the new node put in front.  NULL when a
+ * set has no subtree inside it or names a label the forest does not have; free with phb_free_buf. */
+PHB_API char* phb_consensus_newick(const phb_forest* f, const uint64_t* keys, uint64_t k, uint32_t W,
+                                   uint32_t num_taxa);
+
+/* Flat clusters of ONE connected component of { d <= thresh } under complete linkage or UPGMA -- the part of
+ * C.dendrogram + sliceDendro (PhyBin.hs:358,415-422) that is left once prf_mask_components has split the trees
+ * (single linkage needs nothing more: its flat clusters are the components).
+ *   sub      packed upper triangle (m*(m-1)/2) of the component's m x m distance matrix (prf_fetch_submatrix)
+ *   linkage  0 single, 1 complete, 2 UPGMA (C.Linkage; Main.hs:96-98)
+ *   labels   out, m entries: smallest local index of every tree's flat cluster
+ * Agglomeration as hierarchical-clustering-0.4.6's distance-matrix algorithm does it (stack.yaml:9; source NOT
+ * under /root/reference, restated from the published package -- tie order unpinned): repeatedly merge the pair
+ * of clusters at minimal distance, first in (lower key, higher key) lexicographic order among ties; the merged
+ * cluster keeps the lower key; distances follow Lance-Williams (min / max / size-weighted mean).  Merging stops
+ * at the first distance > thresh, which for these monotone linkages is exactly sliceDendro's cut.
+ * Returns 0, -1 on bad arguments, -2 when m is too large for a dense m x m matrix of doubles. */
+PHB_API int phb_cluster_component(const uint16_t* sub, uint32_t m, int linkage, double thresh, uint32_t* labels);
+/* Same on doubles (tests against scipy use tie-free real distances). */
+PHB_API int phb_cluster_component_f64(const double* sub, uint32_t m, int linkage, double thresh, uint32_t* labels);
 
 /* printDistMat text of a packed uint16 upper triangle; free with phb_free_buf. */
 PHB_API char* phb_print_dist_mat(const uint16_t* upper, uint32_t T);

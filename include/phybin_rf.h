@@ -238,6 +238,34 @@ PRF_API int prf_allbips_fetch(prf_ctx* ctx, uint64_t* keys, uint64_t* tree_off, 
 PRF_API int prf_mask_components(prf_ctx* ctx, const uint32_t* d_mask, uint32_t T, uint32_t* labels,
                                 uint32_t* n_components);
 
+/* Sub-matrix of the last context-owned result for m trees ids[0] < ids[1] < ... (host array): out (host,
+ * m*(m-1)/2 uint16) is the packed upper triangle of the m x m matrix d(ids[i], ids[j]) -- what the host-side
+ * complete-linkage / UPGMA step needs for one component (phb_cluster_component).  The result must cover every
+ * requested pair. */
+PRF_API int prf_fetch_submatrix(prf_ctx* ctx, const uint32_t* ids, uint32_t m, uint16_t* out);
+
+/* ---- strict consensus of every cluster (replaces the intersection inside consensusTree) -------- */
+
+typedef struct prf_consensus_info {
+  uint64_t n_out;       /* bipartitions in all consensus sets together */
+  uint32_t n_clusters;  /* distinct labels */
+  int32_t gpu_launches;
+  float ms_kernels;
+  uint32_t reserved;
+} prf_consensus_info;
+
+/* For every cluster, the bipartitions ALL of its trees have: foldl' S.intersection (allBips hd) (map allBips tl)
+ * (consensusTree, RFDistance.hs:396-400, called per cluster at PhyBin.hs:432-436).  bips / tree_off are laid out
+ * as for prf_hashrf_load (`kind` says where they live; every tree's entries must be distinct, as prf_allbips and
+ * phb_allbips produce them).  labels: HOST array, labels[t] = smallest tree id of t's cluster (what
+ * prf_mask_components returns).  The result stays on the device: per tree t a range cons_off[t] .. cons_off[t+1]
+ * that is empty unless t names a cluster, and then holds the consensus bipartitions in the order they have in
+ * tree t.  bipsToTree (RFDistance.hs:410-445) on those few sets is host work (phb_consensus_newick). */
+PRF_API int prf_consensus(prf_ctx* ctx, const uint64_t* bips, const uint64_t* tree_off, uint32_t T, uint32_t W,
+                          int kind /* prf_memkind */, const uint32_t* labels, prf_consensus_info* info);
+/* Copies the last prf_consensus result to host memory: keys n_out*W words, cons_off T+1 (either may be NULL). */
+PRF_API int prf_consensus_fetch(prf_ctx* ctx, uint64_t* keys, uint64_t* cons_off);
+
 /* ---- helpers -------------------------------------------------------------------------------- */
 
 /* p(a,b) for a < b < T (see layout above); UINT64_MAX on bad arguments. */

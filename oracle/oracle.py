@@ -116,6 +116,17 @@ class Forest:
             stats.update(n_unique=nu.value, build_s=b.value, ingest_s=g.value)
         return out
 
+    def consensus_bips(self, members: Sequence[int]) -> List[Tuple[int, ...]]:
+        """The bipartitions of consensusTree over the given trees, in Set order:
+        foldl' S.intersection (allBips hd) (map allBips tl)  (RFDistance.hs:396-400)."""
+        members = list(members)
+        if not members:
+            raise ValueError("Cannot take the consensusTree of the empty list")  # :397
+        acc = set(self.all_bips(members[0]))
+        for t in members[1:]:
+            acc &= set(self.all_bips(t))
+        return sorted(acc)
+
     def naive(self) -> np.ndarray:
         """fst . naiveDistMatrix (RFDistance.hs:168), same flat layout as hashrf()."""
         T = self.num_trees

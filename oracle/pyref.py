@@ -205,3 +205,89 @@ def print_dist_mat(mat: List[List[int]]) -> str:
     for row in mat:
         o += "".join("%d " % e for e in row) + "0\n"
     return o + rule
+
+
+# ---- strict consensus ----------------------------------------------------------------
+
+def consensus_bips(trees) -> frozenset:
+    """The bipartitions every tree has: foldl' S.intersection (allBips hd) (map allBips tl)
+    (consensusTree, RFDistance.hs:396-400)."""
+    if not trees:
+        raise ValueError("Cannot take the consensusTree of the empty list")  # :397
+    acc = all_bips(trees[0])
+    for t in trees[1:]:
+        acc = acc & all_bips(t)
+    return acc
+
+
+def bips_to_tree(num_taxa: int, bips) -> tuple:
+    """bipsToTree (RFDistance.hs:410-445): start from the num_taxa singleton leaves; visit the bipartitions in
+    increasing size (stable over Set order); the current subtrees that lie inside the bipartition are glommed,
+    in list order, under a new interior node that goes to the FRONT of the list."""
+    ordered = sorted(sorted(bips), key=len)  # L.sortBy (compare `on` bipSize) (S.toList origbip), stable
+    subtrees = [(frozenset([ix]), ("L", ix)) for ix in range(num_taxa)]
+    for bip in ordered:
+        inside = set(bip)
+        in_ = [st for st in subtrees if st[0] <= inside]   # isMatch bip x = denseIsSubset x bip
+        out = [st for st in subtrees if not st[0] <= inside]
+        if not in_:
+            raise ValueError("bipsToTree: Internal error!  No match for bip: %r" % (bip,))
+        union = frozenset().union(*[s for s, _ in in_])
+        subtrees = [(union, ("I", [t for _, t in in_]))] + out
+    if not subtrees:
+        raise ValueError("bipsToTree: internal error")
+    if len(subtrees) == 1:
+        return subtrees[0][1]
+    return ("I", [t for _, t in subtrees])
+
+
+def consensus_tree(num_taxa: int, trees) -> tuple:
+    return bips_to_tree(num_taxa, consensus_bips(trees))
+
+
+def to_newick(names: Sequence[str], t) -> str:
+    """displayStrippedTree (CoreTypes.hs:127-132) on one line: names and parentheses only, ", " separators
+    (the reference lays the same tokens out with a pretty-printer; its parser drops all whitespace, Parser.hs:35)."""
+    def rec(n):
+        if n[0] == "L":
+            return names[n[1]]
+        return "(" + ", ".join(rec(k) for k in n[1]) + ")"
+    return rec(t) + ";"
+
+
+# ---- clustering consumer (SURVEY 8f-1) --------------------------------------------------------------
+
+def flat_clusters(dist, n: int, linkage: str, thresh: float) -> List[int]:
+    """sliceDendro thresh (C.dendrogram linkage items dist)  (PhyBin.hs:358,415-422) as labels[i] = smallest member
+    of i's cluster.  C.dendrogram is hierarchical-clustering-0.4.6 (stack.yaml:9), NOT under /root/reference:
+    PARITY UNPINNED.  Restated from the published package's distance-matrix algorithm, the naive way: find the
+    minimal distance over all active pairs (k1 < k2), the first in lexicographic order wins ties; merge, the new
+    cluster keeps the lower key; Lance-Williams update (single: min, complete: max, UPGMA: size-weighted mean).
+    For these monotone linkages the flat clusters are what has merged before the first distance > thresh."""
+    d = {(i, j): float(dist(i, j)) for i in range(n) for j in range(i + 1, n)}
+    size = {i: 1 for i in range(n)}
+    label = list(range(n))
+    while len(size) > 1:
+        keys = sorted(size)
+        best, pair = None, None
+        for x, i in enumerate(keys):
+            for j in keys[x + 1:]:
+                if best is None or d[(i, j)] < best:
+                    best, pair = d[(i, j)], (i, j)
+        if best > thresh:
+            break
+        a, b = pair
+        for x in keys:
+            if x in (a, b):
+                continue
+            da, db = d[(min(a, x), max(a, x))], d[(min(b, x), max(b, x))]
+            if linkage == "single":
+                v = min(da, db)
+            elif linkage == "complete":
+                v = max(da, db)
+            else:
+                v = (size[a] * da + size[b] * db) / (size[a] + size[b])
+            d[(min(a, x), max(a, x))] = v
+        size[a] += size.pop(b)
+        label = [a if l == b else l for l in label]
+    return label

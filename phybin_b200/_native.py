@@ -32,6 +32,14 @@ class prf_extract_info(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class prf_consensus_info(C.Structure):
+    _fields_ = [("n_out", C.c_uint64), ("n_clusters", C.c_uint32), ("gpu_launches", C.c_int32),
+                ("ms_kernels", C.c_float), ("reserved", C.c_uint32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
 class prf_stats(C.Structure):
     _fields_ = [
         ("n_trees", C.c_uint64), ("n_words", C.c_uint64), ("nnz", C.c_uint64),
@@ -74,6 +82,8 @@ def host_lib():
         L.phb_label_name.argtypes = [vp, C.c_uint32]
         L.phb_tree_num_leaves.restype = C.c_uint32
         L.phb_tree_num_leaves.argtypes = [vp, C.c_uint32]
+        L.phb_file_num_trees.restype = C.c_uint32
+        L.phb_file_num_trees.argtypes = [vp, C.c_uint32]
         L.phb_filter_num_leaves.restype = C.c_uint32
         L.phb_filter_num_leaves.argtypes = [vp, C.c_uint32]
         L.phb_slice.restype = C.c_uint32
@@ -85,6 +95,10 @@ def host_lib():
         L.phb_raw_clades.argtypes = [vp, C.c_uint32, C.c_int, C.POINTER(u64p), C.POINTER(u64p),
                                      C.POINTER(u64p), u64p]
         L.phb_tree_arrays.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), u64p]
+        L.phb_consensus_newick.restype = vp
+        L.phb_consensus_newick.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32]
+        L.phb_cluster_component.argtypes = [vp, C.c_uint32, C.c_int, C.c_double, vp]
+        L.phb_cluster_component_f64.argtypes = [vp, C.c_uint32, C.c_int, C.c_double, vp]
         L.phb_print_dist_mat.restype = vp
         L.phb_print_dist_mat.argtypes = [vp, C.c_uint32]
         L.phb_write_dist_mat.argtypes = [C.c_char_p, vp, C.c_uint32]
@@ -129,6 +143,9 @@ def rf_lib():
                                   C.POINTER(prf_extract_info)]
         L.prf_allbips_result.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), u64p]
         L.prf_allbips_fetch.argtypes = [vp, vp, vp, vp]
+        L.prf_fetch_submatrix.argtypes = [vp, vp, C.c_uint32, vp]
+        L.prf_consensus.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int, vp, C.POINTER(prf_consensus_info)]
+        L.prf_consensus_fetch.argtypes = [vp, vp, vp]
         L.prf_mask_components.argtypes = [vp, vp, C.c_uint32, vp, u32p]
         L.prf_packed_index.restype = C.c_uint64
         L.prf_packed_index.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
@@ -153,7 +170,7 @@ def rf_lib():
 RF_SYMBOLS = [
     "prf_create", "prf_destroy", "prf_last_error", "prf_version", "prf_stream", "prf_hashrf",
     "prf_hashrf_load", "prf_hashrf_compute", "prf_hashrf_partition", "prf_hashrf_export", "prf_hashrf_merge", "prf_fetch", "prf_fetch_mask", "prf_fetch_rows",
-    "prf_tolerant", "prf_tolerant_load", "prf_tolerant_compute", "prf_allbips", "prf_allbips_result", "prf_allbips_fetch",
+    "prf_tolerant", "prf_tolerant_load", "prf_tolerant_compute", "prf_allbips", "prf_allbips_result", "prf_allbips_fetch", "prf_consensus", "prf_consensus_fetch", "prf_fetch_submatrix",
     "prf_mask_components", "prf_packed_index",
     "prf_shard_align", "prf_shard_range", "prf_limits", "prf_launch_count",
 ]

@@ -17,6 +17,7 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <limits>
 #include <unordered_map>
 #include <vector>
 
@@ -32,6 +33,7 @@ struct Forest {
   std::vector<uint32_t> parent, first_child, next_sib;
   std::vector<uint64_t> tree_begin;  // T+1
   std::vector<uint32_t> num_leaves;  // numLeaves (CoreTypes.hs:289): duplicates count twice
+  std::vector<uint32_t> file_trees;  // trees parsed from every input text (phb_parse only; not kept by filters)
   std::string err;
 
   uint32_t T() const { return (uint32_t)num_leaves.size(); }
@@ -490,6 +492,7 @@ phb_forest* phb_parse(int nfiles, const char* const* texts, int name_prefix) {
         f.tree_begin.push_back(g.tree_begin[t] + shift);
         f.num_leaves.push_back(g.num_leaves[t]);
       }
+      f.file_trees.push_back(g.T());
     }
     f.tree_begin.push_back(f.label.size());
   } catch (const std::exception& e) {
@@ -549,6 +552,7 @@ uint32_t phb_num_labels(const phb_forest* f) { return (uint32_t)f->f.label_names
 const char* phb_label_name(const phb_forest* f, uint32_t l) {
   return l < f->f.label_names.size() ? f->f.label_names[l].c_str() : "";
 }
+uint32_t phb_file_num_trees(const phb_forest* f, uint32_t i) { return i < f->f.file_trees.size() ? f->f.file_trees[i] : 0; }
 uint32_t phb_tree_num_leaves(const phb_forest* f, uint32_t t) { return t < f->f.T() ? f->f.num_leaves[t] : 0; }
 
 uint32_t phb_filter_num_leaves(phb_forest* h, uint32_t expected) {
@@ -682,6 +686,160 @@ int phb_tree_arrays(const phb_forest* h, const int32_t** node_label, const uint3
   if (num_leaves) *num_leaves = f.num_leaves.data();
   if (n_nodes) *n_nodes = f.label.size();
   return 0;
+}
+
+// Ord IntSet = lexicographic on the ascending element lists: at the lowest label where the two sets differ,
+// the set that has it is the smaller one unless the other set has nothing above it (a proper prefix is smaller).
+static bool intset_less(const uint64_t* a, const uint64_t* b, uint32_t W) {
+  for (uint32_t w = 0; w < W; ++w) {
+    uint64_t x = a[w] ^ b[w];
+    if (!x) continue;
+    int d = __builtin_ctzll(x);
+    bool a_has = (a[w] >> d) & 1;
+    const uint64_t* other = a_has ? b : a;
+    bool other_has_more = d < 63 && (other[w] >> (d + 1)) != 0;
+    for (uint32_t v = w + 1; v < W && !other_has_more; ++v) other_has_more = other[v] != 0;
+    return a_has ? other_has_more : !other_has_more;
+  }
+  return false;
+}
+
+char* phb_consensus_newick(const phb_forest* h, const uint64_t* keys, uint64_t k, uint32_t W, uint32_t num_taxa) {
+  if (!h || (k && !keys) || W == 0 || W > 64 || num_taxa > 64 * W) return nullptr;
+  const Forest& f = h->f;
+  if (num_taxa > f.label_names.size()) return nullptr;
+  // sorted = L.sortBy (compare `on` bipSize) (S.toList origbip): stable by size over Set order
+  std::vector<const uint64_t*> bip(k);
+  for (uint64_t i = 0; i < k; ++i) bip[i] = keys + i * W;
+  std::sort(bip.begin(), bip.end(), [W](const uint64_t* a, const uint64_t* b) {
+    uint32_t ca = popcount_w(a, W), cb = popcount_w(b, W);
+    return ca != cb ? ca < cb : intset_less(a, b, W);
+  });
+  struct Node { int32_t leaf; std::vector<uint32_t> kids; };
+  std::vector<Node> nodes;
+  struct Sub { std::vector<uint64_t> set; uint32_t node; };
+  std::vector<Sub> subs;  // lvl0: the singleton leaves 0 .. num_taxa-1 (:416-417)
+  for (uint32_t ix = 0; ix < num_taxa; ++ix) {
+    Sub s{std::vector<uint64_t>(W, 0), (uint32_t)nodes.size()};
+    s.set[ix >> 6] = 1ull << (ix & 63);
+    nodes.push_back(Node{(int32_t)ix, {}});
+    subs.push_back(std::move(s));
+  }
+  for (const uint64_t* b : bip) {
+    std::vector<Sub> in, out;
+    for (Sub& s : subs) {
+      bool inside = true;  // isMatch bip x = denseIsSubset x bip (:424)
+      for (uint32_t w = 0; w < W; ++w) inside &= (s.set[w] & ~b[w]) == 0;
+      (inside ? in : out).push_back(std::move(s));
+    }
+    if (in.empty()) return nullptr;  // "bipsToTree: Internal error!  No match for bip" (:436)
+    Sub merged{std::vector<uint64_t>(W, 0), (uint32_t)nodes.size()};
+    Node nd{-1, {}};
+    for (const Sub& s : in) {
+      for (uint32_t w = 0; w < W; ++w) merged.set[w] |= s.set[w];
+      nd.kids.push_back(s.node);
+    }
+    nodes.push_back(std::move(nd));
+    subs.clear();
+    subs.push_back(std::move(merged));  // the merged subtree goes to the front (:443-444)
+    for (Sub& s : out) subs.push_back(std::move(s));
+  }
+  uint32_t root;
+  if (subs.empty()) return nullptr;
+  if (subs.size() == 1) {
+    root = subs[0].node;
+  } else {
+    Node nd{-1, {}};
+    for (const Sub& s : subs) nd.kids.push_back(s.node);
+    root = (uint32_t)nodes.size();
+    nodes.push_back(std::move(nd));
+  }
+  std::string o;
+  struct It { uint32_t v; size_t next; };
+  std::vector<It> st{{root, 0}};
+  while (!st.empty()) {
+    It& it = st.back();
+    const Node& nd = nodes[it.v];
+    if (nd.leaf >= 0) { o += f.label_names[nd.leaf]; st.pop_back(); continue; }
+    if (it.next == 0) o += '(';
+    if (it.next == nd.kids.size()) { o += ')'; st.pop_back(); continue; }
+    if (it.next) o += ", ";
+    uint32_t child = nd.kids[it.next++];
+    st.push_back({child, 0});
+  }
+  o += ';';
+  char* r = (char*)std::malloc(o.size() + 1);
+  if (r) std::memcpy(r, o.c_str(), o.size() + 1);
+  return r;
+}
+
+namespace {
+
+// Agglomerative clustering of m items cut at `thresh`; see phybin_host.h.  d: packed upper triangle, modified.
+int agglomerate(std::vector<double>& d, uint32_t m, int linkage, double thresh, uint32_t* labels) {
+  auto at = [&](uint32_t i, uint32_t j) -> double& {  // i < j
+    return d[(uint64_t)i * (2ull * m - i - 1) / 2 + (j - i - 1)];
+  };
+  auto get = [&](uint32_t i, uint32_t j) -> double& { return i < j ? at(i, j) : at(j, i); };
+  const double inf = std::numeric_limits<double>::infinity();
+  std::vector<char> active(m, 1);
+  std::vector<uint32_t> size(m, 1), parent(m), nn(m, NONE);
+  std::vector<double> nnd(m, inf);
+  for (uint32_t i = 0; i < m; ++i) parent[i] = i;
+  auto rescan = [&](uint32_t i) {  // nearest active j > i, the first one on ties
+    nn[i] = NONE;
+    nnd[i] = inf;
+    for (uint32_t j = i + 1; j < m; ++j)
+      if (active[j] && at(i, j) < nnd[i]) { nnd[i] = at(i, j); nn[i] = j; }
+  };
+  for (uint32_t i = 0; i < m; ++i) rescan(i);
+  for (uint32_t left = m; left > 1; --left) {
+    uint32_t a = NONE;
+    double best = inf;
+    for (uint32_t i = 0; i < m; ++i)
+      if (active[i] && nn[i] != NONE && nnd[i] < best) { best = nnd[i]; a = i; }
+    if (a == NONE || best > thresh) break;  // sliceDendro: dist > dstThresh splits (PhyBin.hs:418-419)
+    const uint32_t b = nn[a];
+    const double na = size[a], nb = size[b];
+    for (uint32_t x = 0; x < m; ++x) {
+      if (!active[x] || x == a || x == b) continue;
+      double &da = get(a, x), db = get(b, x);
+      da = linkage == 0 ? std::min(da, db) : linkage == 1 ? std::max(da, db) : (na * da + nb * db) / (na + nb);
+    }
+    size[a] += size[b];
+    active[b] = 0;
+    parent[b] = a;
+    for (uint32_t i = 0; i < b; ++i) {
+      if (!active[i]) continue;
+      if (i == a || nn[i] == a || nn[i] == b) { rescan(i); continue; }
+      if (i < a) {
+        const double v = at(i, a);
+        if (v < nnd[i] || (v == nnd[i] && a < nn[i])) { nnd[i] = v; nn[i] = a; }
+      }
+    }
+  }
+  for (uint32_t i = 0; i < m; ++i) {
+    uint32_t r = i;
+    while (parent[r] != r) r = parent[r];
+    labels[i] = r;  // merges keep the lower key, so the root is the cluster's smallest index
+  }
+  return 0;
+}
+
+}  // namespace
+
+int phb_cluster_component_f64(const double* sub, uint32_t m, int linkage, double thresh, uint32_t* labels) {
+  if ((m > 1 && !sub) || (m && !labels) || linkage < 0 || linkage > 2) return -1;
+  if (m > 46000) return -2;  // 8.5 GB of doubles
+  std::vector<double> d(sub, sub + (uint64_t)m * (m ? m - 1 : 0) / 2);
+  return agglomerate(d, m, linkage, thresh, labels);
+}
+
+int phb_cluster_component(const uint16_t* sub, uint32_t m, int linkage, double thresh, uint32_t* labels) {
+  if ((m > 1 && !sub) || (m && !labels) || linkage < 0 || linkage > 2) return -1;
+  if (m > 46000) return -2;
+  std::vector<double> d(sub, sub + (uint64_t)m * (m ? m - 1 : 0) / 2);  // fromIntegral (PhyBin.hs:355-356)
+  return agglomerate(d, m, linkage, thresh, labels);
 }
 
 static void append_uint(std::string& o, unsigned x) {

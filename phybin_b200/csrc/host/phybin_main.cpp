@@ -10,6 +10,7 @@
 // program exits with the library's error.
 #include <sys/stat.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -25,7 +26,8 @@
 namespace {
 
 struct Options {
-  bool tolerant = false, rfdist = false, single = false, host_bips = false;
+  bool tolerant = false, rfdist = false, host_bips = false;
+  int linkage = 2;  // C.UPGMA, the reference's default (CoreTypes.hs:265); 0 single, 1 complete
   int editdist = -1, name_prefix = -1, variant = PRF_VARIANT_AUTO;
   std::string out_dir = "phybin_out";
   std::vector<std::string> files;
@@ -55,8 +57,9 @@ Options parse_args(int argc, char** argv) {
     if (!std::strcmp(a, "--hashrf")) o.tolerant = false;
     else if (!std::strcmp(a, "--tolerant")) o.tolerant = true;
     else if (!std::strcmp(a, "--rfdist")) o.rfdist = true;
-    else if (!std::strcmp(a, "--single")) o.single = true;
-    else if (!std::strcmp(a, "--complete") || !std::strcmp(a, "--UPGMA")) o.single = false;
+    else if (!std::strcmp(a, "--single")) o.linkage = 0;  // Main.hs:96-98
+    else if (!std::strcmp(a, "--complete")) o.linkage = 1;
+    else if (!std::strcmp(a, "--UPGMA")) o.linkage = 2;
     else if (starts(a, "--editdist=", &v)) o.editdist = std::atoi(v);
     else if (!std::strcmp(a, "--editdist")) o.editdist = std::atoi(need(a));
     else if (starts(a, "--output=", &v)) o.out_dir = v;
@@ -110,7 +113,27 @@ int main(int argc, char** argv) {
   if (const char* e = phb_error(forest)) die(e);
   const uint32_t n_taxa = phb_num_labels(forest);
   std::printf("Parsed %u trees, %u taxa.\n", phb_num_trees(forest), n_taxa);
+  // treename (Parser.hs:60-68): base name of "<file>[_<index in file>]" plus "_<global index>" when there is
+  // more than one tree in all
+  std::vector<std::string> names;
+  {
+    std::vector<std::string> raw;
+    for (size_t i = 0; i < opt.files.size(); ++i) {
+      const uint32_t k = phb_file_num_trees(forest, (uint32_t)i);
+      for (uint32_t j = 0; j < k; ++j) raw.push_back(k > 1 ? opt.files[i] + "_" + std::to_string(j) : opt.files[i]);
+    }
+    for (size_t g = 0; g < raw.size(); ++g) {
+      std::string b = raw[g].substr(raw[g].find_last_of('/') + 1);  // takeBaseName: no directory, no extension
+      const size_t dot = b.find_last_of('.');
+      if (dot != std::string::npos) b.erase(dot);
+      names.push_back(raw.size() > 1 ? b + "_" + std::to_string(g) : b);
+    }
+  }
   if (!opt.tolerant) {  // HashRF keeps only trees with every taxon (PhyBin.hs:187-194)
+    std::vector<std::string> kept_names;
+    for (uint32_t t = 0; t < phb_num_trees(forest); ++t)
+      if (phb_tree_num_leaves(forest, t) == n_taxa && t < names.size()) kept_names.push_back(names[t]);
+    names.swap(kept_names);
     const uint32_t before = phb_num_trees(forest), kept = phb_filter_num_leaves(forest, n_taxa);
     if (kept != before) std::printf("WARNING: dropped %u trees whose leaf count differs from %u\n", before - kept, n_taxa);
   } else if (phb_has_duplicate_leaves(forest)) {
@@ -181,18 +204,97 @@ int main(int argc, char** argv) {
     phb_free_buf(txt);
   }
   if (opt.editdist >= 0) {
-    // flat clusters at distance <= D from the fused threshold mask.  For single linkage these ARE the
-    // reference's sliceDendro clusters (PhyBin.hs:415-422); for complete/UPGMA they are the connected
-    // components every such cluster is contained in.
+    // sliceDendro D (C.dendrogram linkage trees dist)  (PhyBin.hs:358,415-422): the device splits the trees into the
+    // connected components of { d <= D } (union-find over the fused mask); that is the single-linkage answer, and
+    // complete linkage / UPGMA agglomerate every component on its own from its fetched sub-matrix.
+    static const char* const kLinkage[] = {"SingleLinkage", "CompleteLinkage", "UPGMA"};
+    std::printf("Next, clustering using method %s\n", kLinkage[opt.linkage]);  // PhyBin.hs:363
     std::vector<uint32_t> label(T ? T : 1);
     uint32_t comps = 0;
-    if ((rc = prf_mask_components(ctx, nullptr, T, label.data(), &comps)))  // union-find over the mask, on the GPU
+    if ((rc = prf_mask_components(ctx, nullptr, T, label.data(), &comps)))
       die(std::string("phybin_rf error: ") + prf_last_error(ctx));
+    std::vector<std::vector<uint32_t>> members(T);
+    for (uint32_t t = 0; t < T; ++t) members[label[t]].push_back(t);
+    if (opt.linkage != 0) {
+      std::vector<uint16_t> sub;
+      std::vector<uint32_t> local;
+      for (uint32_t c = 0; c < T; ++c) {
+        const std::vector<uint32_t>& ids = members[c];
+        const uint32_t m = (uint32_t)ids.size();
+        if (m < 3) continue;  // two trees within D of each other are one cluster under every linkage
+        sub.resize((size_t)m * (m - 1) / 2);
+        local.resize(m);
+        if ((rc = prf_fetch_submatrix(ctx, ids.data(), m, sub.data()))) die(std::string("phybin_rf error: ") + prf_last_error(ctx));
+        if (phb_cluster_component(sub.data(), m, opt.linkage, (double)opt.editdist, local.data()))
+          die("component of " + std::to_string(m) + " trees is too large for the host clustering step");
+        for (uint32_t i = 0; i < m; ++i) label[ids[i]] = ids[local[i]];
+      }
+      for (auto& v : members) v.clear();
+      for (uint32_t t = 0; t < T; ++t) members[label[t]].push_back(t);
+    }
+    std::printf("Combining all clusters at distance less than or equal to %d\n", opt.editdist);  // PhyBin.hs:276
+    // sorted0 = reverse (sortBy (compare `on` fst) wlens)  (PhyBin.hs:281): sizes descending.  The order of
+    // equal-sized clusters follows the library's dendrogram in the reference; here: by smallest member, reversed.
+    std::vector<uint32_t> order;
+    for (uint32_t c = 0; c < T; ++c)
+      if (!members[c].empty()) order.push_back(c);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return members[a].size() < members[b].size(); });
+    std::reverse(order.begin(), order.end());
+    std::string sizes = "[";
+    for (size_t i = 0; i < order.size(); ++i) sizes += (i ? "," : "") + std::to_string(members[order[i]].size());
+    sizes += "]";
+    std::printf("After flattening, cluster sizes are: %s\n", sizes.c_str());  // PhyBin.hs:284
+    size_t non_single = 0;
+    for (uint32_t c : order) non_single += members[c].size() > 1;
+    std::printf(" Outcome: %zu clusters found, %zu non-singleton\n", order.size(), non_single);  // reportClusts, PhyBin.hs:375
     uint64_t close = 0;
     for (uint64_t w = 0; w < (P + 31) / 32; ++w) close += (uint64_t)__builtin_popcount(mask[w]);
-    std::printf("%llu of %llu pairs within edit distance %d; %u %s at that threshold\n", (unsigned long long)close,
-                (unsigned long long)P, opt.editdist, comps,
-                opt.single ? "single-linkage clusters" : "connected components (supersets of the complete/UPGMA clusters)");
+    std::printf("%llu of %llu pairs within edit distance %d; %u connected components\n", (unsigned long long)close,
+                (unsigned long long)P, opt.editdist, comps);
+
+    // strict consensus of every cluster: the intersection runs on the device (prf_consensus), bipsToTree here
+    std::vector<uint64_t> ckeys, coff;
+    if (!opt.tolerant) {
+      prf_consensus_info ci{};
+      if (opt.host_bips) {
+        uint64_t *bips = nullptr, *off = nullptr, nnz = 0;
+        if (phb_allbips(forest, W, 0, &bips, &off, &nnz)) die("bipartition extraction failed");
+        rc = prf_consensus(ctx, bips, off, T, W, PRF_MEM_HOST, label.data(), &ci);
+        phb_free_buf(bips);
+        phb_free_buf(off);
+      } else {
+        const uint64_t *d_keys = nullptr, *d_off = nullptr;
+        rc = prf_allbips_result(ctx, &d_keys, &d_off, nullptr, nullptr);  // still resident from the extraction
+        if (!rc) rc = prf_consensus(ctx, d_keys, d_off, T, W, PRF_MEM_DEVICE, label.data(), &ci);
+      }
+      ckeys.resize(std::max<uint64_t>(ci.n_out * W, 1));
+      coff.resize((size_t)T + 1);
+      if (!rc) rc = prf_consensus_fetch(ctx, ckeys.data(), coff.data());
+      if (rc) die(std::string("phybin_rf error: ") + prf_last_error(ctx));
+    }
+    // outputClusters (PhyBin.hs:428-441): cluster<i>_<size>.txt, _consensus.tr, _alltrees.tr
+    const size_t max_files = 1000;
+    for (size_t i = 0; i < order.size() && i < max_files; ++i) {
+      const std::vector<uint32_t>& ids = members[order[i]];
+      const std::string base = opt.out_dir + "/cluster" + std::to_string(i + 1) + "_" + std::to_string(ids.size());
+      std::ofstream txt(base + ".txt"), all(base + "_alltrees.tr");
+      for (uint32_t t : ids) {
+        txt << (t < names.size() ? names[t] : std::to_string(t)) << '\n';
+        char* nw = phb_to_newick(forest, t, t + 1);
+        all << nw;
+        phb_free_buf(nw);
+      }
+      if (!opt.tolerant) {
+        const uint32_t c = order[i];
+        char* cons = phb_consensus_newick(forest, ckeys.data() + coff[c] * W, coff[c + 1] - coff[c], W, n_taxa);
+        if (!cons) die("bipsToTree failed for cluster " + std::to_string(i + 1));
+        std::ofstream(base + "_consensus.tr") << cons << '\n';
+        phb_free_buf(cons);
+      }
+    }
+    std::printf(" [finished] Wrote contents of each cluster to cluster<N>_<size>.txt\n");  // PhyBin.hs:443
+    if (!opt.tolerant) std::printf(" [finished] Wrote representative (consensus) trees to cluster<N>_<size>_consensus.tr\n");
+    if (order.size() > max_files) std::printf("(only the %zu largest clusters were written out)\n", max_files);
     std::ofstream cf(opt.out_dir + "/components.txt");
     for (uint32_t t = 0; t < T; ++t) cf << t << ' ' << label[t] << '\n';
   }

@@ -71,4 +71,18 @@ __global__ void __launch_bounds__(256) cc_flatten_kernel(uint32_t* parent, uint3
   if (r == t) atomicAdd(n_roots, 1u);
 }
 
+// Sub-matrix of one component: out[q], q = packed position of (i, j), i < j < m, in an m x m triangle, is
+// d(ids[i], ids[j]) read from the full packed triangle `src` (which starts at packed position src_begin).
+// ids must be ascending.
+__global__ void __launch_bounds__(256) submatrix_gather_kernel(const uint16_t* __restrict__ src, uint64_t src_begin,
+                                                               uint32_t T, const uint32_t* __restrict__ ids, uint32_t m,
+                                                               uint64_t n_out, uint16_t* __restrict__ out) {
+  const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_out) return;
+  const uint32_t i = row_of(q, m);
+  const uint32_t j = i + 1 + (uint32_t)(q - row_start(i, m));
+  const uint32_t a = ids[i], b = ids[j];
+  out[q] = src[row_start(a, T) + (b - a - 1) - src_begin];
+}
+
 }  // namespace prf

@@ -117,6 +117,15 @@ struct ExtractState {
   DevBuf<uint64_t> leafsets;  // [T * W]  (mode PRF_EXTRACT_CLADES only)
 };
 
+// Result of the last prf_consensus (prf_consensus.cuh).
+struct ConsensusState {
+  bool valid = false;
+  uint32_t T = 0, W = 0;
+  uint64_t n_out = 0;
+  DevBuf<uint64_t> keys;  // [n_out * W]
+  DevBuf<uint64_t> off;   // [T + 1]
+};
+
 struct Ctx {
   int device = 0;
   int sm_count = 148;
@@ -127,6 +136,7 @@ struct Ctx {
   HashRFState h;
   TolerantState tol;
   ExtractState ext;
+  ConsensusState cons;
   RowPlan plan;
   bool debug_small_tiles = false;
   bool debug_no_flip = false;         // tests: keep majority lists as they are

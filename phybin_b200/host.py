@@ -131,6 +131,42 @@ class Forest:
                 _take(lp, T * W).reshape(T, W))
 
 
+    def consensus_newick(self, keys: np.ndarray, num_taxa: Optional[int] = None) -> str:
+        """bipsToTree num_taxa keys (RFDistance.hs:410-445) printed on one line with this forest's label names
+        (phb_consensus_newick).  keys: [k, W] bit sets, e.g. one cluster's range of RFContext.consensus()."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        W = keys.shape[1] if keys.ndim == 2 else self.words
+        L = host_lib()
+        p = L.phb_consensus_newick(self._h, keys.ctypes.data if keys.size else None, len(keys), W,
+                                   self.num_labels if num_taxa is None else num_taxa)
+        if not p:
+            raise ValueError("bipsToTree: a bipartition matches no subtree (or names an unknown label)")
+        s = C.string_at(p).decode()
+        L.phb_free_buf(p)
+        return s
+
+
+LINKAGE = {"single": 0, "complete": 1, "UPGMA": 2}
+
+
+def cluster_component(sub: np.ndarray, m: int, linkage: str, thresh: float) -> np.ndarray:
+    """Flat clusters of one component under `linkage` cut at `thresh` (phb_cluster_component): sub is the packed
+    upper triangle of the component's m x m distances (uint16 from the device, or float64); returns labels[m] =
+    smallest local index of each item's cluster.  The part of C.dendrogram + sliceDendro (PhyBin.hs:358,415-422)
+    that remains after the device split the trees into components."""
+    L = host_lib()
+    labels = np.empty(m, dtype=np.uint32)
+    if sub.dtype == np.float64:
+        sub = np.ascontiguousarray(sub)
+        rc = L.phb_cluster_component_f64(sub.ctypes.data, m, LINKAGE[linkage], float(thresh), labels.ctypes.data)
+    else:
+        sub = np.ascontiguousarray(sub, dtype=np.uint16)
+        rc = L.phb_cluster_component(sub.ctypes.data, m, LINKAGE[linkage], float(thresh), labels.ctypes.data)
+    if rc:
+        raise ValueError("phb_cluster_component: %s" % ("component too large for a dense matrix" if rc == -2 else "bad arguments"))
+    return labels
+
+
 def bits_to_labels(row: np.ndarray) -> Tuple[int, ...]:
     """One W-word bit set -> ascending label tuple (for tests and debugging)."""
     out = []

@@ -16,8 +16,8 @@ from typing import IO, List, Optional, Tuple
 import numpy as np
 
 from . import _native
-from ._native import prf_extract_info, prf_stats, rf_lib, host_lib
-from .host import Forest, bits_to_labels
+from ._native import prf_consensus_info, prf_extract_info, prf_stats, rf_lib, host_lib
+from .host import Forest, bits_to_labels, cluster_component
 
 VARIANT_AUTO, VARIANT_SPARSE, VARIANT_DENSE = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -251,6 +251,59 @@ class RFContext:
         n = C.c_uint32(0)
         self._ck(self._L.prf_mask_components(self._h, d_mask or None, self.T, labels.ctypes.data, C.byref(n)))
         return labels, n.value
+
+    def fetch_submatrix(self, ids) -> np.ndarray:
+        """prf_fetch_submatrix: packed upper triangle of d(ids[i], ids[j]) for ascending tree ids."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        m = len(ids)
+        out = np.empty(m * (m - 1) // 2, dtype=np.uint16)
+        self._ck(self._L.prf_fetch_submatrix(self._h, ids.ctypes.data, m, out.ctypes.data))
+        return out
+
+    def flat_clusters(self, editdist: int, linkage: str = "UPGMA") -> Tuple[np.ndarray, int]:
+        """sliceDendro editdist (C.dendrogram linkage trees dist)  (PhyBin.hs:358,415-422) as flat labels: labels[t] =
+        smallest tree id of t's cluster.  Needs a full-triangle compute with this editdist (its mask).  The device
+        splits the trees into the connected components of {d <= editdist}; single linkage is done there, the other
+        linkages agglomerate every component on the host from its fetched sub-matrix (cluster_component)."""
+        labels, n = self.mask_components()
+        if linkage == "single":
+            return labels, n
+        order = np.argsort(labels, kind="stable")
+        bounds = np.flatnonzero(np.diff(labels[order])) + 1
+        out = labels.copy()
+        for ids in np.split(order, bounds):
+            if len(ids) < 3:  # a component of two trees is one cluster under every linkage
+                continue
+            ids = np.sort(ids).astype(np.uint32)
+            local = cluster_component(self.fetch_submatrix(ids), len(ids), linkage, editdist)
+            out[ids] = ids[local]
+        return out, int(np.count_nonzero(out == np.arange(len(out))))
+
+    def consensus(self, labels: np.ndarray, bips=None, tree_off=None) -> Tuple[np.ndarray, np.ndarray, dict]:
+        """prf_consensus: for every cluster (labels[t] = smallest tree id of t's cluster, as mask_components returns)
+        the bipartitions all its trees share -- the intersection inside consensusTree (RFDistance.hs:396-400).
+        Works on host arrays (bips[nnz, W], tree_off) or, by default, on the last device extraction
+        (allbips / hashrf_load_trees).  Returns (keys[n_out, W], cons_off[T+1], info): cluster c's set is
+        keys[cons_off[c]:cons_off[c+1]]; the ranges of trees that do not name a cluster are empty."""
+        labels = np.ascontiguousarray(labels, dtype=np.uint32)
+        T = len(labels)
+        info = prf_consensus_info()
+        if bips is None:
+            eT, W, mode, _ = self._ext
+            if mode != EXTRACT_BIPS or eT != T:
+                raise PhyBinRFError(-5, "the last device extraction is not the allBips of these trees")
+            k, o, _, _ = self.allbips_result()
+            self._ck(self._L.prf_consensus(self._h, k, o, T, W, MEM_DEVICE, labels.ctypes.data, C.byref(info)))
+        else:
+            bips = np.ascontiguousarray(bips, dtype=np.uint64)
+            tree_off = np.ascontiguousarray(tree_off, dtype=np.uint64)
+            W = bips.shape[1] if bips.ndim == 2 else 1
+            self._ck(self._L.prf_consensus(self._h, bips.ctypes.data, tree_off.ctypes.data, T, W, MEM_HOST,
+                                           labels.ctypes.data, C.byref(info)))
+        keys = np.empty((info.n_out, W), dtype=np.uint64)
+        off = np.empty(T + 1, dtype=np.uint64)
+        self._ck(self._L.prf_consensus_fetch(self._h, keys.ctypes.data, off.ctypes.data))
+        return keys, off, info.as_dict()
 
     # ---- results -----------------------------------------------------------------------------
     def fetch(self, p_begin: int = 0, p_end: Optional[int] = None) -> np.ndarray:

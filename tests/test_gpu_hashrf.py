@@ -369,6 +369,40 @@ def test_cli_matches_reference_output_format(golden, tmp_path):
     assert (out / "distance_matrix.txt").read_text().splitlines()[2:4] == ["0", "1 0"]
 
 
+@pytest.mark.parametrize("name,thr,linkage,host_bips", [("t4", 0, "--UPGMA", False), ("t5", 2, "--complete", False),
+                                                        ("t3", 8, "--UPGMA", True), ("t3", 8, "--single", False)])
+def test_cli_clusters_and_consensus_files(golden, tmp_path, name, thr, linkage, host_bips):
+    """phybin --editdist on the reference's consensus fixtures: every tree of the file ends up in one cluster and
+    cluster1_<size>_consensus.tr holds the reference's consensus bipartitions (for t4 the file is byte-identical
+    to tests/t4_consensus/cluster1_16_consensus.tr)."""
+    import subprocess
+    from phybin_b200 import build
+    cli = build.build_cli()
+    c = golden[name]
+    tr = tmp_path / "alltrees.tr"
+    tr.write_text(c["texts"][0])
+    out = tmp_path / "out"
+    args = [cli, f"--editdist={thr}", linkage, "-o", str(out), str(tr)] + (["--host-bips"] if host_bips else [])
+    r = subprocess.run(args, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    T = c["hashrf_num_trees"]
+    assert f"After flattening, cluster sizes are: [{T}]" in r.stdout and " Outcome: 1 clusters found, 1 non-singleton" in r.stdout
+    assert (out / f"cluster1_{T}.txt").read_text().splitlines() == [f"alltrees_{i}" for i in range(T)]
+    cons = (out / f"cluster1_{T}_consensus.tr").read_text()
+    assert cons == c["consensus_newick"] + "\n"
+    if name == "t4":
+        assert cons.strip() == c["consensus_text"].strip()
+    members = Forest.parse([(out / f"cluster1_{T}_alltrees.tr").read_text()])
+    assert len(members) == T
+    # a tighter cut splits t5 / t3 into several clusters whose sizes add up
+    if thr:
+        r = subprocess.run([cli, "--editdist=0", linkage, "-o", str(tmp_path / "out0"), str(tr)], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        line = [l for l in r.stdout.splitlines() if l.startswith("After flattening")][0]
+        sizes = [int(x) for x in line.split("[")[1].rstrip("]").split(",")]
+        assert sum(sizes) == T and sizes == sorted(sizes, reverse=True) and len(sizes) > 1
+
+
 # ---- multi-GPU build (hash-partitioned dedup), emulated on one GPU ---------------------------------
 
 @pytest.mark.parametrize("world,T,n,family", [(2, 300, 30, 0), (3, 700, 64, 0), (4, 513, 40, NNI_FAMILY), (8, 1000, 100, 0)])
@@ -568,3 +602,88 @@ def test_device_allbips_rejects_bad_input_with_codes(ctx):
         ctx.allbips(wide, EXTRACT_BIPS)
     assert e.value.code == -6
     assert hashRF(1000, wide, ctx, extract="host").rows() == DistanceMatrix(ctx.hashrf(*wide.all_bips())[0], 2).rows()
+
+
+# ---- strict consensus of every cluster on the device ---------------------------------------
+
+def _cluster_sets(keys, off, labels):
+    return {int(c): sorted(bits_to_labels(k) for k in keys[int(off[c]):int(off[c + 1])]) for c in np.unique(labels)}
+
+
+@pytest.mark.parametrize("name", ["t3", "t4", "t5"])
+def test_consensus_of_reference_fixture_clusters(golden, ctx, name):
+    """The reference's consensus fixtures (Main.hs:470-510): one cluster holding every tree of the file."""
+    c = golden[name]
+    f = Forest.parse(c["texts"], c["name_prefix"])
+    ctx.allbips(f, EXTRACT_BIPS)
+    labels = np.zeros(len(f), dtype=np.uint32)
+    keys, off, info = ctx.consensus(labels)
+    assert info["n_clusters"] == 1 and int(off[1]) == info["n_out"] == len(c["consensus_bips"]) and int(off[-1]) == info["n_out"]
+    assert sorted(bits_to_labels(k) for k in keys) == [tuple(b) for b in c["consensus_bips"]]
+    assert f.consensus_newick(keys, c["consensus_num_taxa"]) == c["consensus_newick"]
+
+
+@pytest.mark.parametrize("T,n,nni,thr,seed", [(600, 40, 3, 4, 1), (900, 100, 6, 8, 2), (300, 12, 0, 2, 3), (257, 130, 2, 2, 4)])
+def test_consensus_per_mask_component_vs_oracle(ctx, T, n, nni, thr, seed):
+    f = Forest.synthetic(T, n, 900 + seed, family=NNI_FAMILY if nni else 0, nni_max=max(nni, 1))
+    o = orc.Forest([f.to_newick()])
+    ctx.hashrf_load_trees(f)
+    ctx.hashrf_compute(editdist=thr)
+    labels, ncomp = ctx.mask_components()
+    keys, off, info = ctx.consensus(labels)
+    assert info["n_clusters"] == ncomp
+    got = _cluster_sets(keys, off, labels)
+    for c in np.unique(labels):
+        assert got[int(c)] == o.consensus_bips(np.nonzero(labels == c)[0].tolist())
+    non_reps = np.nonzero(labels != np.arange(T))[0]
+    assert all(off[t] == off[t + 1] for t in non_reps)
+    # same through host arrays, and with an arbitrary partition instead of mask components
+    rng = np.random.default_rng(seed)
+    group = rng.integers(0, 7, size=T)
+    labels2 = np.array([np.nonzero(group == group[t])[0][0] for t in range(T)], dtype=np.uint32)
+    bips, boff = f.all_bips()
+    keys2, off2, _ = ctx.consensus(labels2, bips, boff)
+    got2 = _cluster_sets(keys2, off2, labels2)
+    for c in np.unique(labels2):
+        assert got2[int(c)] == o.consensus_bips(np.nonzero(labels2 == c)[0].tolist())
+        txt = f.consensus_newick(keys2[int(off2[c]):int(off2[c + 1])], n)
+        back = orc.Forest([txt, f.to_newick(0, 1)])  # round trip: the printed tree has exactly the consensus bipartitions
+        assert back.all_bips(0) == got2[int(c)]
+
+
+def test_consensus_rejects_bad_labels(ctx):
+    f = Forest.synthetic(20, 9, 3)
+    bips, off = f.all_bips()
+    ok = np.zeros(20, dtype=np.uint32)
+    ok[10:] = 10
+    keys, coff, info = ctx.consensus(ok, bips, off)
+    assert info["n_clusters"] == 2 and np.count_nonzero(np.diff(coff.astype(np.int64))) <= 2
+    bad = ok.copy()
+    bad[3] = 5  # not the smallest id of its cluster
+    with pytest.raises(PhyBinRFError) as e:
+        ctx.consensus(bad, bips, off)
+    assert e.value.code == -1
+    with pytest.raises(PhyBinRFError):
+        ctx._ck(_native.rf_lib().prf_consensus_fetch(ctx._h, None, None))
+
+
+# ---- flat clusters for every linkage: device components + per-component host agglomeration (SURVEY 8f-1) ---
+
+@pytest.mark.parametrize("T,n,nni,thr", [(150, 30, 4, 4), (120, 12, 0, 6), (90, 40, 8, 10)])
+def test_flat_clusters_all_linkages_vs_naive_restatement(ctx, T, n, nni, thr):
+    from oracle import pyref
+    f = Forest.synthetic(T, n, 4242 + T, family=NNI_FAMILY if nni else 0, nni_max=max(nni, 1))
+    ctx.hashrf_load_trees(f)
+    ctx.hashrf_compute(editdist=thr)
+    upper = ctx.fetch()
+    d = lambda i, j: int(upper[packed_index(T, i, j)])
+    ids = np.array(sorted(random.Random(T).sample(range(T), 17)), dtype=np.uint32)
+    sub = ctx.fetch_submatrix(ids)
+    assert sub.tolist() == [d(int(a), int(b)) for x, a in enumerate(ids) for b in ids[x + 1:]]
+    comp, _ = ctx.mask_components()
+    for linkage in ("single", "complete", "UPGMA"):
+        got, k = ctx.flat_clusters(thr, linkage)
+        assert got.tolist() == pyref.flat_clusters(d, T, linkage, thr) and k == len(set(got.tolist()))
+        assert all(comp[t] == comp[got[t]] for t in range(T))  # every cluster lies inside one component
+    with pytest.raises(PhyBinRFError):
+        ctx.fetch_submatrix(np.array([5, 3], dtype=np.uint32))

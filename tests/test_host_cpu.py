@@ -214,3 +214,39 @@ def test_print_dist_mat_streams_the_same_text_to_a_file(tmp_path):
     ii, jj = np.tril_indices(T, -1)  # the reference's layout: row i holds d(i, 0..i-1)
     lower = upper[(jj * T - jj * (jj + 1) // 2 + (ii - jj - 1))].astype(np.int64)
     assert path.read_text() == text == orc.print_dist_mat(lower, T)
+
+
+# ---- clustering consumer: the host step that follows prf_mask_components ---------------------
+
+def _canon(lbl):
+    first = {}
+    return [first.setdefault(int(l), i) for i, l in enumerate(lbl)]
+
+
+@pytest.mark.parametrize("linkage,method", [("single", "single"), ("complete", "complete"), ("UPGMA", "average")])
+def test_cluster_component_matches_scipy_on_tie_free_distances(linkage, method):
+    from scipy.cluster.hierarchy import fcluster, linkage as scipy_linkage
+    from scipy.spatial.distance import pdist
+    from phybin_b200.host import cluster_component
+    rng = np.random.default_rng(11)
+    for m in (2, 3, 10, 60, 250):
+        d = pdist(rng.random((m, 3)))  # condensed form == packed row-major upper triangle
+        for thr in (0.05, 0.2, 0.5, 2.0):
+            got = cluster_component(d, m, linkage, thr)
+            want = fcluster(scipy_linkage(d, method=method), t=thr, criterion="distance")
+            assert _canon(got) == _canon(want), (m, thr)
+
+
+@pytest.mark.parametrize("linkage", ["single", "complete", "UPGMA"])
+def test_cluster_component_tie_order_matches_naive_restatement(linkage):
+    """Integer distances with many ties: the nearest-neighbour-cached agglomeration picks exactly the pairs the
+    naive distance-matrix algorithm (oracle/pyref.flat_clusters) picks."""
+    from oracle import pyref
+    from phybin_b200.host import cluster_component
+    rng = np.random.default_rng(5)
+    for m in (1, 2, 5, 17, 40):
+        for _ in range(4):
+            A = np.triu(rng.integers(0, 6, size=(m, m)), 1)
+            sub = np.array([A[i, j] for i in range(m) for j in range(i + 1, m)], dtype=np.uint16)
+            for thr in (0, 1, 2, 4):
+                assert cluster_component(sub, m, linkage, thr).tolist() == pyref.flat_clusters(lambda i, j: A[i, j], m, linkage, thr)

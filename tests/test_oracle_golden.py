@@ -149,3 +149,47 @@ def test_random_small_trees_oracle_vs_pyref():
         assert orc.lower_to_rows(f.naive(), T) == pyref.naive_dist_matrix(trees), text
         assert orc.lower_to_rows(f.hashrf(n), T) == pyref.hash_rf(trees), text
         assert np.array_equal(f.hashrf(n, "closed"), f.hashrf(n, "literal"))
+
+
+# ---- strict consensus: the reference's own consensus fixtures ------------------------------
+
+@pytest.mark.parametrize("name", ["t3", "t4", "t5"])
+def test_consensus_matches_reference_fixture_tree(golden, name):
+    """consensusTest (Main.hs:484-510): the bipartitions of tests/t*_consensus/*_consensus.tr equal those of
+    consensusTree over the cluster's trees -- for the C++ oracle, for pyref, and for the host's bipsToTree."""
+    from phybin_b200.host import Forest, bits_to_labels
+    c = golden[name]
+    want = [tuple(b) for b in c["consensus_bips"]]
+    o = orc.Forest(c["texts"], c["name_prefix"])
+    assert o.consensus_bips(range(o.num_trees)) == want
+    names, trees = pyref.parse_newicks(c["texts"], c["name_prefix"])
+    assert sorted(pyref.consensus_bips(trees)) == want
+    assert pyref.to_newick(names, pyref.consensus_tree(c["consensus_num_taxa"], trees)) == c["consensus_newick"]
+    # the tree on disk, parsed together with the cluster's trees, has exactly these bipartitions
+    both = orc.Forest([c["consensus_text"]] + c["texts"], c["name_prefix"])
+    assert both.labels == c["labels"] and both.all_bips(0) == want
+    # host side (product code): bipsToTree + one-line printing
+    f = Forest.parse(c["texts"], c["name_prefix"])
+    keys = np.zeros((len(want), f.words), dtype=np.uint64)
+    for i, b in enumerate(want):
+        for l in b:
+            keys[i, l >> 6] |= np.uint64(1) << np.uint64(l & 63)
+    assert f.consensus_newick(keys[::-1], c["consensus_num_taxa"]) == c["consensus_newick"]
+    if name == "t4":  # same label order as when the reference wrote the file: byte-identical
+        assert c["consensus_newick"] == c["consensus_text"].strip()
+
+
+@pytest.mark.parametrize("name", ["t3", "t4", "t5", "t1", "t2"])
+def test_bips_to_tree_round_trip(golden, name):
+    """testBipConversion (Main.hs:519-530): allBips (bipsToTree n (allBips t)) == allBips t, through the host code."""
+    from phybin_b200.host import Forest, bits_to_labels
+    c = golden[name]
+    f = Forest.parse(c["texts"], c["name_prefix"])
+    f.filter_num_leaves(len(c["labels"]))
+    bips, off = f.all_bips()
+    rebuilt = [f.consensus_newick(bips[int(off[t]):int(off[t + 1])], len(c["labels"])) for t in range(len(f))]
+    g = Forest.parse(["".join(rebuilt)] + c["texts"], c["name_prefix"])  # the last file is labelled first: same table
+    assert g.labels == c["labels"]
+    b2, o2 = g.all_bips()
+    for t in range(len(f)):
+        assert np.array_equal(b2[int(o2[t]):int(o2[t + 1])], bips[int(off[t]):int(off[t + 1])])
