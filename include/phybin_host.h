@@ -113,6 +113,16 @@ PHB_API char* phb_print_dist_mat(const uint16_t* upper, uint32_t T);
 /* Streams the same text to a file; returns 0 on success. */
 PHB_API int phb_write_dist_mat(const char* path, const uint16_t* upper, uint32_t T);
 
+/* Binary form of the matrix for sizes where the text dump is unusable.  Layout, little-endian:
+ *   bytes 0-7 "PHYBINRF", uint32 version = 1, uint32 T, uint64 P = T(T-1)/2, uint32 bits = 16, uint32 layout = 0
+ *   (packed row-major upper triangle, phybin_rf.h), then P uint16 entries.
+ * begin truncates the file and writes the header; append adds entries in packed order (so a caller can stream
+ * prf_fetch chunks without ever holding the matrix); read returns a malloc'd copy (free with phb_free_buf).
+ * All return 0 on success. */
+PHB_API int phb_dist_bin_begin(const char* path, uint32_t T);
+PHB_API int phb_dist_bin_append(const char* path, const uint16_t* entries, uint64_t n);
+PHB_API int phb_dist_bin_read(const char* path, uint32_t* T, uint16_t** upper);
+
 PHB_API void phb_free_buf(void* p);
 
 #ifdef __cplusplus

@@ -102,6 +102,9 @@ def host_lib():
         L.phb_print_dist_mat.restype = vp
         L.phb_print_dist_mat.argtypes = [vp, C.c_uint32]
         L.phb_write_dist_mat.argtypes = [C.c_char_p, vp, C.c_uint32]
+        L.phb_dist_bin_begin.argtypes = [C.c_char_p, C.c_uint32]
+        L.phb_dist_bin_append.argtypes = [C.c_char_p, vp, C.c_uint64]
+        L.phb_dist_bin_read.argtypes = [C.c_char_p, u32p, C.POINTER(vp)]
         L.phb_free_buf.argtypes = [vp]
         _host = L
     return _host

@@ -887,6 +887,52 @@ int phb_write_dist_mat(const char* path, const uint16_t* upper, uint32_t T) {
   return std::fclose(fp) == 0 ? 0 : -1;
 }
 
+namespace {
+struct DistBinHeader {
+  char magic[8];
+  uint32_t version, T;
+  uint64_t P;
+  uint32_t bits, layout;
+};
+static_assert(sizeof(DistBinHeader) == 32, "header layout");
+}  // namespace
+
+int phb_dist_bin_begin(const char* path, uint32_t T) {
+  FILE* fp = path ? std::fopen(path, "wb") : nullptr;
+  if (!fp) return -1;
+  DistBinHeader h{{'P', 'H', 'Y', 'B', 'I', 'N', 'R', 'F'}, 1, T, (uint64_t)T * (T ? T - 1 : 0) / 2, 16, 0};
+  const bool ok = std::fwrite(&h, sizeof h, 1, fp) == 1;
+  return (std::fclose(fp) == 0 && ok) ? 0 : -1;
+}
+
+int phb_dist_bin_append(const char* path, const uint16_t* entries, uint64_t n) {
+  if (!n) return 0;
+  FILE* fp = (path && entries) ? std::fopen(path, "ab") : nullptr;
+  if (!fp) return -1;
+  const bool ok = std::fwrite(entries, 2, n, fp) == n;
+  return (std::fclose(fp) == 0 && ok) ? 0 : -1;
+}
+
+int phb_dist_bin_read(const char* path, uint32_t* T, uint16_t** upper) {
+  FILE* fp = (path && T && upper) ? std::fopen(path, "rb") : nullptr;
+  if (!fp) return -1;
+  DistBinHeader h;
+  int rc = -1;
+  uint16_t* buf = nullptr;
+  if (std::fread(&h, sizeof h, 1, fp) == 1 && !std::memcmp(h.magic, "PHYBINRF", 8) && h.version == 1 && h.bits == 16 &&
+      h.layout == 0 && h.P == (uint64_t)h.T * (h.T ? h.T - 1 : 0) / 2) {
+    buf = (uint16_t*)std::malloc(std::max<uint64_t>(h.P, 1) * 2);
+    if (buf && std::fread(buf, 2, h.P, fp) == h.P && std::fgetc(fp) == EOF) {
+      *T = h.T;
+      *upper = buf;
+      rc = 0;
+    }
+  }
+  if (rc) std::free(buf);
+  std::fclose(fp);
+  return rc;
+}
+
 void phb_free_buf(void* p) { std::free(p); }
 
 }  // extern "C"

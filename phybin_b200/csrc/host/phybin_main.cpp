@@ -26,7 +26,7 @@
 namespace {
 
 struct Options {
-  bool tolerant = false, rfdist = false, host_bips = false;
+  bool tolerant = false, rfdist = false, host_bips = false, binary = false;
   int linkage = 2;  // C.UPGMA, the reference's default (CoreTypes.hs:265); 0 single, 1 complete
   int editdist = -1, name_prefix = -1, variant = PRF_VARIANT_AUTO;
   std::string out_dir = "phybin_out";
@@ -68,6 +68,7 @@ Options parse_args(int argc, char** argv) {
     else if (!std::strcmp(a, "-p") || !std::strcmp(a, "--nameprefix")) o.name_prefix = std::atoi(need(a));
     else if (!std::strcmp(a, "--sparse")) o.variant = PRF_VARIANT_SPARSE;   // not in the reference: force a kernel variant
     else if (!std::strcmp(a, "--dense")) o.variant = PRF_VARIANT_DENSE;
+    else if (!std::strcmp(a, "--binary-matrix")) o.binary = true;  // not in the reference: also write distance_matrix.bin
     else if (!std::strcmp(a, "--host-bips")) o.host_bips = true;  // not in the reference: allBips in the C++ host code
     else if (!std::strcmp(a, "-V") || !std::strcmp(a, "--version")) {
       std::printf("phybin (B200 RF path) -- %s\n", prf_version());
@@ -144,7 +145,8 @@ int main(int argc, char** argv) {
 
   prf_ctx* ctx = prf_create(0);
   if (!ctx) die(std::string("cannot use the GPU: ") + prf_last_error(nullptr));
-  std::vector<uint16_t> upper(P ? P : 1);
+  const bool text_out = T <= 20000;  // the text dump is O(T^2) `show` in the reference too; beyond this only binary
+  std::vector<uint16_t> upper(text_out && P ? P : 1);
   std::vector<uint32_t> mask(opt.editdist >= 0 ? (P + 31) / 32 + 1 : 1);
   prf_stats st{};
   const auto t0 = std::chrono::steady_clock::now();
@@ -180,7 +182,7 @@ int main(int argc, char** argv) {
     }
     if (!rc) rc = prf_tolerant_compute(ctx, 0, P, opt.editdist, nullptr, nullptr, &st);
   }
-  if (!rc && P) rc = prf_fetch(ctx, 0, P, upper.data());
+  if (!rc && P && text_out) rc = prf_fetch(ctx, 0, P, upper.data());
   if (!rc && P && opt.editdist >= 0) rc = prf_fetch_mask(ctx, 0, P, mask.data());
   if (rc) die(std::string("phybin_rf error: ") + prf_last_error(ctx));
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -190,15 +192,27 @@ int main(int argc, char** argv) {
               (unsigned long long)st.n_unique);
 
   mkdir(opt.out_dir.c_str(), 0777);
-  if (T <= 20000) {
+  if (opt.binary) {  // streamed from the device in 64 MB pieces: the host never holds the matrix
+    const std::string path = opt.out_dir + "/distance_matrix.bin";
+    if (phb_dist_bin_begin(path.c_str(), T)) die("cannot write " + path);
+    const uint64_t chunk = 1ull << 25;
+    std::vector<uint16_t> piece(std::min<uint64_t>(chunk, P ? P : 1));
+    for (uint64_t b = 0; b < P; b += chunk) {
+      const uint64_t e = std::min(P, b + chunk);
+      if (prf_fetch(ctx, b, e, piece.data())) die(std::string("phybin_rf error: ") + prf_last_error(ctx));
+      if (phb_dist_bin_append(path.c_str(), piece.data(), e - b)) die("cannot write " + path);
+    }
+    std::printf("Wrote %s (%.1f MB)\n", path.c_str(), (double)P * 2 / 1e6);
+  }
+  if (text_out) {
     const std::string path = opt.out_dir + "/distance_matrix.txt";
     if (phb_write_dist_mat(path.c_str(), upper.data(), T)) die("cannot write " + path);
     std::printf("Wrote %s\n", path.c_str());
   } else {
-    std::printf("distance_matrix.txt skipped: %u trees would be a %.1f GB text file (use the C ABI's prf_fetch_rows)\n", T,
+    std::printf("distance_matrix.txt skipped: %u trees would be a %.1f GB text file (use --binary-matrix or the C ABI's prf_fetch_rows)\n", T,
                 (double)P * 4 / 1e9);
   }
-  if (opt.rfdist && T <= 20000) {
+  if (opt.rfdist && text_out) {
     char* txt = phb_print_dist_mat(upper.data(), T);
     std::fputs(txt, stdout);
     phb_free_buf(txt);

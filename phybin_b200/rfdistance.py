@@ -66,6 +66,30 @@ class DistanceMatrix:
         ii, jj = np.tril_indices(T, -1)
         return self.upper[packed_index(T, jj, ii)].astype(np.int64)
 
+    def save_bin(self, path: str, chunk: int = 1 << 26) -> None:
+        """Binary form (phb_dist_bin_*: 32-byte header + packed uint16 upper triangle), written in chunks."""
+        L = host_lib()
+        if L.phb_dist_bin_begin(str(path).encode(), self.T):
+            raise OSError(f"cannot write {path}")
+        up = np.ascontiguousarray(self.upper, dtype=np.uint16)
+        for b in range(0, len(up), chunk):
+            part = up[b:b + chunk]
+            if L.phb_dist_bin_append(str(path).encode(), part.ctypes.data, len(part)):
+                raise OSError(f"cannot write {path}")
+
+    @classmethod
+    def load_bin(cls, path: str) -> "DistanceMatrix":
+        L = host_lib()
+        T, p = C.c_uint32(0), C.c_void_p()
+        if L.phb_dist_bin_read(str(path).encode(), C.byref(T), C.byref(p)):
+            raise OSError(f"{path} is not a phybin distance matrix file")
+        n = T.value * (T.value - 1) // 2 if T.value else 0
+        up = np.empty(n, dtype=np.uint16)
+        if n:
+            C.memmove(up.ctypes.data, p, n * 2)
+        L.phb_free_buf(p)
+        return cls(up, T.value)
+
     def __repr__(self) -> str:  # `show` of the Haskell value for small matrices
         return str(self.rows()).replace(" ", "")
 

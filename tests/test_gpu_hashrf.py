@@ -367,6 +367,16 @@ def test_cli_matches_reference_output_format(golden, tmp_path):
     assert r.returncode == 0, r.stderr
     assert " Using HashRF-style algorithm..." in r.stdout and " Built matrix for dim 2" in r.stdout
     assert (out / "distance_matrix.txt").read_text().splitlines()[2:4] == ["0", "1 0"]
+    # --binary-matrix streams the packed triangle from the device
+    t5 = tmp_path / "t5.tr"
+    t5.write_text(golden["t5"]["texts"][0])
+    r = subprocess.run([cli, "--binary-matrix", "-o", str(out), str(t5)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    m = DistanceMatrix.load_bin(out / "distance_matrix.bin")
+    assert m.rows() == golden["t5"]["hashrf"]
+    buf = io.StringIO()
+    printDistMat(buf, m)
+    assert buf.getvalue() == (out / "distance_matrix.txt").read_text()
 
 
 @pytest.mark.parametrize("name,thr,linkage,host_bips", [("t4", 0, "--UPGMA", False), ("t5", 2, "--complete", False),

@@ -250,3 +250,19 @@ def test_cluster_component_tie_order_matches_naive_restatement(linkage):
             sub = np.array([A[i, j] for i in range(m) for j in range(i + 1, m)], dtype=np.uint16)
             for thr in (0, 1, 2, 4):
                 assert cluster_component(sub, m, linkage, thr).tolist() == pyref.flat_clusters(lambda i, j: A[i, j], m, linkage, thr)
+
+
+def test_binary_matrix_round_trip(tmp_path):
+    """the packed binary form of the matrix (header + uint16 upper triangle), written in pieces."""
+    from phybin_b200.rfdistance import DistanceMatrix
+    rng = np.random.default_rng(3)
+    for T in (0, 1, 2, 7, 300):
+        up = rng.integers(0, 995, size=T * (T - 1) // 2 if T else 0).astype(np.uint16)
+        path = tmp_path / f"m{T}.bin"
+        DistanceMatrix(up, T).save_bin(path, chunk=1000)
+        assert path.stat().st_size == 32 + 2 * len(up)
+        back = DistanceMatrix.load_bin(path)
+        assert back.T == T and np.array_equal(back.upper, up)
+    (tmp_path / "bad.bin").write_bytes(b"PHYBINRX" + bytes(24))
+    with pytest.raises(OSError):
+        DistanceMatrix.load_bin(tmp_path / "bad.bin")
