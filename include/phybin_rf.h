@@ -11,9 +11,10 @@
  *
  * called from exactly one production site, doCluster (PhyBin.hs:343-364).  The entry points below
  * are what a `foreign import ccall` inside drop-in replacements for those two functions binds
- * (INTEGRATION.md shows the Haskell shim).  The host keeps Newick parsing, --prune/--minbootstrap
- * preprocessing and bipartition extraction (allBips, RFDistance.hs:247); the device receives
- * bit-packed taxon sets and returns the matrix.
+ * (INTEGRATION.md shows the Haskell shim).  The host keeps Newick parsing and --prune/--minbootstrap
+ * preprocessing; the device receives bit-packed taxon sets (allBips, RFDistance.hs:247 -- extracted by the
+ * host, or by prf_allbips below from the parsed trees) and returns the matrix.  The entry points after the
+ * matrix ones serve its consumers in PhyBin.hs: flat clusters at --editdist and their strict consensus.
  *
  * Conventions
  *   - plain pointers and sizes only; every function returns PRF_OK (0) or a negative prf_status
