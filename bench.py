@@ -199,6 +199,8 @@ def run_gpu(args, wl, wl_name):
         my_bips = np.ascontiguousarray(clades_all[b0:b1])
         counts = np.diff(off_all.astype(np.int64))
     nnz = int(off_all[-1])
+    # the parsed trees as flat arrays (prf_allbips input) for the from-trees end-to-end number, N = 1 only
+    tree_arrays = [a.copy() for a in f.tree_arrays()] if (world == 1 and not args.no_e2e) else None
     del f
 
     with torch.cuda.stream(ext):
@@ -350,7 +352,7 @@ def run_gpu(args, wl, wl_name):
     e2e = None
     if world == 1 and not args.no_e2e:
         e2e = run_e2e(ctx, wl, mode, bips_all if mode == "hashrf" else clades_all, off_all,
-                      None if mode == "hashrf" else leaf_all, P, editdist, max(1, min(args.steps, 2)))
+                      None if mode == "hashrf" else leaf_all, P, editdist, max(1, min(args.steps, 2)), tree_arrays)
     elif world > 1 and not args.no_e2e:
         # every rank: its tree shard from pinned host memory -> HBM, all-gather, build, its slice of the matrix,
         # slice -> pinned host memory.  Each GPU uses its own PCIe link, so the copies run in parallel.
@@ -414,8 +416,10 @@ def run_gpu(args, wl, wl_name):
     return 0
 
 
-def run_e2e(ctx, wl, mode, keys, off, leaf, P, editdist, steps):
-    """Host buffers in, host buffers out, through prf_hashrf / prf_tolerant; copies inside the timed region."""
+def run_e2e(ctx, wl, mode, keys, off, leaf, P, editdist, steps, tree_arrays=None):
+    """Host buffers in, host buffers out, through prf_hashrf / prf_tolerant; copies inside the timed region.
+    With tree_arrays also the same job through prf_hashrf_trees / prf_tolerant_trees: parsed trees in (the
+    bipartitions are extracted on the device), matrix out -- reported under e2e["from_trees"]."""
     import numpy as np
     import torch
     T = wl["T"]
@@ -449,10 +453,34 @@ def run_e2e(ctx, wl, mode, keys, off, leaf, P, editdist, steps):
     dt = (time.perf_counter() - t0) / steps
     h2d = int(keys.nbytes + offc.nbytes + (leafc.nbytes if leafc is not None else 0))
     d2h = int(P * 2 + ((P + 31) // 32 * 4 if editdist >= 0 else 0))
-    return {"value": P / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "ms_per_step": dt * 1e3, "steps": steps,
-            "phases_ms": {"h2d": st.ms_h2d, "dedup": st.ms_dedup, "incidence": st.ms_incidence,
-                          "matrix": st.ms_matrix, "d2h": st.ms_d2h}}
+    res = {"value": P / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": dt * 1e3, "steps": steps,
+           "phases_ms": {"h2d": st.ms_h2d, "dedup": st.ms_dedup, "incidence": st.ms_incidence,
+                         "matrix": st.ms_matrix, "d2h": st.ms_d2h}}
+    if tree_arrays is not None:
+        from phybin_b200._native import prf_extract_info
+        info = prf_extract_info()
+        pins = [torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else (a.view(np.int64) if a.dtype == np.uint64 else a)).pin_memory()
+                for a in tree_arrays]
+        fn = L.prf_hashrf_trees if mode == "hashrf" else L.prf_tolerant_trees
+
+        def call_trees():
+            ctx._ck(fn(ctx._h, pins[0].data_ptr(), pins[1].data_ptr(), pins[2].data_ptr(), pins[3].data_ptr(), T, W, editdist,
+                       pin_out.data_ptr(), pin_mask.data_ptr() if pin_mask is not None else None, C.byref(st), C.byref(info)))
+
+        call_trees()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            call_trees()
+        torch.cuda.synchronize()
+        dt2 = (time.perf_counter() - t0) / steps
+        res["from_trees"] = {"value": P / dt2, "unit": UNIT, "ms_per_step": dt2 * 1e3,
+                             "h2d_bytes_per_step": int(sum(a.nbytes for a in tree_arrays)), "d2h_bytes_per_step": d2h,
+                             "extract_ms": info.ms_kernels, "h2d_ms": info.ms_h2d,
+                             "api": "prf_hashrf_trees" if mode == "hashrf" else "prf_tolerant_trees"}
+        del pins
+    return res
 
 
 def main():

@@ -211,13 +211,13 @@ typedef struct prf_extract_info {
  *   num_leaves   numLeaves of every tree (CoreTypes.hs:289-291; duplicate labels count twice) -- the
  *                `size` normBip works with (RFDistance.hs:215,229-239)
  * `kind` says where the four arrays live.  The result stays on the device until the next extraction on
- * this context; it is, per tree, the sorted SET (word-lexicographic order, word 0 first) of
+ * this context; it is, per tree, the SET (every set once, in the pre-order of the first node that yields it) of
  *   mode BIPS:   normBip size c for every non-root node's leaf set c, kept when it has > 1 members
  *                (labelBips :207-221, normBip :229-239 with its [0,size) complement universe and odd-size
  *                tie rule, allBips' filter :248);
  *   mode CLADES: the leaf set of every non-root interior node, plus leafsets[t] = the root's set.
  * PRF_E_UNSUPPORTED when one tree's clade sets do not fit a CTA's shared memory
- * (max_nodes * (8 W + 2) + 2 * pow2(max_nodes) bytes must stay under 200 KB). */
+ * (about interior_nodes * (8 W + 4) + 2 * nodes bytes must stay under 200 KB; at most 16383 nodes per tree). */
 PRF_API int prf_allbips(prf_ctx* ctx, const int32_t* node_label, const uint32_t* node_parent,
                         const uint64_t* tree_begin, const uint32_t* num_leaves, uint32_t T, uint32_t W,
                         int kind /* prf_memkind */, int mode /* prf_extract_mode */, prf_extract_info* info);
@@ -228,6 +228,19 @@ PRF_API int prf_allbips_result(prf_ctx* ctx, const uint64_t** d_keys, const uint
                                const uint64_t** d_leafsets, uint64_t* nnz);
 /* Copies the last extraction to host memory (each destination may be NULL). */
 PRF_API int prf_allbips_fetch(prf_ctx* ctx, uint64_t* keys, uint64_t* tree_off, uint64_t* leafsets);
+
+/* One-shot from parsed trees: prf_allbips (mode BIPS) + prf_hashrf_load + prf_hashrf_compute (+ fetch) -- what a
+ * drop-in hashRF binds when the host does not want to run allBips itself; the tree arrays are host memory, laid
+ * out as for prf_allbips.  out_upper / out_mask / stats as for prf_hashrf; extract may be NULL. */
+PRF_API int prf_hashrf_trees(prf_ctx* ctx, const int32_t* node_label, const uint32_t* node_parent,
+                             const uint64_t* tree_begin, const uint32_t* num_leaves, uint32_t T, uint32_t W,
+                             int32_t editdist, uint16_t* out_upper, uint32_t* out_mask, prf_stats* stats,
+                             prf_extract_info* extract);
+/* Same for the tolerant mode: prf_allbips (mode CLADES) + prf_tolerant_load + prf_tolerant_compute (+ fetch). */
+PRF_API int prf_tolerant_trees(prf_ctx* ctx, const int32_t* node_label, const uint32_t* node_parent,
+                               const uint64_t* tree_begin, const uint32_t* num_leaves, uint32_t T, uint32_t W,
+                               int32_t editdist, uint16_t* out_upper, uint32_t* out_mask, prf_stats* stats,
+                               prf_extract_info* extract);
 
 /* ---- first consumer of the matrix: flat clusters at the --editdist threshold -------------------- */
 

@@ -144,6 +144,9 @@ def rf_lib():
         L.prf_hashrf_merge.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(prf_part), st]
         L.prf_allbips.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
                                   C.POINTER(prf_extract_info)]
+        L.prf_hashrf_trees.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int32, vp, vp, st,
+                                       C.POINTER(prf_extract_info)]
+        L.prf_tolerant_trees.argtypes = L.prf_hashrf_trees.argtypes
         L.prf_allbips_result.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), u64p]
         L.prf_allbips_fetch.argtypes = [vp, vp, vp, vp]
         L.prf_fetch_submatrix.argtypes = [vp, vp, C.c_uint32, vp]
@@ -173,7 +176,7 @@ def rf_lib():
 RF_SYMBOLS = [
     "prf_create", "prf_destroy", "prf_last_error", "prf_version", "prf_stream", "prf_hashrf",
     "prf_hashrf_load", "prf_hashrf_compute", "prf_hashrf_partition", "prf_hashrf_export", "prf_hashrf_merge", "prf_fetch", "prf_fetch_mask", "prf_fetch_rows",
-    "prf_tolerant", "prf_tolerant_load", "prf_tolerant_compute", "prf_allbips", "prf_allbips_result", "prf_allbips_fetch", "prf_consensus", "prf_consensus_fetch", "prf_fetch_submatrix",
+    "prf_tolerant", "prf_tolerant_load", "prf_tolerant_compute", "prf_allbips", "prf_allbips_result", "prf_allbips_fetch", "prf_hashrf_trees", "prf_tolerant_trees", "prf_consensus", "prf_consensus_fetch", "prf_fetch_submatrix",
     "prf_mask_components", "prf_packed_index",
     "prf_shard_align", "prf_shard_range", "prf_limits", "prf_launch_count",
 ]

@@ -382,27 +382,30 @@ uint32_t norm_bip(const uint64_t* b, const uint64_t* universe, uint32_t size, ui
   return popcount_w(src, W);
 }
 
-struct KeyLess {
-  uint32_t W;
-  bool operator()(const uint64_t* a, const uint64_t* b) const {
-    for (uint32_t w = 0; w < W; ++w)
-      if (a[w] != b[w]) return a[w] < b[w];
-    return false;
-  }
-};
-
-// Sorts the W-word keys in `keys` and removes duplicates (a tree's bipartitions are a Set).
-void sort_unique(std::vector<uint64_t>& keys, uint32_t W, std::vector<uint64_t>& out) {
-  size_t k = keys.size() / W;
-  std::vector<const uint64_t*> ptr(k);
-  for (size_t i = 0; i < k; ++i) ptr[i] = &keys[i * W];
-  KeyLess less{W};
-  std::sort(ptr.begin(), ptr.end(), less);
-  const uint64_t* prev = nullptr;
-  for (const uint64_t* q : ptr) {
-    if (prev && !less(prev, q)) continue;
-    out.insert(out.end(), q, q + W);
-    prev = q;
+// Removes duplicates from the W-word keys in `keys` (a tree's bipartitions are a Set), keeping the first
+// occurrence of every key in input order -- the order prf_allbips produces on the device.
+void unique_in_order(std::vector<uint64_t>& keys, uint32_t W, std::vector<uint64_t>& out) {
+  const size_t k = keys.size() / W;
+  size_t cap = 16;
+  while (cap < 2 * k) cap <<= 1;
+  std::vector<uint32_t> tab(cap, NONE);
+  for (size_t i = 0; i < k; ++i) {
+    const uint64_t* key = &keys[i * W];
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (uint32_t w = 0; w < W; ++w) {
+      h ^= key[w] + 0x632BE59BD9B4E019ull * (w + 1);
+      h = (h ^ (h >> 30)) * 0xBF58476D1CE4E5B9ull;
+      h ^= h >> 27;
+    }
+    size_t s = h & (cap - 1);
+    bool fresh = true;
+    while (tab[s] != NONE) {
+      if (!std::memcmp(&keys[(size_t)tab[s] * W], key, W * 8)) { fresh = false; break; }
+      s = (s + 1) & (cap - 1);
+    }
+    if (!fresh) continue;
+    tab[s] = (uint32_t)i;
+    out.insert(out.end(), key, key + W);
   }
 }
 
@@ -647,7 +650,7 @@ int phb_allbips(const phb_forest* h, uint32_t W, int threads, uint64_t** bips, u
       if (norm_bip(&bits[(v - b) * W], universe, size, W, tmp) > 1)  // allBips filter (:248)
         keys.insert(keys.end(), tmp, tmp + W);
     }
-    sort_unique(keys, W, out);
+    unique_in_order(keys, W, out);
   };
   return parallel_trees(f, threads, W, per_tree, bips, tree_off, nnz);
 }
@@ -667,7 +670,7 @@ int phb_raw_clades(const phb_forest* h, uint32_t W, int threads, uint64_t** clad
     keys.clear();
     for (uint64_t v = b + 1; v < e; ++v)
       if (f.label[v] < 0) keys.insert(keys.end(), &bits[(v - b) * W], &bits[(v - b) * W] + W);
-    sort_unique(keys, W, out);
+    unique_in_order(keys, W, out);
   };
   int rc = parallel_trees(f, threads, W, per_tree, clades, tree_off, nnz);
   if (rc) { std::free(ls); return rc; }

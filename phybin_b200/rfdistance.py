@@ -252,6 +252,27 @@ class RFContext:
                                            leaf.ctypes.data if leaf is not None else None))
         return (keys, off) if leaf is None else (keys, off, leaf)
 
+    def hashrf_trees(self, trees: Forest, editdist: int = -1, fetch: bool = True, tolerant: bool = False,
+                     pinned: Optional[tuple] = None):
+        """One-shot prf_hashrf_trees / prf_tolerant_trees: parsed trees in, matrix out (allBips runs on the device).
+        Returns (upper | None, mask | None, stats) like hashrf().  `pinned`: optional (upper, mask) host arrays to fill."""
+        label, parent, begin, leaves = trees.tree_arrays()
+        T, W = len(trees), trees.words
+        P = T * (T - 1) // 2 if T else 0
+        out = pinned[0] if pinned else (np.empty(P, dtype=np.uint16) if fetch else None)
+        mask = pinned[1] if pinned else (np.empty((P + 31) // 32, dtype=np.uint32) if (fetch and editdist >= 0) else None)
+        st, info = prf_stats(), prf_extract_info()
+        fn = self._L.prf_tolerant_trees if tolerant else self._L.prf_hashrf_trees
+        self._ck(fn(self._h, label.ctypes.data if label.size else None, parent.ctypes.data if parent.size else None,
+                    begin.ctypes.data, leaves.ctypes.data if leaves.size else None, T, W, editdist,
+                    out.ctypes.data if out is not None else None, mask.ctypes.data if mask is not None else None,
+                    C.byref(st), C.byref(info)))
+        self.T, self.P = T, P
+        self._ext = (T, W, EXTRACT_CLADES if tolerant else EXTRACT_BIPS, info.nnz)
+        d = st.as_dict()
+        d["extract"] = info.as_dict()
+        return out, mask, d
+
     def hashrf_load_trees(self, trees: Forest, W: Optional[int] = None) -> dict:
         """allBips on the device, then the hashRF build on its device-resident output (no host bipartitions)."""
         info = self.allbips(trees, EXTRACT_BIPS, W)

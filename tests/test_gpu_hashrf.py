@@ -607,11 +607,29 @@ def test_device_allbips_rejects_bad_input_with_codes(ctx):
     assert call(label, parent, begin, leaves, 10, 0) == -6 and call(label, parent, begin, leaves, 10, 1, mode=7) == -1
     with pytest.raises(PhyBinRFError):  # a failed extraction leaves no result behind
         ctx.allbips_result()
-    wide = Forest.synthetic(2, 1000, 1)  # 1998 nodes x 16 words do not fit one CTA's shared memory
-    with pytest.raises(PhyBinRFError) as e:
-        ctx.allbips(wide, EXTRACT_BIPS)
-    assert e.value.code == -6
-    assert hashRF(1000, wide, ctx, extract="host").rows() == DistanceMatrix(ctx.hashrf(*wide.all_bips())[0], 2).rows()
+    # shapes the kernel is not built for are refused with PRF_E_UNSUPPORTED, never silently rerouted:
+    # a 9000-node unary chain above one leaf at W = 16 (9000 sets x 128 B do not fit a CTA's shared memory) ...
+    m = 9000
+    chain_label = np.full(m, -1, dtype=np.int32)
+    chain_label[-1] = 0
+    chain_parent = np.arange(-1, m - 1).astype(np.uint32)
+    chain_begin = np.array([0, m], dtype=np.uint64)
+    one = np.array([1], dtype=np.uint32)
+    assert call(chain_label, chain_parent, chain_begin, one, 1, 16) == -6 and b"shared memory" in L.prf_last_error(ctx._h)
+    assert call(chain_label, chain_parent, chain_begin, one, 1, 1) == 0 and info.nnz == 0  # the same chain fits at W = 1
+    # ... and a tree of 20 000 nodes at any W
+    m = 20000
+    chain_label = np.full(m, -1, dtype=np.int32)
+    chain_label[-1] = 0
+    assert call(chain_label, np.arange(-1, m - 1).astype(np.uint32), np.array([0, m], dtype=np.uint64), one, 1, 1) == -6
+    # a num_leaves that is not the tree's leaf count is an error, not a wrong result
+    wrong = leaves.copy()
+    wrong[2] += 1
+    assert call(label, parent, begin, wrong, 10, 1) == -1
+    # the widest sets the library takes (1000 taxa, W = 16), device and host extraction side by side
+    wide = Forest.synthetic(3, 1000, 1)
+    _assert_extraction_matches_host(ctx, wide)
+    assert hashRF(1000, wide, ctx, extract="host").rows() == hashRF(1000, wide, ctx).rows()
 
 
 # ---- strict consensus of every cluster on the device ---------------------------------------
@@ -697,3 +715,15 @@ def test_flat_clusters_all_linkages_vs_naive_restatement(ctx, T, n, nni, thr):
         assert all(comp[t] == comp[got[t]] for t in range(T))  # every cluster lies inside one component
     with pytest.raises(PhyBinRFError):
         ctx.fetch_submatrix(np.array([5, 3], dtype=np.uint32))
+
+
+def test_one_shot_from_trees_matches_staged_calls(ctx):
+    f = Forest.synthetic(500, 70, 31)
+    up, mask, st = ctx.hashrf_trees(f, editdist=5)
+    want, wmask, _ = ctx.hashrf(*f.all_bips(), editdist=5)
+    assert np.array_equal(up, want) and np.array_equal(mask, wmask)
+    assert st["extract"]["nnz"] == st["nnz"] and st["gpu_launches"] > st["extract"]["gpu_launches"] > 0
+    g = Forest.synthetic(200, 30, 32, p_missing=0.2)
+    up, _, st = ctx.hashrf_trees(g, tolerant=True)
+    want, _, _ = ctx.tolerant(*g.raw_clades())
+    assert np.array_equal(up, want)
