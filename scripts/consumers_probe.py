@@ -15,7 +15,7 @@ T, n, nni, D = (int(x) for x in sys.argv[1:5])
 f = Forest.synthetic(T, n, 0x5EED0003, family=NNI_FAMILY if nni else 0, nni_max=max(nni, 1))
 ctx = RFContext(0)
 out = {"T": T, "n": n, "nni": nni, "editdist": D}
-for rep in range(2):  # the second pass is the warm one
+for rep in range(3):  # the last pass is the warm one (the stream-ordered memory pool has reached its size)
     t0 = time.time()
     st = ctx.hashrf_load_trees(f)
     t1 = time.time()

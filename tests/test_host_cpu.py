@@ -266,3 +266,26 @@ def test_binary_matrix_round_trip(tmp_path):
     (tmp_path / "bad.bin").write_bytes(b"PHYBINRX" + bytes(24))
     with pytest.raises(OSError):
         DistanceMatrix.load_bin(tmp_path / "bad.bin")
+
+
+def test_bips_to_tree_order_matches_restatement_on_wide_sets():
+    """phb_consensus_newick against oracle/pyref.bips_to_tree on random trees of up to 260 taxa (multi-word sets,
+    many equal-sized bipartitions: exercises the IntSet tie order of the size sort, RFDistance.hs:413-414)."""
+    import random
+    from oracle import pyref
+    from tests.util import random_multifurcating_newicks
+    rng = random.Random(5)
+    for n in (4, 5, 9, 40, 70, 130, 260):
+        text = random_multifurcating_newicks(rng, 8, n)
+        names, trees = pyref.parse_newicks([text])
+        f = Forest.parse([text])
+        assert f.labels == names
+        bips, off = f.all_bips()
+        for t, tr in enumerate(trees):
+            want = pyref.to_newick(names, pyref.bips_to_tree(n, sorted(pyref.all_bips(tr))))
+            rows = bips[int(off[t]):int(off[t + 1])]
+            assert f.consensus_newick(rows[::-1], n) == want  # any input order
+    # a set that no subtree lies inside is the reference's "No match for bip" error
+    f = Forest.parse(["(a,b,c,d);"])
+    with pytest.raises(ValueError):
+        f.consensus_newick(np.zeros((1, 1), dtype=np.uint64), 4)
