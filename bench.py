@@ -317,6 +317,19 @@ def run_gpu(args, wl, wl_name):
             assert total == want, f"checksum identity failed: {total} != {want}"
             selfcheck["checksum"] = total
 
+    # ---- what the mask feeds (untimed, N = 1): flat clusters at --editdist, as doCluster / sliceDendro use it ------
+    consumer = None
+    if world == 1 and editdist >= 0 and d_mask is not None and P:
+        t0 = time.perf_counter()
+        _, ncomp = ctx.mask_components(d_mask.data_ptr())
+        t1 = time.perf_counter()
+        _, nclu = ctx.flat_clusters(editdist, "UPGMA", d_mask.data_ptr(), d_out.data_ptr())
+        t2 = time.perf_counter()
+        consumer = {"what": "connected components of {d <= editdist} on the device (prf_mask_components), then UPGMA flat "
+                            "clusters per component on the host (sliceDendro editdist . C.dendrogram UPGMA)",
+                    "components_ms": (t1 - t0) * 1e3, "n_components": int(ncomp),
+                    "upgma_flat_clusters_ms": (t2 - t1) * 1e3, "n_clusters": int(nclu)}
+
     # ---- roofline of the dominant kernel (the matrix kernel), per launch ---------------------------
     peaks, peak_src = load_peaks()
     my_pairs = p_end - p_begin
@@ -406,7 +419,7 @@ def run_gpu(args, wl, wl_name):
                        "parallelism": f"packed-range shard x{world}" + ((" + hash-partitioned build (NCCL all-to-all of keys, all-gather of the per-class structures)" if sharded else " + NCCL all-gather of bipartition keys") if world > 1 else ""),
                        "l2": "output per step (>= 2 B/pair) far exceeds the 126 MB L2; no explicit flush"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks, "device_s": dev_s, "wall_s": wall, "selfcheck": selfcheck,
+            "clocks": clocks, "device_s": dev_s, "wall_s": wall, "selfcheck": selfcheck, "consumer": consumer,
         }
         print(json.dumps(line), flush=True)
     torch.cuda.synchronize(dev)

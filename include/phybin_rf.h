@@ -252,11 +252,13 @@ PRF_API int prf_tolerant_trees(prf_ctx* ctx, const int32_t* node_label, const ui
 PRF_API int prf_mask_components(prf_ctx* ctx, const uint32_t* d_mask, uint32_t T, uint32_t* labels,
                                 uint32_t* n_components);
 
-/* Sub-matrix of the last context-owned result for m trees ids[0] < ids[1] < ... (host array): out (host,
- * m*(m-1)/2 uint16) is the packed upper triangle of the m x m matrix d(ids[i], ids[j]) -- what the host-side
- * complete-linkage / UPGMA step needs for one component (phb_cluster_component).  The result must cover every
- * requested pair. */
-PRF_API int prf_fetch_submatrix(prf_ctx* ctx, const uint32_t* ids, uint32_t m, uint16_t* out);
+/* Sub-matrix for m trees ids[0] < ids[1] < ... (host array): out (host, m*(m-1)/2 uint16) is the packed upper
+ * triangle of the m x m matrix d(ids[i], ids[j]) -- what the host-side complete-linkage / UPGMA step needs for
+ * one component (phb_cluster_component).  d_matrix: a DEVICE buffer holding the whole packed triangle of T trees
+ * (as written by *_compute), or NULL for the context-owned result of the last compute (T is then ignored and the
+ * result must cover every requested pair). */
+PRF_API int prf_fetch_submatrix(prf_ctx* ctx, const uint16_t* d_matrix, uint32_t T, const uint32_t* ids, uint32_t m,
+                                uint16_t* out);
 
 /* ---- strict consensus of every cluster (replaces the intersection inside consensusTree) -------- */
 

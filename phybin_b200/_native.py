@@ -149,7 +149,7 @@ def rf_lib():
         L.prf_tolerant_trees.argtypes = L.prf_hashrf_trees.argtypes
         L.prf_allbips_result.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), u64p]
         L.prf_allbips_fetch.argtypes = [vp, vp, vp, vp]
-        L.prf_fetch_submatrix.argtypes = [vp, vp, C.c_uint32, vp]
+        L.prf_fetch_submatrix.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, vp]
         L.prf_consensus.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int, vp, C.POINTER(prf_consensus_info)]
         L.prf_consensus_fetch.argtypes = [vp, vp, vp]
         L.prf_mask_components.argtypes = [vp, vp, C.c_uint32, vp, u32p]

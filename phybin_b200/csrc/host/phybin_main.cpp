@@ -238,7 +238,7 @@ int main(int argc, char** argv) {
         if (m < 3) continue;  // two trees within D of each other are one cluster under every linkage
         sub.resize((size_t)m * (m - 1) / 2);
         local.resize(m);
-        if ((rc = prf_fetch_submatrix(ctx, ids.data(), m, sub.data()))) die(std::string("phybin_rf error: ") + prf_last_error(ctx));
+        if ((rc = prf_fetch_submatrix(ctx, nullptr, T, ids.data(), m, sub.data()))) die(std::string("phybin_rf error: ") + prf_last_error(ctx));
         if (phb_cluster_component(sub.data(), m, opt.linkage, (double)opt.editdist, local.data()))
           die("component of " + std::to_string(m) + " trees is too large for the host clustering step");
         for (uint32_t i = 0; i < m; ++i) label[ids[i]] = ids[local[i]];

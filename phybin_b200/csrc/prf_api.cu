@@ -908,20 +908,29 @@ PRF_API int prf_mask_components(prf_ctx* h, const uint32_t* d_mask, uint32_t T, 
   return PRF_OK;
 }
 
-PRF_API int prf_fetch_submatrix(prf_ctx* h, const uint32_t* ids, uint32_t m, uint16_t* out) {
+PRF_API int prf_fetch_submatrix(prf_ctx* h, const uint16_t* d_matrix, uint32_t T, const uint32_t* ids, uint32_t m,
+                                uint16_t* out) {
   if (!h) return PRF_E_INVALID;
   Ctx* ctx = &h->c;
   ctx->err.clear();
-  if (!ctx->out_valid) return ctx->fail(PRF_E_STATE, "no context-owned result to fetch");
-  const uint32_t T = ctx->h.loaded ? ctx->h.T : (ctx->tol.loaded ? ctx->tol.T : 0);
+  const uint16_t* src = d_matrix;
+  uint64_t src_begin = 0;
+  if (!src) {
+    if (!ctx->out_valid) return ctx->fail(PRF_E_STATE, "no context-owned result to fetch");
+    T = ctx->h.loaded ? ctx->h.T : (ctx->tol.loaded ? ctx->tol.T : 0);
+    src = ctx->out.p;
+    src_begin = ctx->out_begin;
+  }
   if (m && !ids) return ctx->fail(PRF_E_INVALID, "ids is NULL");
   for (uint32_t i = 0; i < m; ++i)
     if (ids[i] >= T || (i && ids[i] <= ids[i - 1])) return ctx->fail(PRF_E_INVALID, "ids must be ascending tree ids below %u", T);
   const uint64_t n_out = (uint64_t)m * (m ? m - 1 : 0) / 2;
   if (!n_out) return PRF_OK;
   if (!out) return ctx->fail(PRF_E_INVALID, "out is NULL");
-  const uint64_t lo = row_start(ids[0], T) + (ids[1] - ids[0] - 1), hi = row_start(ids[m - 2], T) + (ids[m - 1] - ids[m - 2] - 1);
-  if (lo < ctx->out_begin || hi >= ctx->out_end) return ctx->fail(PRF_E_INVALID, "the computed range does not cover these pairs");
+  if (!d_matrix) {
+    const uint64_t lo = row_start(ids[0], T) + (ids[1] - ids[0] - 1), hi = row_start(ids[m - 2], T) + (ids[m - 1] - ids[m - 2] - 1);
+    if (lo < ctx->out_begin || hi >= ctx->out_end) return ctx->fail(PRF_E_INVALID, "the computed range does not cover these pairs");
+  }
   PRF_CK(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   DevBuf<uint32_t> d_ids;
@@ -929,7 +938,7 @@ PRF_API int prf_fetch_submatrix(prf_ctx* h, const uint32_t* ids, uint32_t m, uin
   PRF_CK(ctx, d_ids.alloc(m, s));
   PRF_CK(ctx, d_out.alloc(n_out, s));
   PRF_CK(ctx, cudaMemcpyAsync(d_ids.p, ids, (size_t)m * 4, cudaMemcpyHostToDevice, s));
-  submatrix_gather_kernel<<<grid_for(n_out), 256, 0, s>>>(ctx->out.p, ctx->out_begin, T, d_ids.p, m, n_out, d_out.p);
+  submatrix_gather_kernel<<<grid_for(n_out), 256, 0, s>>>(src, src_begin, T, d_ids.p, m, n_out, d_out.p);
   PRF_LAUNCHED(ctx);
   PRF_CK(ctx, cudaMemcpyAsync(out, d_out.p, n_out * 2, cudaMemcpyDeviceToHost, s));
   PRF_CK(ctx, cudaStreamSynchronize(s));

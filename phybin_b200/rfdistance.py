@@ -297,20 +297,22 @@ class RFContext:
         self._ck(self._L.prf_mask_components(self._h, d_mask or None, self.T, labels.ctypes.data, C.byref(n)))
         return labels, n.value
 
-    def fetch_submatrix(self, ids) -> np.ndarray:
-        """prf_fetch_submatrix: packed upper triangle of d(ids[i], ids[j]) for ascending tree ids."""
+    def fetch_submatrix(self, ids, d_matrix: int = 0) -> np.ndarray:
+        """prf_fetch_submatrix: packed upper triangle of d(ids[i], ids[j]) for ascending tree ids, read from the
+        context-owned result or from a device buffer holding the whole packed triangle (d_matrix)."""
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
         m = len(ids)
         out = np.empty(m * (m - 1) // 2, dtype=np.uint16)
-        self._ck(self._L.prf_fetch_submatrix(self._h, ids.ctypes.data, m, out.ctypes.data))
+        self._ck(self._L.prf_fetch_submatrix(self._h, d_matrix or None, self.T, ids.ctypes.data, m, out.ctypes.data))
         return out
 
-    def flat_clusters(self, editdist: int, linkage: str = "UPGMA") -> Tuple[np.ndarray, int]:
+    def flat_clusters(self, editdist: int, linkage: str = "UPGMA", d_mask: int = 0, d_matrix: int = 0) -> Tuple[np.ndarray, int]:
         """sliceDendro editdist (C.dendrogram linkage trees dist)  (PhyBin.hs:358,415-422) as flat labels: labels[t] =
-        smallest tree id of t's cluster.  Needs a full-triangle compute with this editdist (its mask).  The device
-        splits the trees into the connected components of {d <= editdist}; single linkage is done there, the other
-        linkages agglomerate every component on the host from its fetched sub-matrix (cluster_component)."""
-        labels, n = self.mask_components()
+        smallest tree id of t's cluster.  Needs a full-triangle compute with this editdist (its mask; context-owned,
+        or the caller's device buffers d_mask / d_matrix).  The device splits the trees into the connected components
+        of {d <= editdist}; single linkage is done there, the other linkages agglomerate every component on the host
+        from its fetched sub-matrix (cluster_component)."""
+        labels, n = self.mask_components(d_mask)
         if linkage == "single":
             return labels, n
         order = np.argsort(labels, kind="stable")
@@ -320,7 +322,7 @@ class RFContext:
             if len(ids) < 3:  # a component of two trees is one cluster under every linkage
                 continue
             ids = np.sort(ids).astype(np.uint32)
-            local = cluster_component(self.fetch_submatrix(ids), len(ids), linkage, editdist)
+            local = cluster_component(self.fetch_submatrix(ids, d_matrix), len(ids), linkage, editdist)
             out[ids] = ids[local]
         return out, int(np.count_nonzero(out == np.arange(len(out))))
 

@@ -727,3 +727,24 @@ def test_one_shot_from_trees_matches_staged_calls(ctx):
     up, _, st = ctx.hashrf_trees(g, tolerant=True)
     want, _, _ = ctx.tolerant(*g.raw_clades())
     assert np.array_equal(up, want)
+
+
+def test_flat_clusters_from_caller_owned_device_buffers(ctx):
+    """The staged API lets the caller own the matrix and the mask (bench.py, multi-GPU ranks): the consumers read
+    those buffers through their device pointers."""
+    import torch
+    T, thr = 400, 6
+    f = Forest.synthetic(T, 30, 99, family=NNI_FAMILY, nni_max=4)
+    ctx.hashrf_load_trees(f)
+    ctx.hashrf_compute(editdist=thr)
+    want = {lk: ctx.flat_clusters(thr, lk)[0] for lk in ("single", "complete", "UPGMA")}
+    P = T * (T - 1) // 2
+    d_out = torch.empty(P, dtype=torch.int16, device="cuda:0")
+    d_mask = torch.empty((P + 31) // 32, dtype=torch.int32, device="cuda:0")
+    torch.cuda.synchronize()
+    ctx.hashrf_compute(0, P, thr, 0, d_out.data_ptr(), d_mask.data_ptr())
+    for lk, w in want.items():
+        got, _ = ctx.flat_clusters(thr, lk, d_mask.data_ptr(), d_out.data_ptr())
+        assert np.array_equal(got, w)
+    ids = np.array([3, 17, 44, 399], dtype=np.uint32)
+    assert np.array_equal(ctx.fetch_submatrix(ids, d_out.data_ptr()), ctx.fetch()[[packed_index(T, int(a), int(b)) for x, a in enumerate(ids) for b in ids[x + 1:]]])
