@@ -193,3 +193,27 @@ def test_bips_to_tree_round_trip(golden, name):
     b2, o2 = g.all_bips()
     for t in range(len(f)):  # as sets: the order inside a tree follows its node order
         assert sorted(map(tuple, b2[int(o2[t]):int(o2[t + 1])].tolist())) == sorted(map(tuple, bips[int(off[t]):int(off[t + 1])].tolist()))
+
+
+def test_consensus_property_on_random_clusters():
+    """The property consensusTest asserts on the fixtures (Main.hs:505-508), on random inputs: the tree rebuilt by
+    bipsToTree from the intersection has exactly the intersection as its bipartitions -- for both restatements."""
+    import random
+    from tests.util import random_multifurcating_newicks
+    rng = random.Random(21)
+    for n in (4, 6, 10, 25, 70):
+        for _ in range(3):
+            # similar trees (so that the intersection is not empty): one random tree, some copies, a few others
+            base = random_multifurcating_newicks(rng, 1, n)
+            text = base * rng.randint(1, 3) + random_multifurcating_newicks(rng, rng.randint(0, 2), n)
+            names, trees = pyref.parse_newicks([text])
+            if any(pyref.num_leaves(t) != n for t in trees):
+                continue
+            inter = pyref.consensus_bips(trees)
+            rebuilt = pyref.bips_to_tree(n, inter)
+            assert pyref.all_bips(rebuilt) == inter
+            o = orc.Forest([text])
+            assert o.consensus_bips(range(o.num_trees)) == sorted(inter)
+            # the printed tree parses back to the same bipartitions under the same label table
+            back = orc.Forest([pyref.to_newick(names, rebuilt), text])
+            assert back.labels == names and back.all_bips(0) == sorted(inter)
