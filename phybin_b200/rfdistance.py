@@ -244,6 +244,8 @@ class RFContext:
     def allbips_fetch(self):
         """Host copies of the last extraction: (keys[nnz, W], tree_off[T+1]) or, in mode EXTRACT_CLADES,
         (clades[nnz, W], tree_off[T+1], leafsets[T, W])."""
+        if getattr(self, "_ext", None) is None:
+            raise PhyBinRFError(-5, "no extraction result on this context (call allbips first)")
         T, W, mode, nnz = self._ext
         keys = np.empty((nnz, W), dtype=np.uint64)
         off = np.empty(T + 1, dtype=np.uint64)
@@ -336,6 +338,8 @@ class RFContext:
         T = len(labels)
         info = prf_consensus_info()
         if bips is None:
+            if getattr(self, "_ext", None) is None:
+                raise PhyBinRFError(-5, "no device extraction on this context: pass bips / tree_off, or call allbips first")
             eT, W, mode, _ = self._ext
             if mode != EXTRACT_BIPS or eT != T:
                 raise PhyBinRFError(-5, "the last device extraction is not the allBips of these trees")
