@@ -162,6 +162,9 @@ def rf_lib():
         L.prf_launch_count.argtypes = [vp]
         # test-only entry points (not in phybin_rf.h)
         L.prf_debug_small_tiles.argtypes = [vp, C.c_int]
+        L.prf_debug_short_max.argtypes = [vp, C.c_uint32]
+        L.prf_debug_heavy_min.argtypes = [vp, C.c_uint32]
+        L.prf_debug_sparse_kernel.argtypes = [vp, C.c_int, C.c_int]
         L.prf_debug_no_flip.argtypes = [vp, C.c_int]
         L.prf_debug_row_plan.restype = C.c_longlong
         L.prf_debug_row_plan.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, vp, C.c_uint64]

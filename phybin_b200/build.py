@@ -69,14 +69,56 @@ def build_host(force: bool = False) -> str:
     return HOST_SO
 
 
-def build_cuda(force: bool = False) -> str:
+def _includes(path: str, seen=None) -> List[str]:
+    """Transitive quoted includes of a source file inside csrc/ and include/ (its rebuild dependencies)."""
+    seen = seen if seen is not None else set()
+    if path in seen or not os.path.exists(path):
+        return []
+    seen.add(path)
+    out = [path]
+    with open(path) as f:
+        for ln in f:
+            ln = ln.strip()
+            if ln.startswith('#include "'):
+                name = ln.split('"')[1]
+                for d in (CSRC, INC):
+                    out += _includes(os.path.join(d, name), seen)
+    return out
+
+
+def build_cuda(force: bool = False, extra_flags: List[str] | None = None, out: str | None = None) -> str:
+    """One object per .cu translation unit, compiled in parallel (only the units whose sources changed), then linked."""
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(LIBDIR, exist_ok=True)
+    out = out or RF_SO
+    tag = "" if out == RF_SO else "." + os.path.basename(out)
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
     cu = _sources("", [".cu"])
-    deps = cu + _sources("", [".cuh", ".h"]) + [os.path.join(INC, "phybin_rf.h")]
-    if force or _newer(RF_SO, deps):
-        _run([nvcc_path()] + NVCC_FLAGS + ["-shared", "-I", INC, "-I", CSRC, "-o", RF_SO] + cu
-             + ["-lcudart"], log=os.path.join(LIBDIR, "nvcc_build.log"))
-    return RF_SO
+    nvcc = nvcc_path()
+    jobs, objs = [], []
+    for src in cu:
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + tag + ".o")
+        objs.append(obj)
+        if force or _newer(obj, _includes(src)):
+            jobs.append((src, obj))
+
+    def compile_one(job):
+        src, obj = job
+        _run([nvcc] + NVCC_FLAGS + (extra_flags or []) + ["-c", "-I", INC, "-I", CSRC, "-o", obj, src], log=obj[:-2] + ".log")
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            list(ex.map(compile_one, jobs))
+    if jobs or not os.path.exists(out):
+        _run([nvcc, "-shared", "-o", out] + objs + ["-lcudart"])
+        with open(os.path.join(LIBDIR, "nvcc_build.log"), "w") as lf:   # one log, as before: ptxas -v of every unit
+            for obj in objs:
+                lg = obj[:-2] + ".log"
+                if os.path.exists(lg):
+                    with open(lg) as f:
+                        lf.write(f.read())
+    return out
 
 
 def build_cli(force: bool = False) -> str:

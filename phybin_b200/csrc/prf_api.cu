@@ -7,75 +7,14 @@
 #include <new>
 
 #include "prf_common.cuh"
+#include "prf_internal.h"
 #include "prf_primitives.cuh"
-#include "prf_incidence.cuh"
-#include "prf_sparse.cuh"
-#include "prf_dense.cuh"
 #include "prf_shard.cuh"
-#include "prf_cluster.cuh"
-#include "prf_tolerant.cuh"
-#include "prf_extract.cuh"
-#include "prf_consensus.cuh"
 
 using namespace prf;
 
-struct prf_ctx {
-  Ctx c;
-};
-
 static thread_local std::string g_create_error;
 
-namespace {
-
-int check_range(Ctx* ctx, uint64_t P, uint64_t p_begin, uint64_t p_end) {
-  if (p_begin > p_end || p_end > P)
-    return ctx->fail(PRF_E_INVALID, "packed range [%llu, %llu) outside [0, %llu]",
-                     (unsigned long long)p_begin, (unsigned long long)p_end, (unsigned long long)P);
-  if (p_begin % kShardAlign != 0 && p_begin != P)
-    return ctx->fail(PRF_E_INVALID, "p_begin=%llu is not a multiple of prf_shard_align()=%llu",
-                     (unsigned long long)p_begin, (unsigned long long)kShardAlign);
-  return PRF_OK;
-}
-
-float ev_ms(cudaEvent_t a, cudaEvent_t b) {
-  float ms = 0.f;
-  if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return 0.f; }
-  return ms;
-}
-
-// Points *d_out / *d_mask at context-owned buffers covering [p_begin, p_end) when the caller
-// passed none.
-int own_output(Ctx* ctx, uint64_t p_begin, uint64_t p_end, bool want_mask, uint16_t** d_out, uint32_t** d_mask) {
-  uint64_t n = p_end - p_begin;
-  if (!*d_out) {
-    ctx->out_valid = false;
-    if (ctx->out.n < n) PRF_CK(ctx, ctx->out.alloc(n, ctx->stream));
-    *d_out = ctx->out.p;
-    ctx->out_begin = p_begin;
-    ctx->out_end = p_end;
-    ctx->out_valid = true;
-  }
-  if (want_mask && !*d_mask) {
-    ctx->mask_valid = false;
-    uint64_t words = (n + 31) / 32;
-    if (ctx->mask.n < words) PRF_CK(ctx, ctx->mask.alloc(words, ctx->stream));
-    *d_mask = ctx->mask.p;
-    ctx->mask_begin = p_begin;
-    ctx->mask_end = p_end;
-    ctx->mask_valid = true;
-  }
-  return PRF_OK;
-}
-
-int upload(Ctx* ctx, void* dst, const void* src, size_t bytes, int kind) {
-  if (!bytes) return PRF_OK;
-  PRF_CK(ctx, cudaMemcpyAsync(dst, src, bytes,
-                              kind == PRF_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                              ctx->stream));
-  return PRF_OK;
-}
-
-}  // namespace
 
 extern "C" {
 
@@ -187,6 +126,7 @@ PRF_API int prf_hashrf_load(prf_ctx* h, const uint64_t* bips, const uint64_t* tr
   cudaStream_t s = ctx->stream;
   uint64_t launches0 = ctx->launches;
   ctx->h.loaded = false;
+  ctx->tol.loaded = false;
   ctx->out_valid = ctx->mask_valid = false;
 
   trace_mark("hashrf_load: enter");
@@ -261,15 +201,16 @@ PRF_API int prf_hashrf_compute(prf_ctx* h, uint64_t p_begin, uint64_t p_end, int
     // 2 * Kpad int8 ops at the ~0.9 Pop/s the operand traffic allows.  Both write the same 2 B per pair.
     const double pairs = (double)(p_end - p_begin);
     const double hits = (double)H.stats.n_hits * (H.P ? pairs / (double)H.P : 0.0);
-    const double kpad = (double)((H.n_shared + kDK - 1) / kDK * kDK);
+    const double kpad = (double)dense_kpad(H.n_shared);
     const double t_sparse = hits * 1.9e-12 + (H.uniform_nb ? 0.0 : pairs * 0.9e-12), t_dense = pairs * kpad * 2.0 / 0.9e15;
-    const double operand = (double)((H.T + kDN - 1) / kDN * kDN) * kpad;
+    const double operand = (double)dense_tpad(H.T) * kpad;
     use = (H.n_shared > 0 && operand < 32e9 && t_dense < t_sparse) ? PRF_VARIANT_DENSE : PRF_VARIANT_SPARSE;
   }
   PRF_CK(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
   if (p_end > p_begin) {
     if (use == PRF_VARIANT_DENSE) rc = launch_dense(ctx, p_begin, p_end, editdist, d_out, d_mask);
-    else rc = launch_sparse(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    else if (ctx->sparse_kernel == 1) rc = launch_sparse(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    else rc = launch_rows(ctx, p_begin, p_end, editdist, d_out, d_mask);
     if (rc) return rc;
   }
   PRF_CK(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
@@ -464,12 +405,15 @@ PRF_API int prf_hashrf_merge(prf_ctx* h, uint32_t T, uint32_t W, uint32_t world,
   PRF_CK(ctx, cudaEventRecord(ctx->ev[2], s));
   // build into fresh buffers: a part may alias the context's current structure
   DevBuf<uint16_t> nb;
-  DevBuf<uint32_t> roff, members, lid, nb32, cnt, mm;  // mm: min |B|, max |B|, max ranges per tree
+  DevBuf<uint32_t> roff, members, lid, nb32, cnt, mm, soff, singles;  // mm: min |B|, max |B|, max ranges per tree
   DevBuf<uint2> ranges;
+  PRF_CK(ctx, soff.alloc((size_t)T + 1, s));  // the parts carry every list as ranges (built with short_max == 0)
+  PRF_CK(ctx, cudaMemsetAsync(soff.p, 0, soff.bytes(), s));
+  PRF_CK(ctx, singles.alloc(1, s));
   PRF_CK(ctx, nb.alloc((size_t)T + 16, s));
   PRF_CK(ctx, cudaMemsetAsync(nb.p, 0, nb.bytes(), s));
   PRF_CK(ctx, roff.alloc((size_t)T + 1, s));
-  PRF_CK(ctx, members.alloc(n_members, s));
+  PRF_CK(ctx, members.alloc((size_t)n_members + 4, s));
   PRF_CK(ctx, lid.alloc(n_members, s));
   PRF_CK(ctx, ranges.alloc(n_ranges, s));
   PRF_CK(ctx, nb32.alloc((size_t)T + 1, s));
@@ -512,6 +456,11 @@ PRF_API int prf_hashrf_merge(prf_ctx* h, uint32_t T, uint32_t W, uint32_t world,
   H.roff = std::move(roff);
   H.ranges = std::move(ranges);
   H.members = std::move(members);
+  H.soff = std::move(soff);
+  H.singles = std::move(singles);
+  // the merged ranges of a tree interleave the parts: all of them take the warp-per-list walk
+  PRF_CK(ctx, H.nheavy.alloc((size_t)T + 1, s));
+  PRF_CK(ctx, cudaMemcpyAsync(H.nheavy.p, cnt.p, ((size_t)T + 1) * 4, cudaMemcpyDeviceToDevice, s));
   H.lid = std::move(lid);
   H.n_shared = (uint32_t)n_lists;
   H.n_shared_nnz = n_members;
@@ -536,535 +485,6 @@ PRF_API int prf_hashrf_merge(prf_ctx* h, uint32_t T, uint32_t W, uint32_t world,
   ctx->tol.loaded = false;
   ctx->out_valid = ctx->mask_valid = false;
   if (stats) *stats = st;
-  return PRF_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
-// tolerant
-// ---------------------------------------------------------------------------------------------
-
-PRF_API int prf_tolerant_load(prf_ctx* h, const uint64_t* clades, const uint64_t* tree_off,
-                              const uint64_t* leafsets, uint32_t T, uint32_t W, int kind, prf_stats* stats) {
-  if (!h) return PRF_E_INVALID;
-  Ctx* ctx = &h->c;
-  ctx->err.clear();
-  if (!tree_off || (T && !leafsets)) return ctx->fail(PRF_E_INVALID, "tree_off / leafsets is NULL");
-  if (W == 0 || W > kTolMaxWords) return ctx->fail(PRF_E_UNSUPPORTED, "tolerant mode supports W in 1..%u, got %u", kTolMaxWords, W);
-  if (kind != PRF_MEM_HOST && kind != PRF_MEM_DEVICE) return ctx->fail(PRF_E_INVALID, "bad memory kind %d", kind);
-  PRF_CK(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t s = ctx->stream;
-  uint64_t launches0 = ctx->launches;
-  TolerantState& S = ctx->tol;
-  S = TolerantState{};
-  ctx->out_valid = ctx->mask_valid = false;
-  PRF_CK(ctx, cudaEventRecord(ctx->ev[0], s));
-  std::vector<uint64_t> hoff((size_t)T + 1);
-  if (kind == PRF_MEM_HOST) {
-    std::memcpy(hoff.data(), tree_off, ((size_t)T + 1) * 8);
-  } else {
-    PRF_CK(ctx, cudaMemcpyAsync(hoff.data(), tree_off, ((size_t)T + 1) * 8, cudaMemcpyDeviceToHost, s));
-    PRF_CK(ctx, cudaStreamSynchronize(s));
-  }
-  if (hoff[0] != 0) return ctx->fail(PRF_E_INVALID, "tree_off[0] must be 0");
-  uint32_t maxc = 0;
-  for (uint32_t t = 0; t < T; ++t) {
-    if (hoff[t + 1] < hoff[t]) return ctx->fail(PRF_E_INVALID, "tree_off is not ascending at tree %u", t);
-    maxc = std::max<uint64_t>(maxc, hoff[t + 1] - hoff[t]);
-  }
-  uint64_t nnz = hoff[T];
-  if (nnz && !clades) return ctx->fail(PRF_E_INVALID, "clades is NULL");
-  if (maxc > kTolMaxClades)
-    return ctx->fail(PRF_E_UNSUPPORTED, "a tree has %u interior clades; tolerant mode supports <= %u", maxc, kTolMaxClades);
-  PRF_CK(ctx, S.off.alloc((size_t)T + 1, s));
-  PRF_CK(ctx, S.clades.alloc(nnz * W, s));
-  PRF_CK(ctx, S.leafsets.alloc((size_t)T * W, s));
-  int rc;
-  if ((rc = upload(ctx, S.off.p, hoff.data(), ((size_t)T + 1) * 8, PRF_MEM_HOST))) return rc;
-  if ((rc = upload(ctx, S.clades.p, clades, nnz * W * 8, kind))) return rc;
-  if ((rc = upload(ctx, S.leafsets.p, leafsets, (size_t)T * W * 8, kind))) return rc;
-  PRF_CK(ctx, cudaEventRecord(ctx->ev[1], s));
-  PRF_CK(ctx, cudaStreamSynchronize(s));
-  S.T = T;
-  S.W = W;
-  S.nnz = nnz;
-  S.max_clades = maxc;
-  S.P = (uint64_t)T * (T ? T - 1 : 0) / 2;
-  S.loaded = true;
-  ctx->h.loaded = false;
-  S.stats = prf_stats{};
-  S.stats.n_trees = T;
-  S.stats.n_words = W;
-  S.stats.nnz = nnz;
-  S.stats.n_pairs = S.P;
-  S.stats.max_bips = maxc;
-  S.stats.ms_h2d = ev_ms(ctx->ev[0], ctx->ev[1]);
-  S.stats.gpu_launches = (int32_t)(ctx->launches - launches0);
-  if (stats) *stats = S.stats;
-  return PRF_OK;
-}
-
-PRF_API int prf_tolerant_compute(prf_ctx* h, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out,
-                                 uint32_t* d_mask, prf_stats* stats) {
-  if (!h) return PRF_E_INVALID;
-  Ctx* ctx = &h->c;
-  ctx->err.clear();
-  TolerantState& S = ctx->tol;
-  if (!S.loaded) return ctx->fail(PRF_E_STATE, "prf_tolerant_compute before a successful prf_tolerant_load");
-  int rc = check_range(ctx, S.P, p_begin, p_end);
-  if (rc) return rc;
-  PRF_CK(ctx, cudaSetDevice(ctx->device));
-  uint64_t launches0 = ctx->launches;
-  if ((rc = own_output(ctx, p_begin, p_end, editdist >= 0, &d_out, &d_mask))) return rc;
-  if (editdist < 0) d_mask = nullptr;
-  PRF_CK(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
-  if (p_end > p_begin && (rc = launch_tolerant(ctx, p_begin, p_end, editdist, d_out, d_mask))) return rc;
-  PRF_CK(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
-  if (stats) {
-    PRF_CK(ctx, cudaStreamSynchronize(ctx->stream));
-    prf_stats st = S.stats;
-    st.ms_matrix = ev_ms(ctx->ev[4], ctx->ev[5]);
-    st.gpu_launches = (int32_t)(ctx->launches - launches0);
-    *stats = st;
-  }
-  return PRF_OK;
-}
-
-PRF_API int prf_tolerant(prf_ctx* h, const uint64_t* clades, const uint64_t* tree_off, const uint64_t* leafsets,
-                         uint32_t T, uint32_t W, int32_t editdist, uint16_t* out_upper, uint32_t* out_mask,
-                         prf_stats* stats) {
-  if (!h) return PRF_E_INVALID;
-  Ctx* ctx = &h->c;
-  prf_stats st{}, st2{};
-  int rc = prf_tolerant_load(h, clades, tree_off, leafsets, T, W, PRF_MEM_HOST, &st);
-  if (rc) return rc;
-  uint64_t P = ctx->tol.P;
-  if ((rc = prf_tolerant_compute(h, 0, P, editdist, nullptr, nullptr, &st2))) return rc;
-  PRF_CK(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
-  if (out_upper && (rc = prf_fetch(h, 0, P, out_upper))) return rc;
-  if (out_mask && editdist >= 0 && (rc = prf_fetch_mask(h, 0, P, out_mask))) return rc;
-  PRF_CK(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
-  PRF_CK(ctx, cudaStreamSynchronize(ctx->stream));
-  if (stats) {
-    *stats = st2;
-    stats->ms_h2d = st.ms_h2d;
-    stats->ms_d2h = ev_ms(ctx->ev[6], ctx->ev[7]);
-    stats->ms_total = ev_ms(ctx->ev[0], ctx->ev[7]);
-    stats->gpu_launches = st.gpu_launches + st2.gpu_launches;
-  }
-  return PRF_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
-// bipartition extraction on the device
-// ---------------------------------------------------------------------------------------------
-
-PRF_API int prf_allbips(prf_ctx* h, const int32_t* node_label, const uint32_t* node_parent, const uint64_t* tree_begin,
-                        const uint32_t* num_leaves, uint32_t T, uint32_t W, int kind, int mode, prf_extract_info* info) {
-  if (!h) return PRF_E_INVALID;
-  Ctx* ctx = &h->c;
-  ctx->err.clear();
-  if (!tree_begin || (T && !num_leaves)) return ctx->fail(PRF_E_INVALID, "tree_begin / num_leaves is NULL");
-  if (W == 0 || W > kMaxWords) return ctx->fail(PRF_E_UNSUPPORTED, "W=%u words per set; supported 1..%u", W, kMaxWords);
-  if (kind != PRF_MEM_HOST && kind != PRF_MEM_DEVICE) return ctx->fail(PRF_E_INVALID, "bad memory kind %d", kind);
-  if (mode != PRF_EXTRACT_BIPS && mode != PRF_EXTRACT_CLADES) return ctx->fail(PRF_E_INVALID, "unknown extraction mode %d", mode);
-  PRF_CK(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t s = ctx->stream;
-  const uint64_t launches0 = ctx->launches;
-  ExtractState& E = ctx->ext;
-  E = ExtractState{};
-  PRF_CK(ctx, cudaEventRecord(ctx->ev[0], s));
-
-  // tree offsets are needed on the host (largest tree -> shared memory per warp) and on the device
-  std::vector<uint64_t> hbeg((size_t)T + 1);
-  if (kind == PRF_MEM_HOST) {
-    std::memcpy(hbeg.data(), tree_begin, ((size_t)T + 1) * 8);
-  } else {
-    PRF_CK(ctx, cudaMemcpyAsync(hbeg.data(), tree_begin, ((size_t)T + 1) * 8, cudaMemcpyDeviceToHost, s));
-    PRF_CK(ctx, cudaStreamSynchronize(s));
-  }
-  if (hbeg[0] != 0) return ctx->fail(PRF_E_INVALID, "tree_begin[0] must be 0");
-  std::vector<uint32_t> hleaves_own;
-  const uint32_t* hleaves = num_leaves;  // needed on the host too: they decide how many nodes own a set
-  if (kind == PRF_MEM_DEVICE && T) {
-    hleaves_own.resize(T);
-    PRF_CK(ctx, cudaMemcpyAsync(hleaves_own.data(), num_leaves, (size_t)T * 4, cudaMemcpyDeviceToHost, s));
-    PRF_CK(ctx, cudaStreamSynchronize(s));
-    hleaves = hleaves_own.data();
-  }
-  uint32_t max_nodes = 1, max_slots = 1;
-  for (uint32_t t = 0; t < T; ++t) {
-    if (hbeg[t + 1] < hbeg[t]) return ctx->fail(PRF_E_INVALID, "tree_begin is not ascending at tree %u", t);
-    const uint64_t m = hbeg[t + 1] - hbeg[t];
-    if (m >= kExtractMaxNodes) return ctx->fail(PRF_E_UNSUPPORTED, "tree %u has %llu nodes; supported < %u", t, (unsigned long long)m, kExtractMaxNodes);
-    max_nodes = std::max(max_nodes, (uint32_t)m);
-    max_slots = std::max(max_slots, extract_slots((uint32_t)m, hleaves[t]));
-  }
-  const uint64_t n_nodes = hbeg[T];
-  if (n_nodes >= 0xffffffffull) return ctx->fail(PRF_E_UNSUPPORTED, "%llu nodes; supported < 2^32 - 1", (unsigned long long)n_nodes);
-  if (n_nodes && (!node_label || !node_parent)) return ctx->fail(PRF_E_INVALID, "node_label / node_parent is NULL");
-  const size_t warp_bytes = extract_warp_bytes(max_slots, max_nodes, W);
-  if (warp_bytes > kExtractSmemBudget)
-    return ctx->fail(PRF_E_UNSUPPORTED, "a tree with %u interior nodes x %u words needs %zu bytes of shared memory; the limit is %zu",
-                     max_slots, W, warp_bytes, kExtractSmemBudget);
-  // the kernel is latency-bound (a dependent sweep per tree): pick the CTA shape that keeps most warps resident
-  uint32_t warps = 1, best = 0;
-  for (uint32_t ctas = 1; ctas <= 4; ++ctas) {
-    const size_t per_cta = (size_t)(220 * 1024) / ctas - 1024;
-    const uint32_t w = (uint32_t)std::min<size_t>(8, std::min(per_cta, kExtractSmemBudget) / warp_bytes);
-    if (w * ctas > best) { best = w * ctas; warps = w; }
-  }
-
-  DevBuf<int32_t> d_label_own;
-  DevBuf<uint32_t> d_parent_own, d_leaves_own, count, off32, err;
-  DevBuf<uint64_t> d_begin_own, scratch;
-  const int32_t* d_label = node_label;
-  const uint32_t *d_parent = node_parent, *d_leaves = num_leaves;
-  const uint64_t* d_begin = tree_begin;
-  int rc;
-  if (kind == PRF_MEM_HOST) {
-    PRF_CK(ctx, d_label_own.alloc(n_nodes, s));
-    PRF_CK(ctx, d_parent_own.alloc(n_nodes, s));
-    PRF_CK(ctx, d_leaves_own.alloc(T, s));
-    PRF_CK(ctx, d_begin_own.alloc((size_t)T + 1, s));
-    if ((rc = upload(ctx, d_label_own.p, node_label, n_nodes * 4, kind))) return rc;
-    if ((rc = upload(ctx, d_parent_own.p, node_parent, n_nodes * 4, kind))) return rc;
-    if ((rc = upload(ctx, d_leaves_own.p, num_leaves, (size_t)T * 4, kind))) return rc;
-    if ((rc = upload(ctx, d_begin_own.p, tree_begin, ((size_t)T + 1) * 8, kind))) return rc;
-    d_label = d_label_own.p; d_parent = d_parent_own.p; d_leaves = d_leaves_own.p; d_begin = d_begin_own.p;
-  }
-  PRF_CK(ctx, cudaEventRecord(ctx->ev[1], s));
-  PRF_CK(ctx, scratch.alloc(n_nodes * W, s));
-  PRF_CK(ctx, count.alloc((size_t)T + 1, s));
-  PRF_CK(ctx, off32.alloc((size_t)T + 1, s));
-  PRF_CK(ctx, err.alloc(1, s));
-  PRF_CK(ctx, cudaMemsetAsync(err.p, 0, 4, s));
-  PRF_CK(ctx, cudaMemsetAsync(count.p + T, 0, 4, s));  // the scan's last element becomes the total
-  PRF_CK(ctx, E.off.alloc((size_t)T + 1, s));
-  if (mode == PRF_EXTRACT_CLADES) {
-    PRF_CK(ctx, E.leafsets.alloc((size_t)T * W, s));
-    PRF_CK(ctx, cudaMemsetAsync(E.leafsets.p, 0, E.leafsets.bytes(), s));
-  }
-  if (T) {
-    switch (W) {
-#define PRF_W_CASE(w)                                                                                                     \
-  case w:                                                                                                                 \
-    rc = launch_extract_w<w>(ctx, mode, d_label, d_parent, d_begin, d_leaves, T, warps, (uint32_t)warp_bytes, max_slots,   \
-                             max_nodes, scratch.p, count.p, E.leafsets.p, err.p);                                         \
-    break;
-      PRF_W_CASE(1) PRF_W_CASE(2) PRF_W_CASE(3) PRF_W_CASE(4) PRF_W_CASE(5) PRF_W_CASE(6) PRF_W_CASE(7) PRF_W_CASE(8)
-      PRF_W_CASE(9) PRF_W_CASE(10) PRF_W_CASE(11) PRF_W_CASE(12) PRF_W_CASE(13) PRF_W_CASE(14) PRF_W_CASE(15) PRF_W_CASE(16)
-#undef PRF_W_CASE
-      default: rc = PRF_E_UNSUPPORTED;
-    }
-    if (rc) return rc;
-  }
-  if ((rc = exclusive_scan(ctx, LoadU32{count.p}, (uint64_t)T + 1, off32.p, nullptr))) return rc;
-  uint32_t hnnz = 0, herr = 0;
-  PRF_CK(ctx, cudaMemcpyAsync(&hnnz, off32.p + T, 4, cudaMemcpyDeviceToHost, s));
-  PRF_CK(ctx, cudaMemcpyAsync(&herr, err.p, 4, cudaMemcpyDeviceToHost, s));
-  PRF_CK(ctx, cudaStreamSynchronize(s));
-  if (herr & 1u) return ctx->fail(PRF_E_INVALID, "a node's parent is not an interior node that precedes it inside its own tree (nodes must be in pre-order)");
-  if (herr & 2u) return ctx->fail(PRF_E_INVALID, "a leaf label does not fit %u words", W);
-  if (herr & 4u) return ctx->fail(PRF_E_INVALID, "a tree's num_leaves is not its number of leaf nodes, or exceeds the %u labels %u words hold", 64 * W, W);
-  PRF_CK(ctx, E.keys.alloc((size_t)hnnz * W, s));
-  extract_pack_kernel<<<(T + 1 + 7) / 8, 256, 0, s>>>(scratch.p, d_begin, off32.p, T, W, E.keys.p, E.off.p);
-  PRF_LAUNCHED(ctx);
-  PRF_CK(ctx, cudaEventRecord(ctx->ev[2], s));
-  PRF_CK(ctx, cudaStreamSynchronize(s));
-  E.valid = true;
-  E.mode = mode;
-  E.T = T;
-  E.W = W;
-  E.nnz = hnnz;
-  if (info) {
-    info->nnz = hnnz;
-    info->max_nodes = max_nodes;
-    info->gpu_launches = (int32_t)(ctx->launches - launches0);
-    info->ms_h2d = ev_ms(ctx->ev[0], ctx->ev[1]);
-    info->ms_kernels = ev_ms(ctx->ev[1], ctx->ev[2]);
-  }
-  return PRF_OK;
-}
-
-PRF_API int prf_allbips_result(prf_ctx* h, const uint64_t** d_keys, const uint64_t** d_tree_off, const uint64_t** d_leafsets,
-                               uint64_t* nnz) {
-  if (!h) return PRF_E_INVALID;
-  Ctx* ctx = &h->c;
-  ctx->err.clear();
-  const ExtractState& E = ctx->ext;
-  if (!E.valid) return ctx->fail(PRF_E_STATE, "no extraction result on this context (call prf_allbips first)");
-  if (d_keys) *d_keys = E.keys.p;
-  if (d_tree_off) *d_tree_off = E.off.p;
-  if (d_leafsets) *d_leafsets = E.mode == PRF_EXTRACT_CLADES ? E.leafsets.p : nullptr;
-  if (nnz) *nnz = E.nnz;
-  return PRF_OK;
-}
-
-PRF_API int prf_allbips_fetch(prf_ctx* h, uint64_t* keys, uint64_t* tree_off, uint64_t* leafsets) {
-  if (!h) return PRF_E_INVALID;
-  Ctx* ctx = &h->c;
-  ctx->err.clear();
-  const ExtractState& E = ctx->ext;
-  if (!E.valid) return ctx->fail(PRF_E_STATE, "no extraction result on this context (call prf_allbips first)");
-  if (leafsets && E.mode != PRF_EXTRACT_CLADES) return ctx->fail(PRF_E_STATE, "the last extraction was not in mode PRF_EXTRACT_CLADES");
-  PRF_CK(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t s = ctx->stream;
-  if (keys && E.nnz) PRF_CK(ctx, cudaMemcpyAsync(keys, E.keys.p, E.nnz * E.W * 8, cudaMemcpyDeviceToHost, s));
-  if (tree_off) PRF_CK(ctx, cudaMemcpyAsync(tree_off, E.off.p, ((size_t)E.T + 1) * 8, cudaMemcpyDeviceToHost, s));
-  if (leafsets && E.T) PRF_CK(ctx, cudaMemcpyAsync(leafsets, E.leafsets.p, (size_t)E.T * E.W * 8, cudaMemcpyDeviceToHost, s));
-  PRF_CK(ctx, cudaStreamSynchronize(s));
-  return PRF_OK;
-}
-
-static int trees_one_shot(prf_ctx* h, bool tolerant, const int32_t* node_label, const uint32_t* node_parent,
-                          const uint64_t* tree_begin, const uint32_t* num_leaves, uint32_t T, uint32_t W, int32_t editdist,
-                          uint16_t* out_upper, uint32_t* out_mask, prf_stats* stats, prf_extract_info* extract) {
-  if (!h) return PRF_E_INVALID;
-  Ctx* ctx = &h->c;
-  prf_extract_info ei{};
-  int rc = prf_allbips(h, node_label, node_parent, tree_begin, num_leaves, T, W, PRF_MEM_HOST,
-                       tolerant ? PRF_EXTRACT_CLADES : PRF_EXTRACT_BIPS, &ei);
-  if (rc) return rc;
-  if (extract) *extract = ei;
-  const ExtractState& E = ctx->ext;
-  prf_stats st{}, st2{};
-  rc = tolerant ? prf_tolerant_load(h, E.keys.p, E.off.p, E.leafsets.p, T, W, PRF_MEM_DEVICE, &st)
-                : prf_hashrf_load(h, E.keys.p, E.off.p, T, W, PRF_MEM_DEVICE, &st);
-  if (rc) return rc;
-  const uint64_t P = tolerant ? ctx->tol.P : ctx->h.P;
-  rc = tolerant ? prf_tolerant_compute(h, 0, P, editdist, nullptr, nullptr, &st2)
-                : prf_hashrf_compute(h, 0, P, editdist, PRF_VARIANT_AUTO, nullptr, nullptr, &st2);
-  if (rc) return rc;
-  PRF_CK(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
-  if (out_upper && (rc = prf_fetch(h, 0, P, out_upper))) return rc;
-  if (out_mask && editdist >= 0 && (rc = prf_fetch_mask(h, 0, P, out_mask))) return rc;
-  PRF_CK(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
-  PRF_CK(ctx, cudaStreamSynchronize(ctx->stream));
-  if (stats) {
-    *stats = st2;
-    stats->ms_h2d = ei.ms_h2d;  // the only host-to-device traffic: the tree arrays
-    stats->ms_dedup = st.ms_dedup;
-    stats->ms_incidence = st.ms_incidence;
-    stats->ms_d2h = ev_ms(ctx->ev[6], ctx->ev[7]);
-    stats->ms_total = ei.ms_h2d + ei.ms_kernels + st.ms_total + st2.ms_matrix + stats->ms_d2h;
-    stats->gpu_launches = ei.gpu_launches + st.gpu_launches + st2.gpu_launches;
-  }
-  return PRF_OK;
-}
-
-PRF_API int prf_hashrf_trees(prf_ctx* h, const int32_t* node_label, const uint32_t* node_parent, const uint64_t* tree_begin,
-                             const uint32_t* num_leaves, uint32_t T, uint32_t W, int32_t editdist, uint16_t* out_upper,
-                             uint32_t* out_mask, prf_stats* stats, prf_extract_info* extract) {
-  return trees_one_shot(h, false, node_label, node_parent, tree_begin, num_leaves, T, W, editdist, out_upper, out_mask, stats,
-                        extract);
-}
-
-PRF_API int prf_tolerant_trees(prf_ctx* h, const int32_t* node_label, const uint32_t* node_parent, const uint64_t* tree_begin,
-                               const uint32_t* num_leaves, uint32_t T, uint32_t W, int32_t editdist, uint16_t* out_upper,
-                               uint32_t* out_mask, prf_stats* stats, prf_extract_info* extract) {
-  return trees_one_shot(h, true, node_label, node_parent, tree_begin, num_leaves, T, W, editdist, out_upper, out_mask, stats,
-                        extract);
-}
-
-// ---------------------------------------------------------------------------------------------
-// flat clusters from the threshold mask
-// ---------------------------------------------------------------------------------------------
-
-PRF_API int prf_mask_components(prf_ctx* h, const uint32_t* d_mask, uint32_t T, uint32_t* labels, uint32_t* n_components) {
-  if (!h) return PRF_E_INVALID;
-  Ctx* ctx = &h->c;
-  ctx->err.clear();
-  if (!labels && T) return ctx->fail(PRF_E_INVALID, "labels is NULL");
-  const uint64_t P = (uint64_t)T * (T ? T - 1 : 0) / 2;
-  if (!d_mask) {
-    if (!ctx->mask_valid || ctx->mask_begin != 0 || ctx->mask_end != P)
-      return ctx->fail(PRF_E_STATE, "no context-owned mask covering the whole triangle (compute with editdist >= 0 first)");
-    d_mask = ctx->mask.p;
-  }
-  PRF_CK(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t s = ctx->stream;
-  DevBuf<uint32_t> parent, label, roots;
-  PRF_CK(ctx, parent.alloc(T, s));
-  PRF_CK(ctx, label.alloc(T, s));
-  PRF_CK(ctx, roots.alloc(1, s));
-  PRF_CK(ctx, cudaMemsetAsync(roots.p, 0, 4, s));
-  uint32_t hroots = 0;
-  if (T) {
-    cc_init_kernel<<<grid_for(T), 256, 0, s>>>(parent.p, T);
-    PRF_LAUNCHED(ctx);
-    const uint64_t n_words = (P + 31) / 32;
-    if (n_words) {
-      if (n_words > 0x7fffffffull * 256) return ctx->fail(PRF_E_UNSUPPORTED, "mask too large for one launch");
-      cc_hook_kernel<<<(uint32_t)((n_words + 255) / 256), 256, 0, s>>>(d_mask, n_words, 0, P, T, parent.p);
-      PRF_LAUNCHED(ctx);
-    }
-    cc_flatten_kernel<<<grid_for(T), 256, 0, s>>>(parent.p, T, label.p, roots.p);
-    PRF_LAUNCHED(ctx);
-    PRF_CK(ctx, cudaMemcpyAsync(labels, label.p, (size_t)T * 4, cudaMemcpyDeviceToHost, s));
-  }
-  PRF_CK(ctx, cudaMemcpyAsync(&hroots, roots.p, 4, cudaMemcpyDeviceToHost, s));
-  PRF_CK(ctx, cudaStreamSynchronize(s));
-  if (n_components) *n_components = hroots;
-  return PRF_OK;
-}
-
-PRF_API int prf_fetch_submatrix(prf_ctx* h, const uint16_t* d_matrix, uint32_t T, const uint32_t* ids, uint32_t m,
-                                uint16_t* out) {
-  if (!h) return PRF_E_INVALID;
-  Ctx* ctx = &h->c;
-  ctx->err.clear();
-  const uint16_t* src = d_matrix;
-  uint64_t src_begin = 0;
-  if (!src) {
-    if (!ctx->out_valid) return ctx->fail(PRF_E_STATE, "no context-owned result to fetch");
-    T = ctx->h.loaded ? ctx->h.T : (ctx->tol.loaded ? ctx->tol.T : 0);
-    src = ctx->out.p;
-    src_begin = ctx->out_begin;
-  }
-  if (m && !ids) return ctx->fail(PRF_E_INVALID, "ids is NULL");
-  for (uint32_t i = 0; i < m; ++i)
-    if (ids[i] >= T || (i && ids[i] <= ids[i - 1])) return ctx->fail(PRF_E_INVALID, "ids must be ascending tree ids below %u", T);
-  const uint64_t n_out = (uint64_t)m * (m ? m - 1 : 0) / 2;
-  if (!n_out) return PRF_OK;
-  if (!out) return ctx->fail(PRF_E_INVALID, "out is NULL");
-  if (!d_matrix) {
-    const uint64_t lo = row_start(ids[0], T) + (ids[1] - ids[0] - 1), hi = row_start(ids[m - 2], T) + (ids[m - 1] - ids[m - 2] - 1);
-    if (lo < ctx->out_begin || hi >= ctx->out_end) return ctx->fail(PRF_E_INVALID, "the computed range does not cover these pairs");
-  }
-  PRF_CK(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t s = ctx->stream;
-  DevBuf<uint32_t> d_ids;
-  DevBuf<uint16_t> d_out;
-  PRF_CK(ctx, d_ids.alloc(m, s));
-  PRF_CK(ctx, d_out.alloc(n_out, s));
-  PRF_CK(ctx, cudaMemcpyAsync(d_ids.p, ids, (size_t)m * 4, cudaMemcpyHostToDevice, s));
-  submatrix_gather_kernel<<<grid_for(n_out), 256, 0, s>>>(src, src_begin, T, d_ids.p, m, n_out, d_out.p);
-  PRF_LAUNCHED(ctx);
-  PRF_CK(ctx, cudaMemcpyAsync(out, d_out.p, n_out * 2, cudaMemcpyDeviceToHost, s));
-  PRF_CK(ctx, cudaStreamSynchronize(s));
-  return PRF_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
-// strict consensus of every cluster
-// ---------------------------------------------------------------------------------------------
-
-PRF_API int prf_consensus(prf_ctx* h, const uint64_t* bips, const uint64_t* tree_off, uint32_t T, uint32_t W, int kind,
-                          const uint32_t* labels, prf_consensus_info* info) {
-  if (!h) return PRF_E_INVALID;
-  Ctx* ctx = &h->c;
-  ctx->err.clear();
-  if (!tree_off || (T && !labels)) return ctx->fail(PRF_E_INVALID, "tree_off / labels is NULL");
-  if (W == 0 || W > kMaxWords) return ctx->fail(PRF_E_UNSUPPORTED, "W=%u words per set; supported 1..%u", W, kMaxWords);
-  if (kind != PRF_MEM_HOST && kind != PRF_MEM_DEVICE) return ctx->fail(PRF_E_INVALID, "bad memory kind %d", kind);
-  PRF_CK(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t s = ctx->stream;
-  const uint64_t launches0 = ctx->launches;
-  ConsensusState& R = ctx->cons;
-  R = ConsensusState{};
-
-  std::vector<uint64_t> hoff((size_t)T + 1);
-  if (kind == PRF_MEM_HOST) {
-    std::memcpy(hoff.data(), tree_off, ((size_t)T + 1) * 8);
-  } else {
-    PRF_CK(ctx, cudaMemcpyAsync(hoff.data(), tree_off, ((size_t)T + 1) * 8, cudaMemcpyDeviceToHost, s));
-    PRF_CK(ctx, cudaStreamSynchronize(s));
-  }
-  if (hoff[0] != 0) return ctx->fail(PRF_E_INVALID, "tree_off[0] must be 0");
-  for (uint32_t t = 0; t < T; ++t)
-    if (hoff[t + 1] < hoff[t]) return ctx->fail(PRF_E_INVALID, "tree_off is not ascending at tree %u", t);
-  const uint64_t nnz = hoff[T];
-  if (nnz >= 0xffffffffull) return ctx->fail(PRF_E_UNSUPPORTED, "nnz=%llu entries; supported < 2^32 - 1", (unsigned long long)nnz);
-  if (nnz && !bips) return ctx->fail(PRF_E_INVALID, "bips is NULL");
-  // cluster sizes; a label must be the smallest tree id of its cluster
-  std::vector<uint32_t> size(T ? T : 1, 0);
-  uint32_t n_clusters = 0;
-  for (uint32_t t = 0; t < T; ++t) {
-    const uint32_t c = labels[t];
-    if (c > t || labels[c] != c)
-      return ctx->fail(PRF_E_INVALID, "labels[%u]=%u is not the smallest tree id of a cluster", t, c);
-    ++size[c];
-    n_clusters += c == t;
-  }
-  uint64_t rep_entries = 0;
-  for (uint32_t t = 0; t < T; ++t)
-    if (labels[t] == t && size[t] >= 2) rep_entries += hoff[t + 1] - hoff[t];
-  uint64_t cap = 1024;
-  while (cap < 2 * rep_entries) cap <<= 1;
-
-  DevBuf<uint64_t> d_off_own, d_bips_own;
-  DevBuf<uint32_t> d_labels, d_size, cnt, pos;
-  DevBuf<unsigned long long> slots;
-  const uint64_t *d_off = tree_off, *d_bips = bips;
-  int rc;
-  if (kind == PRF_MEM_HOST) {
-    PRF_CK(ctx, d_off_own.alloc((size_t)T + 1, s));
-    PRF_CK(ctx, d_bips_own.alloc(nnz * W, s));
-    if ((rc = upload(ctx, d_off_own.p, tree_off, ((size_t)T + 1) * 8, kind))) return rc;
-    if ((rc = upload(ctx, d_bips_own.p, bips, nnz * W * 8, kind))) return rc;
-    d_off = d_off_own.p;
-    d_bips = d_bips_own.p;
-  } else if (nnz && (reinterpret_cast<uintptr_t>(bips) & 15)) {
-    return ctx->fail(PRF_E_INVALID, "device bips pointer must be 16-byte aligned");
-  }
-  PRF_CK(ctx, d_labels.alloc(T, s));
-  PRF_CK(ctx, d_size.alloc(T, s));
-  if ((rc = upload(ctx, d_labels.p, labels, (size_t)T * 4, PRF_MEM_HOST))) return rc;
-  if ((rc = upload(ctx, d_size.p, size.data(), (size_t)T * 4, PRF_MEM_HOST))) return rc;
-  PRF_CK(ctx, cnt.alloc(nnz + 1, s));
-  PRF_CK(ctx, pos.alloc(nnz + 1, s));
-  PRF_CK(ctx, slots.alloc(cap, s));
-  PRF_CK(ctx, cudaMemsetAsync(cnt.p, 0, (nnz + 1) * 4, s));
-  PRF_CK(ctx, cudaMemsetAsync(slots.p, 0xff, cap * 8, s));
-  PRF_CK(ctx, R.off.alloc((size_t)T + 1, s));
-  PRF_CK(ctx, cudaEventRecord(ctx->ev[0], s));
-  if (T) {
-    switch (W) {
-#define PRF_W_CASE(w) \
-  case w: rc = launch_cons_table_w<w>(ctx, d_bips, d_off, d_labels.p, d_size.p, T, slots.p, cap - 1, cnt.p); break;
-      PRF_W_CASE(1) PRF_W_CASE(2) PRF_W_CASE(3) PRF_W_CASE(4) PRF_W_CASE(5) PRF_W_CASE(6) PRF_W_CASE(7) PRF_W_CASE(8)
-      PRF_W_CASE(9) PRF_W_CASE(10) PRF_W_CASE(11) PRF_W_CASE(12) PRF_W_CASE(13) PRF_W_CASE(14) PRF_W_CASE(15) PRF_W_CASE(16)
-#undef PRF_W_CASE
-      default: rc = PRF_E_UNSUPPORTED;
-    }
-    if (rc) return rc;
-    cons_flag_kernel<<<(T + 7) / 8, 256, 0, s>>>(d_off, d_labels.p, d_size.p, T, cnt.p);
-    PRF_LAUNCHED(ctx);
-  }
-  if ((rc = exclusive_scan(ctx, LoadU32{cnt.p}, nnz + 1, pos.p, nullptr))) return rc;
-  uint32_t n_out = 0;
-  PRF_CK(ctx, cudaMemcpyAsync(&n_out, pos.p + nnz, 4, cudaMemcpyDeviceToHost, s));
-  PRF_CK(ctx, cudaStreamSynchronize(s));
-  PRF_CK(ctx, R.keys.alloc((size_t)n_out * W, s));
-  cons_gather_kernel<<<(T + 1 + 7) / 8, 256, 0, s>>>(d_bips, d_off, cnt.p, pos.p, T, W, R.keys.p, R.off.p);
-  PRF_LAUNCHED(ctx);
-  PRF_CK(ctx, cudaEventRecord(ctx->ev[1], s));
-  PRF_CK(ctx, cudaStreamSynchronize(s));
-  R.valid = true;
-  R.T = T;
-  R.W = W;
-  R.n_out = n_out;
-  if (info) {
-    info->n_out = n_out;
-    info->n_clusters = n_clusters;
-    info->gpu_launches = (int32_t)(ctx->launches - launches0);
-    info->ms_kernels = ev_ms(ctx->ev[0], ctx->ev[1]);
-    info->reserved = 0;
-  }
-  return PRF_OK;
-}
-
-PRF_API int prf_consensus_fetch(prf_ctx* h, uint64_t* keys, uint64_t* cons_off) {
-  if (!h) return PRF_E_INVALID;
-  Ctx* ctx = &h->c;
-  ctx->err.clear();
-  const ConsensusState& R = ctx->cons;
-  if (!R.valid) return ctx->fail(PRF_E_STATE, "no consensus result on this context (call prf_consensus first)");
-  PRF_CK(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t s = ctx->stream;
-  if (keys && R.n_out) PRF_CK(ctx, cudaMemcpyAsync(keys, R.keys.p, R.n_out * R.W * 8, cudaMemcpyDeviceToHost, s));
-  if (cons_off) PRF_CK(ctx, cudaMemcpyAsync(cons_off, R.off.p, ((size_t)R.T + 1) * 8, cudaMemcpyDeviceToHost, s));
-  PRF_CK(ctx, cudaStreamSynchronize(s));
   return PRF_OK;
 }
 
@@ -1098,6 +518,27 @@ PRF_API int prf_debug_wide_slots(prf_ctx* h, int on) {
 PRF_API int prf_debug_no_flip(prf_ctx* h, int on) {
   if (!h) return PRF_E_INVALID;
   h->c.debug_no_flip = on != 0;
+  return PRF_OK;
+}
+
+PRF_API int prf_debug_short_max(prf_ctx* h, uint32_t short_max) {
+  if (!h) return PRF_E_INVALID;
+  h->c.short_max = short_max;
+  return PRF_OK;
+}
+
+// Lists of at least this many members take the warp-per-list walk (0 = chosen from T).
+PRF_API int prf_debug_heavy_min(prf_ctx* h, uint32_t heavy_min) {
+  if (!h) return PRF_E_INVALID;
+  h->c.heavy_min = heavy_min;
+  return PRF_OK;
+}
+
+// which: 0 = rows kernel (one warp per row), 1 = round-1 CTA-per-row kernel (loads must then use short_max 0)
+PRF_API int prf_debug_sparse_kernel(prf_ctx* h, int which, int cfg) {
+  if (!h) return PRF_E_INVALID;
+  h->c.sparse_kernel = which;
+  h->c.rows_cfg = cfg;
   return PRF_OK;
 }
 

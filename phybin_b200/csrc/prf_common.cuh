@@ -63,7 +63,10 @@ struct HashRFState {
   uint32_t nb_shift_stride = 0;
   DevBuf<uint32_t> roff;         // [T+1] per-tree offsets into `ranges`
   DevBuf<uint2> ranges;          // member-list suffixes (begin, end) into `members`, tree-major
+  DevBuf<uint32_t> nheavy;       // [T] how many of a tree's ranges (its first ones) belong to heavy lists
   DevBuf<uint32_t> members;      // inverted lists of the shared bipartitions, ascending tree ids
+  DevBuf<uint32_t> soff;         // [T+1] per-tree offsets into `singles`
+  DevBuf<uint32_t> singles;      // per tree a: the trees b > a sharing a short-list bipartition with a (with multiplicity)
   // tree-major incidence over shared bipartition ids (dense variant input)
   uint32_t n_shared = 0;
   uint64_t n_shared_nnz = 0;
@@ -139,6 +142,10 @@ struct Ctx {
   ConsensusState cons;
   RowPlan plan;
   bool debug_small_tiles = false;
+  uint32_t short_max = 8;             // lists of at most this many members are expanded into per-row singles
+  uint32_t heavy_min = 0;             // tests: lists of at least this many members are "heavy" (0 = from T)
+  int rows_cfg = 0;                   // tests / tuning: instantiation of the rows kernel
+  int sparse_kernel = 0;              // 0 = rows kernel (round 2); 1 = round-1 CTA-per-row kernel (needs short_max == 0)
   bool debug_no_flip = false;         // tests: keep majority lists as they are
   bool debug_wide_slots = false;      // tests: force the 8-byte-slot dedup table
   DevBuf<unsigned long long> timing;  // PRF_TIMING builds only
@@ -209,10 +216,35 @@ __host__ __device__ inline uint32_t row_of(uint64_t p, uint64_t T) {
   return (uint32_t)a;
 }
 
+inline uint32_t grid_for(uint64_t n, uint32_t tpb = 256) { return (uint32_t)((n + tpb - 1) / tpb); }
+inline int bits_for(uint64_t n_values) {  // bits needed to represent 0..n_values-1
+  int b = 0;
+  while (b < 63 && (1ull << b) < n_values) ++b;
+  return b;
+}
+
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
+}
+
+constexpr uint64_t kEmptySlot = ~0ull;
+
+template <int W>
+__device__ __forceinline__ void load_key(const uint64_t* __restrict__ bips, uint64_t e, uint64_t (&k)[W]) {
+  const uint64_t* p = bips + e * W;
+  if constexpr (W % 2 == 0) {
+#pragma unroll
+    for (int w = 0; w < W; w += 2) {
+      ulonglong2 q = *reinterpret_cast<const ulonglong2*>(p + w);
+      k[w] = q.x;
+      k[w + 1] = q.y;
+    }
+  } else {
+#pragma unroll
+    for (int w = 0; w < W; ++w) k[w] = p[w];
+  }
 }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }

@@ -15,7 +15,7 @@
 // Every tree's entries must be distinct (prf_allbips / phb_allbips output is).
 #pragma once
 
-#include "prf_incidence.cuh"
+#include "prf_primitives.cuh"
 
 namespace prf {
 

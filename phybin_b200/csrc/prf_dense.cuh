@@ -30,7 +30,8 @@
 #include <algorithm>
 
 #include "prf_common.cuh"
-#include "prf_sparse.cuh"  // smem_addr
+#include "prf_async.cuh"
+#include "prf_internal.h"
 
 namespace prf {
 
@@ -330,7 +331,7 @@ static int dense_prepare(Ctx* ctx) {
   return PRF_OK;
 }
 
-static int launch_dense(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out, uint32_t* d_mask) {
+int launch_dense(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out, uint32_t* d_mask) {
   HashRFState& H = ctx->h;
   cudaStream_t s = ctx->stream;
   int rc = dense_prepare(ctx);

@@ -14,24 +14,6 @@
 
 namespace prf {
 
-constexpr uint64_t kEmptySlot = ~0ull;
-
-template <int W>
-__device__ __forceinline__ void load_key(const uint64_t* __restrict__ bips, uint64_t e, uint64_t (&k)[W]) {
-  const uint64_t* p = bips + e * W;
-  if constexpr (W % 2 == 0) {
-#pragma unroll
-    for (int w = 0; w < W; w += 2) {
-      ulonglong2 q = *reinterpret_cast<const ulonglong2*>(p + w);
-      k[w] = q.x;
-      k[w + 1] = q.y;
-    }
-  } else {
-#pragma unroll
-    for (int w = 0; w < W; ++w) k[w] = p[w];
-  }
-}
-
 // counters[0] = unique keys (claims), [1] = shared lists, [2] = duplicate (slot, tree) entries
 // One warp per tree; lanes stride over the tree's entries.  Finds (or claims) the slot of every key.
 //   slots[s]  = (tag << 32) | representative entry, kEmptySlot when free
@@ -243,16 +225,30 @@ __global__ void __launch_bounds__(256) list_heads_kernel(const uint32_t* __restr
 // Position k holds tree a = tree[k] inside list l = [head_pos[l], head_pos[l+1]).  Its suffix
 // (k+1, end) lists the trees b > a sharing that bipartition.  Pass 1 counts the non-empty suffixes
 // per tree (and accumulates sum m(m-1)/2 at list heads), pass 2 stores them.
+//
+// Lists of at most `short_max` members are not walked by the matrix kernel: their pairs are expanded into
+// per-row "singles" (tree a gets the column b of every later member), counted in scount / stored by the
+// fill pass.  Only the longer lists produce suffix ranges.
 __global__ void __launch_bounds__(256) range_count_kernel(const uint32_t* __restrict__ lid,
                                                           const uint32_t* __restrict__ tree,
                                                           const uint32_t* __restrict__ head_pos, uint32_t n,
-                                                          uint32_t* rcount, unsigned long long* counters) {
+                                                          uint32_t short_max, uint32_t heavy_min, uint32_t* rcount,
+                                                          uint32_t* hcount, uint32_t* scount,
+                                                          unsigned long long* counters) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long hits = 0, longest = 0;
   if (k < n) {
     const uint32_t l = lid[k];
     const uint32_t end = head_pos[l + 1];
-    if (k + 1 < end) atomicAdd(&rcount[tree[k]], 1u);
+    if (k + 1 < end) {
+      const uint32_t m = end - head_pos[l];
+      if (m <= short_max) {
+        atomicAdd(&scount[tree[k]], end - k - 1);
+      } else {
+        atomicAdd(&rcount[tree[k]], 1u);
+        if (m >= heavy_min) atomicAdd(&hcount[tree[k]], 1u);
+      }
+    }
     if (k > 0 && lid[k - 1] == l && tree[k - 1] == tree[k]) atomicAdd(&counters[2], 1ull);  // listed twice by one tree (rare)
     if (k == head_pos[l]) {
       const unsigned long long m = end - k;
@@ -284,14 +280,26 @@ __global__ void __launch_bounds__(256) range_count_kernel(const uint32_t* __rest
 __global__ void __launch_bounds__(256) range_fill_kernel(const uint32_t* __restrict__ lid,
                                                          const uint32_t* __restrict__ tree,
                                                          const uint32_t* __restrict__ head_pos, uint32_t n,
-                                                         const uint32_t* __restrict__ roff, uint32_t* cursor,
-                                                         uint2* __restrict__ ranges) {
+                                                         uint32_t short_max, uint32_t heavy_min,
+                                                         const uint32_t* __restrict__ roff,
+                                                         const uint32_t* __restrict__ hcount, uint32_t* hcursor,
+                                                         uint32_t* cursor, uint2* __restrict__ ranges,
+                                                         const uint32_t* __restrict__ soff, uint32_t* scursor,
+                                                         uint32_t* __restrict__ singles) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const uint32_t end = head_pos[lid[k] + 1];
+  const uint32_t l = lid[k], end = head_pos[l + 1];
   if (k + 1 < end) {
     const uint32_t a = tree[k];
-    ranges[roff[a] + atomicAdd(&cursor[a], 1u)] = make_uint2(k + 1, end);
+    const uint32_t m = end - head_pos[l];
+    if (m <= short_max) {
+      uint32_t o = soff[a] + atomicAdd(&scursor[a], end - k - 1);
+      for (uint32_t j = k + 1; j < end; ++j) singles[o++] = tree[j];
+    } else if (m >= heavy_min) {  // a tree's heavy lists first, its light lists behind them
+      ranges[roff[a] + atomicAdd(&hcursor[a], 1u)] = make_uint2(k + 1, end);
+    } else {
+      ranges[roff[a] + hcount[a] + atomicAdd(&cursor[a], 1u)] = make_uint2(k + 1, end);
+    }
   }
 }
 
@@ -377,28 +385,6 @@ __global__ void __launch_bounds__(256) drop_dups_kernel(const uint32_t* __restri
   }
 }
 
-// nb32 -> uint16 + min/max.  mm[0] = min, mm[1] = max.
-// Also mm[2] = most suffix ranges of one tree (roff is the exclusive scan of the per-tree counts).
-__global__ void __launch_bounds__(256) finish_nb_kernel(const uint32_t* __restrict__ nb32, uint32_t T,
-                                                        uint16_t* __restrict__ nb16, uint32_t* mm,
-                                                        const uint32_t* __restrict__ roff) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t v = t < T ? nb32[t] : 0, lo = t < T ? v : 0xffffffffu, hi = v;
-  uint32_t rmax = t < T ? roff[t + 1] - roff[t] : 0;
-  if (t < T) nb16[t] = (uint16_t)(v > 0xffffu ? 0xffffu : v);
-#pragma unroll
-  for (int d = 16; d; d >>= 1) {
-    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
-    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
-    rmax = max(rmax, __shfl_xor_sync(0xffffffffu, rmax, d));
-  }
-  if (lane_id() == 0) {
-    atomicMin(&mm[0], lo);
-    atomicMax(&mm[1], hi);
-    atomicMax(&mm[2], rmax);
-  }
-}
-
 // nb_shift[k * stride + j] = nb[j + k] (0 past the end), k = 0..7
 __global__ void __launch_bounds__(256) nb_shift_kernel(const uint16_t* __restrict__ nb, uint32_t T, uint32_t stride,
                                                        uint16_t* __restrict__ out) {
@@ -416,10 +402,9 @@ static void launch_dedup(Ctx* ctx, const uint64_t* bips, const uint64_t* off, ui
                                                                 ent_slot, counters);
 }
 
-static inline uint32_t grid_for(uint64_t n, uint32_t tpb = 256) { return (uint32_t)((n + tpb - 1) / tpb); }
 
 // The shifted copies of |B_t| the sparse kernel's producer bulk-loads (non-uniform |B_t| only).
-static int build_nb_shift(Ctx* ctx) {
+int build_nb_shift(Ctx* ctx) {
   HashRFState& H = ctx->h;
   if (H.uniform_nb || H.T == 0) return PRF_OK;
   const uint32_t stride = (H.T + 16 + 7) / 8 * 8 + 8;
@@ -430,14 +415,8 @@ static int build_nb_shift(Ctx* ctx) {
   return PRF_OK;
 }
 
-static inline int bits_for(uint64_t n_values) {  // bits needed to represent 0..n_values-1
-  int b = 0;
-  while (b < 63 && (1ull << b) < n_values) ++b;
-  return b;
-}
-
 // d_bips: nnz*W words, d_off: T+1 offsets, both already on the device.
-static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off, uint32_t T, uint32_t W,
+int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off, uint32_t T, uint32_t W,
                         uint64_t nnz) {
   cudaStream_t s = ctx->stream;
   HashRFState& H = ctx->h;
@@ -520,9 +499,21 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
   const uint32_t n_lists0 = h01[1];
   H.n_shared_nnz = n_sh_nnz;
 
-  DevBuf<uint32_t> slot_sorted, lid_ex, head_pos, rcount, cursor;
+  DevBuf<uint32_t> slot_sorted, lid_ex, head_pos, rcount, cursor, scount, scursor, hcursor;
+  const uint32_t short_max = ctx->short_max;
+  // lists expected to put more than ~48 members into a tile of the rows kernel are walked by the whole warp
+  const uint32_t heavy_min = ctx->sparse_kernel == 1 ? 0u
+                             : ctx->heavy_min ? ctx->heavy_min
+                                              : std::max<uint32_t>(short_max + 1, (uint32_t)(48ull * T / 7680) + 1);
+  PRF_CK(ctx, hcursor.alloc((size_t)T + 1, s));
+  PRF_CK(ctx, H.nheavy.alloc((size_t)T + 1, s));
+  PRF_CK(ctx, scount.alloc((size_t)T + 1, s));
+  PRF_CK(ctx, scursor.alloc((size_t)T + 1, s));
+  PRF_CK(ctx, H.soff.alloc((size_t)T + 1, s));
+  // upper bound: an entry of a short list is followed by at most short_max - 1 later members
+  PRF_CK(ctx, H.singles.alloc((size_t)n_sh_nnz * (short_max > 1 ? (short_max - 1) / 2 + 1 : 0) + 1, s));
   PRF_CK(ctx, slot_sorted.alloc(n_sh_nnz, s));
-  PRF_CK(ctx, H.members.alloc(n_sh_nnz, s));
+  PRF_CK(ctx, H.members.alloc((size_t)n_sh_nnz + 4, s));  // +4: the rows kernel reads members in aligned groups of 4
   PRF_CK(ctx, head_pos.alloc((size_t)n_sh_nnz + 1, s));
   PRF_CK(ctx, rcount.alloc((size_t)T + 1, s));
   PRF_CK(ctx, cursor.alloc((size_t)T + 1, s));
@@ -545,6 +536,10 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
   for (int pass = 0; pass < 2; ++pass) {
     PRF_CK(ctx, cudaMemsetAsync(rcount.p, 0, rcount.bytes(), s));
     PRF_CK(ctx, cudaMemsetAsync(cursor.p, 0, cursor.bytes(), s));
+    PRF_CK(ctx, cudaMemsetAsync(scount.p, 0, scount.bytes(), s));
+    PRF_CK(ctx, cudaMemsetAsync(scursor.p, 0, scursor.bytes(), s));
+    PRF_CK(ctx, cudaMemsetAsync(hcursor.p, 0, hcursor.bytes(), s));
+    PRF_CK(ctx, cudaMemsetAsync(H.nheavy.p, 0, H.nheavy.bytes(), s));
     PRF_CK(ctx, cudaMemsetAsync(counters.p + 2, 0, 32, s));
     const uint32_t* lid_p = slot_sorted.p;
     if (n_sorted) {
@@ -560,13 +555,16 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
         PRF_LAUNCHED(ctx);
         lid_p = H.lid.p;
       }
-      range_count_kernel<<<grid_for(n_sorted), 256, 0, s>>>(lid_p, H.members.p, head_pos.p, n_sorted, rcount.p, counters.p);
+      range_count_kernel<<<grid_for(n_sorted), 256, 0, s>>>(lid_p, H.members.p, head_pos.p, n_sorted, short_max, heavy_min, rcount.p,
+                                                            H.nheavy.p, scount.p, counters.p);
       PRF_LAUNCHED(ctx);
     }
     if ((rc = exclusive_scan(ctx, LoadU32{rcount.p}, (uint64_t)T + 1, H.roff.p, nullptr))) return rc;
+    if ((rc = exclusive_scan(ctx, LoadU32{scount.p}, (uint64_t)T + 1, H.soff.p, nullptr))) return rc;
     if (n_sorted) {
-      range_fill_kernel<<<grid_for(n_sorted), 256, 0, s>>>(lid_p, H.members.p, head_pos.p, n_sorted, H.roff.p, cursor.p,
-                                                           H.ranges.p);
+      range_fill_kernel<<<grid_for(n_sorted), 256, 0, s>>>(lid_p, H.members.p, head_pos.p, n_sorted, short_max, heavy_min, H.roff.p,
+                                                           H.nheavy.p, hcursor.p, cursor.p, H.ranges.p, H.soff.p, scursor.p,
+                                                           H.singles.p);
       PRF_LAUNCHED(ctx);
     }
     if (T) {
@@ -585,7 +583,7 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
     DevBuf<uint32_t> dup_before, slot2, mem2;
     PRF_CK(ctx, dup_before.alloc(n_sorted, s));
     PRF_CK(ctx, slot2.alloc(n_sorted, s));
-    PRF_CK(ctx, mem2.alloc(n_sorted, s));
+    PRF_CK(ctx, mem2.alloc((size_t)n_sorted + 4, s));
     if ((rc = exclusive_scan(ctx, DupFlag{slot_sorted.p, H.members.p}, n_sorted, dup_before.p, nullptr))) return rc;
     drop_dups_kernel<<<grid_for(n_sorted), 256, 0, s>>>(slot_sorted.p, H.members.p, dup_before.p, n_sorted,
                                                         slot2.p, mem2.p, nb32.p);
@@ -609,7 +607,7 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
     uint32_t n2 = 0;
     PRF_CK(ctx, cudaMemcpyAsync(&n2, scalars.p + 2, 4, cudaMemcpyDeviceToHost, s));
     PRF_CK(ctx, cudaStreamSynchronize(s));
-    PRF_CK(ctx, mem2.alloc(n2, s));
+    PRF_CK(ctx, mem2.alloc((size_t)n2 + 4, s));
     PRF_CK(ctx, lid2.alloc(n2, s));
     flip_copy_kernel<<<grid_for(n_sorted), 256, 0, s>>>(H.lid.p, H.members.p, head_pos.p, head2.p, n_sorted, T, mem2.p,
                                                         lid2.p, hcnt.p);
@@ -624,19 +622,27 @@ static int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off,
     n_sorted = n2;
     // ranges, hits and |D_t| statistics over the flipped lists
     PRF_CK(ctx, H.ranges.alloc(n_sorted, s));
+    PRF_CK(ctx, H.singles.alloc((size_t)n_sorted * (short_max > 1 ? (short_max - 1) / 2 + 1 : 0) + 1, s));
     PRF_CK(ctx, cudaMemsetAsync(rcount.p, 0, rcount.bytes(), s));
     PRF_CK(ctx, cudaMemsetAsync(cursor.p, 0, cursor.bytes(), s));
+    PRF_CK(ctx, cudaMemsetAsync(scount.p, 0, scount.bytes(), s));
+    PRF_CK(ctx, cudaMemsetAsync(scursor.p, 0, scursor.bytes(), s));
+    PRF_CK(ctx, cudaMemsetAsync(hcursor.p, 0, hcursor.bytes(), s));
+    PRF_CK(ctx, cudaMemsetAsync(H.nheavy.p, 0, H.nheavy.bytes(), s));
     PRF_CK(ctx, cudaMemsetAsync(counters.p + 3, 0, 16, s));
     const uint32_t mm_reset[3] = {0xffffffffu, 0u, 0u};
     PRF_CK(ctx, cudaMemcpyAsync(scalars.p + 4, mm_reset, 12, cudaMemcpyHostToDevice, s));
     if (n_sorted) {
-      range_count_kernel<<<grid_for(n_sorted), 256, 0, s>>>(H.lid.p, H.members.p, head2.p, n_sorted, rcount.p, counters.p);
+      range_count_kernel<<<grid_for(n_sorted), 256, 0, s>>>(H.lid.p, H.members.p, head2.p, n_sorted, short_max, heavy_min, rcount.p,
+                                                            H.nheavy.p, scount.p, counters.p);
       PRF_LAUNCHED(ctx);
     }
     if ((rc = exclusive_scan(ctx, LoadU32{rcount.p}, (uint64_t)T + 1, H.roff.p, nullptr))) return rc;
+    if ((rc = exclusive_scan(ctx, LoadU32{scount.p}, (uint64_t)T + 1, H.soff.p, nullptr))) return rc;
     if (n_sorted) {
-      range_fill_kernel<<<grid_for(n_sorted), 256, 0, s>>>(H.lid.p, H.members.p, head2.p, n_sorted, H.roff.p, cursor.p,
-                                                           H.ranges.p);
+      range_fill_kernel<<<grid_for(n_sorted), 256, 0, s>>>(H.lid.p, H.members.p, head2.p, n_sorted, short_max, heavy_min, H.roff.p,
+                                                           H.nheavy.p, hcursor.p, cursor.p, H.ranges.p, H.soff.p, scursor.p,
+                                                           H.singles.p);
       PRF_LAUNCHED(ctx);
     }
     finish_nb_kernel<<<grid_for(T), 256, 0, s>>>(nb32.p, T, H.nb.p, scalars.p + 4, H.roff.p);

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_tile_reduce_kernel(F f, uin
 }
 
 // One CTA: in-place exclusive scan of `m` tile sums; the grand total goes to *total.
-__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(uint32_t* tile_sums, uint32_t m,
+static __global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(uint32_t* tile_sums, uint32_t m,
                                                                        uint32_t* total) {
   uint32_t carry = 0;
   for (uint32_t base = 0; base < m; base += kScanThreads) {
@@ -112,6 +112,28 @@ int exclusive_scan(Ctx* ctx, F f, uint64_t n, uint32_t* out, uint32_t* d_total) 
   scan_tile_apply_kernel<F><<<tiles, kScanThreads, 0, s>>>(f, n, sums.p, out);
   PRF_LAUNCHED(ctx);
   return PRF_OK;
+}
+
+// nb32 -> uint16 + min/max.  mm[0] = min, mm[1] = max.
+// Also mm[2] = most suffix ranges of one tree (roff is the exclusive scan of the per-tree counts).
+static __global__ void __launch_bounds__(256) finish_nb_kernel(const uint32_t* __restrict__ nb32, uint32_t T,
+                                                        uint16_t* __restrict__ nb16, uint32_t* mm,
+                                                        const uint32_t* __restrict__ roff) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t v = t < T ? nb32[t] : 0, lo = t < T ? v : 0xffffffffu, hi = v;
+  uint32_t rmax = t < T ? roff[t + 1] - roff[t] : 0;
+  if (t < T) nb16[t] = (uint16_t)(v > 0xffffu ? 0xffffu : v);
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    rmax = max(rmax, __shfl_xor_sync(0xffffffffu, rmax, d));
+  }
+  if (lane_id() == 0) {
+    atomicMin(&mm[0], lo);
+    atomicMax(&mm[1], hi);
+    atomicMax(&mm[2], rmax);
+  }
 }
 
 struct LoadU32 {

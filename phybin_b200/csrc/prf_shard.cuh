@@ -18,7 +18,7 @@
 //   every    merge_* kernels -> merged structure installed as the context's loaded problem
 #pragma once
 
-#include "prf_incidence.cuh"
+#include "prf_primitives.cuh"
 
 namespace prf {
 

@@ -38,40 +38,12 @@
 #include <algorithm>
 
 #include "prf_common.cuh"
+#include "prf_async.cuh"
 
 namespace prf {
 
 constexpr int kGroupRows = 256;   // most rows in a group item
 constexpr int kWalkUnroll = 4;
-
-__device__ __forceinline__ uint32_t smem_addr(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(ok)
-      : "r"(smem_addr(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Waiting warps back off with nanosleep so that they leave the issue slots to the working warps.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t sleep_ns = 0) {
-  while (!mbar_try(bar, parity)) {
-    if (sleep_ns) __nanosleep(sleep_ns);
-  }
-}
 
 struct RowParams {
   uint32_t T;
@@ -709,7 +681,7 @@ __global__ void __launch_bounds__(32 * (kWalkers + 2 + kHelper), (kTile > 16384 
 }
 
 // Cuts packed positions [p_begin, p_end) into work items, longest first.
-static void build_row_plan(uint32_t T, uint64_t p_begin, uint64_t p_end, uint32_t tile, std::vector<RowItem>& rows,
+void build_row_plan(uint32_t T, uint64_t p_begin, uint64_t p_end, uint32_t tile, std::vector<RowItem>& rows,
                            std::vector<RowItem>& groups) {
   rows.clear();
   groups.clear();
@@ -817,7 +789,7 @@ static int launch_sparse_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t e
   return PRF_OK;
 }
 
-static int launch_sparse(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out,
+int launch_sparse(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out,
                          uint32_t* d_mask) {
   // the tiny-tile build exists so that small test inputs exercise multi-tile rows and cursor spill
   // With a threshold mask the emitter would be the bottleneck (one warp, 16 K compares per tile): one of

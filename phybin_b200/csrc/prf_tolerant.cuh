@@ -274,7 +274,7 @@ static int launch_tolerant_w(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t
   return PRF_OK;
 }
 
-static int launch_tolerant(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out,
+int launch_tolerant(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out,
                            uint32_t* d_mask) {
   switch (ctx->tol.W) {
     case 1: return launch_tolerant_w<1>(ctx, p_begin, p_end, editdist, d_out, d_mask);

@@ -92,7 +92,11 @@ def _local_load(ctx: RFContext, recv_keys: torch.Tensor, counts_all: torch.Tenso
     """counts_all [T] int32: entries of every tree in my class, tree order == order of recv_keys."""
     off = torch.zeros(T + 1, dtype=torch.int64, device=recv_keys.device)
     torch.cumsum(counts_all.to(torch.int64), 0, out=off[1:])
-    ctx.hashrf_load(recv_keys.data_ptr(), off.data_ptr(), T, W, MEM_DEVICE)
+    ctx._L.prf_debug_short_max(ctx._h, 0)   # the exported parts carry every list as suffix ranges
+    try:
+        ctx.hashrf_load(recv_keys.data_ptr(), off.data_ptr(), T, W, MEM_DEVICE)
+    finally:
+        ctx._L.prf_debug_short_max(ctx._h, 8)
     part = prf_part()
     ctx._ck(ctx._L.prf_hashrf_export(ctx._h, C.byref(part)))
     return part

@@ -17,12 +17,20 @@ from tests.util import oracle_packed, random_multifurcating_newicks
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["default", "small_tiles"])
+@pytest.fixture(scope="module", params=["default", "small_tiles", "small_tiles_light", "no_singles_light"])
 def ctx(request):
-    """Every test runs twice: with the production tile size, and with the 256-entry debug tiles that
-    make even small inputs exercise multi-tile rows, cursor carry-over and the cursor spill area."""
+    """Every test runs in four configurations of the sparse matrix kernel (prf_rows.cuh):
+      default            production tiles; list classes chosen by the build (singles / light / heavy)
+      small_tiles        256-entry debug tiles: small inputs exercise multi-tile rows, cursor carry-over and the
+                         cursor spill area; lists longer than 8 members take the warp-per-list walk
+      small_tiles_light  same tiles, every list longer than 8 members takes the lane-per-list walk
+      no_singles_light   production tiles, no list is expanded into singles, all take the lane-per-list walk"""
     c = RFContext(0)
-    c.debug_small_tiles(request.param == "small_tiles")
+    c.debug_small_tiles(request.param.startswith("small_tiles"))
+    if request.param.endswith("light"):
+        c._L.prf_debug_heavy_min(c._h, 1 << 30)
+    if request.param == "no_singles_light":
+        c._L.prf_debug_short_max(c._h, 0)
     yield c
     c.close()
 
