@@ -204,10 +204,12 @@ PRF_API int prf_hashrf_compute(prf_ctx* h, uint64_t p_begin, uint64_t p_end, int
     const double kpad = (double)dense_kpad(H.n_shared);
     const double t_sparse = hits * 1.9e-12 + (H.uniform_nb ? 0.0 : pairs * 0.9e-12), t_dense = pairs * kpad * 2.0 / 0.9e15;
     const double operand = (double)dense_tpad(H.T) * kpad;
-    use = (H.n_shared > 0 && operand < 32e9 && t_dense < t_sparse) ? PRF_VARIANT_DENSE : PRF_VARIANT_SPARSE;
+    use = (H.n_shared > 0 && H.lid.p && operand < 32e9 && t_dense < t_sparse) ? PRF_VARIANT_DENSE : PRF_VARIANT_SPARSE;
   }
   PRF_CK(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
   if (p_end > p_begin) {
+    if (use == PRF_VARIANT_DENSE && !H.lid.p && H.n_shared)
+      return ctx->fail(PRF_E_UNSUPPORTED, "the dense variant needs the incidence of a single-context build");
     if (use == PRF_VARIANT_DENSE) rc = launch_dense(ctx, p_begin, p_end, editdist, d_out, d_mask);
     else if (ctx->sparse_kernel == 1) rc = launch_sparse(ctx, p_begin, p_end, editdist, d_out, d_mask);
     else rc = launch_rows(ctx, p_begin, p_end, editdist, d_out, d_mask);
@@ -359,7 +361,7 @@ PRF_API int prf_hashrf_export(prf_ctx* h, prf_part* out) {
   if (!H.loaded) return ctx->fail(PRF_E_STATE, "prf_hashrf_export before a successful prf_hashrf_load");
   out->n_trees = H.T;
   out->n_ranges = H.n_ranges;
-  out->n_members = H.n_shared_nnz;
+  out->n_members = H.n_lmembers;  // the walked lists, each padded to a multiple of 4 members
   out->n_lists = H.n_shared;
   out->nnz = H.stats.nnz;
   out->n_unique = H.stats.n_unique;
@@ -367,8 +369,8 @@ PRF_API int prf_hashrf_export(prf_ctx* h, prf_part* out) {
   out->nb = H.nb.p;
   out->roff = H.roff.p;
   out->ranges = H.ranges.p;
-  out->members = H.members.p;
-  out->lid = H.lid.p;
+  out->members = H.lmembers.p;
+  out->lid = nullptr;
   return PRF_OK;
 }
 
@@ -414,7 +416,6 @@ PRF_API int prf_hashrf_merge(prf_ctx* h, uint32_t T, uint32_t W, uint32_t world,
   PRF_CK(ctx, cudaMemsetAsync(nb.p, 0, nb.bytes(), s));
   PRF_CK(ctx, roff.alloc((size_t)T + 1, s));
   PRF_CK(ctx, members.alloc((size_t)n_members + 4, s));
-  PRF_CK(ctx, lid.alloc(n_members, s));
   PRF_CK(ctx, ranges.alloc(n_ranges, s));
   PRF_CK(ctx, nb32.alloc((size_t)T + 1, s));
   PRF_CK(ctx, cnt.alloc((size_t)T + 1, s));
@@ -433,7 +434,7 @@ PRF_API int prf_hashrf_merge(prf_ctx* h, uint32_t T, uint32_t W, uint32_t world,
   }
   for (uint32_t r = 0; r < world; ++r)
     if (P.n_members[r]) {
-      merge_members_kernel<<<grid_for(P.n_members[r]), 256, 0, s>>>(P, r, members.p, lid.p);
+      merge_members_kernel<<<grid_for(P.n_members[r]), 256, 0, s>>>(P, r, members.p);
       PRF_LAUNCHED(ctx);
     }
   uint32_t hmm[3] = {0, 0, 0};
@@ -455,13 +456,13 @@ PRF_API int prf_hashrf_merge(prf_ctx* h, uint32_t T, uint32_t W, uint32_t world,
   H.nb = std::move(nb);
   H.roff = std::move(roff);
   H.ranges = std::move(ranges);
-  H.members = std::move(members);
+  H.lmembers = std::move(members);  // (the merged structure has no unpadded incidence: the dense variant is not available on it)
+  H.n_lmembers = n_members;
   H.soff = std::move(soff);
   H.singles = std::move(singles);
   // the merged ranges of a tree interleave the parts: all of them take the warp-per-list walk
   PRF_CK(ctx, H.nheavy.alloc((size_t)T + 1, s));
   PRF_CK(ctx, cudaMemcpyAsync(H.nheavy.p, cnt.p, ((size_t)T + 1) * 4, cudaMemcpyDeviceToDevice, s));
-  H.lid = std::move(lid);
   H.n_shared = (uint32_t)n_lists;
   H.n_shared_nnz = n_members;
   H.n_ranges = n_ranges;
@@ -541,6 +542,15 @@ PRF_API int prf_debug_sparse_kernel(prf_ctx* h, int which, int cfg) {
   h->c.rows_cfg = cfg;
   return PRF_OK;
 }
+
+#ifdef PRF_CALIB
+// Calibration builds only (scripts/rows_calib.py; never in libphybin_rf.so): wrong results by design.
+PRF_API int prf_debug_calib(prf_ctx* h, int mode) {
+  if (!h) return PRF_E_INVALID;
+  h->c.calib = mode;
+  return PRF_OK;
+}
+#endif
 
 PRF_API int prf_debug_small_tiles(prf_ctx* h, int on) {
   if (!h) return PRF_E_INVALID;

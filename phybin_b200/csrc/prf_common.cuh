@@ -65,6 +65,9 @@ struct HashRFState {
   DevBuf<uint2> ranges;          // member-list suffixes (begin, end) into `members`, tree-major
   DevBuf<uint32_t> nheavy;       // [T] how many of a tree's ranges (its first ones) belong to heavy lists
   DevBuf<uint32_t> members;      // inverted lists of the shared bipartitions, ascending tree ids
+  DevBuf<uint32_t> lmembers;     // the lists the sparse kernel walks (more than short_max members), each padded with
+                                 // 0xffffffff to a multiple of 4 members; `ranges` index this array
+  uint64_t n_lmembers = 0;
   DevBuf<uint32_t> soff;         // [T+1] per-tree offsets into `singles`
   DevBuf<uint32_t> singles;      // per tree a: the trees b > a sharing a short-list bipartition with a (with multiplicity)
   // tree-major incidence over shared bipartition ids (dense variant input)
@@ -144,6 +147,7 @@ struct Ctx {
   bool debug_small_tiles = false;
   uint32_t short_max = 8;             // lists of at most this many members are expanded into per-row singles
   uint32_t heavy_min = 0;             // tests: lists of at least this many members are "heavy" (0 = from T)
+  int calib = 0;                      // PRF_CALIB builds: calibration mode of the rows kernel (wrong results)
   int rows_cfg = 0;                   // tests / tuning: instantiation of the rows kernel
   int sparse_kernel = 0;              // 0 = rows kernel (round 2); 1 = round-1 CTA-per-row kernel (needs short_max == 0)
   bool debug_no_flip = false;         // tests: keep majority lists as they are

@@ -277,6 +277,17 @@ __global__ void __launch_bounds__(256) range_count_kernel(const uint32_t* __rest
     if (longest) atomicMax(&counters[4], longest);
   }
 }
+// Space of list l in the padded array of walked lists: 0 for short lists, else its length rounded up to 4.
+struct PadLen {
+  const uint32_t* head_pos;
+  const uint32_t* n_lists;  // device scalar
+  uint32_t short_max;
+  __device__ uint32_t operator()(uint64_t l) const {
+    if (l >= *n_lists) return 0;
+    const uint32_t m = head_pos[l + 1] - head_pos[l];
+    return m <= short_max ? 0u : (m + 3u) & ~3u;
+  }
+};
 __global__ void __launch_bounds__(256) range_fill_kernel(const uint32_t* __restrict__ lid,
                                                          const uint32_t* __restrict__ tree,
                                                          const uint32_t* __restrict__ head_pos, uint32_t n,
@@ -285,20 +296,28 @@ __global__ void __launch_bounds__(256) range_fill_kernel(const uint32_t* __restr
                                                          const uint32_t* __restrict__ hcount, uint32_t* hcursor,
                                                          uint32_t* cursor, uint2* __restrict__ ranges,
                                                          const uint32_t* __restrict__ soff, uint32_t* scursor,
-                                                         uint32_t* __restrict__ singles) {
+                                                         uint32_t* __restrict__ singles,
+                                                         const uint32_t* __restrict__ phead,
+                                                         uint32_t* __restrict__ lmembers) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const uint32_t l = lid[k], end = head_pos[l + 1];
+  const uint32_t m = end - head_pos[l];
+  const uint32_t pk = phead[l] + (k - head_pos[l]), pend = phead[l] + m;  // my position / the list's end in lmembers
+  if (m > short_max) {
+    lmembers[pk] = tree[k];
+    if (k + 1 == end)
+      for (uint32_t j = pend; j < ((pend + 3u) & ~3u); ++j) lmembers[j] = 0xffffffffu;  // pad to a multiple of 4
+  }
   if (k + 1 < end) {
     const uint32_t a = tree[k];
-    const uint32_t m = end - head_pos[l];
     if (m <= short_max) {
       uint32_t o = soff[a] + atomicAdd(&scursor[a], end - k - 1);
       for (uint32_t j = k + 1; j < end; ++j) singles[o++] = tree[j];
     } else if (m >= heavy_min) {  // a tree's heavy lists first, its light lists behind them
-      ranges[roff[a] + atomicAdd(&hcursor[a], 1u)] = make_uint2(k + 1, end);
+      ranges[roff[a] + atomicAdd(&hcursor[a], 1u)] = make_uint2(pk + 1, pend);
     } else {
-      ranges[roff[a] + hcount[a] + atomicAdd(&cursor[a], 1u)] = make_uint2(k + 1, end);
+      ranges[roff[a] + hcount[a] + atomicAdd(&cursor[a], 1u)] = make_uint2(pk + 1, pend);
     }
   }
 }
@@ -506,12 +525,16 @@ int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off, uint32
                              : ctx->heavy_min ? ctx->heavy_min
                                               : std::max<uint32_t>(short_max + 1, (uint32_t)(48ull * T / 7680) + 1);
   PRF_CK(ctx, hcursor.alloc((size_t)T + 1, s));
+  DevBuf<uint32_t> phead;
   PRF_CK(ctx, H.nheavy.alloc((size_t)T + 1, s));
   PRF_CK(ctx, scount.alloc((size_t)T + 1, s));
   PRF_CK(ctx, scursor.alloc((size_t)T + 1, s));
   PRF_CK(ctx, H.soff.alloc((size_t)T + 1, s));
   // upper bound: an entry of a short list is followed by at most short_max - 1 later members
   PRF_CK(ctx, H.singles.alloc((size_t)n_sh_nnz * (short_max > 1 ? (short_max - 1) / 2 + 1 : 0) + 1, s));
+  // walked lists padded to multiples of 4 members: at most twice the entries (four times when one-member lists are walked)
+  PRF_CK(ctx, phead.alloc((size_t)n_sh_nnz + 2, s));
+  PRF_CK(ctx, H.lmembers.alloc((size_t)n_sh_nnz * (short_max ? 2 : 4) + 8, s));
   PRF_CK(ctx, slot_sorted.alloc(n_sh_nnz, s));
   PRF_CK(ctx, H.members.alloc((size_t)n_sh_nnz + 4, s));  // +4: the rows kernel reads members in aligned groups of 4
   PRF_CK(ctx, head_pos.alloc((size_t)n_sh_nnz + 1, s));
@@ -562,9 +585,12 @@ int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off, uint32
     if ((rc = exclusive_scan(ctx, LoadU32{rcount.p}, (uint64_t)T + 1, H.roff.p, nullptr))) return rc;
     if ((rc = exclusive_scan(ctx, LoadU32{scount.p}, (uint64_t)T + 1, H.soff.p, nullptr))) return rc;
     if (n_sorted) {
+      // scalars[1] = number of lists (ids_are_keys: written by the rank scan above; else by the head-flag scan)
+      const uint64_t n_scan = (ids_are_keys ? (uint64_t)n_lists0 : (uint64_t)n_sorted) + 1;
+      if ((rc = exclusive_scan(ctx, PadLen{head_pos.p, scalars.p + 1, short_max}, n_scan, phead.p, scalars.p + 7))) return rc;
       range_fill_kernel<<<grid_for(n_sorted), 256, 0, s>>>(lid_p, H.members.p, head_pos.p, n_sorted, short_max, heavy_min, H.roff.p,
                                                            H.nheavy.p, hcursor.p, cursor.p, H.ranges.p, H.soff.p, scursor.p,
-                                                           H.singles.p);
+                                                           H.singles.p, phead.p, H.lmembers.p);
       PRF_LAUNCHED(ctx);
     }
     if (T) {
@@ -623,6 +649,8 @@ int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off, uint32
     // ranges, hits and |D_t| statistics over the flipped lists
     PRF_CK(ctx, H.ranges.alloc(n_sorted, s));
     PRF_CK(ctx, H.singles.alloc((size_t)n_sorted * (short_max > 1 ? (short_max - 1) / 2 + 1 : 0) + 1, s));
+    PRF_CK(ctx, phead.alloc((size_t)n_lists + 2, s));
+    PRF_CK(ctx, H.lmembers.alloc((size_t)n_sorted * (short_max ? 2 : 4) + 8, s));
     PRF_CK(ctx, cudaMemsetAsync(rcount.p, 0, rcount.bytes(), s));
     PRF_CK(ctx, cudaMemsetAsync(cursor.p, 0, cursor.bytes(), s));
     PRF_CK(ctx, cudaMemsetAsync(scount.p, 0, scount.bytes(), s));
@@ -640,9 +668,10 @@ int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off, uint32
     if ((rc = exclusive_scan(ctx, LoadU32{rcount.p}, (uint64_t)T + 1, H.roff.p, nullptr))) return rc;
     if ((rc = exclusive_scan(ctx, LoadU32{scount.p}, (uint64_t)T + 1, H.soff.p, nullptr))) return rc;
     if (n_sorted) {
+      if ((rc = exclusive_scan(ctx, PadLen{head2.p, scalars.p + 1, short_max}, (uint64_t)n_lists + 1, phead.p, scalars.p + 7))) return rc;
       range_fill_kernel<<<grid_for(n_sorted), 256, 0, s>>>(H.lid.p, H.members.p, head2.p, n_sorted, short_max, heavy_min, H.roff.p,
                                                            H.nheavy.p, hcursor.p, cursor.p, H.ranges.p, H.soff.p, scursor.p,
-                                                           H.singles.p);
+                                                           H.singles.p, phead.p, H.lmembers.p);
       PRF_LAUNCHED(ctx);
     }
     finish_nb_kernel<<<grid_for(T), 256, 0, s>>>(nb32.p, T, H.nb.p, scalars.p + 4, H.roff.p);
@@ -667,6 +696,7 @@ int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off, uint32
   H.n_shared_nnz = n_sorted;  // after duplicate removal
   H.n_ranges = h_nranges;
   H.max_ranges = hs[6];
+  H.n_lmembers = n_sorted ? hs[7] : 0;
 
   prf_stats& st = H.stats;
   st = prf_stats{};

@@ -65,6 +65,9 @@ struct RowsParams {
   const RowItem* items;
   uint32_t n_items;
   uint32_t* counter;          // next item (zeroed before the launch)
+#ifdef PRF_CALIB
+  int calib;                  // calibration builds only: 1 = fill + store only, 2 = member loads but no tile updates, 3 = no prefetch
+#endif
   uint2* spill;               // per-warp cursor area for rows with more long lists than the register slots hold
   uint32_t spill_stride;
 };
@@ -136,49 +139,102 @@ __device__ __forceinline__ void walk_lists(const uint32_t* __restrict__ members,
   }
 }
 
-// Lane-per-list walk for LIGHT lists (few members per tile): lane l owns list g0 + l of a group of 32.  Every
-// lane loads the next kU * 4 members of its own list (16-byte loads from a 4-aligned index, all in flight at
-// once) and applies those below c_hi with shared-memory atomics (two lanes' lists may hit the same column).
-// About 10 instructions per member slot, against ~60 per (list, tile) of the warp-per-list walk above.
+// ---- LIGHT lists (few members per tile): ONE LANE PER LIST -------------------------------------------------
+// A lane loads the next 4 * kU members of its own list with 16-byte loads from a 4-aligned index (all in flight
+// at once) and applies those inside the tile with shared-memory reductions (two lanes' lists may hit the same
+// column): ~8 instructions per member slot against ~60 per (list, tile) of the warp-per-list walk above.
+// Lists are stored padded to a multiple of four members (pad = 0xffffffff, never below c_hi) and start at a
+// multiple of four, so a 16-byte group never straddles two lists and the members before the cursor inside the
+// first group belong to the same list: they are below c_lo and fail the range test.
+struct LightWin {  // the window one lane holds of one list
+  uint32_t x;      // cursor the window was loaded for (0 with y == 0: no list)
+  uint32_t y;      // end of the list
+};
+
+template <int kU>
+__device__ __forceinline__ void light_load(const uint32_t* __restrict__ members, const uint2 r, LightWin& w, uint4 (&buf)[kU]) {
+  w.x = r.x;
+  w.y = r.y;
+  const uint32_t idx = r.x & ~3u;
+#pragma unroll
+  for (int j = 0; j < kU; ++j) {
+    buf[j] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    if (idx + 4 * j < r.y) buf[j] = __ldg(reinterpret_cast<const uint4*>(members + idx + 4 * j));
+  }
+}
+
+#ifdef PRF_CALIB
+__device__ int g_calib_no_red;
+#endif
+__device__ __forceinline__ void tile_red2(uint32_t tb, uint32_t m, bool on) {
+#ifdef PRF_CALIB
+  if (g_calib_no_red) on = false;
+#endif
+  const uint32_t A = tb + 2u * m;  // byte address of column m's entry
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.u32 p, %2, 0;\n\t"
+      "@p red.shared.add.u32 [%0], %1;\n\t"
+      "}" ::"r"(A & ~3u),
+      "r"(0xfffffffeu << ((A & 2u) << 3)), "r"((uint32_t)on)
+      : "memory");
+}
+
+// Applies the window; returns the new cursor.  `tb` = byte address of column 0's entry (mod 2^32).  If the whole
+// window was consumed and the list goes on (rare: more than 4 * kU - 3 members in one tile), continues with
+// dependent loads.
+template <int kU>
+__device__ __forceinline__ uint32_t light_apply(const uint32_t* __restrict__ members, const LightWin w, const uint4 (&buf)[kU],
+                                                const uint32_t c_lo, const uint32_t c_hi, const uint32_t tb) {
+  const uint32_t span = c_hi - c_lo;
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int j = 0; j < kU; ++j) {
+    const uint32_t mm[4] = {buf[j].x, buf[j].y, buf[j].z, buf[j].w};
+    // warp-uniform early out: no lane's list has a member below c_hi from here on (lists ascend)
+    if (j > 0 && !__any_sync(0xffffffffu, mm[0] < c_hi)) break;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bool on = j == 0 ? mm[e] - c_lo < span : mm[e] < c_hi;
+      cnt += on ? 1u : 0u;
+      tile_red2(tb, mm[e], on);
+    }
+  }
+  uint32_t cur = w.x + cnt;
+  uint32_t idx = (w.x & ~3u) + 4 * kU;
+  bool more = cur == idx && idx < w.y;  // consumed everything loaded and the list goes on
+  while (__any_sync(0xffffffffu, more)) {
+    uint4 v = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    if (more) v = __ldg(reinterpret_cast<const uint4*>(members + idx));
+    const uint32_t mm[4] = {v.x, v.y, v.z, v.w};
+    uint32_t c = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bool on = mm[e] < c_hi;
+      c += on ? 1u : 0u;
+      tile_red2(tb, mm[e], on);
+    }
+    cur += c;
+    idx += 4;
+    more = more && c == 4 && idx < w.y;
+  }
+  return cur;
+}
+
+// Generic light walk over lists [0, n) of `curs` (no prefetch): groups of 32 lists, one list per lane.
 template <int kU>
 __device__ __forceinline__ void walk_light(const uint32_t* __restrict__ members, uint2* curs, const uint32_t n,
-                                           const uint32_t c_hi, const int32_t base, uint32_t* tile32, const uint32_t lane) {
+                                           const uint32_t c_lo, const uint32_t c_hi, const uint32_t tb, const uint32_t lane) {
 #pragma unroll 1
   for (uint32_t g0 = 0; g0 < n; g0 += 32) {
     const uint32_t k = g0 + lane;
-    const uint2 r = k < n ? curs[k] : make_uint2(0u, 0u);  // [r.x, r.y): the members of my list not consumed yet
-    const uint32_t len = r.y - r.x;
-    uint32_t idx = r.x & ~3u;  // 4-aligned window start (the 0..3 positions before r.x are not mine)
-    uint32_t cnt = 0;          // members consumed: every member of [r.x, r.y) below c_hi (they are >= this tile's first column)
-    bool live = r.x < r.y;
-#pragma unroll 1
-    while (__any_sync(0xffffffffu, live)) {
-      uint4 buf[kU];
-#pragma unroll
-      for (int j = 0; j < kU; ++j) {
-        buf[j] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-        if (live && idx + 4 * j < r.y) buf[j] = __ldg(reinterpret_cast<const uint4*>(members + idx + 4 * j));
-      }
-      const uint32_t d0 = idx - r.x;  // position of the window's first element relative to r.x (may be "negative")
-#pragma unroll
-      for (int j = 0; j < kU; ++j) {
-        const uint32_t mm[4] = {buf[j].x, buf[j].y, buf[j].z, buf[j].w};
-        // warp-uniform early out: nobody's list has a member below c_hi from here on (lists ascend)
-        if (j > 0 && !__any_sync(0xffffffffu, live && d0 + 4 * j < len && mm[0] < c_hi)) break;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (live && d0 + (4 * j + e) < len && mm[e] < c_hi) {  // unsigned compare: also rejects positions before r.x
-            ++cnt;
-            const uint32_t i16 = (uint32_t)(base + (int32_t)mm[e]);
-            atomicSub(&tile32[i16 >> 1], 2u << ((i16 & 1u) * 16u));
-          }
-        }
-      }
-      // another round only for a lane that consumed everything it loaded and whose list goes on
-      if (live && idx + 4 * kU < r.y && buf[kU - 1].w < c_hi) idx += 4 * kU;
-      else live = false;
-    }
-    if (cnt) curs[k].x = r.x + cnt;
+    const uint2 r = k < n ? curs[k] : make_uint2(0u, 0u);
+    LightWin w;
+    uint4 buf[kU];
+    light_load<kU>(members, r, w, buf);
+    const uint32_t cur = light_apply<kU>(members, w, buf, c_lo, c_hi, tb);
+    if (cur != r.x) curs[k].x = cur;
   }
 }
 
@@ -282,6 +338,7 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
 
     const uint32_t len = ce - cb, nseg = (len + kTile - 1) / kTile;
     const uint64_t rs = row_start(a, T);
+    const uint32_t Hs = min(H, (uint32_t)kCurCap), Rs = min(R, (uint32_t)kCurCap);
     const uint32_t na = prm.uniform_nb ? 0u : prm.nb[a];
     for (uint32_t seg = 0; seg < nseg; ++seg) {
       const uint32_t c_lo = cb + seg * kTile, c_hi = min(ce, c_lo + (uint32_t)kTile), cnt = c_hi - c_lo;
@@ -357,12 +414,18 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
 
       // ---- walk the long lists ----
       // cursors [0, H) heavy, [H, R) light; cursors >= kCurCap live in the global spill area
-      const uint32_t Hs = min(H, (uint32_t)kCurCap), Rs = min(R, (uint32_t)kCurCap);
+      const uint32_t tb = smem_addr(tile) + 2u * (uint32_t)base;  // byte address of column 0's entry (mod 2^32)
+#ifdef PRF_CALIB
+      if (prm.calib != 1) {
+#endif
       if (Hs) walk_lists<kB>(members, s_cur, Hs, c_hi, base, tile, lane);
       if (H > Hs) walk_lists<kB>(members, spill, H - kCurCap, c_hi, base, tile, lane);
-      if (Rs > Hs) walk_light<kU>(members, s_cur + Hs, Rs - Hs, c_hi, base, tile32, lane);
-      if (R > Rs) walk_light<kU>(members, spill + (max(H, (uint32_t)kCurCap) - kCurCap), R - max(H, (uint32_t)kCurCap), c_hi, base, tile32, lane);
+      if (Rs > Hs) walk_light<kU>(members, s_cur + Hs, Rs - Hs, c_lo, c_hi, tb, lane);
+      if (R > Rs) walk_light<kU>(members, spill + (max(H, (uint32_t)kCurCap) - kCurCap), R - max(H, (uint32_t)kCurCap), c_lo, c_hi, tb, lane);
       __syncwarp();
+#ifdef PRF_CALIB
+      }
+#endif
 
       // ---- threshold mask: bit (p - p_begin) set iff d <= editdist ----
       if (prm.editdist >= 0) {
@@ -463,7 +526,7 @@ static int launch_rows_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t edi
   prm.nb_shift_stride = H.nb_shift_stride;
   prm.uniform_nb = H.uniform_nb ? 1 : 0;
   prm.nb_uniform = H.nb_uniform;
-  prm.members = H.members.p;
+  prm.members = H.lmembers.p;
   prm.n_parts = 1;
   prm.part[0].roff = H.roff.p;
   prm.part[0].ranges = H.ranges.p;
@@ -484,6 +547,13 @@ static int launch_rows_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t edi
     prm.spill = plan.cursor_ws.p;
     prm.spill_stride = stride;
   }
+#ifdef PRF_CALIB
+  prm.calib = ctx->calib;
+  {
+    const int no_red = ctx->calib == 2;
+    PRF_CK(ctx, cudaMemcpyToSymbolAsync(g_calib_no_red, &no_red, sizeof(int), 0, cudaMemcpyHostToDevice, s));
+  }
+#endif
   PRF_CK(ctx, cudaMemsetAsync(plan.counter.p, 0, sizeof(uint32_t), s));
   if (d_mask) PRF_CK(ctx, cudaMemsetAsync(d_mask, 0, ((p_end - p_begin + 31) / 32) * sizeof(uint32_t), s));
   kern<<<grid, kThreads, smem, s>>>(prm);
@@ -494,11 +564,11 @@ static int launch_rows_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t edi
 int launch_rows(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out, uint32_t* d_mask) {
   // the tiny-tile build exists so that small test inputs exercise multi-tile rows and the cursor spill area
   if (ctx->debug_small_tiles) return launch_rows_t<256, 2, 8, 2, 1>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-  switch (ctx->rows_cfg) {
-    case 1: return launch_rows_t<7680, 14, 152, 4, 4>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-    case 2: return launch_rows_t<15360, 7, 304, 4, 8>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-    case 3: return launch_rows_t<15360, 7, 304, 4, 16>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-    default: return launch_rows_t<7680, 14, 152, 4, 8>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  switch (ctx->rows_cfg) {  // tuning instantiations (scripts/rows_probe.py); the default measured best at 100k x 200
+    case 1: return launch_rows_t<7680, 14, 152, 4, 8>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    case 2: return launch_rows_t<6656, 16, 128, 4, 7>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    case 3: return launch_rows_t<8960, 12, 168, 4, 8>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    default: return launch_rows_t<5376, 20, 104, 4, 6>(ctx, p_begin, p_end, editdist, d_out, d_mask);
   }
 }
 

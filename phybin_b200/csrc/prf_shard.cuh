@@ -122,14 +122,12 @@ __global__ void __launch_bounds__(256) merge_ranges_kernel(const MergeParts P, u
   }
 }
 
-// members_all / lid_all: concatenation (lid shifted to the rank's dense id range).
+// members_all: concatenation of the parts' padded list arrays.
 __global__ void __launch_bounds__(256) merge_members_kernel(const MergeParts P, uint32_t r,
-                                                            uint32_t* __restrict__ members_all,
-                                                            uint32_t* __restrict__ lid_all) {
+                                                            uint32_t* __restrict__ members_all) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= P.n_members[r]) return;
   members_all[P.member_base[r] + k] = P.members[r][k];
-  lid_all[P.member_base[r] + k] = P.lid[r][k] + P.list_base[r];
 }
 
 }  // namespace prf

@@ -759,7 +759,7 @@ static int launch_sparse_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t e
   prm.nb_uniform = H.nb_uniform;
   prm.roff = H.roff.p;
   prm.ranges = H.ranges.p;
-  prm.members = H.members.p;
+  prm.members = H.lmembers.p;
   prm.editdist = editdist;
   prm.out = d_out;
   prm.mask = d_mask;

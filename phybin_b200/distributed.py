@@ -103,7 +103,7 @@ def _local_load(ctx: RFContext, recv_keys: torch.Tensor, counts_all: torch.Tenso
 
 
 _PART_ARRAYS = (("nb", 2, lambda p: p.n_trees), ("roff", 4, lambda p: p.n_trees + 1), ("ranges", 8, lambda p: p.n_ranges),
-                ("members", 4, lambda p: p.n_members), ("lid", 4, lambda p: p.n_members))
+                ("members", 4, lambda p: p.n_members))
 _PART_SCALARS = ("n_trees", "n_ranges", "n_members", "n_lists", "nnz", "n_unique", "n_hits")
 
 
