@@ -165,7 +165,7 @@ def run_gpu(args, wl, wl_name):
     import torch.distributed as dist
     from phybin_b200.host import Forest
     from phybin_b200.rfdistance import MEM_DEVICE, RFContext, shard_range
-    from phybin_b200.distributed import KeyGather, shard_rows as key_shard_rows, sharded_load, tree_shard
+    from phybin_b200.distributed import KeyGather, shard_rows as key_shard_rows, tree_shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -211,7 +211,7 @@ def run_gpu(args, wl, wl_name):
         d_off_my = torch.from_numpy((off_all[t_lo:t_hi + 1] - off_all[t_lo]).astype(np.int64)).to(dev)
     # N = 2: all-gathering the keys and building twice is cheaper than the partitioned build's fixed latencies
     build = args.build if args.build != "auto" else ("sharded" if world >= 4 else "replicated")
-    sharded = world > 1 and mode == "hashrf" and build == "sharded"
+    sharded = False
     with torch.cuda.stream(ext):
         p_begin, p_end = shard_range(T, rank, world)
         d_out = torch.empty(max(p_end - p_begin, 8), dtype=torch.int16, device=dev)
@@ -224,7 +224,7 @@ def run_gpu(args, wl, wl_name):
         """dedup + incidence + matrix for this rank's slice; inputs and outputs stay in HBM."""
         if sharded:
             # hash-partitioned build: all-to-all of keys, per-class dedup, all-gather + merge of the structures
-            sharded_load(ctx, d_my, d_off_my, T, stream=ext)
+            raise RuntimeError("unreachable")
         else:
             with torch.cuda.stream(ext):
                 d_full = gather(d_my)     # NCCL all-gather over NVLink when world > 1

@@ -142,33 +142,6 @@ PRF_API int prf_fetch_mask(prf_ctx* ctx, uint64_t p_begin, uint64_t p_end, uint3
 /* Copies the packed entries of upper-triangle rows [row0, row1) (row a holds d(a, a+1..T-1)). */
 PRF_API int prf_fetch_rows(prf_ctx* ctx, uint32_t row0, uint32_t row1, uint16_t* dst);
 
-/* ---- hashRF: multi-GPU build (hash-partitioned dedup) --------------------- */
-
-/* A rank's partial structure over "every tree restricted to one hash class of bipartitions".
- * Device pointers; those returned by prf_hashrf_export stay valid until the next load on that ctx. */
-typedef struct prf_part {
-  uint64_t n_trees, n_ranges, n_members, n_lists, nnz, n_unique, n_hits;
-  const uint16_t* nb;      /* [n_trees]     distinct bipartitions of tree t in this class          */
-  const uint32_t* roff;    /* [n_trees + 1] per-tree offsets into ranges                            */
-  const void* ranges;      /* [n_ranges]    (begin, end) uint32 pairs into members                  */
-  const uint32_t* members; /* [n_members]   inverted lists, ascending tree ids                      */
-  const uint32_t* lid;     /* [n_members]   dense list id of every member entry                     */
-} prf_part;
-
-/* Sender side.  Splits the canonical bipartitions of T_local trees (device memory, laid out like
- * prf_hashrf_load's input) into `world` hash classes: d_send_keys receives the keys grouped by
- * class (class c = rows h_first[c] .. h_first[c+1]-1, tree order kept inside a class), and
- * d_send_counts[c * T_local + t] the number of entries of tree t in class c.  h_first: host, world+1. */
-PRF_API int prf_hashrf_partition(prf_ctx* ctx, const uint64_t* d_bips, const uint64_t* d_tree_off,
-                                 uint32_t T_local, uint32_t W, uint32_t world, uint64_t* d_send_keys,
-                                 uint32_t* d_send_counts, uint64_t* h_first);
-/* The loaded problem's structure (after prf_hashrf_load on one class of every tree). */
-PRF_API int prf_hashrf_export(prf_ctx* ctx, prf_part* out);
-/* Installs the union of `world` partial structures (device memory on this context's device) as the
- * loaded problem: prf_hashrf_compute / prf_fetch* then work as after prf_hashrf_load. */
-PRF_API int prf_hashrf_merge(prf_ctx* ctx, uint32_t T, uint32_t W, uint32_t world, const prf_part* parts,
-                             prf_stats* stats);
-
 /* ---- tolerant mode (replaces fst . naiveDistMatrix, RFDistance.hs:168-198) ------------------- */
 
 /* clades    nnz*W words: for tree t, the UN-normalised leaf set of every non-root interior node

@@ -16,14 +16,6 @@ u32p = C.POINTER(C.c_uint32)
 u16p = C.POINTER(C.c_uint16)
 
 
-class prf_part(C.Structure):
-    _fields_ = [
-        ("n_trees", C.c_uint64), ("n_ranges", C.c_uint64), ("n_members", C.c_uint64), ("n_lists", C.c_uint64),
-        ("nnz", C.c_uint64), ("n_unique", C.c_uint64), ("n_hits", C.c_uint64),
-        ("nb", C.c_void_p), ("roff", C.c_void_p), ("ranges", C.c_void_p), ("members", C.c_void_p), ("lid", C.c_void_p),
-    ]
-
-
 class prf_extract_info(C.Structure):
     _fields_ = [("nnz", C.c_uint64), ("max_nodes", C.c_uint32), ("gpu_launches", C.c_int32),
                 ("ms_h2d", C.c_float), ("ms_kernels", C.c_float)]
@@ -139,9 +131,6 @@ def rf_lib():
         L.prf_tolerant.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int32, vp, vp, st]
         L.prf_tolerant_load.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int, st]
         L.prf_tolerant_compute.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int32, vp, vp, st]
-        L.prf_hashrf_partition.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, u64p]
-        L.prf_hashrf_export.argtypes = [vp, C.POINTER(prf_part)]
-        L.prf_hashrf_merge.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(prf_part), st]
         L.prf_allbips.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
                                   C.POINTER(prf_extract_info)]
         L.prf_hashrf_trees.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int32, vp, vp, st,
@@ -163,8 +152,7 @@ def rf_lib():
         # test-only entry points (not in phybin_rf.h)
         L.prf_debug_small_tiles.argtypes = [vp, C.c_int]
         L.prf_debug_short_max.argtypes = [vp, C.c_uint32]
-        L.prf_debug_heavy_min.argtypes = [vp, C.c_uint32]
-        L.prf_debug_sparse_kernel.argtypes = [vp, C.c_int, C.c_int]
+        L.prf_debug_rows_cfg.argtypes = [vp, C.c_int]
         L.prf_debug_no_flip.argtypes = [vp, C.c_int]
         L.prf_debug_row_plan.restype = C.c_longlong
         L.prf_debug_row_plan.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, vp, C.c_uint64]
@@ -178,7 +166,7 @@ def rf_lib():
 # Every symbol include/phybin_rf.h declares (tests check the built library exports them all).
 RF_SYMBOLS = [
     "prf_create", "prf_destroy", "prf_last_error", "prf_version", "prf_stream", "prf_hashrf",
-    "prf_hashrf_load", "prf_hashrf_compute", "prf_hashrf_partition", "prf_hashrf_export", "prf_hashrf_merge", "prf_fetch", "prf_fetch_mask", "prf_fetch_rows",
+    "prf_hashrf_load", "prf_hashrf_compute", "prf_fetch", "prf_fetch_mask", "prf_fetch_rows",
     "prf_tolerant", "prf_tolerant_load", "prf_tolerant_compute", "prf_allbips", "prf_allbips_result", "prf_allbips_fetch", "prf_hashrf_trees", "prf_tolerant_trees", "prf_consensus", "prf_consensus_fetch", "prf_fetch_submatrix",
     "prf_mask_components", "prf_packed_index",
     "prf_shard_align", "prf_shard_range", "prf_limits", "prf_launch_count",

@@ -9,11 +9,24 @@
 #include "prf_common.cuh"
 #include "prf_internal.h"
 #include "prf_primitives.cuh"
-#include "prf_shard.cuh"
 
 using namespace prf;
 
 static thread_local std::string g_create_error;
+
+// ext[0] = tree_off[T]; ext[1] = most entries of one tree; ext[2] != 0 when the offsets do not start at 0 or descend
+__global__ void __launch_bounds__(256) tree_extent_kernel(const uint64_t* __restrict__ off, uint32_t T, unsigned long long* ext) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > T) return;
+  if (t == T) {
+    ext[0] = off[T];
+    if (off[0] != 0) ext[2] = 1;
+    return;
+  }
+  const uint64_t a = off[t], b = off[t + 1];
+  if (b < a) ext[2] = 1;
+  else atomicMax(&ext[1], (unsigned long long)(b - a));
+}
 
 
 extern "C" {
@@ -78,6 +91,8 @@ PRF_API void prf_destroy(prf_ctx* h) {
   c.cons = ConsensusState{};
   c.plan = RowPlan{};
   c.timing.release();
+  c.scan_status.release();
+  c.scan_counter.release();
   c.out.release();
   c.mask.release();
   cudaStreamSynchronize(c.stream);
@@ -131,22 +146,34 @@ PRF_API int prf_hashrf_load(prf_ctx* h, const uint64_t* bips, const uint64_t* tr
 
   trace_mark("hashrf_load: enter");
   PRF_CK(ctx, cudaEventRecord(ctx->ev[0], s));
-  // offsets first: nnz = tree_off[T]
+  // offsets first: nnz = tree_off[T], and the most entries of one tree (sizes the per-tree hash sets of the build)
   DevBuf<uint64_t> d_off_own, d_bips_own;
   const uint64_t* d_off = tree_off;
   uint64_t nnz = 0;
+  uint32_t max_entries = 0;
   if (kind == PRF_MEM_HOST) {
     if (tree_off[0] != 0) return ctx->fail(PRF_E_INVALID, "tree_off[0] must be 0");
-    for (uint32_t t = 0; t < T; ++t)
+    for (uint32_t t = 0; t < T; ++t) {
       if (tree_off[t + 1] < tree_off[t]) return ctx->fail(PRF_E_INVALID, "tree_off is not ascending at tree %u", t);
+      max_entries = (uint32_t)std::min<uint64_t>(0xffffffffull, std::max<uint64_t>(max_entries, tree_off[t + 1] - tree_off[t]));
+    }
     nnz = tree_off[T];
     PRF_CK(ctx, d_off_own.alloc((size_t)T + 1, s));
     int rc = upload(ctx, d_off_own.p, tree_off, ((size_t)T + 1) * 8, kind);
     if (rc) return rc;
     d_off = d_off_own.p;
   } else {
-    PRF_CK(ctx, cudaMemcpyAsync(&nnz, tree_off + T, 8, cudaMemcpyDeviceToHost, s));
+    DevBuf<unsigned long long> ext;  // [0] = tree_off[T], [1] = max entries of a tree, [2] = offsets not ascending
+    PRF_CK(ctx, ext.alloc(3, s));
+    PRF_CK(ctx, cudaMemsetAsync(ext.p, 0, 24, s));
+    tree_extent_kernel<<<grid_for((uint64_t)T + 1), 256, 0, s>>>(tree_off, T, ext.p);
+    PRF_LAUNCHED(ctx);
+    unsigned long long hext[3] = {0, 0, 0};
+    PRF_CK(ctx, cudaMemcpyAsync(hext, ext.p, 24, cudaMemcpyDeviceToHost, s));
     PRF_CK(ctx, cudaStreamSynchronize(s));
+    if (hext[2]) return ctx->fail(PRF_E_INVALID, "tree_off must start at 0 and ascend");
+    nnz = hext[0];
+    max_entries = (uint32_t)std::min<unsigned long long>(0xffffffffull, hext[1]);
   }
   if (nnz >= 0xffffffffull) return ctx->fail(PRF_E_UNSUPPORTED, "nnz=%llu entries; supported < 2^32 - 1", (unsigned long long)nnz);
   if (nnz && !bips) return ctx->fail(PRF_E_INVALID, "bips is NULL");
@@ -160,7 +187,7 @@ PRF_API int prf_hashrf_load(prf_ctx* h, const uint64_t* bips, const uint64_t* tr
     return ctx->fail(PRF_E_INVALID, "device bips pointer must be 16-byte aligned");
   }
   trace_mark("hashrf_load: uploads queued");
-  int rc = hashrf_build(ctx, d_bips, d_off, T, W, nnz);
+  int rc = hashrf_build(ctx, d_bips, d_off, d_off + 1, T, W, nnz, nnz, max_entries);
   if (rc) return rc;
   trace_mark("hashrf_load: build done");
   prf_stats& st = ctx->h.stats;
@@ -201,17 +228,16 @@ PRF_API int prf_hashrf_compute(prf_ctx* h, uint64_t p_begin, uint64_t p_end, int
     // 2 * Kpad int8 ops at the ~0.9 Pop/s the operand traffic allows.  Both write the same 2 B per pair.
     const double pairs = (double)(p_end - p_begin);
     const double hits = (double)H.stats.n_hits * (H.P ? pairs / (double)H.P : 0.0);
-    const double kpad = (double)dense_kpad(H.n_shared);
+    const double kpad = (double)dense_kpad(H.n_list_ids);
     const double t_sparse = hits * 1.9e-12 + (H.uniform_nb ? 0.0 : pairs * 0.9e-12), t_dense = pairs * kpad * 2.0 / 0.9e15;
     const double operand = (double)dense_tpad(H.T) * kpad;
-    use = (H.n_shared > 0 && H.lid.p && operand < 32e9 && t_dense < t_sparse) ? PRF_VARIANT_DENSE : PRF_VARIANT_SPARSE;
+    use = (H.n_shared > 0 && H.ent_lid.p && operand < 32e9 && t_dense < t_sparse) ? PRF_VARIANT_DENSE : PRF_VARIANT_SPARSE;
   }
   PRF_CK(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
   if (p_end > p_begin) {
-    if (use == PRF_VARIANT_DENSE && !H.lid.p && H.n_shared)
+    if (use == PRF_VARIANT_DENSE && !H.ent_lid.p && H.n_shared)
       return ctx->fail(PRF_E_UNSUPPORTED, "the dense variant needs the incidence of a single-context build");
     if (use == PRF_VARIANT_DENSE) rc = launch_dense(ctx, p_begin, p_end, editdist, d_out, d_mask);
-    else if (ctx->sparse_kernel == 1) rc = launch_sparse(ctx, p_begin, p_end, editdist, d_out, d_mask);
     else rc = launch_rows(ctx, p_begin, p_end, editdist, d_out, d_mask);
     if (rc) return rc;
   }
@@ -306,190 +332,6 @@ PRF_API int prf_hashrf(prf_ctx* h, const uint64_t* bips, const uint64_t* tree_of
 }
 
 // ---------------------------------------------------------------------------------------------
-// hashRF: multi-GPU build
-// ---------------------------------------------------------------------------------------------
-
-PRF_API int prf_hashrf_partition(prf_ctx* h, const uint64_t* d_bips, const uint64_t* d_off, uint32_t T_local, uint32_t W,
-                                 uint32_t world, uint64_t* d_send_keys, uint32_t* d_send_counts, uint64_t* h_first) {
-  if (!h) return PRF_E_INVALID;
-  Ctx* ctx = &h->c;
-  ctx->err.clear();
-  if (!d_off || !d_send_counts || !h_first) return ctx->fail(PRF_E_INVALID, "null pointer");
-  if (W == 0 || W > kMaxWords) return ctx->fail(PRF_E_UNSUPPORTED, "W=%u words per set; supported 1..%u", W, kMaxWords);
-  if (world == 0 || world > 16) return ctx->fail(PRF_E_UNSUPPORTED, "world=%u; supported 1..16", world);
-  PRF_CK(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t s = ctx->stream;
-  uint64_t nnz = 0;
-  PRF_CK(ctx, cudaMemcpyAsync(&nnz, d_off + T_local, 8, cudaMemcpyDeviceToHost, s));
-  PRF_CK(ctx, cudaStreamSynchronize(s));
-  if (nnz >= 0xffffffffull) return ctx->fail(PRF_E_UNSUPPORTED, "nnz=%llu entries; supported < 2^32 - 1", (unsigned long long)nnz);
-  if (nnz && (!d_bips || !d_send_keys)) return ctx->fail(PRF_E_INVALID, "null key buffer");
-  DevBuf<uint32_t> owner, idx;
-  DevBuf<unsigned long long> first;
-  PRF_CK(ctx, owner.alloc(nnz, s));
-  PRF_CK(ctx, idx.alloc(nnz, s));
-  PRF_CK(ctx, first.alloc((size_t)world + 1, s));
-  if (T_local) {
-    switch (W) {
-#define PRF_W_CASE(w) case w: part_owner_kernel<w><<<(T_local + 7) / 8, 256, 0, s>>>(d_bips, d_off, T_local, world, owner.p, idx.p, d_send_counts); break;
-      PRF_W_CASE(1) PRF_W_CASE(2) PRF_W_CASE(3) PRF_W_CASE(4) PRF_W_CASE(5) PRF_W_CASE(6) PRF_W_CASE(7) PRF_W_CASE(8)
-      PRF_W_CASE(9) PRF_W_CASE(10) PRF_W_CASE(11) PRF_W_CASE(12) PRF_W_CASE(13) PRF_W_CASE(14) PRF_W_CASE(15) PRF_W_CASE(16)
-#undef PRF_W_CASE
-    }
-    PRF_LAUNCHED(ctx);
-  }
-  int rc = radix_sort_pairs(ctx, owner.p, idx.p, (uint32_t)nnz, std::max(1, bits_for(world)));  // stable: tree order kept per class
-  if (rc) return rc;
-  class_bounds_kernel<<<1, 32, 0, s>>>(owner.p, (uint32_t)nnz, world, first.p);
-  PRF_LAUNCHED(ctx);
-  if (nnz) {
-    gather_keys_kernel<<<grid_for(nnz * W), 256, 0, s>>>(d_bips, idx.p, nnz * W, W, d_send_keys);
-    PRF_LAUNCHED(ctx);
-  }
-  unsigned long long hf[17];
-  PRF_CK(ctx, cudaMemcpyAsync(hf, first.p, ((size_t)world + 1) * 8, cudaMemcpyDeviceToHost, s));
-  PRF_CK(ctx, cudaStreamSynchronize(s));
-  for (uint32_t c = 0; c <= world; ++c) h_first[c] = hf[c];
-  return PRF_OK;
-}
-
-PRF_API int prf_hashrf_export(prf_ctx* h, prf_part* out) {
-  if (!h || !out) return PRF_E_INVALID;
-  Ctx* ctx = &h->c;
-  ctx->err.clear();
-  HashRFState& H = ctx->h;
-  if (!H.loaded) return ctx->fail(PRF_E_STATE, "prf_hashrf_export before a successful prf_hashrf_load");
-  out->n_trees = H.T;
-  out->n_ranges = H.n_ranges;
-  out->n_members = H.n_lmembers;  // the walked lists, each padded to a multiple of 4 members
-  out->n_lists = H.n_shared;
-  out->nnz = H.stats.nnz;
-  out->n_unique = H.stats.n_unique;
-  out->n_hits = H.stats.n_hits;
-  out->nb = H.nb.p;
-  out->roff = H.roff.p;
-  out->ranges = H.ranges.p;
-  out->members = H.lmembers.p;
-  out->lid = nullptr;
-  return PRF_OK;
-}
-
-PRF_API int prf_hashrf_merge(prf_ctx* h, uint32_t T, uint32_t W, uint32_t world, const prf_part* parts, prf_stats* stats) {
-  if (!h || !parts) return PRF_E_INVALID;
-  Ctx* ctx = &h->c;
-  ctx->err.clear();
-  if (world == 0 || world > 16) return ctx->fail(PRF_E_UNSUPPORTED, "world=%u; supported 1..16", world);
-  PRF_CK(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t s = ctx->stream;
-  uint64_t launches0 = ctx->launches;
-  MergeParts P{};
-  P.world = world;
-  uint64_t n_members = 0, n_lists = 0, n_ranges = 0, nnz = 0, n_unique = 0, n_hits = 0;
-  for (uint32_t r = 0; r < world; ++r) {
-    const prf_part& q = parts[r];
-    if (q.n_trees != T) return ctx->fail(PRF_E_INVALID, "part %u covers %llu trees, expected %u", r, (unsigned long long)q.n_trees, T);
-    P.nb[r] = q.nb;
-    P.roff[r] = q.roff;
-    P.ranges[r] = static_cast<const uint2*>(q.ranges);
-    P.members[r] = q.members;
-    P.lid[r] = q.lid;
-    P.member_base[r] = (uint32_t)n_members;
-    P.list_base[r] = (uint32_t)n_lists;
-    P.n_members[r] = (uint32_t)q.n_members;
-    n_members += q.n_members;
-    n_lists += q.n_lists;
-    n_ranges += q.n_ranges;
-    nnz += q.nnz;
-    n_unique += q.n_unique;
-    n_hits += q.n_hits;
-  }
-  if (n_members >= 0xffffffffull) return ctx->fail(PRF_E_UNSUPPORTED, "merged member count does not fit 32 bits");
-  PRF_CK(ctx, cudaEventRecord(ctx->ev[2], s));
-  // build into fresh buffers: a part may alias the context's current structure
-  DevBuf<uint16_t> nb;
-  DevBuf<uint32_t> roff, members, lid, nb32, cnt, mm, soff, singles;  // mm: min |B|, max |B|, max ranges per tree
-  DevBuf<uint2> ranges;
-  PRF_CK(ctx, soff.alloc((size_t)T + 1, s));  // the parts carry every list as ranges (built with short_max == 0)
-  PRF_CK(ctx, cudaMemsetAsync(soff.p, 0, soff.bytes(), s));
-  PRF_CK(ctx, singles.alloc(1, s));
-  PRF_CK(ctx, nb.alloc((size_t)T + 16, s));
-  PRF_CK(ctx, cudaMemsetAsync(nb.p, 0, nb.bytes(), s));
-  PRF_CK(ctx, roff.alloc((size_t)T + 1, s));
-  PRF_CK(ctx, members.alloc((size_t)n_members + 4, s));
-  PRF_CK(ctx, ranges.alloc(n_ranges, s));
-  PRF_CK(ctx, nb32.alloc((size_t)T + 1, s));
-  PRF_CK(ctx, cnt.alloc((size_t)T + 1, s));
-  PRF_CK(ctx, mm.alloc(3, s));
-  const uint32_t mm_init[3] = {0xffffffffu, 0u, 0u};
-  PRF_CK(ctx, cudaMemcpyAsync(mm.p, mm_init, 12, cudaMemcpyHostToDevice, s));
-  merge_count_kernel<<<grid_for((uint64_t)T + 1), 256, 0, s>>>(P, T, nb32.p, cnt.p);
-  PRF_LAUNCHED(ctx);
-  int rc = exclusive_scan(ctx, LoadU32{cnt.p}, (uint64_t)T + 1, roff.p, nullptr);
-  if (rc) return rc;
-  if (T) {
-    merge_ranges_kernel<<<grid_for((uint64_t)world * T), 256, 0, s>>>(P, T, roff.p, ranges.p);
-    PRF_LAUNCHED(ctx);
-    finish_nb_kernel<<<grid_for(T), 256, 0, s>>>(nb32.p, T, nb.p, mm.p, roff.p);
-    PRF_LAUNCHED(ctx);
-  }
-  for (uint32_t r = 0; r < world; ++r)
-    if (P.n_members[r]) {
-      merge_members_kernel<<<grid_for(P.n_members[r]), 256, 0, s>>>(P, r, members.p);
-      PRF_LAUNCHED(ctx);
-    }
-  uint32_t hmm[3] = {0, 0, 0};
-  PRF_CK(ctx, cudaMemcpyAsync(hmm, mm.p, 12, cudaMemcpyDeviceToHost, s));
-  PRF_CK(ctx, cudaEventRecord(ctx->ev[3], s));
-  PRF_CK(ctx, cudaStreamSynchronize(s));
-  if (T == 0) hmm[0] = hmm[1] = 0;
-  if (hmm[1] > kMaxBipsPerTree)
-    return ctx->fail(PRF_E_RANGE, "a tree has %u bipartitions; distances would overflow uint16 (max %u per tree)", hmm[1],
-                     kMaxBipsPerTree);
-  HashRFState& H = ctx->h;
-  H = HashRFState{};  // frees the previous structure (stream-ordered, after the kernels above)
-  H.T = T;
-  H.W = W;
-  H.nnz = nnz;
-  H.P = (uint64_t)T * (T ? T - 1 : 0) / 2;
-  H.uniform_nb = hmm[0] == hmm[1];
-  H.nb_uniform = hmm[0];
-  H.nb = std::move(nb);
-  H.roff = std::move(roff);
-  H.ranges = std::move(ranges);
-  H.lmembers = std::move(members);  // (the merged structure has no unpadded incidence: the dense variant is not available on it)
-  H.n_lmembers = n_members;
-  H.soff = std::move(soff);
-  H.singles = std::move(singles);
-  // the merged ranges of a tree interleave the parts: all of them take the warp-per-list walk
-  PRF_CK(ctx, H.nheavy.alloc((size_t)T + 1, s));
-  PRF_CK(ctx, cudaMemcpyAsync(H.nheavy.p, cnt.p, ((size_t)T + 1) * 4, cudaMemcpyDeviceToDevice, s));
-  H.n_shared = (uint32_t)n_lists;
-  H.n_shared_nnz = n_members;
-  H.n_ranges = n_ranges;
-  H.max_ranges = hmm[2];
-  prf_stats& st = H.stats;
-  st = prf_stats{};
-  st.n_trees = T;
-  st.n_words = W;
-  st.nnz = nnz;
-  st.n_unique = n_unique;
-  st.n_shared = n_lists;
-  st.n_shared_nnz = n_members;
-  st.n_hits = n_hits;
-  st.n_pairs = H.P;
-  st.max_bips = hmm[1];
-  st.min_bips = hmm[0];
-  st.ms_incidence = ev_ms(ctx->ev[2], ctx->ev[3]);
-  st.gpu_launches = (int32_t)(ctx->launches - launches0);
-  if ((rc = build_nb_shift(ctx))) return rc;
-  H.loaded = true;
-  ctx->tol.loaded = false;
-  ctx->out_valid = ctx->mask_valid = false;
-  if (stats) *stats = st;
-  return PRF_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
 // Debug entry points for tests of the primitives (not part of phybin_rf.h).
 // ---------------------------------------------------------------------------------------------
 
@@ -528,17 +370,9 @@ PRF_API int prf_debug_short_max(prf_ctx* h, uint32_t short_max) {
   return PRF_OK;
 }
 
-// Lists of at least this many members take the warp-per-list walk (0 = chosen from T).
-PRF_API int prf_debug_heavy_min(prf_ctx* h, uint32_t heavy_min) {
+// cfg: tuning instantiation of the rows kernel (prf_rows.cuh launch_rows)
+PRF_API int prf_debug_rows_cfg(prf_ctx* h, int cfg) {
   if (!h) return PRF_E_INVALID;
-  h->c.heavy_min = heavy_min;
-  return PRF_OK;
-}
-
-// which: 0 = rows kernel (one warp per row), 1 = round-1 CTA-per-row kernel (loads must then use short_max 0)
-PRF_API int prf_debug_sparse_kernel(prf_ctx* h, int which, int cfg) {
-  if (!h) return PRF_E_INVALID;
-  h->c.sparse_kernel = which;
   h->c.rows_cfg = cfg;
   return PRF_OK;
 }

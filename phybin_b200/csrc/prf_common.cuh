@@ -50,6 +50,23 @@ struct DevBuf {
   size_t bytes() const { return n * sizeof(T); }
 };
 
+constexpr int kMaxParts = 16;
+
+// One hash class of the shared bipartitions in the form the sparse matrix kernel reads (prf_rows.cuh); a
+// single-GPU build has one part holding everything, a multi-GPU build one part per rank (prf_team.cuh).
+//   long lists  (more than short_max member trees): members bucketed by COLUMN BLOCK (B = 1 << block_log2 consecutive
+//               tree ids); bucket (l, j) = lmem[boff[l * NB + j] .. boff[l * NB + j + 1]) holds `tree & (B - 1)` of the
+//               list's members inside block j in any order, padded with 0xffff to a multiple of 8 entries
+//   short lists expanded into per-tree "singles": for tree a the trees b > a it shares such a bipartition with
+struct ListPart {
+  const uint32_t* roff;     // [T + 1] offsets into rlist
+  const uint32_t* rlist;    // per tree: ids of the long lists that contain it
+  const uint32_t* boff;     // [n_long * NB + 1]
+  const uint16_t* lmem;
+  const uint32_t* soff;     // [T + 1] offsets into singles
+  const uint32_t* singles;
+};
+
 // Device-resident state of a loaded hashRF problem (the incidence in the form the kernels use).
 struct HashRFState {
   bool loaded = false;
@@ -57,26 +74,27 @@ struct HashRFState {
   uint64_t nnz = 0, P = 0;
   bool uniform_nb = false;       // every tree has the same |B|
   uint32_t nb_uniform = 0;
-  DevBuf<uint16_t> nb;           // [T]   |B_t| (distinct bipartitions)
+  DevBuf<uint16_t> nb;           // [T]   |B_t| (distinct bipartitions; |D_t| when majority lists were flipped)
+  DevBuf<uint16_t> nb0;          // [T]   |B_t| before the flip (only when n_flipped > 0: the dense variant's operand is unflipped)
   DevBuf<uint16_t> nb_shift;     // 8 copies of nb shifted by 0..7 entries (only when |B_t| is not uniform): any run
                                  // nb[c..] is then a 16-byte aligned bulk copy away from a 16-byte aligned tile
   uint32_t nb_shift_stride = 0;
-  DevBuf<uint32_t> roff;         // [T+1] per-tree offsets into `ranges`
-  DevBuf<uint2> ranges;          // member-list suffixes (begin, end) into `members`, tree-major
-  DevBuf<uint32_t> nheavy;       // [T] how many of a tree's ranges (its first ones) belong to heavy lists
-  DevBuf<uint32_t> members;      // inverted lists of the shared bipartitions, ascending tree ids
-  DevBuf<uint32_t> lmembers;     // the lists the sparse kernel walks (more than short_max members), each padded with
-                                 // 0xffffffff to a multiple of 4 members; `ranges` index this array
-  uint64_t n_lmembers = 0;
-  DevBuf<uint32_t> soff;         // [T+1] per-tree offsets into `singles`
-  DevBuf<uint32_t> singles;      // per tree a: the trees b > a sharing a short-list bipartition with a (with multiplicity)
-  // tree-major incidence over shared bipartition ids (dense variant input)
-  uint32_t n_shared = 0;
-  uint64_t n_shared_nnz = 0;
-  uint64_t n_ranges = 0;         // roff[T]
-  uint32_t max_ranges = 0;       // most suffix ranges of one tree
+  uint32_t block_log2 = 13, NB = 0;  // column block size of the bucketed lists, number of blocks = ceil(T / B)
+  uint32_t n_parts = 0;
+  ListPart part[kMaxParts];
+  uint32_t max_lists = 0;        // most long lists of one tree (summed over the parts)
+  // the buffers behind part[0] of a single-context build
+  DevBuf<uint32_t> roff, rlist, boff, soff, singles;
+  DevBuf<uint16_t> lmem;
+  uint32_t n_long = 0;           // long lists
+  uint64_t n_lmem = 0;           // entries of lmem (with padding)
+  // tree-major incidence over ALL shared bipartitions (dense variant input; single-context builds only)
+  DevBuf<uint32_t> ent_lid;      // [entry] dense id (0 .. n_shared-1) of the entry's list, 0xffffffff = bipartition of one tree only
+  DevBuf<uint64_t> ent_tb, ent_te;  // [T] entry range of every tree
+  uint32_t n_shared = 0;         // shared bipartitions (lists of >= 2 trees)
+  uint32_t n_list_ids = 0;       // list ids in use (a tree listing a bipartition twice can leave an id with one tree)
+  uint64_t n_shared_nnz = 0;     // their entries
   uint32_t n_flipped = 0;        // bipartitions held by > T/2 trees, stored as the list of trees lacking them
-  DevBuf<uint32_t> lid;          // [n_shared_nnz] dense id (0..n_shared-1) of the list each member entry belongs to
   // dense variant: tiled uint8 operand, built lazily by the first dense compute (prf_dense.cuh)
   bool dense_ready = false;
   uint32_t dense_Tpad = 0, dense_Kpad = 0;
@@ -144,12 +162,13 @@ struct Ctx {
   ExtractState ext;
   ConsensusState cons;
   RowPlan plan;
+  DevBuf<unsigned long long> scan_status;  // decoupled look-back scan: tile status words (prf_primitives.cuh)
+  DevBuf<uint32_t> scan_counter;
+  uint32_t scan_gen = 0;
   bool debug_small_tiles = false;
-  uint32_t short_max = 8;             // lists of at most this many members are expanded into per-row singles
-  uint32_t heavy_min = 0;             // tests: lists of at least this many members are "heavy" (0 = from T)
+  uint32_t short_max = 8;             // lists of at most this many trees are expanded into per-row singles
   int calib = 0;                      // PRF_CALIB builds: calibration mode of the rows kernel (wrong results)
   int rows_cfg = 0;                   // tests / tuning: instantiation of the rows kernel
-  int sparse_kernel = 0;              // 0 = rows kernel (round 2); 1 = round-1 CTA-per-row kernel (needs short_max == 0)
   bool debug_no_flip = false;         // tests: keep majority lists as they are
   bool debug_wide_slots = false;      // tests: force the 8-byte-slot dedup table
   DevBuf<unsigned long long> timing;  // PRF_TIMING builds only

@@ -70,15 +70,19 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
       : "memory");
 }
 
-// Scatter the shared incidence into the tiled operand (see layout above).  One thread per entry.
-__global__ void __launch_bounds__(256) dense_scatter_kernel(const uint32_t* __restrict__ members,
-                                                            const uint32_t* __restrict__ lid, uint32_t n,
+// Scatter the shared incidence into the tiled operand (see layout above).  One warp per tree over the build's
+// per-entry list ids (HashRFState::ent_lid).
+__global__ void __launch_bounds__(256) dense_scatter_kernel(const uint64_t* __restrict__ tb, const uint64_t* __restrict__ te,
+                                                            uint32_t T, const uint32_t* __restrict__ ent_lid,
                                                             uint32_t row_groups, uint8_t* __restrict__ At) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const uint32_t t = members[k], l = lid[k];
-  const size_t off = ((size_t)(l >> 7) * row_groups + (t >> 3)) * 1024 + ((l & 127u) >> 4) * 128 + (t & 7u) * 16 + (l & 15u);
-  At[off] = 1;
+  const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  for (uint64_t e = tb[t] + lane_id(); e < te[t]; e += 32) {
+    const uint32_t l = ent_lid[e];
+    if (l == 0xffffffffu) continue;
+    const size_t off = ((size_t)(l >> 7) * row_groups + (t >> 3)) * 1024 + ((l & 127u) >> 4) * 128 + (t & 7u) * 16 + (l & 15u);
+    At[off] = 1;
+  }
 }
 
 struct DenseParams {
@@ -311,7 +315,7 @@ static int dense_prepare(Ctx* ctx) {
   if (H.dense_ready) return PRF_OK;
   cudaStream_t s = ctx->stream;
   const uint32_t Tpad = (H.T + kDN - 1) / kDN * kDN;
-  const uint32_t Kpad = std::max<uint32_t>(kDK, (H.n_shared + kDK - 1) / kDK * kDK);
+  const uint32_t Kpad = std::max<uint32_t>(kDK, (H.n_list_ids + kDK - 1) / kDK * kDK);
   const size_t bytes = (size_t)Tpad * Kpad;
   size_t free_b = 0, total_b = 0;
   PRF_CK(ctx, cudaMemGetInfo(&free_b, &total_b));
@@ -320,9 +324,9 @@ static int dense_prepare(Ctx* ctx) {
                      Kpad);
   PRF_CK(ctx, H.dense_At.alloc(bytes, s));
   PRF_CK(ctx, cudaMemsetAsync(H.dense_At.p, 0, bytes, s));
-  if (H.n_shared_nnz) {
-    dense_scatter_kernel<<<(uint32_t)((H.n_shared_nnz + 255) / 256), 256, 0, s>>>(H.members.p, H.lid.p, (uint32_t)H.n_shared_nnz,
-                                                                                  Tpad / 8, H.dense_At.p);
+  if (!H.ent_lid.p) return ctx->fail(PRF_E_UNSUPPORTED, "the dense variant needs the incidence of a single-context build");
+  if (H.T && H.n_list_ids) {
+    dense_scatter_kernel<<<(H.T + 7) / 8, 256, 0, s>>>(H.ent_tb.p, H.ent_te.p, H.T, H.ent_lid.p, Tpad / 8, H.dense_At.p);
     PRF_LAUNCHED(ctx);
   }
   H.dense_Tpad = Tpad;
@@ -356,8 +360,9 @@ int launch_dense(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, u
   prm.T = H.T;
   prm.p_begin = p_begin;
   prm.p_end = p_end;
-  prm.nb = H.nb.p;
-  prm.uniform_nb = H.uniform_nb ? 1 : 0;
+  // the operand is the ORIGINAL incidence: with majority lists flipped for the sparse kernel, |B_t| before the flip
+  prm.nb = H.n_flipped ? H.nb0.p : H.nb.p;
+  prm.uniform_nb = H.n_flipped ? 0 : (H.uniform_nb ? 1 : 0);
   prm.nb_uniform = H.nb_uniform;
   prm.At = H.dense_At.p;
   prm.row_groups = H.dense_Tpad / 8;

@@ -3,10 +3,10 @@
 //       full-key verification (a 64-bit hash only routes; equality is always decided on the key).
 //       A bit per slot records "seen by a second entry": bipartitions present in one tree only
 //       (~3/4 of them on random topologies) can never be shared, they only count in |B_t|.
-//   K2  trees x unique-bipartitions incidence in the form the matrix kernels want: the entries of
-//       shared bipartitions, stably radix-sorted by table slot, are the inverted lists
-//       (bipartition -> ascending tree ids); per tree, the list suffixes "members after me" are
-//       what the sparse kernel walks.
+//   K2  trees x shared-bipartitions incidence in the form the matrix kernel wants (ListPart, prf_common.cuh),
+//       WITHOUT a sort: the rank of a shared slot in the "seen twice" bitmap is the dense list id; list sizes
+//       are counted with atomics; lists of more than short_max trees are counting-sorted into (list, column
+//       block) buckets (any order inside a bucket), the others expanded into per-tree singles.
 // The reference's Map DenseLabelSet (IntSet of tree ids) (:289-297) is exactly this inverted index.
 #pragma once
 
@@ -20,14 +20,15 @@ namespace prf {
 //   shared[s/32] bit s%32 = some entry other than the representative landed in s
 template <int W>
 __global__ void __launch_bounds__(256) dedup_insert_kernel(const uint64_t* __restrict__ bips,
-                                                           const uint64_t* __restrict__ tree_off,
+                                                           const uint64_t* __restrict__ tb,
+                                                           const uint64_t* __restrict__ te,
                                                            uint32_t T, unsigned long long* slots,
                                                            uint32_t* shared_bits, uint64_t cap_mask,
                                                            uint32_t* __restrict__ ent_slot,
                                                            unsigned long long* counters) {
   const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= T) return;
-  const uint64_t e0 = tree_off[t], e1 = tree_off[t + 1];
+  const uint64_t e0 = tb[t], e1 = te[t];
   uint32_t claims = 0;
   for (uint64_t e = e0 + lane_id(); e < e1; e += 32) {
     uint64_t k[W];
@@ -71,7 +72,8 @@ __global__ void __launch_bounds__(256) dedup_insert_kernel(const uint64_t* __res
 // loaded with an evict-first policy), so the random probes and CAS are L2 hits instead of DRAM sectors.
 template <int W>
 __global__ void __launch_bounds__(256) dedup_insert32_kernel(const uint64_t* __restrict__ bips,
-                                                             const uint64_t* __restrict__ tree_off, uint32_t T,
+                                                             const uint64_t* __restrict__ tb,
+                                                             const uint64_t* __restrict__ te, uint32_t T,
                                                              uint32_t* slots, uint32_t* shared_bits, uint32_t cap,
                                                              uint32_t* __restrict__ ent_slot,
                                                              unsigned long long* counters) {
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(256) dedup_insert32_kernel(const uint64_t* __r
   if (t >= T) return;
   uint64_t policy;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-  const uint64_t e0 = tree_off[t], e1 = tree_off[t + 1];
+  const uint64_t e0 = tb[t], e1 = te[t];
   uint32_t claims = 0;
   for (uint64_t e = e0 + lane_id(); e < e1; e += 32) {
     uint64_t k[W];
@@ -122,285 +124,328 @@ __global__ void __launch_bounds__(256) dedup_insert32_kernel(const uint64_t* __r
   if (lane_id() == 0 && claims) atomicAdd(&counters[0], (unsigned long long)claims);
 }
 
-// Per tree: number of entries whose bipartition is shared; also |B_t| before duplicate removal.
-__global__ void __launch_bounds__(256) count_shared_kernel(const uint64_t* __restrict__ tree_off, uint32_t T,
-                                                           const uint32_t* __restrict__ ent_slot,
-                                                           const uint32_t* __restrict__ shared_bits,
-                                                           uint32_t* __restrict__ sc, uint32_t* __restrict__ nb32) {
-  const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (t >= T) return;
-  const uint64_t e0 = tree_off[t], e1 = tree_off[t + 1];
-  uint32_t c = 0;
-  for (uint64_t e = e0 + lane_id(); e < e1; e += 32) {
-    const uint32_t s = ent_slot[e];
-    c += (shared_bits[s >> 5] >> (s & 31)) & 1u;
-  }
-#pragma unroll
-  for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-  if (lane_id() == 0) {
-    sc[t] = c;
-    nb32[t] = (uint32_t)(e1 - e0);
-  }
-}
-
 // Number of shared slots in one 32-slot word of the bitmap (scanned into per-word ranks).
 struct PopcWord {
   const uint32_t* bits;
   __device__ uint32_t operator()(uint64_t w) const { return __popc(bits[w]); }
 };
 
-// Writes the (list id, tree) pairs of the shared entries in tree order (stable warp compaction).  The
-// list id is the rank of the entry's slot among the shared slots (per-word rank + popcount below the
-// slot's bit): dense ids in slot order, so two 10-bit radix passes sort them and the sorted key array
-// IS the per-entry list id.
-__global__ void __launch_bounds__(256) gather_shared_kernel(const uint64_t* __restrict__ tree_off, uint32_t T,
-                                                            const uint32_t* __restrict__ ent_slot,
-                                                            const uint32_t* __restrict__ shared_bits,
-                                                            const uint32_t* __restrict__ wrank,
-                                                            const uint32_t* __restrict__ soff,
-                                                            uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-  const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (t >= T) return;
-  const uint64_t e0 = tree_off[t], e1 = tree_off[t + 1];
-  uint32_t pos = soff[t];
-  const uint32_t lt = lanemask_lt();
-  for (uint64_t eb = e0; eb < e1; eb += 32) {
-    const uint64_t e = eb + lane_id();
-    uint32_t id = 0;
-    bool sh = false;
-    if (e < e1) {
-      const uint32_t s = ent_slot[e];
-      const uint32_t word = shared_bits[s >> 5];
-      sh = (word >> (s & 31)) & 1u;
-      id = wrank[s >> 5] + __popc(word & ((1u << (s & 31)) - 1u));
-    }
-    const uint32_t m = __ballot_sync(0xffffffffu, sh);
-    if (sh) {
-      const uint32_t o = pos + __popc(m & lt);
-      keys[o] = id;
-      vals[o] = t;
-    }
-    pos += __popc(m);
-  }
-}
-
-// Sorted dense ids (every id 0..L-1 occurs): head_pos[l] = first position of list l, head_pos[L] = n.
-__global__ void __launch_bounds__(256) id_heads_kernel(const uint32_t* __restrict__ lid, uint32_t n, uint32_t n_lists,
-                                                       uint32_t* __restrict__ head_pos) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  if (k == 0 || lid[k] != lid[k - 1]) head_pos[lid[k]] = k;
-  if (k == n - 1) head_pos[n_lists] = n;
-}
-
-// Sorted (slot, tree) pairs: a list starts where the slot changes.
-struct HeadFlag {
-  const uint32_t* slot;
-  __device__ uint32_t operator()(uint64_t k) const { return k == 0 || slot[k] != slot[k - 1]; }
-};
-// A pair that repeats its predecessor is a bipartition listed twice by one tree.
-struct DupFlag {
-  const uint32_t* slot;
-  const uint32_t* tree;
-  __device__ uint32_t operator()(uint64_t k) const {
-    return k > 0 && slot[k] == slot[k - 1] && tree[k] == tree[k - 1];
-  }
-};
-
-// head_pos[l] = first sorted position of list l; head_pos[L] = n.  Also raises counters[2] when
-// a duplicate pair is seen.
-__global__ void __launch_bounds__(256) list_heads_kernel(const uint32_t* __restrict__ slot,
-                                                         const uint32_t* __restrict__ tree,
-                                                         const uint32_t* __restrict__ lid_ex, uint32_t n,
-                                                         uint32_t* __restrict__ head_pos,
-                                                         unsigned long long* counters, uint32_t* __restrict__ lid_out) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const bool head = k == 0 || slot[k] != slot[k - 1];
-  lid_out[k] = lid_ex[k] + (head ? 1 : 0) - 1;
-  if (head) head_pos[lid_ex[k]] = k;
-  if (k == n - 1) head_pos[lid_ex[k] + (head ? 1 : 0)] = n;
-}
-
-// Position k holds tree a = tree[k] inside list l = [head_pos[l], head_pos[l+1]).  Its suffix
-// (k+1, end) lists the trees b > a sharing that bipartition.  Pass 1 counts the non-empty suffixes
-// per tree (and accumulates sum m(m-1)/2 at list heads), pass 2 stores them.
-//
-// Lists of at most `short_max` members are not walked by the matrix kernel: their pairs are expanded into
-// per-row "singles" (tree a gets the column b of every later member), counted in scount / stored by the
-// fill pass.  Only the longer lists produce suffix ranges.
-__global__ void __launch_bounds__(256) range_count_kernel(const uint32_t* __restrict__ lid,
-                                                          const uint32_t* __restrict__ tree,
-                                                          const uint32_t* __restrict__ head_pos, uint32_t n,
-                                                          uint32_t short_max, uint32_t heavy_min, uint32_t* rcount,
-                                                          uint32_t* hcount, uint32_t* scount,
-                                                          unsigned long long* counters) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long hits = 0, longest = 0;
-  if (k < n) {
-    const uint32_t l = lid[k];
-    const uint32_t end = head_pos[l + 1];
-    if (k + 1 < end) {
-      const uint32_t m = end - head_pos[l];
-      if (m <= short_max) {
-        atomicAdd(&scount[tree[k]], end - k - 1);
-      } else {
-        atomicAdd(&rcount[tree[k]], 1u);
-        if (m >= heavy_min) atomicAdd(&hcount[tree[k]], 1u);
+// ---- K2a: entries -> list ids, per-list sizes -------------------------------------------------------------
+// One warp per tree.  ent[e]: in = table slot of entry e, out = dense list id (rank of the slot among the
+// shared slots) or 0xffffffff when the bipartition is held by this tree only.  A tree's entries are a SET
+// (S.Set DenseLabelSet): an exact per-warp hash set in shared memory drops a list id the tree already has.
+// lcnt[l] = trees holding list l; nb32[t] = |B_t| (distinct entries).
+__global__ void __launch_bounds__(256) list_count_kernel(const uint64_t* __restrict__ tb, const uint64_t* __restrict__ te,
+                                                         uint32_t T, uint32_t* __restrict__ ent,
+                                                         const uint32_t* __restrict__ shared_bits,
+                                                         const uint32_t* __restrict__ wrank, uint32_t set_slots,
+                                                         uint32_t* lcnt, uint32_t* __restrict__ nb32) {
+  extern __shared__ uint32_t s_sets[];
+  const uint32_t warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = lane_id();
+  uint32_t* set = s_sets + (size_t)warp * set_slots;
+  for (uint32_t t = blockIdx.x * warps + warp; t < T; t += gridDim.x * warps) {
+    const uint64_t e0 = tb[t], e1 = te[t];
+    for (uint32_t i = lane; i < set_slots; i += 32) set[i] = 0xffffffffu;
+    __syncwarp();
+    uint32_t dups = 0;
+    for (uint64_t eb = e0; eb < e1; eb += 32) {
+      const uint64_t e = eb + lane;
+      if (e < e1) {
+        const uint32_t s = ent[e];
+        const uint32_t word = shared_bits[s >> 5];
+        uint32_t l = 0xffffffffu;
+        if ((word >> (s & 31)) & 1u) {
+          l = wrank[s >> 5] + __popc(word & ((1u << (s & 31)) - 1u));
+          uint32_t h = (l * 0x9E3779B1u) & (set_slots - 1);
+          for (;;) {
+            const uint32_t old = atomicCAS(&set[h], 0xffffffffu, l);
+            if (old == 0xffffffffu) break;
+            if (old == l) {  // the tree listed this bipartition before
+              l = 0xffffffffu;
+              ++dups;
+              break;
+            }
+            h = (h + 1) & (set_slots - 1);
+          }
+          if (l != 0xffffffffu) atomicAdd(&lcnt[l], 1u);
+        }
+        ent[e] = l;
       }
     }
-    if (k > 0 && lid[k - 1] == l && tree[k - 1] == tree[k]) atomicAdd(&counters[2], 1ull);  // listed twice by one tree (rare)
-    if (k == head_pos[l]) {
-      const unsigned long long m = end - k;
-      hits = m * (m - 1) / 2;
-      longest = m;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) dups += __shfl_xor_sync(0xffffffffu, dups, d);
+    if (lane == 0) nb32[t] = (uint32_t)(e1 - e0) - dups;
+    __syncwarp();
+  }
+}
+
+// ---- K2b: per-list classification -------------------------------------------------------------------------
+struct ListCounts {  // device scalars written by the build (read back once)
+  unsigned long long n_hits;      // sum over lists m (m - 1) / 2
+  unsigned long long n_entries;   // sum over lists of >= 2 trees of m
+  unsigned long long short_pairs; // sum over short lists m (m - 1) / 2  (= number of singles)
+  unsigned long long long_members;  // sum over long lists m
+  uint32_t n_lists;               // shared slots (rank scan total)
+  uint32_t n_lists2;              // lists of >= 2 trees (a tree that lists a bipartition twice can leave a list of 1)
+  uint32_t n_long;
+  uint32_t short_members;         // sum over short lists of m
+  uint32_t longest;
+  uint32_t nb_min, nb_max, max_lists;
+  uint32_t n_unique_lo, n_unique_hi;
+  uint32_t n_lmem;                // padded size of lmem
+  uint32_t n_heavy;               // lists held by more than half of the trees
+};
+
+struct IsLong {
+  const uint32_t* lcnt;
+  const ListCounts* c;
+  uint32_t short_max;
+  __device__ uint32_t operator()(uint64_t l) const { return l < c->n_lists && lcnt[l] > short_max ? 1u : 0u; }
+};
+struct ShortLen {
+  const uint32_t* lcnt;
+  const ListCounts* c;
+  uint32_t short_max;
+  __device__ uint32_t operator()(uint64_t l) const {
+    if (l >= c->n_lists) return 0;
+    const uint32_t m = lcnt[l];
+    return m >= 2 && m <= short_max ? m : 0u;
+  }
+};
+// With `flip`, a list held by more than half of the trees counts with the T - m trees that LACK it (majority flip).
+__global__ void __launch_bounds__(256) list_stats_kernel(const uint32_t* __restrict__ lcnt, uint32_t short_max, uint32_t T,
+                                                         int flip, ListCounts* c) {
+  const uint32_t n = c->n_lists;
+  unsigned long long hits = 0, ent = 0, sp = 0, lm = 0;
+  uint32_t n2 = 0, longest = 0, heavy = 0;
+  for (uint32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < n; l += gridDim.x * blockDim.x) {
+    const unsigned long long m0 = lcnt[l];
+    if (m0 >= 2) {
+      const bool hv = 2 * m0 > T && m0 > short_max;  // (short lists stay singles whatever their share of the trees)
+      const unsigned long long m = hv && flip ? T - m0 : m0;
+      ++n2;
+      ent += m;
+      hits += m ? m * (m - 1) / 2 : 0;
+      if (m0 <= short_max) sp += m0 * (m0 - 1) / 2;
+      else lm += m;
+      longest = max(longest, (uint32_t)m0);
+      if (hv) ++heavy;
     }
   }
 #pragma unroll
   for (int d = 16; d; d >>= 1) {
     hits += __shfl_xor_sync(0xffffffffu, hits, d);
+    ent += __shfl_xor_sync(0xffffffffu, ent, d);
+    sp += __shfl_xor_sync(0xffffffffu, sp, d);
+    lm += __shfl_xor_sync(0xffffffffu, lm, d);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, d);
+    heavy += __shfl_xor_sync(0xffffffffu, heavy, d);
     longest = max(longest, __shfl_xor_sync(0xffffffffu, longest, d));
   }
-  // one pair of global atomics per block, not per warp: both targets are single hot addresses
-  __shared__ unsigned long long s_hits[8], s_long[8];
   if (lane_id() == 0) {
-    s_hits[threadIdx.x >> 5] = hits;
-    s_long[threadIdx.x >> 5] = longest;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) {
-      hits += s_hits[w];
-      longest = max(longest, s_long[w]);
-    }
-    if (hits) atomicAdd(&counters[3], hits);
-    if (longest) atomicMax(&counters[4], longest);
+    if (hits) atomicAdd(&c->n_hits, hits);
+    if (ent) atomicAdd(&c->n_entries, ent);
+    if (sp) atomicAdd(&c->short_pairs, sp);
+    if (lm) atomicAdd(&c->long_members, lm);
+    if (n2) atomicAdd(&c->n_lists2, n2);
+    if (heavy) atomicAdd(&c->n_heavy, heavy);
+    if (longest) atomicMax(&c->longest, longest);
   }
 }
-// Space of list l in the padded array of walked lists: 0 for short lists, else its length rounded up to 4.
-struct PadLen {
-  const uint32_t* head_pos;
-  const uint32_t* n_lists;  // device scalar
-  uint32_t short_max;
-  __device__ uint32_t operator()(uint64_t l) const {
-    if (l >= *n_lists) return 0;
-    const uint32_t m = head_pos[l + 1] - head_pos[l];
-    return m <= short_max ? 0u : (m + 3u) & ~3u;
-  }
-};
-__global__ void __launch_bounds__(256) range_fill_kernel(const uint32_t* __restrict__ lid,
-                                                         const uint32_t* __restrict__ tree,
-                                                         const uint32_t* __restrict__ head_pos, uint32_t n,
-                                                         uint32_t short_max, uint32_t heavy_min,
-                                                         const uint32_t* __restrict__ roff,
-                                                         const uint32_t* __restrict__ hcount, uint32_t* hcursor,
-                                                         uint32_t* cursor, uint2* __restrict__ ranges,
-                                                         const uint32_t* __restrict__ soff, uint32_t* scursor,
-                                                         uint32_t* __restrict__ singles,
-                                                         const uint32_t* __restrict__ phead,
-                                                         uint32_t* __restrict__ lmembers) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const uint32_t l = lid[k], end = head_pos[l + 1];
-  const uint32_t m = end - head_pos[l];
-  const uint32_t pk = phead[l] + (k - head_pos[l]), pend = phead[l] + m;  // my position / the list's end in lmembers
-  if (m > short_max) {
-    lmembers[pk] = tree[k];
-    if (k + 1 == end)
-      for (uint32_t j = pend; j < ((pend + 3u) & ~3u); ++j) lmembers[j] = 0xffffffffu;  // pad to a multiple of 4
-  }
-  if (k + 1 < end) {
-    const uint32_t a = tree[k];
-    if (m <= short_max) {
-      uint32_t o = soff[a] + atomicAdd(&scursor[a], end - k - 1);
-      for (uint32_t j = k + 1; j < end; ++j) singles[o++] = tree[j];
-    } else if (m >= heavy_min) {  // a tree's heavy lists first, its light lists behind them
-      ranges[roff[a] + atomicAdd(&hcursor[a], 1u)] = make_uint2(pk + 1, pend);
-    } else {
-      ranges[roff[a] + hcount[a] + atomicAdd(&cursor[a], 1u)] = make_uint2(pk + 1, pend);
+
+// ---- K2c: bucket sizes of the long lists, raw member arrays of the short lists ------------------------------
+// One warp per tree over ent (list ids).  bcnt[ll * NB + (t >> block_log2)] counts the members of long list ll
+// inside t's column block; a short list's members go to sraw[sbase[l] ..) in arrival order; rcnt[t] = long lists
+// of tree t.
+__global__ void __launch_bounds__(256) bucket_count_kernel(const uint64_t* __restrict__ tb, const uint64_t* __restrict__ te,
+                                                           uint32_t T, const uint32_t* __restrict__ ent,
+                                                           const uint32_t* __restrict__ lcnt, const uint32_t* __restrict__ llid,
+                                                           const uint32_t* __restrict__ sbase, uint32_t short_max,
+                                                           uint32_t block_log2, uint32_t NB, uint32_t* bcnt, uint32_t* sfill,
+                                                           uint32_t* __restrict__ sraw, uint32_t* __restrict__ rcnt,
+                                                           const uint32_t* __restrict__ fid, uint32_t* fbits, uint32_t fwords,
+                                                           uint32_t* __restrict__ hcnt) {
+  const uint32_t warps = blockDim.x >> 5, lane = lane_id();
+  for (uint32_t t = blockIdx.x * warps + (threadIdx.x >> 5); t < T; t += gridDim.x * warps) {
+    const uint64_t e0 = tb[t], e1 = te[t];
+    uint32_t nl = 0, nh = 0;
+    for (uint64_t e = e0 + lane; e < e1; e += 32) {
+      const uint32_t l = ent[e];
+      if (l == 0xffffffffu) continue;
+      const uint32_t m = lcnt[l];
+      if (fid && 2ull * m > T && m > short_max) {  // majority list: only its bitmap of holders is kept
+        ++nh;
+        atomicOr(&fbits[(size_t)fid[l] * fwords + (t >> 5)], 1u << (t & 31));
+      } else if (m > short_max) {
+        ++nl;
+        atomicAdd(&bcnt[(size_t)llid[l] * NB + (t >> block_log2)], 1u);
+      } else if (m >= 2) {
+        sraw[sbase[l] + atomicAdd(&sfill[l], 1u)] = t;
+      }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      nl += __shfl_xor_sync(0xffffffffu, nl, d);
+      nh += __shfl_xor_sync(0xffffffffu, nh, d);
+    }
+    if (lane == 0) {
+      rcnt[t] = nl;
+      if (hcnt) hcnt[t] = nh;
     }
   }
 }
 
-// ---- majority flip -----------------------------------------------------------------------------------
-// [u in B_a] xor [u in B_b] is unchanged when membership of bipartition u is complemented for EVERY
-// tree, so a list held by more than half of the trees can be replaced by the (shorter) list of trees
-// that lack it: d(a,b) = |D_a| + |D_b| - 2 |D_a n D_b| with D_t = B_t xor {majority bipartitions}.
-// Similar trees (few differences from a common backbone) become a sparse problem again.
-struct FlipLen {
-  const uint32_t* head_pos;
-  uint32_t T, n_lists;
+// ---- majority flip -------------------------------------------------------------------------------------------
+// [u in B_a] xor [u in B_b] is unchanged when membership of bipartition u is complemented for EVERY tree, so a
+// list held by more than half of the trees is replaced by the (shorter) list of trees that LACK it:
+// d(a,b) = |D_a| + |D_b| - 2 |D_a n D_b| with D_t = B_t xor {majority bipartitions}.  Similar trees (few
+// differences from a common backbone) become a sparse problem again.
+struct IsHeavy {
+  const uint32_t* lcnt;
+  const ListCounts* c;
+  uint32_t T, short_max;
   __device__ uint32_t operator()(uint64_t l) const {
-    if (l >= n_lists) return 0;
-    const uint32_t m = head_pos[l + 1] - head_pos[l];
-    return 2ull * m > T ? T - m : m;
+    return l < c->n_lists && lcnt[l] > short_max && 2ull * lcnt[l] > T ? 1u : 0u;
   }
 };
-// light lists are copied (one thread per entry); members of heavy lists are only counted per tree
-__global__ void __launch_bounds__(256) flip_copy_kernel(const uint32_t* __restrict__ lid,
-                                                        const uint32_t* __restrict__ tree,
-                                                        const uint32_t* __restrict__ head_pos,
-                                                        const uint32_t* __restrict__ head2, uint32_t n, uint32_t T,
-                                                        uint32_t* __restrict__ tree2, uint32_t* __restrict__ lid2,
-                                                        uint32_t* hcnt) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const uint32_t l = lid[k], h = head_pos[l], m = head_pos[l + 1] - h;
-  if (2ull * m > T) {
-    atomicAdd(&hcnt[tree[k]], 1u);
-  } else {
-    const uint32_t o = head2[l] + (k - h);
-    tree2[o] = tree[k];
-    lid2[o] = l;
-  }
+// fll[f] = long-list id of majority list f
+__global__ void __launch_bounds__(256) flip_ids_kernel(const uint32_t* __restrict__ lcnt, const uint32_t* __restrict__ llid,
+                                                       const uint32_t* __restrict__ fid, const ListCounts* c, uint32_t T,
+                                                       uint32_t short_max, uint32_t* __restrict__ fll) {
+  const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < c->n_lists && lcnt[l] > short_max && 2ull * lcnt[l] > T) fll[fid[l]] = llid[l];
 }
-// heavy lists: one thread per gap between consecutive members writes the trees of the gap
-__global__ void __launch_bounds__(256) flip_complement_kernel(const uint32_t* __restrict__ lid,
-                                                              const uint32_t* __restrict__ tree,
-                                                              const uint32_t* __restrict__ head_pos,
-                                                              const uint32_t* __restrict__ head2, uint32_t n, uint32_t T,
-                                                              uint32_t* __restrict__ tree2, uint32_t* __restrict__ lid2,
-                                                              unsigned long long* counters) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const uint32_t l = lid[k], h = head_pos[l], e = head_pos[l + 1], m = e - h;
-  if (2ull * m <= T) return;
-  if (k == h) atomicAdd(&counters[5], 1ull);  // number of heavy lists
-  const uint32_t i = k - h;                   // members before me in the list
-  const uint32_t base = head2[l];
-  // gap before member i: trees (previous member, this member)
-  const uint32_t lo = i ? tree[k - 1] + 1 : 0u, hi = tree[k];
-  for (uint32_t t = lo; t < hi; ++t) {
-    tree2[base + t - i] = t;
-    lid2[base + t - i] = l;
-  }
-  if (k + 1 == e)  // gap after the last member
-    for (uint32_t t = tree[k] + 1; t < T; ++t) {
-      tree2[base + t - (i + 1)] = t;
-      lid2[base + t - (i + 1)] = l;
+// One warp per (majority list f, column block j): pass 0 counts the trees of the block lacking the bipartition
+// into bcnt, pass 1 writes their column offsets into the bucket.
+__global__ void __launch_bounds__(256) flip_buckets_kernel(const uint32_t* __restrict__ fbits, uint32_t fwords,
+                                                           const uint32_t* __restrict__ fll, uint32_t n_heavy, uint32_t T,
+                                                           uint32_t block_log2, uint32_t NB, int pass, uint32_t* bcnt,
+                                                           const uint32_t* __restrict__ boff, uint16_t* __restrict__ lmem) {
+  const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = lane_id();
+  if (w >= n_heavy * NB) return;
+  const uint32_t f = w / NB, j = w - f * NB;
+  const uint32_t t0 = j << block_log2, t1 = min(T, t0 + (1u << block_log2));
+  const uint32_t* bits = fbits + (size_t)f * fwords;
+  const size_t b = (size_t)fll[f] * NB + j;
+  uint32_t run = 0;
+  for (uint32_t wb = t0 >> 5; wb < (t1 + 31) >> 5; wb += 32) {
+    const uint32_t wi = wb + lane;
+    uint32_t z = 0;  // trees of word wi lacking the bipartition
+    if (wi < (t1 + 31) >> 5) {
+      z = ~bits[wi];
+      const uint32_t lo = wi << 5;
+      if (lo + 32 > t1) z &= (1u << (t1 - lo)) - 1u;
     }
+    const uint32_t n = __popc(z);
+    uint32_t inc = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= (uint32_t)d) inc += x;
+    }
+    if (pass == 1) {
+      uint32_t o = boff[b] + run + inc - n;
+      while (z) {
+        const uint32_t bit = __ffs(z) - 1;
+        z &= z - 1;
+        lmem[o++] = (uint16_t)(((wi << 5) + bit) & ((1u << block_log2) - 1u));
+      }
+    }
+    run += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  if (pass == 0 && lane == 0) bcnt[b] = run;
 }
-__global__ void __launch_bounds__(256) flip_nb_kernel(uint32_t* nb32, const uint32_t* __restrict__ hcnt, uint32_t T,
-                                                      const unsigned long long* counters) {
+__global__ void __launch_bounds__(256) nb16_kernel(const uint32_t* __restrict__ nb32, uint32_t T, uint16_t* __restrict__ nb16) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < T) nb32[t] = nb32[t] + (uint32_t)counters[5] - 2u * hcnt[t];
+  if (t < T) nb16[t] = (uint16_t)min(nb32[t], 0xffffu);
+}
+// |D_t| and the number of lists of tree t with the majority lists flipped
+__global__ void __launch_bounds__(256) flip_trees_kernel(uint32_t* nb32, uint32_t* rcnt, const uint32_t* __restrict__ hcnt,
+                                                         uint32_t T, uint32_t n_heavy) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  nb32[t] = nb32[t] + n_heavy - 2u * hcnt[t];
+  rcnt[t] += n_heavy - hcnt[t];
+}
+// One warp per tree: the majority lists it LACKS go behind its ordinary long lists in rlist.
+__global__ void __launch_bounds__(256) flip_rlist_kernel(const uint32_t* __restrict__ fbits, uint32_t fwords,
+                                                         const uint32_t* __restrict__ fll, uint32_t n_heavy, uint32_t T,
+                                                         const uint32_t* __restrict__ roff, const uint32_t* __restrict__ hcnt,
+                                                         uint32_t* __restrict__ rlist) {
+  const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = lane_id(), lt = lanemask_lt();
+  if (t >= T) return;
+  uint32_t pos = roff[t + 1] - (n_heavy - hcnt[t]);
+  for (uint32_t fb = 0; fb < n_heavy; fb += 32) {
+    const uint32_t f = fb + lane;
+    const bool lacks = f < n_heavy && !((fbits[(size_t)f * fwords + (t >> 5)] >> (t & 31)) & 1u);
+    const uint32_t bal = __ballot_sync(0xffffffffu, lacks);
+    if (lacks) rlist[pos + __popc(bal & lt)] = fll[f];
+    pos += __popc(bal);
+  }
 }
 
-// Slow path (a caller listed a bipartition twice in one tree): drop the repeats.
-__global__ void __launch_bounds__(256) drop_dups_kernel(const uint32_t* __restrict__ slot,
-                                                        const uint32_t* __restrict__ tree,
-                                                        const uint32_t* __restrict__ dup_before, uint32_t n,
-                                                        uint32_t* __restrict__ slot_out,
-                                                        uint32_t* __restrict__ tree_out, uint32_t* nb32) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const bool dup = k > 0 && slot[k] == slot[k - 1] && tree[k] == tree[k - 1];
-  if (dup) {
-    atomicSub(&nb32[tree[k]], 1u);
-  } else {
-    const uint32_t o = k - dup_before[k];
-    slot_out[o] = slot[k];
-    tree_out[o] = tree[k];
+struct Pad8 {  // bucket sizes rounded up to the 16-byte groups the matrix kernel loads
+  const uint32_t* bcnt;
+  uint64_t n;
+  __device__ uint32_t operator()(uint64_t i) const { return i < n ? (bcnt[i] + 7u) & ~7u : 0u; }
+};
+
+// ---- K2d: fill the buckets and the trees' list arrays ------------------------------------------------------
+// bcnt doubles as the fill cursor (counted down); lmem was preset to 0xffff (the padding value).
+__global__ void __launch_bounds__(256) bucket_fill_kernel(const uint64_t* __restrict__ tb, const uint64_t* __restrict__ te,
+                                                          uint32_t T, const uint32_t* __restrict__ ent,
+                                                          const uint32_t* __restrict__ lcnt, const uint32_t* __restrict__ llid,
+                                                          uint32_t short_max, uint32_t block_log2, uint32_t NB, uint32_t* bcnt,
+                                                          const uint32_t* __restrict__ boff, uint16_t* __restrict__ lmem,
+                                                          const uint32_t* __restrict__ roff, uint32_t* __restrict__ rlist,
+                                                          int flip) {
+  const uint32_t warps = blockDim.x >> 5, lane = lane_id(), lt = lanemask_lt();
+  for (uint32_t t = blockIdx.x * warps + (threadIdx.x >> 5); t < T; t += gridDim.x * warps) {
+    const uint64_t e0 = tb[t], e1 = te[t];
+    uint32_t pos = roff[t];
+    for (uint64_t eb = e0; eb < e1; eb += 32) {
+      const uint64_t e = eb + lane;
+      uint32_t ll = 0xffffffffu;
+      if (e < e1) {
+        const uint32_t l = ent[e];
+        if (l != 0xffffffffu && lcnt[l] > short_max && !(flip && 2ull * lcnt[l] > T)) ll = llid[l];
+      }
+      const bool is = ll != 0xffffffffu;
+      const uint32_t bal = __ballot_sync(0xffffffffu, is);
+      if (is) {
+        const size_t b = (size_t)ll * NB + (t >> block_log2);
+        lmem[boff[b] + (atomicSub(&bcnt[b], 1u) - 1u)] = (uint16_t)(t & ((1u << block_log2) - 1u));
+        rlist[pos + __popc(bal & lt)] = ll;
+      }
+      pos += __popc(bal);
+    }
+  }
+}
+
+// ---- K2e: singles ------------------------------------------------------------------------------------------
+// One thread per short list: tree a gets the column b of every member b > a.  Pass 0 counts per tree, pass 1 fills.
+__global__ void __launch_bounds__(256) singles_kernel(const uint32_t* __restrict__ lcnt, const uint32_t* __restrict__ sbase,
+                                                      const uint32_t* __restrict__ sraw, uint32_t short_max, const ListCounts* c,
+                                                      int pass, uint32_t* scount, const uint32_t* __restrict__ soff,
+                                                      uint32_t* scur, uint32_t* __restrict__ singles) {
+  const uint32_t n = c->n_lists;
+  for (uint32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < n; l += gridDim.x * blockDim.x) {
+    const uint32_t m = lcnt[l];
+    if (m < 2 || m > short_max) continue;
+    const uint32_t* mem = sraw + sbase[l];
+    for (uint32_t i = 0; i < m; ++i) {
+      const uint32_t a = mem[i];
+      uint32_t k = 0;
+      for (uint32_t j = 0; j < m; ++j) k += mem[j] > a ? 1u : 0u;
+      if (!k) continue;
+      if (pass == 0) {
+        atomicAdd(&scount[a], k);
+      } else {
+        uint32_t o = soff[a] + atomicAdd(&scur[a], k);
+        for (uint32_t j = 0; j < m; ++j)
+          if (mem[j] > a) singles[o++] = mem[j];
+      }
+    }
   }
 }
 
@@ -413,16 +458,33 @@ __global__ void __launch_bounds__(256) nb_shift_kernel(const uint16_t* __restric
   out[i] = j + k < T ? nb[j + k] : (uint16_t)0;
 }
 
-template <int W>
-static void launch_dedup(Ctx* ctx, const uint64_t* bips, const uint64_t* off, uint32_t T,
-                         unsigned long long* slots, uint32_t* shared_bits, uint64_t cap_mask,
-                         uint32_t* ent_slot, unsigned long long* counters) {
-  dedup_insert_kernel<W><<<(T + 7) / 8, 256, 0, ctx->stream>>>(bips, off, T, slots, shared_bits, cap_mask,
-                                                                ent_slot, counters);
+// nb32 -> uint16, min / max |B_t| and the most long lists of one tree
+__global__ void __launch_bounds__(256) finish_trees_kernel(const uint32_t* __restrict__ nb32, const uint32_t* __restrict__ rcnt,
+                                                           uint32_t T, uint16_t* __restrict__ nb16, ListCounts* c) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t v = t < T ? nb32[t] : 0, lo = t < T ? v : 0xffffffffu, hi = v, ml = t < T ? rcnt[t] : 0;
+  if (t < T) nb16[t] = (uint16_t)(v > 0xffffu ? 0xffffu : v);
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    ml = max(ml, __shfl_xor_sync(0xffffffffu, ml, d));
+  }
+  if (lane_id() == 0) {
+    atomicMin(&c->nb_min, lo);
+    atomicMax(&c->nb_max, hi);
+    atomicMax(&c->max_lists, ml);
+  }
 }
 
+template <int W>
+static void launch_dedup(Ctx* ctx, const uint64_t* bips, const uint64_t* tb, const uint64_t* te, uint32_t T,
+                         unsigned long long* slots, uint32_t* shared_bits, uint64_t cap_mask, uint32_t* ent_slot,
+                         unsigned long long* counters) {
+  dedup_insert_kernel<W><<<(T + 7) / 8, 256, 0, ctx->stream>>>(bips, tb, te, T, slots, shared_bits, cap_mask, ent_slot, counters);
+}
 
-// The shifted copies of |B_t| the sparse kernel's producer bulk-loads (non-uniform |B_t| only).
+// The shifted copies of |B_t| the sparse kernel's fill bulk-loads (non-uniform |B_t| only).
 int build_nb_shift(Ctx* ctx) {
   HashRFState& H = ctx->h;
   if (H.uniform_nb || H.T == 0) return PRF_OK;
@@ -434,9 +496,10 @@ int build_nb_shift(Ctx* ctx) {
   return PRF_OK;
 }
 
-// d_bips: nnz*W words, d_off: T+1 offsets, both already on the device.
-int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off, uint32_t T, uint32_t W,
-                        uint64_t nnz) {
+// d_bips: keys (W words per entry); tree t's entries are [tb[t], te[t]) (device arrays); `span` = one past the
+// largest entry index; max_entries = most entries of one tree.
+int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* tb, const uint64_t* te, uint32_t T, uint32_t W,
+                 uint64_t span, uint64_t nnz, uint32_t max_entries) {
   cudaStream_t s = ctx->stream;
   HashRFState& H = ctx->h;
   H = HashRFState{};
@@ -444,36 +507,55 @@ int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off, uint32
   H.W = W;
   H.nnz = nnz;
   H.P = (uint64_t)T * (T ? T - 1 : 0) / 2;
+  H.block_log2 = ctx->debug_small_tiles ? 8 : 13;
+  const uint32_t NB = T ? ((T - 1) >> H.block_log2) + 1 : 1;
+  H.NB = NB;
+  const uint32_t short_max = ctx->short_max;
+  if (max_entries > 4096)
+    return ctx->fail(PRF_E_UNSUPPORTED, "a tree lists %u bipartition entries; supported <= 4096", max_entries);
 
   // compact 4-byte slots whenever the entry index fits 25 bits (see dedup_insert32_kernel)
-  const bool compact = nnz < (1ull << 25) - 1 && !ctx->debug_wide_slots;
+  const bool compact = span < (1ull << 25) - 1 && !ctx->debug_wide_slots;
   uint64_t cap = 1024;
-  if (compact) {
-    static const double factor = [] { const char* e = getenv("PRF_DEDUP_FACTOR"); return e ? atof(e) : 1.25; }();
-    cap = std::max<uint64_t>(1024, ((uint64_t)(nnz * factor) + 31) / 32 * 32);  // load factor <= 0.8, multiple of the bitmap word
-  } else {
-    while (cap < nnz + nnz / 2) cap <<= 1;  // load factor <= 2/3 even if every key is distinct
-  }
+  if (compact) cap = std::max<uint64_t>(1024, ((uint64_t)(nnz * 1.25) + 31) / 32 * 32);  // load factor <= 0.8, multiple of the bitmap word
+  else while (cap < nnz + nnz / 2) cap <<= 1;  // load factor <= 2/3 even if every key is distinct
+  if (!compact && cap > (1ull << 32)) return ctx->fail(PRF_E_UNSUPPORTED, "nnz=%llu entries: the dedup table would exceed 2^32 slots", (unsigned long long)nnz);
 
   DevBuf<unsigned long long> slots, counters;
-  DevBuf<uint32_t> slots32;
-  DevBuf<uint32_t> shared_bits, ent_slot, nb32, sc, soff, scalars;
+  DevBuf<uint32_t> slots32, shared_bits, wrank, nb32, rcnt, lcnt, llid, sbase, sfill;
+  DevBuf<ListCounts> cnts;
+  const size_t Lmax = (size_t)(nnz / 2) + 2;  // a shared slot holds at least two entries
   if (compact) PRF_CK(ctx, slots32.alloc(cap, s));
   else PRF_CK(ctx, slots.alloc(cap, s));
   PRF_CK(ctx, shared_bits.alloc(cap / 32, s));
-  PRF_CK(ctx, ent_slot.alloc(nnz, s));
+  PRF_CK(ctx, wrank.alloc(cap / 32, s));
+  PRF_CK(ctx, H.ent_lid.alloc(std::max<uint64_t>(span, 1), s));
+  PRF_CK(ctx, H.ent_tb.alloc(std::max<uint32_t>(T, 1), s));
+  PRF_CK(ctx, H.ent_te.alloc(std::max<uint32_t>(T, 1), s));
   PRF_CK(ctx, nb32.alloc((size_t)T + 1, s));
-  PRF_CK(ctx, sc.alloc((size_t)T + 1, s));
-  PRF_CK(ctx, soff.alloc((size_t)T + 1, s));
-  PRF_CK(ctx, counters.alloc(6, s));
-  PRF_CK(ctx, scalars.alloc(8, s));
+  PRF_CK(ctx, rcnt.alloc((size_t)T + 1, s));
+  PRF_CK(ctx, lcnt.alloc(Lmax, s));
+  PRF_CK(ctx, llid.alloc(Lmax, s));
+  PRF_CK(ctx, sbase.alloc(Lmax, s));
+  PRF_CK(ctx, sfill.alloc(Lmax, s));
+  PRF_CK(ctx, counters.alloc(2, s));
+  PRF_CK(ctx, cnts.alloc(1, s));
   PRF_CK(ctx, cudaMemsetAsync(shared_bits.p, 0, shared_bits.bytes(), s));
   PRF_CK(ctx, cudaMemsetAsync(counters.p, 0, counters.bytes(), s));
-  PRF_CK(ctx, cudaMemsetAsync(sc.p, 0, sc.bytes(), s));
+  PRF_CK(ctx, cudaMemsetAsync(lcnt.p, 0, lcnt.bytes(), s));
+  PRF_CK(ctx, cudaMemsetAsync(sfill.p, 0, sfill.bytes(), s));
+  PRF_CK(ctx, cudaMemsetAsync(rcnt.p, 0, rcnt.bytes(), s));
   if (compact) PRF_CK(ctx, cudaMemsetAsync(slots32.p, 0, slots32.bytes(), s));
   else PRF_CK(ctx, cudaMemsetAsync(slots.p, 0xff, slots.bytes(), s));
-  uint32_t mm_init[8] = {0, 0, 0, 0, 0xffffffffu, 0u, 0, 0};
-  PRF_CK(ctx, cudaMemcpyAsync(scalars.p, mm_init, sizeof mm_init, cudaMemcpyHostToDevice, s));
+  ListCounts c0{};
+  c0.nb_min = 0xffffffffu;
+  PRF_CK(ctx, cudaMemcpyAsync(cnts.p, &c0, sizeof c0, cudaMemcpyHostToDevice, s));
+  if (T) {
+    PRF_CK(ctx, cudaMemcpyAsync(H.ent_tb.p, tb, (size_t)T * 8, cudaMemcpyDeviceToDevice, s));
+    PRF_CK(ctx, cudaMemcpyAsync(H.ent_te.p, te, (size_t)T * 8, cudaMemcpyDeviceToDevice, s));
+  }
+  tb = H.ent_tb.p;  // the caller's arrays may go away after the load; the dense variant reads ent_lid later
+  te = H.ent_te.p;
 
   trace_mark("build: temporaries allocated");
   PRF_CK(ctx, cudaEventRecord(ctx->ev[1], s));
@@ -483,10 +565,10 @@ int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off, uint32
 #define PRF_W_CASE(w)                                                                                                  \
   case w:                                                                                                              \
     if (compact)                                                                                                       \
-      dedup_insert32_kernel<w><<<(T + 7) / 8, 256, 0, s>>>(d_bips, d_off, T, slots32.p, shared_bits.p, (uint32_t)cap,   \
-                                                           ent_slot.p, counters.p);                                    \
+      dedup_insert32_kernel<w><<<(T + 7) / 8, 256, 0, s>>>(d_bips, tb, te, T, slots32.p, shared_bits.p, (uint32_t)cap,  \
+                                                           H.ent_lid.p, counters.p);                                   \
     else                                                                                                               \
-      launch_dedup<w>(ctx, d_bips, d_off, T, slots.p, shared_bits.p, cap - 1, ent_slot.p, counters.p);                 \
+      launch_dedup<w>(ctx, d_bips, tb, te, T, slots.p, shared_bits.p, cap - 1, H.ent_lid.p, counters.p);               \
     break;
       PRF_W_CASE(1) PRF_W_CASE(2) PRF_W_CASE(3) PRF_W_CASE(4) PRF_W_CASE(5) PRF_W_CASE(6) PRF_W_CASE(7)
       PRF_W_CASE(8) PRF_W_CASE(9) PRF_W_CASE(10) PRF_W_CASE(11) PRF_W_CASE(12) PRF_W_CASE(13)
@@ -498,218 +580,140 @@ int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off, uint32
   }
   PRF_CK(ctx, cudaEventRecord(ctx->ev[2], s));
 
-  // ---- K2: incidence ----
+  // ---- K2: lists ----
   int rc;
-  uint32_t n_sh_nnz = 0;
+  const int grid_t = std::max(1, std::min<int>((int)((T + 7) / 8), ctx->sm_count * 8));
+  if ((rc = exclusive_scan(ctx, PopcWord{shared_bits.p}, cap / 32, wrank.p, &cnts.p->n_lists))) return rc;
+  uint32_t set_slots = 64;
+  while (set_slots < 2 * max_entries) set_slots <<= 1;
   if (T) {
-    count_shared_kernel<<<(T + 7) / 8, 256, 0, s>>>(d_off, T, ent_slot.p, shared_bits.p, sc.p, nb32.p);
+    const int warps = (int)std::min<uint32_t>(8, (48 * 1024) / (set_slots * 4));
+    list_count_kernel<<<std::max(1, std::min<int>((int)((T + warps - 1) / warps), ctx->sm_count * 8)), 32 * warps,
+                        (size_t)warps * set_slots * 4, s>>>(tb, te, T, H.ent_lid.p, shared_bits.p, wrank.p, set_slots, lcnt.p, nb32.p);
     PRF_LAUNCHED(ctx);
   }
-  if ((rc = exclusive_scan(ctx, LoadU32{sc.p}, (uint64_t)T + 1, soff.p, scalars.p + 0))) return rc;
-  // rank of every shared slot = dense list id (in slot order); scalars[1] = number of lists
-  DevBuf<uint32_t> wrank;
-  PRF_CK(ctx, wrank.alloc(cap / 32, s));
-  if ((rc = exclusive_scan(ctx, PopcWord{shared_bits.p}, cap / 32, wrank.p, scalars.p + 1))) return rc;
-  uint32_t h01[2] = {0, 0};
-  PRF_CK(ctx, cudaMemcpyAsync(h01, scalars.p + 0, 8, cudaMemcpyDeviceToHost, s));
-  PRF_CK(ctx, cudaStreamSynchronize(s));
-  trace_mark("build: dedup + count synced");
-  n_sh_nnz = h01[0];
-  const uint32_t n_lists0 = h01[1];
-  H.n_shared_nnz = n_sh_nnz;
+  if ((rc = exclusive_scan(ctx, IsLong{lcnt.p, cnts.p, short_max}, Lmax, llid.p, &cnts.p->n_long))) return rc;
+  if ((rc = exclusive_scan(ctx, ShortLen{lcnt.p, cnts.p, short_max}, Lmax, sbase.p, &cnts.p->short_members))) return rc;
+  const int flip_ok = ctx->debug_no_flip ? 0 : 1;
+  list_stats_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(lcnt.p, short_max, T, flip_ok, cnts.p);
+  PRF_LAUNCHED(ctx);
+  ListCounts hc{};
+  unsigned long long hcount[2] = {0, 0};
+  PRF_CK(ctx, cudaMemcpyAsync(&hc, cnts.p, sizeof hc, cudaMemcpyDeviceToHost, s));
+  PRF_CK(ctx, cudaMemcpyAsync(hcount, counters.p, sizeof hcount, cudaMemcpyDeviceToHost, s));
+  PRF_CK(ctx, cudaStreamSynchronize(s));  // the one read-back inside the build: sizes of what follows
+  trace_mark("build: lists counted");
+  if (hc.long_members >= 0xfffffff0ull || hc.short_pairs >= 0xfffffff0ull || (uint64_t)hc.n_long * NB >= 0xfffffff0ull)
+    return ctx->fail(PRF_E_UNSUPPORTED, "shared-bipartition structure does not fit 32-bit offsets");
 
-  DevBuf<uint32_t> slot_sorted, lid_ex, head_pos, rcount, cursor, scount, scursor, hcursor;
-  const uint32_t short_max = ctx->short_max;
-  // lists expected to put more than ~48 members into a tile of the rows kernel are walked by the whole warp
-  const uint32_t heavy_min = ctx->sparse_kernel == 1 ? 0u
-                             : ctx->heavy_min ? ctx->heavy_min
-                                              : std::max<uint32_t>(short_max + 1, (uint32_t)(48ull * T / 7680) + 1);
-  PRF_CK(ctx, hcursor.alloc((size_t)T + 1, s));
-  DevBuf<uint32_t> phead;
-  PRF_CK(ctx, H.nheavy.alloc((size_t)T + 1, s));
+  // majority flip (only when some list is held by more than half of the trees): bitmaps of the holders
+  const uint32_t n_heavy = flip_ok && T ? hc.n_heavy : 0;
+  const uint32_t fwords = (T + 31) / 32;
+  DevBuf<uint32_t> fid, fll, fbits, hcnt;
+  if (n_heavy) {
+    PRF_CK(ctx, fid.alloc(Lmax, s));
+    PRF_CK(ctx, fll.alloc(n_heavy, s));
+    PRF_CK(ctx, fbits.alloc((size_t)n_heavy * fwords, s));
+    PRF_CK(ctx, hcnt.alloc((size_t)T + 1, s));
+    PRF_CK(ctx, cudaMemsetAsync(fbits.p, 0, fbits.bytes(), s));
+    if ((rc = exclusive_scan(ctx, IsHeavy{lcnt.p, cnts.p, T, short_max}, Lmax, fid.p, nullptr))) return rc;
+    flip_ids_kernel<<<grid_for(hc.n_lists), 256, 0, s>>>(lcnt.p, llid.p, fid.p, cnts.p, T, short_max, fll.p);
+    PRF_LAUNCHED(ctx);
+  }
+  H.n_flipped = n_heavy;
+  const uint64_t n_buckets = (uint64_t)hc.n_long * NB;
+  const uint64_t lmem_cap = hc.long_members + 7 * n_buckets + 8;
+  DevBuf<uint32_t> bcnt, sraw, scount, scur;
+  PRF_CK(ctx, bcnt.alloc(n_buckets + 1, s));
+  PRF_CK(ctx, sraw.alloc((size_t)hc.short_members + 1, s));
   PRF_CK(ctx, scount.alloc((size_t)T + 1, s));
-  PRF_CK(ctx, scursor.alloc((size_t)T + 1, s));
-  PRF_CK(ctx, H.soff.alloc((size_t)T + 1, s));
-  // upper bound: an entry of a short list is followed by at most short_max - 1 later members
-  PRF_CK(ctx, H.singles.alloc((size_t)n_sh_nnz * (short_max > 1 ? (short_max - 1) / 2 + 1 : 0) + 1, s));
-  // walked lists padded to multiples of 4 members: at most twice the entries (four times when one-member lists are walked)
-  PRF_CK(ctx, phead.alloc((size_t)n_sh_nnz + 2, s));
-  PRF_CK(ctx, H.lmembers.alloc((size_t)n_sh_nnz * (short_max ? 2 : 4) + 8, s));
-  PRF_CK(ctx, slot_sorted.alloc(n_sh_nnz, s));
-  PRF_CK(ctx, H.members.alloc((size_t)n_sh_nnz + 4, s));  // +4: the rows kernel reads members in aligned groups of 4
-  PRF_CK(ctx, head_pos.alloc((size_t)n_sh_nnz + 1, s));
-  PRF_CK(ctx, rcount.alloc((size_t)T + 1, s));
-  PRF_CK(ctx, cursor.alloc((size_t)T + 1, s));
+  PRF_CK(ctx, scur.alloc((size_t)T + 1, s));
+  PRF_CK(ctx, H.boff.alloc(n_buckets + 1, s));
+  PRF_CK(ctx, H.lmem.alloc(lmem_cap, s));
   PRF_CK(ctx, H.roff.alloc((size_t)T + 1, s));
-  PRF_CK(ctx, H.ranges.alloc(n_sh_nnz, s));  // upper bound: at most one suffix per shared entry
+  PRF_CK(ctx, H.rlist.alloc(hc.long_members + 1, s));
+  PRF_CK(ctx, H.soff.alloc((size_t)T + 1, s));
+  PRF_CK(ctx, H.singles.alloc(hc.short_pairs + 1, s));
   PRF_CK(ctx, H.nb.alloc((size_t)T + 16, s));  // slack: the matrix kernel reads |B| in aligned 32-bit pairs
   PRF_CK(ctx, cudaMemsetAsync(H.nb.p, 0, H.nb.bytes(), s));
-  uint32_t n_sorted = n_sh_nnz;
-  if (n_sh_nnz) {
-    gather_shared_kernel<<<(T + 7) / 8, 256, 0, s>>>(d_off, T, ent_slot.p, shared_bits.p, wrank.p, soff.p, slot_sorted.p,
-                                                     H.members.p);
+  PRF_CK(ctx, cudaMemsetAsync(bcnt.p, 0, bcnt.bytes(), s));
+  PRF_CK(ctx, cudaMemsetAsync(scount.p, 0, scount.bytes(), s));
+  PRF_CK(ctx, cudaMemsetAsync(scur.p, 0, scur.bytes(), s));
+  PRF_CK(ctx, cudaMemsetAsync(H.lmem.p, 0xff, H.lmem.bytes(), s));
+  if (T) {
+    bucket_count_kernel<<<grid_t, 256, 0, s>>>(tb, te, T, H.ent_lid.p, lcnt.p, llid.p, sbase.p, short_max, H.block_log2, NB,
+                                               bcnt.p, sfill.p, sraw.p, rcnt.p, fid.p, fbits.p, fwords, hcnt.p);
     PRF_LAUNCHED(ctx);
-    // stable sort by list id: inside a list the trees stay ascending
-    if ((rc = radix_sort_pairs(ctx, slot_sorted.p, H.members.p, n_sh_nnz, bits_for(n_lists0)))) return rc;
+    if (n_heavy) {
+      flip_buckets_kernel<<<(n_heavy * NB + 7) / 8, 256, 0, s>>>(fbits.p, fwords, fll.p, n_heavy, T, H.block_log2, NB, 0, bcnt.p,
+                                                                 nullptr, nullptr);
+      PRF_LAUNCHED(ctx);
+      PRF_CK(ctx, H.nb0.alloc((size_t)T + 16, s));
+      PRF_CK(ctx, cudaMemsetAsync(H.nb0.p, 0, H.nb0.bytes(), s));
+      nb16_kernel<<<grid_for(T), 256, 0, s>>>(nb32.p, T, H.nb0.p);
+      PRF_LAUNCHED(ctx);
+      flip_trees_kernel<<<grid_for(T), 256, 0, s>>>(nb32.p, rcnt.p, hcnt.p, T, n_heavy);
+      PRF_LAUNCHED(ctx);
+    }
   }
-  bool ids_are_keys = true;  // until duplicates force the generic path, the sorted keys are the list ids
-  unsigned long long hc[6] = {0, 0, 0, 0, 0, 0};
-  uint32_t hs[8] = {0};
-  uint32_t h_nranges = 0;
-  for (int pass = 0; pass < 2; ++pass) {
-    PRF_CK(ctx, cudaMemsetAsync(rcount.p, 0, rcount.bytes(), s));
-    PRF_CK(ctx, cudaMemsetAsync(cursor.p, 0, cursor.bytes(), s));
-    PRF_CK(ctx, cudaMemsetAsync(scount.p, 0, scount.bytes(), s));
-    PRF_CK(ctx, cudaMemsetAsync(scursor.p, 0, scursor.bytes(), s));
-    PRF_CK(ctx, cudaMemsetAsync(hcursor.p, 0, hcursor.bytes(), s));
-    PRF_CK(ctx, cudaMemsetAsync(H.nheavy.p, 0, H.nheavy.bytes(), s));
-    PRF_CK(ctx, cudaMemsetAsync(counters.p + 2, 0, 32, s));
-    const uint32_t* lid_p = slot_sorted.p;
-    if (n_sorted) {
-      if (ids_are_keys) {
-        id_heads_kernel<<<grid_for(n_sorted), 256, 0, s>>>(slot_sorted.p, n_sorted, n_lists0, head_pos.p);
-        PRF_LAUNCHED(ctx);
-      } else {
-        if (!lid_ex.p) PRF_CK(ctx, lid_ex.alloc(n_sh_nnz, s));
-        if (!H.lid.p) PRF_CK(ctx, H.lid.alloc(n_sh_nnz, s));
-        if ((rc = exclusive_scan(ctx, HeadFlag{slot_sorted.p}, n_sorted, lid_ex.p, scalars.p + 1))) return rc;
-        list_heads_kernel<<<grid_for(n_sorted), 256, 0, s>>>(slot_sorted.p, H.members.p, lid_ex.p, n_sorted,
-                                                             head_pos.p, counters.p, H.lid.p);
-        PRF_LAUNCHED(ctx);
-        lid_p = H.lid.p;
-      }
-      range_count_kernel<<<grid_for(n_sorted), 256, 0, s>>>(lid_p, H.members.p, head_pos.p, n_sorted, short_max, heavy_min, rcount.p,
-                                                            H.nheavy.p, scount.p, counters.p);
-      PRF_LAUNCHED(ctx);
-    }
-    if ((rc = exclusive_scan(ctx, LoadU32{rcount.p}, (uint64_t)T + 1, H.roff.p, nullptr))) return rc;
-    if ((rc = exclusive_scan(ctx, LoadU32{scount.p}, (uint64_t)T + 1, H.soff.p, nullptr))) return rc;
-    if (n_sorted) {
-      // scalars[1] = number of lists (ids_are_keys: written by the rank scan above; else by the head-flag scan)
-      const uint64_t n_scan = (ids_are_keys ? (uint64_t)n_lists0 : (uint64_t)n_sorted) + 1;
-      if ((rc = exclusive_scan(ctx, PadLen{head_pos.p, scalars.p + 1, short_max}, n_scan, phead.p, scalars.p + 7))) return rc;
-      range_fill_kernel<<<grid_for(n_sorted), 256, 0, s>>>(lid_p, H.members.p, head_pos.p, n_sorted, short_max, heavy_min, H.roff.p,
-                                                           H.nheavy.p, hcursor.p, cursor.p, H.ranges.p, H.soff.p, scursor.p,
-                                                           H.singles.p, phead.p, H.lmembers.p);
-      PRF_LAUNCHED(ctx);
-    }
-    if (T) {
-      finish_nb_kernel<<<grid_for(T), 256, 0, s>>>(nb32.p, T, H.nb.p, scalars.p + 4, H.roff.p);
-      PRF_LAUNCHED(ctx);
-    }
-    PRF_CK(ctx, cudaMemcpyAsync(hc, counters.p, sizeof hc, cudaMemcpyDeviceToHost, s));
-    PRF_CK(ctx, cudaMemcpyAsync(hs, scalars.p, sizeof hs, cudaMemcpyDeviceToHost, s));
-    PRF_CK(ctx, cudaMemcpyAsync(&h_nranges, H.roff.p + T, 4, cudaMemcpyDeviceToHost, s));
-    PRF_CK(ctx, cudaEventRecord(ctx->ev[3], s));
-    PRF_CK(ctx, cudaStreamSynchronize(s));
-    trace_mark("build: lists synced");
-    if (hc[2] == 0 || pass == 1) break;
-    // a tree listed some bipartition more than once: its bipartitions are a set -- drop the repeats
-    // from the sorted pairs, fix |B_t|, and rebuild the lists once more
-    DevBuf<uint32_t> dup_before, slot2, mem2;
-    PRF_CK(ctx, dup_before.alloc(n_sorted, s));
-    PRF_CK(ctx, slot2.alloc(n_sorted, s));
-    PRF_CK(ctx, mem2.alloc((size_t)n_sorted + 4, s));
-    if ((rc = exclusive_scan(ctx, DupFlag{slot_sorted.p, H.members.p}, n_sorted, dup_before.p, nullptr))) return rc;
-    drop_dups_kernel<<<grid_for(n_sorted), 256, 0, s>>>(slot_sorted.p, H.members.p, dup_before.p, n_sorted,
-                                                        slot2.p, mem2.p, nb32.p);
+  if ((rc = exclusive_scan(ctx, Pad8{bcnt.p, n_buckets}, n_buckets + 1, H.boff.p, &cnts.p->n_lmem))) return rc;
+  if ((rc = exclusive_scan(ctx, LoadU32{rcnt.p}, (uint64_t)T + 1, H.roff.p, nullptr))) return rc;
+  if (T) {
+    bucket_fill_kernel<<<grid_t, 256, 0, s>>>(tb, te, T, H.ent_lid.p, lcnt.p, llid.p, short_max, H.block_log2, NB, bcnt.p,
+                                              H.boff.p, H.lmem.p, H.roff.p, H.rlist.p, n_heavy ? 1 : 0);
     PRF_LAUNCHED(ctx);
-    slot_sorted = std::move(slot2);
-    H.members = std::move(mem2);
-    ids_are_keys = false;
-    n_sorted -= (uint32_t)hc[2];
-    uint32_t mm_reset[3] = {0xffffffffu, 0u, 0u};
-    PRF_CK(ctx, cudaMemcpyAsync(scalars.p + 4, mm_reset, 12, cudaMemcpyHostToDevice, s));
+    if (n_heavy) {
+      flip_buckets_kernel<<<(n_heavy * NB + 7) / 8, 256, 0, s>>>(fbits.p, fwords, fll.p, n_heavy, T, H.block_log2, NB, 1, bcnt.p,
+                                                                 H.boff.p, H.lmem.p);
+      PRF_LAUNCHED(ctx);
+      flip_rlist_kernel<<<(T + 7) / 8, 256, 0, s>>>(fbits.p, fwords, fll.p, n_heavy, T, H.roff.p, hcnt.p, H.rlist.p);
+      PRF_LAUNCHED(ctx);
+    }
+    if (hc.short_members) {
+      singles_kernel<<<ctx->sm_count * 4, 256, 0, s>>>(lcnt.p, sbase.p, sraw.p, short_max, cnts.p, 0, scount.p, nullptr, nullptr, nullptr);
+      PRF_LAUNCHED(ctx);
+    }
   }
-  if (ids_are_keys) H.lid = std::move(slot_sorted);
-  // ---- majority flip (only when some bipartition is held by more than half of the trees) ----
-  uint32_t n_lists = n_sorted ? hs[1] : 0;
-  if (n_sorted && 2ull * hc[4] > T && !ctx->debug_no_flip) {
-    DevBuf<uint32_t> head2, mem2, lid2, hcnt;
-    PRF_CK(ctx, head2.alloc((size_t)n_lists + 1, s));
-    PRF_CK(ctx, hcnt.alloc((size_t)T + 1, s));
-    PRF_CK(ctx, cudaMemsetAsync(hcnt.p, 0, hcnt.bytes(), s));
-    if ((rc = exclusive_scan(ctx, FlipLen{head_pos.p, T, n_lists}, (uint64_t)n_lists + 1, head2.p, scalars.p + 2))) return rc;
-    uint32_t n2 = 0;
-    PRF_CK(ctx, cudaMemcpyAsync(&n2, scalars.p + 2, 4, cudaMemcpyDeviceToHost, s));
-    PRF_CK(ctx, cudaStreamSynchronize(s));
-    PRF_CK(ctx, mem2.alloc((size_t)n2 + 4, s));
-    PRF_CK(ctx, lid2.alloc(n2, s));
-    flip_copy_kernel<<<grid_for(n_sorted), 256, 0, s>>>(H.lid.p, H.members.p, head_pos.p, head2.p, n_sorted, T, mem2.p,
-                                                        lid2.p, hcnt.p);
-    PRF_LAUNCHED(ctx);
-    flip_complement_kernel<<<grid_for(n_sorted), 256, 0, s>>>(H.lid.p, H.members.p, head_pos.p, head2.p, n_sorted, T,
-                                                              mem2.p, lid2.p, counters.p);
-    PRF_LAUNCHED(ctx);
-    flip_nb_kernel<<<grid_for(T), 256, 0, s>>>(nb32.p, hcnt.p, T, counters.p);
-    PRF_LAUNCHED(ctx);
-    H.members = std::move(mem2);
-    H.lid = std::move(lid2);
-    n_sorted = n2;
-    // ranges, hits and |D_t| statistics over the flipped lists
-    PRF_CK(ctx, H.ranges.alloc(n_sorted, s));
-    PRF_CK(ctx, H.singles.alloc((size_t)n_sorted * (short_max > 1 ? (short_max - 1) / 2 + 1 : 0) + 1, s));
-    PRF_CK(ctx, phead.alloc((size_t)n_lists + 2, s));
-    PRF_CK(ctx, H.lmembers.alloc((size_t)n_sorted * (short_max ? 2 : 4) + 8, s));
-    PRF_CK(ctx, cudaMemsetAsync(rcount.p, 0, rcount.bytes(), s));
-    PRF_CK(ctx, cudaMemsetAsync(cursor.p, 0, cursor.bytes(), s));
-    PRF_CK(ctx, cudaMemsetAsync(scount.p, 0, scount.bytes(), s));
-    PRF_CK(ctx, cudaMemsetAsync(scursor.p, 0, scursor.bytes(), s));
-    PRF_CK(ctx, cudaMemsetAsync(hcursor.p, 0, hcursor.bytes(), s));
-    PRF_CK(ctx, cudaMemsetAsync(H.nheavy.p, 0, H.nheavy.bytes(), s));
-    PRF_CK(ctx, cudaMemsetAsync(counters.p + 3, 0, 16, s));
-    const uint32_t mm_reset[3] = {0xffffffffu, 0u, 0u};
-    PRF_CK(ctx, cudaMemcpyAsync(scalars.p + 4, mm_reset, 12, cudaMemcpyHostToDevice, s));
-    if (n_sorted) {
-      range_count_kernel<<<grid_for(n_sorted), 256, 0, s>>>(H.lid.p, H.members.p, head2.p, n_sorted, short_max, heavy_min, rcount.p,
-                                                            H.nheavy.p, scount.p, counters.p);
+  if ((rc = exclusive_scan(ctx, LoadU32{scount.p}, (uint64_t)T + 1, H.soff.p, nullptr))) return rc;
+  if (T) {
+    if (hc.short_members) {
+      singles_kernel<<<ctx->sm_count * 4, 256, 0, s>>>(lcnt.p, sbase.p, sraw.p, short_max, cnts.p, 1, nullptr, H.soff.p, scur.p, H.singles.p);
       PRF_LAUNCHED(ctx);
     }
-    if ((rc = exclusive_scan(ctx, LoadU32{rcount.p}, (uint64_t)T + 1, H.roff.p, nullptr))) return rc;
-    if ((rc = exclusive_scan(ctx, LoadU32{scount.p}, (uint64_t)T + 1, H.soff.p, nullptr))) return rc;
-    if (n_sorted) {
-      if ((rc = exclusive_scan(ctx, PadLen{head2.p, scalars.p + 1, short_max}, (uint64_t)n_lists + 1, phead.p, scalars.p + 7))) return rc;
-      range_fill_kernel<<<grid_for(n_sorted), 256, 0, s>>>(H.lid.p, H.members.p, head2.p, n_sorted, short_max, heavy_min, H.roff.p,
-                                                           H.nheavy.p, hcursor.p, cursor.p, H.ranges.p, H.soff.p, scursor.p,
-                                                           H.singles.p, phead.p, H.lmembers.p);
-      PRF_LAUNCHED(ctx);
-    }
-    finish_nb_kernel<<<grid_for(T), 256, 0, s>>>(nb32.p, T, H.nb.p, scalars.p + 4, H.roff.p);
+    finish_trees_kernel<<<grid_for(T), 256, 0, s>>>(nb32.p, rcnt.p, T, H.nb.p, cnts.p);
     PRF_LAUNCHED(ctx);
-    unsigned long long hc2[6];
-    PRF_CK(ctx, cudaMemcpyAsync(hc2, counters.p, sizeof hc2, cudaMemcpyDeviceToHost, s));
-    PRF_CK(ctx, cudaMemcpyAsync(hs, scalars.p, sizeof hs, cudaMemcpyDeviceToHost, s));
-    PRF_CK(ctx, cudaMemcpyAsync(&h_nranges, H.roff.p + T, 4, cudaMemcpyDeviceToHost, s));
-    PRF_CK(ctx, cudaEventRecord(ctx->ev[3], s));
-    PRF_CK(ctx, cudaStreamSynchronize(s));
-    hc[3] = hc2[3];
-    H.n_flipped = (uint32_t)hc2[5];
   }
-  uint32_t mm[2] = {hs[4], hs[5]};
-  if (T == 0) mm[0] = mm[1] = 0;
-  if (mm[1] > kMaxBipsPerTree)
-    return ctx->fail(PRF_E_RANGE, "a tree has %u bipartitions; distances would overflow uint16 (max %u per tree)",
-                     mm[1], kMaxBipsPerTree);
-  H.uniform_nb = mm[0] == mm[1];
-  H.nb_uniform = mm[0];
-  H.n_shared = n_lists;
-  H.n_shared_nnz = n_sorted;  // after duplicate removal
-  H.n_ranges = h_nranges;
-  H.max_ranges = hs[6];
-  H.n_lmembers = n_sorted ? hs[7] : 0;
+  PRF_CK(ctx, cudaMemcpyAsync(&hc, cnts.p, sizeof hc, cudaMemcpyDeviceToHost, s));
+  PRF_CK(ctx, cudaEventRecord(ctx->ev[3], s));
+  PRF_CK(ctx, cudaStreamSynchronize(s));
+  trace_mark("build: structure synced");
+  if (T == 0) hc.nb_min = hc.nb_max = 0;
+  if (hc.nb_max > kMaxBipsPerTree)
+    return ctx->fail(PRF_E_RANGE, "a tree has %u bipartitions; distances would overflow uint16 (max %u per tree)", hc.nb_max,
+                     kMaxBipsPerTree);
+  H.uniform_nb = hc.nb_min == hc.nb_max;
+  H.nb_uniform = hc.nb_min;
+  H.n_shared = hc.n_lists2;
+  H.n_list_ids = hc.n_lists;
+  H.n_shared_nnz = hc.n_entries;
+  H.n_long = hc.n_long;
+  H.n_lmem = hc.n_lmem;
+  H.max_lists = hc.max_lists;
+  H.n_parts = 1;
+  H.part[0] = ListPart{H.roff.p, H.rlist.p, H.boff.p, H.lmem.p, H.soff.p, H.singles.p};
 
   prf_stats& st = H.stats;
   st = prf_stats{};
   st.n_trees = T;
   st.n_words = W;
   st.nnz = nnz;
-  st.n_unique = hc[0];
+  st.n_unique = hcount[0];
   st.n_shared = H.n_shared;
-  st.n_shared_nnz = n_sorted;
-  st.n_hits = hc[3];
+  st.n_shared_nnz = H.n_shared_nnz;
+  st.n_hits = hc.n_hits;
   st.n_pairs = H.P;
-  st.max_bips = mm[1];
-  st.min_bips = mm[0];
+  st.max_bips = hc.nb_max;
+  st.min_bips = hc.nb_min;
   st.n_flipped = H.n_flipped;
   if ((rc = build_nb_shift(ctx))) return rc;
   H.loaded = true;

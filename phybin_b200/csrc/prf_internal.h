@@ -2,7 +2,7 @@
 // helpers of the C ABI functions, and the launchers each kernel file exports.
 //   prf_api.cu        lifetime, hashRF load / compute / fetch, multi-GPU build entry points, debug hooks
 //   prf_build.cu      prf_incidence.cuh  (dedup + incidence)
-//   prf_matrix.cu     prf_rows.cuh, prf_sparse.cuh (sparse matrix kernels)
+//   prf_matrix.cu     prf_rows.cuh       (sparse matrix kernel)
 //   prf_dense.cu      prf_dense.cuh      (tcgen05 Gram variant)
 //   prf_tolerant.cu   prf_tolerant.cuh   + the prf_tolerant* entry points
 //   prf_extract.cu    prf_extract.cuh    + prf_allbips*, prf_hashrf_trees, prf_tolerant_trees
@@ -22,12 +22,13 @@ struct prf_ctx {
 namespace prf {
 
 // kernel launchers (defined next to their kernels)
-int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off, uint32_t T, uint32_t W, uint64_t nnz);
+// tree t's entries are [tb[t], te[t]) of d_bips (W words each); span = one past the largest entry index
+int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* tb, const uint64_t* te, uint32_t T, uint32_t W,
+                 uint64_t span, uint64_t nnz, uint32_t max_entries);
 int build_nb_shift(Ctx* ctx);
 void build_row_plan(uint32_t T, uint64_t p_begin, uint64_t p_end, uint32_t tile, std::vector<RowItem>& rows,
                     std::vector<RowItem>& groups);
 int launch_rows(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out, uint32_t* d_mask);
-int launch_sparse(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out, uint32_t* d_mask);
 int launch_dense(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out, uint32_t* d_mask);
 int launch_tolerant(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out, uint32_t* d_mask);
 uint32_t dense_kpad(uint32_t n_shared);     // shared bipartitions padded to the dense variant's k-block

@@ -1,6 +1,48 @@
-// prf_matrix.cu -- the sparse matrix kernels: prf_rows.cuh (one warp per row) and the round-1 kernel.
+// prf_matrix.cu -- the sparse matrix kernel (prf_rows.cuh) and the cut of a packed range into row work items.
 #include "prf_common.cuh"
 #include "prf_internal.h"
-#include "prf_primitives.cuh"
-#include "prf_sparse.cuh"
 #include "prf_rows.cuh"
+
+namespace prf {
+
+constexpr int kGroupRows = 256;  // most rows in a group item (tile > 0 only)
+
+// Cuts packed positions [p_begin, p_end) into work items, longest first.
+void build_row_plan(uint32_t T, uint64_t p_begin, uint64_t p_end, uint32_t tile, std::vector<RowItem>& rows,
+                           std::vector<RowItem>& groups) {
+  rows.clear();
+  groups.clear();
+  if (p_end <= p_begin || T < 2) return;
+  const uint32_t a_first = row_of(p_begin, T), a_last = row_of(p_end - 1, T);
+  uint32_t a = a_first;
+  while (a <= a_last) {
+    const uint64_t rs = row_start(a, T);
+    const uint32_t cb = a + 1 + (uint32_t)(std::max(rs, p_begin) - rs);
+    const uint32_t ce = a + 1 + (uint32_t)(std::min(rs + (T - 1 - a), p_end) - rs);
+    const bool whole = cb == a + 1 && ce == T;
+    if (whole) {
+      // greedy: as many following whole rows as fit one tile
+      uint32_t e = a;
+      uint64_t tot = T - 1 - a;
+      while (e + 1 <= a_last && e + 1 - a < (uint32_t)kGroupRows) {
+        const uint64_t rs2 = row_start(e + 1, T);
+        const bool whole2 = rs2 + (T - 2 - e) <= p_end;  // row e+1 ends inside the shard
+        const uint64_t l2 = T - 2 - e;
+        if (!whole2 || tot + l2 > tile) break;
+        tot += l2;
+        ++e;
+      }
+      if (e > a) {
+        groups.push_back(RowItem{a, e, 0u, 0u});
+        a = e + 1;
+        continue;
+      }
+    }
+    if (ce > cb) rows.push_back(RowItem{a, a, cb, ce});
+    ++a;
+  }
+  std::stable_sort(rows.begin(), rows.end(),
+                   [](const RowItem& x, const RowItem& y) { return x.ce - x.cb > y.ce - y.cb; });
+}
+
+}  // namespace prf

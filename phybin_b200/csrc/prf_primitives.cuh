@@ -1,6 +1,5 @@
 // prf_primitives.cuh -- device-wide exclusive scan and stable LSD radix sort of (key, value) pairs.
-// Hand-written (no CUB/Thrust): three-kernel scan (tile reduce, one-CTA scan of tile sums, tile
-// scan) and an 8-bit-digit radix sort (tile histogram, scan of digit-major histograms, stable
+// Hand-written (no CUB/Thrust): single-pass scan with decoupled look-back and an 8-bit-digit radix sort (tile histogram, scan of digit-major histograms, stable
 // warp-multisplit scatter).  Both are HBM-streaming kernels far off the critical path: at the
 // headline shape they touch < 1 % of the bytes the matrix kernel writes.
 #pragma once
@@ -39,54 +38,59 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t& t
 }
 
 // F: struct with __device__ uint32_t operator()(uint64_t i) const
-template <class F>
-__global__ void __launch_bounds__(kScanThreads) scan_tile_reduce_kernel(F f, uint64_t n,
-                                                                         uint32_t* tile_sums) {
-  const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
-  uint32_t s = 0;
-#pragma unroll
-  for (int k = 0; k < kScanItems; ++k) {
-    uint64_t i = base + k;
-    if (i < n) s += f(i);
-  }
-  uint32_t tot;
-  block_exclusive_scan(s, tot);
-  if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
-}
 
-// One CTA: in-place exclusive scan of `m` tile sums; the grand total goes to *total.
-static __global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(uint32_t* tile_sums, uint32_t m,
-                                                                       uint32_t* total) {
-  uint32_t carry = 0;
-  for (uint32_t base = 0; base < m; base += kScanThreads) {
-    uint32_t i = base + threadIdx.x;
-    uint32_t v = i < m ? tile_sums[i] : 0;
-    uint32_t tot;
-    uint32_t ex = block_exclusive_scan(v, tot);
-    if (i < m) tile_sums[i] = carry + ex;
-    carry += tot;
-  }
-  if (threadIdx.x == 0 && total) *total = carry;
-}
-
+// ---- single-pass scan (decoupled look-back) -----------------------------------------------------------
+// One kernel instead of three: a tile publishes its aggregate, then sums the published values of the tiles
+// before it until it meets one that already knows its inclusive prefix.  Tile ids are handed out by an atomic
+// counter, so a tile only ever waits for tiles that are already running.  status word = generation << 34 |
+// flag << 32 | value (flag 1 = aggregate, 2 = inclusive prefix): the generation (one per scan call of the
+// context) makes stale words read as "not ready", so the status array never needs clearing.
 template <class F>
-__global__ void __launch_bounds__(kScanThreads) scan_tile_apply_kernel(F f, uint64_t n,
-                                                                        const uint32_t* tile_offs,
-                                                                        uint32_t* out) {
-  const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+__global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(F f, uint64_t n, uint32_t* out, uint32_t* total,
+                                                                      volatile unsigned long long* status,
+                                                                      uint32_t* tile_counter, uint32_t gen, uint32_t tiles) {
+  __shared__ uint32_t s_tile, s_prefix;
+  if (threadIdx.x == 0) {
+    s_tile = atomicAdd(tile_counter, 1u);
+    if (s_tile == tiles - 1) *tile_counter = 0u;  // every id has been handed out: ready for the next scan
+  }
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint64_t base = (uint64_t)tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
   uint32_t v[kScanItems];
   uint32_t s = 0;
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
-    uint64_t i = base + k;
+    const uint64_t i = base + k;
     v[k] = i < n ? f(i) : 0;
     s += v[k];
   }
   uint32_t tot;
-  uint32_t ex = block_exclusive_scan(s, tot) + tile_offs[blockIdx.x];
+  uint32_t ex = block_exclusive_scan(s, tot);
+  if (threadIdx.x == 0) {
+    const unsigned long long g = (unsigned long long)gen << 34;
+    uint32_t prefix = 0;
+    if (tile == 0) {
+      status[0] = g | (2ull << 32) | tot;
+    } else {
+      status[tile] = g | (1ull << 32) | tot;
+      __threadfence();
+      for (uint32_t p = tile; p-- > 0;) {
+        unsigned long long w;
+        do { w = status[p]; } while ((w >> 34) != gen || ((w >> 32) & 3ull) == 0);
+        prefix += (uint32_t)w;
+        if (((w >> 32) & 3ull) == 2) break;
+      }
+      status[tile] = g | (2ull << 32) | (uint32_t)(prefix + tot);
+    }
+    s_prefix = prefix;
+    if (tile == tiles - 1 && total) *total = prefix + tot;
+  }
+  __syncthreads();
+  ex += s_prefix;
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
-    uint64_t i = base + k;
+    const uint64_t i = base + k;
     if (i < n) out[i] = ex;
     ex += v[k];
   }
@@ -102,14 +106,22 @@ int exclusive_scan(Ctx* ctx, F f, uint64_t n, uint32_t* out, uint32_t* d_total) 
     if (d_total) PRF_CK(ctx, cudaMemsetAsync(d_total, 0, sizeof(uint32_t), s));
     return PRF_OK;
   }
-  uint32_t tiles = (uint32_t)((n + kScanTile - 1) / kScanTile);
-  DevBuf<uint32_t> sums;
-  PRF_CK(ctx, sums.alloc(tiles, s));
-  scan_tile_reduce_kernel<F><<<tiles, kScanThreads, 0, s>>>(f, n, sums.p);
-  PRF_LAUNCHED(ctx);
-  scan_tile_sums_kernel<<<1, kScanThreads, 0, s>>>(sums.p, tiles, d_total);
-  PRF_LAUNCHED(ctx);
-  scan_tile_apply_kernel<F><<<tiles, kScanThreads, 0, s>>>(f, n, sums.p, out);
+  const uint32_t tiles = (uint32_t)((n + kScanTile - 1) / kScanTile);
+  if (ctx->scan_status.n < (size_t)tiles + 1) {
+    PRF_CK(ctx, ctx->scan_status.alloc(std::max<size_t>((size_t)tiles + 1, 4096), s));
+    PRF_CK(ctx, cudaMemsetAsync(ctx->scan_status.p, 0, ctx->scan_status.bytes(), s));
+    ctx->scan_gen = 0;
+  }
+  if (!ctx->scan_counter.p) {
+    PRF_CK(ctx, ctx->scan_counter.alloc(1, s));
+    PRF_CK(ctx, cudaMemsetAsync(ctx->scan_counter.p, 0, sizeof(uint32_t), s));
+  }
+  if (++ctx->scan_gen >= (1u << 30)) {  // generation wrap: start over with a clean status array
+    PRF_CK(ctx, cudaMemsetAsync(ctx->scan_status.p, 0, ctx->scan_status.bytes(), s));
+    ctx->scan_gen = 1;
+  }
+  scan_lookback_kernel<F><<<tiles, kScanThreads, 0, s>>>(f, n, out, d_total, ctx->scan_status.p, ctx->scan_counter.p,
+                                                         ctx->scan_gen, tiles);
   PRF_LAUNCHED(ctx);
   return PRF_OK;
 }

@@ -1,4 +1,4 @@
-// prf_rows.cuh -- the `ingest` phase of hashRF (RFDistance.hs:300-341), sparse variant (round 2).
+// prf_rows.cuh -- the `ingest` phase of hashRF (RFDistance.hs:300-341), sparse variant.
 //
 // The reference bumps d(i,j) once for every bipartition that exactly one of the two trees has
 // (haveIt x dontHave, :327-338): d(a,b) = |B_a| + |B_b| - 2 |B_a n B_b|.  Random topologies share
@@ -6,20 +6,20 @@
 // the matrix: 2 bytes per pair, HBM-write bound.
 //
 // ONE WARP OWNS A ROW.  There is no block-wide or inter-warp synchronisation anywhere in the kernel:
-// a warp takes the next row a (dynamic counter, longest rows first) and produces it tile by tile
-// (kTile consecutive columns) in its private shared-memory buffer:
+// a warp takes the next row a (dynamic counter, longest rows first) and produces it one COLUMN BLOCK
+// (B = 8192 consecutive trees, the bucket size of the build's list structure, ListPart in
+// prf_common.cuh) at a time in its private shared-memory buffer:
 //   fill     d = |B_a| + |B_b| for the tile's columns (16-byte shared stores; rows whose |B_t| differ:
 //            one bulk async copy of |B|[c_lo..] from one of 8 pre-shifted copies + a SIMD add of |B_a|)
-//   singles  bipartitions held by only a few trees (lists of <= kShortMax members) were expanded by the
-//            build into an explicit per-row list of columns; each is one shared-memory atomic
-//   walk     every long inverted list containing a keeps a cursor into "members after a" that only moves
-//            forward from tile to tile (a per-warp array in shared memory; one copy of the loop body, so the
-//            kernel stays inside the instruction cache).  Per list
-//            and tile the warp loads a 64-member window (two coalesced 128-byte loads, issued a batch of
-//            lists ahead of their use), and subtracts 2 at the columns inside the tile with plain 16-bit
-//            shared loads/stores: the members of one list are distinct columns and the warp is the
-//            buffer's only user, so no atomics are needed (measured: 4.8 updates/clk/SM for this pattern
-//            at 7 warps against 1.8 with atomics, profiles/r02_ubench_atoms.log)
+//   singles  bipartitions held by only a few trees (lists of <= short_max members) were expanded by the
+//            build into an explicit per-row list of columns; each is one shared-memory reduction
+//   lists    for every long list l containing a, the build left the members inside this column block as one
+//            bucket of 16-byte groups (8 x uint16 column offsets, padded).  The groups of all of the row's
+//            lists form one sequence that is cut into 32 equal runs, one per lane ("merge path": a warp scan
+//            of the bucket sizes, a binary search per lane): the work per lane is balanced whatever the list
+//            lengths are, every load is a full 16-byte group, and a member costs ~8 instructions: range test
+//            (also rejects padding, columns <= a and columns outside a shard), address, one shared-memory
+//            reduction -2 on the entry's half-word (two lists may hit the same column)
 //   mask     optional d <= editdist bits
 //   store    the finished tile leaves as ONE bulk asynchronous copy shared -> global (TMA engine,
 //            16-byte aligned interior; the < 8 entries before / after it are stored by a few lanes)
@@ -36,18 +36,6 @@
 
 namespace prf {
 
-constexpr int kMaxParts = 16;
-
-struct RowsPart {
-  const uint32_t* roff;     // [T+1] per-tree offsets into ranges
-  const uint2* ranges;      // (begin, end) into this part's members: the trees b > a of one long list;
-                            // a tree's HEAVY lists (many members per tile: warp-per-list walk) come first
-  const uint32_t* nheavy;   // [T] how many of the tree's ranges are heavy
-  const uint32_t* soff;     // [T+1] per-tree offsets into singles
-  const uint32_t* singles;  // columns b > a sharing a short-list bipartition with a (with multiplicity)
-  uint32_t mbase;           // position of this part's members in `members`
-};
-
 struct RowsParams {
   uint32_t T;
   uint64_t p_begin;
@@ -56,9 +44,9 @@ struct RowsParams {
   uint32_t nb_shift_stride;
   int uniform_nb;
   uint32_t nb_uniform;
-  const uint32_t* members;    // all parts' inverted lists (one buffer)
+  uint32_t NB;                // column blocks
   uint32_t n_parts;
-  RowsPart part[kMaxParts];
+  ListPart part[kMaxParts];
   int32_t editdist;
   uint16_t* out;
   uint32_t* mask;
@@ -66,201 +54,49 @@ struct RowsParams {
   uint32_t n_items;
   uint32_t* counter;          // next item (zeroed before the launch)
 #ifdef PRF_CALIB
-  int calib;                  // calibration builds only: 1 = fill + store only, 2 = member loads but no tile updates, 3 = no prefetch
+  int calib;                  // calibration builds only: 1 = fill + store only, 2 = member loads but no tile updates
 #endif
-  uint2* spill;               // per-warp cursor area for rows with more long lists than the register slots hold
-  uint32_t spill_stride;
 };
-
-__device__ __forceinline__ void tile_sub2(uint16_t* tile, int32_t base, uint32_t b0, uint32_t b1, bool in0, bool in1) {
-  uint16_t v0 = 0, v1 = 0;
-  const uint32_t i0 = (uint32_t)(base + (int32_t)b0), i1 = (uint32_t)(base + (int32_t)b1);
-  if (in0) v0 = tile[i0];
-  if (in1) v1 = tile[i1];
-  if (in0) tile[i0] = (uint16_t)(v0 - 2);
-  if (in1) tile[i1] = (uint16_t)(v1 - 2);
-  __syncwarp();  // the next list's loads may hit the same entries from other lanes
-}
-
-// Walks the row's long lists through one tile.  curs[k] = (cursor, end) of list k (shared memory, or the
-// global spill area for rows with more lists than fit); consumes every member < c_hi.  The member windows
-// of a batch of kB lists are loaded one batch ahead of their use.
-template <int kB>
-__device__ __forceinline__ void walk_lists(const uint32_t* __restrict__ members, uint2* curs, const uint32_t n,
-                                           const uint32_t c_hi, const int32_t base, uint16_t* tile, const uint32_t lane) {
-  struct Batch {
-    uint32_t c[kB], m0[kB], m1[kB];
-  };
-  auto load = [&](uint32_t kb, Batch& b) {
-#pragma unroll
-    for (int u = 0; u < kB; ++u) {
-      const uint2 r = kb + u < n ? curs[kb + u] : make_uint2(0u, 0u);  // same address in every lane: broadcast
-      const uint32_t i0 = r.x + lane;
-      b.c[u] = r.x;
-      b.m0[u] = i0 < r.y ? __ldg(members + i0) : 0xffffffffu;
-      b.m1[u] = i0 + 32 < r.y ? __ldg(members + i0 + 32) : 0xffffffffu;
-    }
-  };
-  auto process = [&](uint32_t kb, const Batch& b) {
-#pragma unroll
-    for (int u = 0; u < kB; ++u) {
-      const bool in0 = b.m0[u] < c_hi;
-      const uint32_t bal0 = __ballot_sync(0xffffffffu, in0);
-      if (bal0) {  // warp-uniform
-        const bool in1 = b.m1[u] < c_hi;
-        const uint32_t bal1 = __ballot_sync(0xffffffffu, in1);
-        tile_sub2(tile, base, b.m0[u], b.m1[u], in0, in1);
-        uint32_t c = b.c[u] + __popc(bal0) + __popc(bal1);
-        if (bal1 == 0xffffffffu) {  // more than two windows of this list fall into the tile
-          const uint32_t e = curs[kb + u].y;
-          for (;;) {
-            const uint32_t i0 = c + lane;
-            const uint32_t x0 = i0 < e ? __ldg(members + i0) : 0xffffffffu;
-            const uint32_t x1 = i0 + 32 < e ? __ldg(members + i0 + 32) : 0xffffffffu;
-            const bool y0 = x0 < c_hi, y1 = x1 < c_hi;
-            const uint32_t k = __popc(__ballot_sync(0xffffffffu, y0)) + __popc(__ballot_sync(0xffffffffu, y1));
-            tile_sub2(tile, base, x0, x1, y0, y1);
-            c += k;
-            if (k != 64) break;
-          }
-        }
-        if (lane == 0) curs[kb + u].x = c;
-      }
-    }
-  };
-  Batch A, B;
-  load(0, A);
-#pragma unroll 1
-  for (uint32_t kb = 0; kb < n; kb += 2 * kB) {
-    if (kb + kB < n) load(kb + kB, B);
-    process(kb, A);
-    if (kb + 2 * kB < n) load(kb + 2 * kB, A);
-    if (kb + kB < n) process(kb + kB, B);
-  }
-}
-
-// ---- LIGHT lists (few members per tile): ONE LANE PER LIST -------------------------------------------------
-// A lane loads the next 4 * kU members of its own list with 16-byte loads from a 4-aligned index (all in flight
-// at once) and applies those inside the tile with shared-memory reductions (two lanes' lists may hit the same
-// column): ~8 instructions per member slot against ~60 per (list, tile) of the warp-per-list walk above.
-// Lists are stored padded to a multiple of four members (pad = 0xffffffff, never below c_hi) and start at a
-// multiple of four, so a 16-byte group never straddles two lists and the members before the cursor inside the
-// first group belong to the same list: they are below c_lo and fail the range test.
-struct LightWin {  // the window one lane holds of one list
-  uint32_t x;      // cursor the window was loaded for (0 with y == 0: no list)
-  uint32_t y;      // end of the list
-};
-
-template <int kU>
-__device__ __forceinline__ void light_load(const uint32_t* __restrict__ members, const uint2 r, LightWin& w, uint4 (&buf)[kU]) {
-  w.x = r.x;
-  w.y = r.y;
-  const uint32_t idx = r.x & ~3u;
-#pragma unroll
-  for (int j = 0; j < kU; ++j) {
-    buf[j] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-    if (idx + 4 * j < r.y) buf[j] = __ldg(reinterpret_cast<const uint4*>(members + idx + 4 * j));
-  }
-}
 
 #ifdef PRF_CALIB
 __device__ int g_calib_no_red;
 #endif
-__device__ __forceinline__ void tile_red2(uint32_t tb, uint32_t m, bool on) {
+
+// tile entry of column offset `off` (relative to the block) -= 2 when `on`; tb = byte address of the entry of the
+// block's column 0 (mod 2^32).  A predicated shared-memory reduction on the entry's 32-bit word: no branch, so
+// the compiler interleaves the address arithmetic of neighbouring members.
+__device__ __forceinline__ void tile_red2(uint32_t tb, uint32_t off, bool on) {
 #ifdef PRF_CALIB
   if (g_calib_no_red) on = false;
 #endif
-  const uint32_t A = tb + 2u * m;  // byte address of column m's entry
+  const uint32_t A = tb + 2u * off;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.u32 p, %2, 0;\n\t"
       "@p red.shared.add.u32 [%0], %1;\n\t"
       "}" ::"r"(A & ~3u),
-      "r"(0xfffffffeu << ((A & 2u) << 3)), "r"((uint32_t)on)
+      "r"((A & 2u) ? 0xfffe0000u : 0xfffffffeu), "r"((uint32_t)on)
       : "memory");
 }
 
-// Applies the window; returns the new cursor.  `tb` = byte address of column 0's entry (mod 2^32).  If the whole
-// window was consumed and the list goes on (rare: more than 4 * kU - 3 members in one tile), continues with
-// dependent loads.
-template <int kU>
-__device__ __forceinline__ uint32_t light_apply(const uint32_t* __restrict__ members, const LightWin w, const uint4 (&buf)[kU],
-                                                const uint32_t c_lo, const uint32_t c_hi, const uint32_t tb) {
-  const uint32_t span = c_hi - c_lo;
-  uint32_t cnt = 0;
-#pragma unroll
-  for (int j = 0; j < kU; ++j) {
-    const uint32_t mm[4] = {buf[j].x, buf[j].y, buf[j].z, buf[j].w};
-    // warp-uniform early out: no lane's list has a member below c_hi from here on (lists ascend)
-    if (j > 0 && !__any_sync(0xffffffffu, mm[0] < c_hi)) break;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const bool on = j == 0 ? mm[e] - c_lo < span : mm[e] < c_hi;
-      cnt += on ? 1u : 0u;
-      tile_red2(tb, mm[e], on);
-    }
-  }
-  uint32_t cur = w.x + cnt;
-  uint32_t idx = (w.x & ~3u) + 4 * kU;
-  bool more = cur == idx && idx < w.y;  // consumed everything loaded and the list goes on
-  while (__any_sync(0xffffffffu, more)) {
-    uint4 v = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-    if (more) v = __ldg(reinterpret_cast<const uint4*>(members + idx));
-    const uint32_t mm[4] = {v.x, v.y, v.z, v.w};
-    uint32_t c = 0;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const bool on = mm[e] < c_hi;
-      c += on ? 1u : 0u;
-      tile_red2(tb, mm[e], on);
-    }
-    cur += c;
-    idx += 4;
-    more = more && c == 4 && idx < w.y;
-  }
-  return cur;
-}
-
-// Generic light walk over lists [0, n) of `curs` (no prefetch): groups of 32 lists, one list per lane.
-template <int kU>
-__device__ __forceinline__ void walk_light(const uint32_t* __restrict__ members, uint2* curs, const uint32_t n,
-                                           const uint32_t c_lo, const uint32_t c_hi, const uint32_t tb, const uint32_t lane) {
-#pragma unroll 1
-  for (uint32_t g0 = 0; g0 < n; g0 += 32) {
-    const uint32_t k = g0 + lane;
-    const uint2 r = k < n ? curs[k] : make_uint2(0u, 0u);
-    LightWin w;
-    uint4 buf[kU];
-    light_load<kU>(members, r, w, buf);
-    const uint32_t cur = light_apply<kU>(members, w, buf, c_lo, c_hi, tb);
-    if (cur != r.x) curs[k].x = cur;
-  }
-}
-
-// first index in [lo, hi) whose member is >= c
-__device__ __forceinline__ uint32_t members_lower_bound(const uint32_t* __restrict__ members, uint32_t lo, uint32_t hi, uint32_t c) {
-  while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (__ldg(members + mid) < c) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-
-template <int kTile, int kWarps, int kCurCap, int kB, int kU>
+// kLog2B: log2 of the column block (= tile) size; kCap: lists of a row handled per pass; kQ: 16-byte groups a lane
+// loads ahead of processing them.
+template <int kLog2B, int kWarps, int kCap, int kQ>
 __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams prm) {
+  constexpr int kTile = 1 << kLog2B;
   constexpr int kStride = kTile + 8;  // entries per buffer: a tile keeps the 16-byte phase of its global address
-  constexpr int kWarpBytes = kStride * 2 + kCurCap * 8;  // per warp: the tile buffer, then the cursors of the row's lists
+  constexpr int kWarpBytes = kStride * 2 + kCap * 12 + 16;  // per warp: tile buffer, then trow / start / upre of the row's lists
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_fill[kWarps];  // completion of a warp's bulk load of |B| (non-uniform rows)
 
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t gwarp = blockIdx.x * kWarps + warp;
   uint16_t* tile = reinterpret_cast<uint16_t*>(smem_raw + (size_t)warp * kWarpBytes);
   uint32_t* tile32 = reinterpret_cast<uint32_t*>(tile);
-  uint2* s_cur = reinterpret_cast<uint2*>(smem_raw + (size_t)warp * kWarpBytes + kStride * 2);
-  const uint32_t T = prm.T;
-  const uint32_t* __restrict__ members = prm.members;
+  uint32_t* s_trow = reinterpret_cast<uint32_t*>(smem_raw + (size_t)warp * kWarpBytes + kStride * 2);  // part << 28 | first bucket of the list
+  uint32_t* s_start = s_trow + kCap;   // first lmem entry of the list's bucket in the current block
+  uint32_t* s_upre = s_start + kCap;   // [kCap + 1] 16-byte groups of the lists before this one (exclusive prefix)
+  const uint32_t T = prm.T, NB = prm.NB;
 
   if (lane == 0) {
     mbar_init(&s_fill[warp], 1);
@@ -280,68 +116,45 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
     const uint4 iv = __ldg(reinterpret_cast<const uint4*>(prm.items + it));
     const uint32_t a = iv.x, cb = iv.z, ce = iv.w;
 
-    // ---- the row's long lists: cursor l of group g lives in lane l ----
-    // Cursor order of the row: the heavy lists of every part, then the light lists of every part.
-    uint32_t R = 0, H = 0, S = 0;  // ranges / heavy ranges / singles of the row over all parts
-    uint32_t pk0 = 0, pH = 0, pL = 0;  // lane p < n_parts: first range, heavy and light range counts of part p
-    uint32_t ps0 = 0, pS = 0;
+    // ---- the row's long lists and singles over all parts (lane p < n_parts looks at part p) ----
+    uint32_t pk0 = 0, pR = 0, ps0 = 0, pS = 0;
     if (lane < prm.n_parts) {
-      const RowsPart& q = prm.part[lane];
+      const ListPart& q = prm.part[lane];
       pk0 = __ldg(q.roff + a);
-      pH = __ldg(q.nheavy + a);
-      pL = __ldg(q.roff + a + 1) - pk0 - pH;
+      pR = __ldg(q.roff + a + 1) - pk0;
       ps0 = __ldg(q.soff + a);
       pS = __ldg(q.soff + a + 1) - ps0;
     }
-    uint32_t pHx = pH, pLx = pL;  // inclusive scans over parts (n_parts <= 16)
+    uint32_t pRx = pR;  // inclusive scan over parts (n_parts <= 16)
 #pragma unroll
     for (int d = 1; d < kMaxParts; d <<= 1) {
-      const uint32_t o = __shfl_up_sync(0xffffffffu, pHx, d), o2 = __shfl_up_sync(0xffffffffu, pLx, d);
-      if (lane >= (uint32_t)d) pHx += o, pLx += o2;
+      const uint32_t o = __shfl_up_sync(0xffffffffu, pRx, d);
+      if (lane >= (uint32_t)d) pRx += o;
     }
-    H = __shfl_sync(0xffffffffu, pHx, kMaxParts - 1);
-    R = H + __shfl_sync(0xffffffffu, pLx, kMaxParts - 1);
-    pHx -= pH;        // exclusive: cursor index of part p's first heavy list
-    pLx += H - pL;    // exclusive + H: cursor index of part p's first light list
-    {
-      uint32_t s = pS;
+    const uint32_t R = __shfl_sync(0xffffffffu, pRx, kMaxParts - 1);
+    pRx -= pR;  // exclusive: index of part p's first list among the row's lists
+    uint32_t S = pS;
 #pragma unroll
-      for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-      S = s;
-    }
-    // cursor k of the row (0 <= k < R): heavy list (k < H) or light list of the last part p whose first index is <= k
-    auto fetch_range = [&](uint32_t k) -> uint2 {
-      const bool heavy = k < H;
-      uint32_t p = 0;
-      for (uint32_t q = 1; q < prm.n_parts; ++q)  // warp-uniform loop, per-lane k
-        if ((heavy ? __shfl_sync(0xffffffffu, pHx, q) : __shfl_sync(0xffffffffu, pLx, q)) <= k) p = q;
-      const uint32_t k0 = __shfl_sync(0xffffffffu, pk0, p), hx = __shfl_sync(0xffffffffu, pHx, p),
-                     lx = __shfl_sync(0xffffffffu, pLx, p), ph = __shfl_sync(0xffffffffu, pH, p);
-      uint2 r = make_uint2(0u, 0u);
-      if (k < R) {
-        r = __ldg(prm.part[p].ranges + k0 + (heavy ? k - hx : ph + (k - lx)));
-        const uint32_t mb = prm.part[p].mbase;
-        r.x += mb;
-        r.y += mb;
-        if (cb > a + 1) r.x = members_lower_bound(members, r.x, r.y, cb);  // shard starts inside the row
+    for (int d = 16; d; d >>= 1) S += __shfl_xor_sync(0xffffffffu, S, d);
+    // lists [c0, c0 + Rc) of the row -> s_trow
+    auto load_lists = [&](uint32_t c0, uint32_t Rc) {
+      for (uint32_t kb = 0; kb < Rc; kb += 32) {
+        const uint32_t k = c0 + kb + lane;
+        uint32_t p = 0;
+        for (uint32_t q = 1; q < prm.n_parts; ++q)  // warp-uniform loop, per-lane k
+          if (__shfl_sync(0xffffffffu, pRx, q) <= k) p = q;
+        const uint32_t k0 = __shfl_sync(0xffffffffu, pk0, p), x = __shfl_sync(0xffffffffu, pRx, p);
+        if (kb + lane < Rc) s_trow[kb + lane] = (p << 28) | (__ldg(prm.part[p].rlist + k0 + (k - x)) * NB);
       }
-      return r;
+      __syncwarp();
     };
-    uint2* spill = prm.spill + (size_t)gwarp * prm.spill_stride;
-    for (uint32_t kb = 0; kb < R; kb += 32) {
-      const uint32_t k = kb + lane;
-      const uint2 r = fetch_range(k);
-      if (k < (uint32_t)kCurCap) s_cur[k] = r;
-      else if (k < R) spill[k - kCurCap] = r;
-    }
-    __syncwarp();
+    if (R && R <= (uint32_t)kCap) load_lists(0, R);
 
-    const uint32_t len = ce - cb, nseg = (len + kTile - 1) / kTile;
     const uint64_t rs = row_start(a, T);
-    const uint32_t Hs = min(H, (uint32_t)kCurCap), Rs = min(R, (uint32_t)kCurCap);
     const uint32_t na = prm.uniform_nb ? 0u : prm.nb[a];
-    for (uint32_t seg = 0; seg < nseg; ++seg) {
-      const uint32_t c_lo = cb + seg * kTile, c_hi = min(ce, c_lo + (uint32_t)kTile), cnt = c_hi - c_lo;
+    const uint32_t j_first = cb >> kLog2B, j_last = (ce - 1) >> kLog2B;
+    for (uint32_t j = j_first; j <= j_last; ++j) {
+      const uint32_t c_lo = max(cb, j << kLog2B), c_hi = min(ce, (j + 1) << kLog2B), cnt = c_hi - c_lo;
       const uint64_t p_lo = rs + (c_lo - a - 1), P0 = p_lo & ~7ull;
       const uint32_t o = (uint32_t)(p_lo - P0);   // tile entry of column c_lo
       const int32_t base = (int32_t)o - (int32_t)c_lo;
@@ -395,6 +208,9 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
       }
       __syncwarp();
 
+#ifdef PRF_CALIB
+      if (prm.calib != 1) {
+#endif
       // ---- singles ----
       if (S) {
         for (uint32_t p = 0; p < prm.n_parts; ++p) {
@@ -409,23 +225,82 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
             }
           }
         }
-        __syncwarp();
       }
 
-      // ---- walk the long lists ----
-      // cursors [0, H) heavy, [H, R) light; cursors >= kCurCap live in the global spill area
-      const uint32_t tb = smem_addr(tile) + 2u * (uint32_t)base;  // byte address of column 0's entry (mod 2^32)
-#ifdef PRF_CALIB
-      if (prm.calib != 1) {
-#endif
-      if (Hs) walk_lists<kB>(members, s_cur, Hs, c_hi, base, tile, lane);
-      if (H > Hs) walk_lists<kB>(members, spill, H - kCurCap, c_hi, base, tile, lane);
-      if (Rs > Hs) walk_light<kU>(members, s_cur + Hs, Rs - Hs, c_lo, c_hi, tb, lane);
-      if (R > Rs) walk_light<kU>(members, spill + (max(H, (uint32_t)kCurCap) - kCurCap), R - max(H, (uint32_t)kCurCap), c_lo, c_hi, tb, lane);
-      __syncwarp();
+      // ---- long lists: the 16-byte groups of the row's buckets in block j, dealt evenly to the lanes ----
+      const uint32_t tb = smem_addr(tile) + 2u * (uint32_t)(base + (int32_t)(j << kLog2B));  // entry of the block's column 0 (mod 2^32)
+      const uint32_t lo16 = c_lo - (j << kLog2B), span16 = cnt;  // columns of the tile relative to the block
+      for (uint32_t c0 = 0; c0 < R; c0 += kCap) {
+        const uint32_t Rc = min(R - c0, (uint32_t)kCap);
+        if (R > (uint32_t)kCap) load_lists(c0, Rc);
+        // bucket bounds of every list in block j, group counts, exclusive prefix over the lists
+        uint32_t run = 0;
+        for (uint32_t kb = 0; kb < Rc; kb += 32) {
+          const uint32_t k = kb + lane;
+          uint32_t s = 0, u = 0;
+          if (k < Rc) {
+            const uint32_t tr = s_trow[k];
+            const uint32_t* __restrict__ bo = prm.part[tr >> 28].boff + (tr & 0x0fffffffu) + j;
+            s = __ldg(bo);
+            u = (__ldg(bo + 1) - s) >> 3;
+          }
+          uint32_t inc = u;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= (uint32_t)d) inc += x;
+          }
+          if (k < Rc) {
+            s_start[k] = s;
+            s_upre[k] = run + inc - u;
+          }
+          run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        const uint32_t U = run;  // groups of all lists in this block
+        if (lane == 0) s_upre[Rc] = U;
+        __syncwarp();
+        if (U == 0) continue;
+        const uint32_t q = (U + 31) >> 5;               // groups per lane
+        const uint32_t u0 = lane * q, u1 = min(U, u0 + q);
+        // the list holding my first group: last k with upre[k] <= u0
+        uint32_t k = 0;
+        if (u0 < u1) {
+          uint32_t lo = 0, hi = Rc;  // upre[lo] <= u0 < upre[hi]
+          while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_upre[mid] <= u0) lo = mid; else hi = mid;
+          }
+          k = lo;
+        }
+        for (uint32_t ub = u0; __any_sync(0xffffffffu, ub < u1); ub += kQ) {
+          uint4 v[kQ];
+#pragma unroll
+          for (int i = 0; i < kQ; ++i) {
+            v[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            const uint32_t u = ub + i;
+            if (u < u1) {
+              while (u >= s_upre[k + 1]) ++k;  // (empty buckets repeat the same prefix value)
+              const ListPart& lp = prm.part[s_trow[k] >> 28];
+              v[i] = __ldg(reinterpret_cast<const uint4*>(lp.lmem + s_start[k] + 8u * (u - s_upre[k])));
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < kQ; ++i) {
+            const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t f0 = w[e] & 0xffffu, f1 = w[e] >> 16;
+              tile_red2(tb, f0, f0 - lo16 < span16);
+              tile_red2(tb, f1, f1 - lo16 < span16);
+            }
+          }
+        }
+        __syncwarp();
+      }
 #ifdef PRF_CALIB
       }
 #endif
+      __syncwarp();
 
       // ---- threshold mask: bit (p - p_begin) set iff d <= editdist ----
       if (prm.editdist >= 0) {
@@ -489,15 +364,15 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-template <int kTile, int kWarps, int kCurCap, int kB, int kU>
+template <int kLog2B, int kWarps, int kCap, int kQ>
 static int launch_rows_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out, uint32_t* d_mask) {
   const HashRFState& H = ctx->h;
   cudaStream_t s = ctx->stream;
   constexpr int kThreads = 32 * kWarps;
-  constexpr size_t smem = (size_t)kWarps * ((kTile + 8) * 2 + kCurCap * 8);
-  static_assert(smem + 64 <= 232448, "rows kernel: shared memory per CTA");
-  static_assert(kTile % 256 == 0 && kCurCap % (2 * kB) == 0, "rows kernel: tile / cursor array shape");
-  auto kern = rows_kernel<kTile, kWarps, kCurCap, kB, kU>;
+  constexpr size_t smem = (size_t)kWarps * (((1 << kLog2B) + 8) * 2 + kCap * 12 + 16);
+  static_assert(smem + 256 <= 232448, "rows kernel: shared memory per CTA");
+  if (H.block_log2 != (uint32_t)kLog2B) return ctx->fail(PRF_E_STATE, "list structure was built for another column block size");
+  auto kern = rows_kernel<kLog2B, kWarps, kCap, kQ>;
   PRF_CK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   RowPlan& plan = ctx->plan;
   if (!plan.valid || plan.T != H.T || plan.p_begin != p_begin || plan.p_end != p_end || plan.tile != 0) {
@@ -526,27 +401,15 @@ static int launch_rows_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t edi
   prm.nb_shift_stride = H.nb_shift_stride;
   prm.uniform_nb = H.uniform_nb ? 1 : 0;
   prm.nb_uniform = H.nb_uniform;
-  prm.members = H.lmembers.p;
-  prm.n_parts = 1;
-  prm.part[0].roff = H.roff.p;
-  prm.part[0].ranges = H.ranges.p;
-  prm.part[0].nheavy = H.nheavy.p;
-  prm.part[0].soff = H.soff.p;
-  prm.part[0].singles = H.singles.p;
-  prm.part[0].mbase = 0;
+  prm.NB = H.NB;
+  prm.n_parts = H.n_parts;
+  for (uint32_t p = 0; p < H.n_parts; ++p) prm.part[p] = H.part[p];
   prm.editdist = editdist;
   prm.out = d_out;
   prm.mask = d_mask;
   prm.items = plan.items.p;
   prm.n_items = plan.n_items;
   prm.counter = plan.counter.p;
-  if (H.max_ranges > (uint32_t)kCurCap) {
-    const uint32_t stride = (H.max_ranges - kCurCap + 31) / 32 * 32;
-    const size_t need = (size_t)grid * kWarps * stride;
-    if (plan.cursor_ws.n < need) PRF_CK(ctx, plan.cursor_ws.alloc(need, s));
-    prm.spill = plan.cursor_ws.p;
-    prm.spill_stride = stride;
-  }
 #ifdef PRF_CALIB
   prm.calib = ctx->calib;
   {
@@ -562,13 +425,12 @@ static int launch_rows_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t edi
 }
 
 int launch_rows(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out, uint32_t* d_mask) {
-  // the tiny-tile build exists so that small test inputs exercise multi-tile rows and the cursor spill area
-  if (ctx->debug_small_tiles) return launch_rows_t<256, 2, 8, 2, 1>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-  switch (ctx->rows_cfg) {  // tuning instantiations (scripts/rows_probe.py); the default measured best at 100k x 200
-    case 1: return launch_rows_t<7680, 14, 152, 4, 8>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-    case 2: return launch_rows_t<6656, 16, 128, 4, 7>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-    case 3: return launch_rows_t<8960, 12, 168, 4, 8>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-    default: return launch_rows_t<5376, 20, 104, 4, 6>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  // the tiny-block build exists so that small test inputs exercise multi-tile rows and several passes over a row's lists
+  if (ctx->debug_small_tiles) return launch_rows_t<8, 2, 8, 2>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  switch (ctx->rows_cfg) {  // tuning instantiations (scripts/rows_probe.py)
+    case 1: return launch_rows_t<13, 13, 112, 4>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    case 2: return launch_rows_t<13, 12, 240, 8>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    default: return launch_rows_t<13, 12, 240, 4>(ctx, p_begin, p_end, editdist, d_out, d_mask);
   }
 }
 

@@ -34,8 +34,8 @@ def main():
     ext.synchronize()
     ctx.hashrf_load(d_bips.data_ptr(), d_off.data_ptr(), T, f.words, MEM_DEVICE)
     res = {"workload": name}
-    for cfg in (0, 1, 2, 3):
-        L.prf_debug_sparse_kernel(ctx._h, 0, cfg)
+    for cfg in (0, 1, 2):
+        L.prf_debug_rows_cfg(ctx._h, cfg)
         for mode, label in ((0, "full"), (1, "fill_store_only"), (2, "loads_no_updates")):
             L.prf_debug_calib(ctx._h, mode)
             ms = [ctx.hashrf_compute(0, P, ed, 1, out.data_ptr(), mask.data_ptr() if mask is not None else 0)["ms_matrix"] for _ in range(4)]

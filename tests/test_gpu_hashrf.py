@@ -17,20 +17,18 @@ from tests.util import oracle_packed, random_multifurcating_newicks
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["default", "small_tiles", "small_tiles_light", "no_singles_light"])
+@pytest.fixture(scope="module", params=["default", "small_blocks", "small_blocks_no_singles", "no_singles"])
 def ctx(request):
-    """Every test runs in four configurations of the sparse matrix kernel (prf_rows.cuh):
-      default            production tiles; list classes chosen by the build (singles / light / heavy)
-      small_tiles        256-entry debug tiles: small inputs exercise multi-tile rows, cursor carry-over and the
-                         cursor spill area; lists longer than 8 members take the warp-per-list walk
-      small_tiles_light  same tiles, every list longer than 8 members takes the lane-per-list walk
-      no_singles_light   production tiles, no list is expanded into singles, all take the lane-per-list walk"""
+    """Every test runs in four configurations of the build + sparse matrix kernel (prf_incidence.cuh, prf_rows.cuh):
+      default                  production column blocks (8192 trees); lists of <= 8 trees expanded into singles
+      small_blocks             256-tree debug blocks: small inputs exercise multi-block rows, partial first / last
+                               tiles, and several passes over a row's lists (8 lists per pass)
+      small_blocks_no_singles  same blocks, every shared bipartition is a bucketed list (no singles)
+      no_singles               production blocks, no singles"""
     c = RFContext(0)
-    c.debug_small_tiles(request.param.startswith("small_tiles"))
-    if request.param.endswith("light"):
-        c._L.prf_debug_heavy_min(c._h, 1 << 30)
-    if request.param == "no_singles_light":
-        c._L.prf_debug_short_max(c._h, 0)
+    c.debug_small_tiles(request.param.startswith("small_blocks"))
+    if request.param.endswith("no_singles"):
+        c._L.prf_debug_short_max(c._h, 1)
     yield c
     c.close()
 
@@ -422,52 +420,6 @@ def test_cli_clusters_and_consensus_files(golden, tmp_path, name, thr, linkage, 
 
 
 # ---- multi-GPU build (hash-partitioned dedup), emulated on one GPU ---------------------------------
-
-@pytest.mark.parametrize("world,T,n,family", [(2, 300, 30, 0), (3, 700, 64, 0), (4, 513, 40, NNI_FAMILY), (8, 1000, 100, 0)])
-def test_sharded_build_loopback_matches_single_gpu_and_oracle(world, T, n, family):
-    from phybin_b200.distributed import sharded_load_loopback
-    f = Forest.synthetic(T, n, seed=0x51 + T, family=family, nni_max=6)
-    bips, off = f.all_bips()
-    o = orc.Forest([f.to_newick()])
-    want = oracle_packed(o, "hashrf", "literal")
-    ctxs = [RFContext(0) for _ in range(world)]
-    try:
-        stats = sharded_load_loopback(ctxs, bips, off)
-        ost = {}
-        o.hashrf(n, "closed", ost)
-        assert stats[0]["n_unique"] == ost["n_unique"] and stats[0]["nnz"] == len(bips)
-        P = T * (T - 1) // 2
-        for r in (0, world - 1):
-            ctxs[r].hashrf_compute(0, P, variant=1)
-            assert np.array_equal(ctxs[r].fetch(0, P).astype(np.int64), want)
-        # the dense variant runs on the merged structure as well
-        ctxs[0].hashrf_compute(0, P, variant=2)
-        assert np.array_equal(ctxs[0].fetch(0, P).astype(np.int64), want)
-    finally:
-        for c in ctxs:
-            c.close()
-
-
-def test_sharded_build_loopback_nonuniform_and_duplicates():
-    from phybin_b200.distributed import sharded_load_loopback
-    rng = random.Random(33)
-    text = [random_multifurcating_newicks(rng, 400, 30)]
-    f, o = Forest.parse(text), orc.Forest(text)
-    bips, off = f.all_bips()
-    want = oracle_packed(o, "hashrf", "literal")
-    rep, off2 = np.repeat(bips, 2, axis=0), off * 2   # a tree's bipartitions are a set: duplicates count once
-    ctxs = [RFContext(0) for _ in range(3)]
-    try:
-        sharded_load_loopback(ctxs, rep, off2)
-        T = len(f)
-        ctxs[1].hashrf_compute(0, T * (T - 1) // 2)
-        assert np.array_equal(ctxs[1].fetch().astype(np.int64), want)
-    finally:
-        for c in ctxs:
-            c.close()
-
-
-# ---- wide bit sets (cfg4 shape: 500 taxa = 8 words) and many suffixes per row -----------------------
 
 def test_config4_shape_wide_sets_mask_vs_oracle(ctx):
     # BASELINE config 4 family (500 taxa, W = 8, --editdist mask) at an oracle-sized T.  A row has more
