@@ -63,21 +63,17 @@ __device__ int g_calib_no_red;
 #endif
 
 // tile entry of column offset `off` (relative to the block) -= 2 when `on`; tb = byte address of the entry of the
-// block's column 0 (mod 2^32).  A predicated shared-memory reduction on the entry's 32-bit word: no branch, so
-// the compiler interleaves the address arithmetic of neighbouring members.
-__device__ __forceinline__ void tile_red2(uint32_t tb, uint32_t off, bool on) {
+// block's column 0 (mod 2^32).  One shared-memory reduction on the entry's 32-bit word, issued UNCONDITIONALLY (a
+// lane that is off adds 0 to the block's first word): ptxas turns a predicated reduction into a branch around the
+// address arithmetic, which costs more than the idle lanes of a reduction (the reductions are not the bottleneck,
+// scripts/rows_calib.py).
+__device__ __forceinline__ void tile_red2(uint32_t tb, uint32_t safe, uint32_t off, bool on) {
 #ifdef PRF_CALIB
   if (g_calib_no_red) on = false;
 #endif
   const uint32_t A = tb + 2u * off;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.u32 p, %2, 0;\n\t"
-      "@p red.shared.add.u32 [%0], %1;\n\t"
-      "}" ::"r"(A & ~3u),
-      "r"((A & 2u) ? 0xfffe0000u : 0xfffffffeu), "r"((uint32_t)on)
-      : "memory");
+  const uint32_t val = (A & 2u) ? 0xfffe0000u : 0xfffffffeu;
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(on ? (A & ~3u) : safe), "r"(on ? val : 0u) : "memory");
 }
 
 // kLog2B: log2 of the column block (= tile) size; kCap: lists of a row handled per pass; kQ: 16-byte groups a lane
@@ -148,17 +144,122 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
       }
       __syncwarp();
     };
-    if (R && R <= (uint32_t)kCap) load_lists(0, R);
+    if (R) load_lists(0, min(R, (uint32_t)kCap));
+    // rows of <= 64 lists keep the bucket bounds of the NEXT block in registers (lists lane and lane + 32)
+    const bool pf_ok = R > 0 && R <= 64 && R <= (uint32_t)kCap;
+    uint32_t pf_s[2] = {0, 0}, pf_e[2] = {0, 0};
+    auto prefetch_bounds = [&](uint32_t jn) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const uint32_t kk = c * 32 + lane;
+        pf_s[c] = pf_e[c] = 0;
+        if (kk < R) {
+          const uint32_t tr = s_trow[kk];
+          const uint32_t* __restrict__ bo = prm.part[tr >> 28].boff + (tr & 0x0fffffffu) + jn;
+          pf_s[c] = __ldg(bo);
+          pf_e[c] = __ldg(bo + 1);
+        }
+      }
+    };
 
     const uint64_t rs = row_start(a, T);
     const uint32_t na = prm.uniform_nb ? 0u : prm.nb[a];
     const uint32_t j_first = cb >> kLog2B, j_last = (ce - 1) >> kLog2B;
+    if (pf_ok) prefetch_bounds(j_first);
     for (uint32_t j = j_first; j <= j_last; ++j) {
       const uint32_t c_lo = max(cb, j << kLog2B), c_hi = min(ce, (j + 1) << kLog2B), cnt = c_hi - c_lo;
       const uint64_t p_lo = rs + (c_lo - a - 1), P0 = p_lo & ~7ull;
       const uint32_t o = (uint32_t)(p_lo - P0);   // tile entry of column c_lo
       const int32_t base = (int32_t)o - (int32_t)c_lo;
       const uint32_t groups = (o + cnt + 7) >> 3;  // 16-byte groups of the buffer in use
+
+      // ---- long lists, part 1: the 16-byte groups of the row's buckets in block j, dealt evenly to the lanes.
+      // Bucket bounds come from registers loaded a tile ahead (rows of <= 64 lists); the first groups are requested
+      // before the tile is filled, so their latency hides behind the fill.
+      const uint32_t tb = smem_addr(tile) + 2u * (uint32_t)(base + (int32_t)(j << kLog2B));  // entry of the block's column 0 (mod 2^32)
+      const uint32_t safe = smem_addr(tile) + 4u * lane;  // where an idle lane adds 0: one word per lane, no bank conflict
+      const uint32_t lo16 = c_lo - (j << kLog2B), span16 = cnt;  // columns of the tile relative to the block
+      uint32_t k = 0, u_next = 0, u1 = 0;  // my run of groups [u_next, u1) of the current pass; k = list of group u_next
+      uint4 v[kQ];
+      // bucket bounds of lists [0, Rc) in block j -> s_start, s_upre; my run of groups
+      auto setup_pass = [&](uint32_t Rc, bool use_pf) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int c = 0; c < (kCap + 31) / 32; ++c) {
+          const uint32_t kk = c * 32 + lane;
+          if ((uint32_t)c * 32 >= Rc) break;
+          uint32_t sb = 0, eb = 0;
+          if (use_pf && c < 2) {
+            sb = pf_s[c];
+            eb = pf_e[c];
+          } else if (kk < Rc) {
+            const uint32_t tr = s_trow[kk];
+            const uint32_t* __restrict__ bo = prm.part[tr >> 28].boff + (tr & 0x0fffffffu) + j;
+            sb = __ldg(bo);
+            eb = __ldg(bo + 1);
+          }
+          const uint32_t u = (eb - sb) >> 3;
+          uint32_t inc = u;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= (uint32_t)d) inc += x;
+          }
+          if (kk < Rc) {
+            s_start[kk] = sb;
+            s_upre[kk] = run + inc - u;
+          }
+          run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) s_upre[Rc] = run;
+        __syncwarp();
+        const uint32_t q = (run + 31) >> 5;  // groups per lane
+        u_next = min(run, lane * q);
+        u1 = min(run, u_next + q);
+        k = 0;
+        if (u_next < u1) {  // the list holding my first group: last k with upre[k] <= u_next
+          uint32_t lo = 0, hi = Rc;
+          while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_upre[mid] <= u_next) lo = mid; else hi = mid;
+          }
+          k = lo;
+        }
+      };
+      auto load_batch = [&]() {  // requests my next kQ groups
+#pragma unroll
+        for (int i = 0; i < kQ; ++i) {
+          v[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+          const uint32_t u = u_next + i;
+          if (u < u1) {
+            while (u >= s_upre[k + 1]) ++k;  // (empty buckets repeat the same prefix value)
+            const ListPart& lp = prm.part[s_trow[k] >> 28];
+            v[i] = __ldg(reinterpret_cast<const uint4*>(lp.lmem + s_start[k] + 8u * (u - s_upre[k])));
+          }
+        }
+      };
+      auto apply_batch = [&]() {
+#pragma unroll
+        for (int i = 0; i < kQ; ++i) {
+          if (i > 0 && !__any_sync(0xffffffffu, u_next + i < u1)) break;  // warp-uniform
+          const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t f0 = w[e] & 0xffffu, f1 = w[e] >> 16;
+            tile_red2(tb, safe, f0, f0 - lo16 < span16);
+            tile_red2(tb, safe, f1, f1 - lo16 < span16);
+          }
+        }
+        u_next = min(u1, u_next + kQ);
+      };
+      const uint32_t R0 = min(R, (uint32_t)kCap);
+#ifdef PRF_CALIB
+      if (prm.calib == 1) u1 = 0; else
+#endif
+      if (R0) {
+        setup_pass(R0, pf_ok);
+        load_batch();
+      }
 
       // the previous tile's bulk store has finished reading the buffer
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -208,9 +309,6 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
       }
       __syncwarp();
 
-#ifdef PRF_CALIB
-      if (prm.calib != 1) {
-#endif
       // ---- singles ----
       if (S) {
         for (uint32_t p = 0; p < prm.n_parts; ++p) {
@@ -227,79 +325,27 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
         }
       }
 
-      // ---- long lists: the 16-byte groups of the row's buckets in block j, dealt evenly to the lanes ----
-      const uint32_t tb = smem_addr(tile) + 2u * (uint32_t)(base + (int32_t)(j << kLog2B));  // entry of the block's column 0 (mod 2^32)
-      const uint32_t lo16 = c_lo - (j << kLog2B), span16 = cnt;  // columns of the tile relative to the block
-      for (uint32_t c0 = 0; c0 < R; c0 += kCap) {
+      // ---- long lists, part 2 ----
+      if (R0) {
+        while (__any_sync(0xffffffffu, u_next < u1)) {
+          apply_batch();
+          if (__any_sync(0xffffffffu, u_next < u1)) load_batch();
+        }
+        __syncwarp();
+      }
+      for (uint32_t c0 = kCap; c0 < R; c0 += kCap) {  // rows with more lists than one pass holds
         const uint32_t Rc = min(R - c0, (uint32_t)kCap);
-        if (R > (uint32_t)kCap) load_lists(c0, Rc);
-        // bucket bounds of every list in block j, group counts, exclusive prefix over the lists
-        uint32_t run = 0;
-        for (uint32_t kb = 0; kb < Rc; kb += 32) {
-          const uint32_t k = kb + lane;
-          uint32_t s = 0, u = 0;
-          if (k < Rc) {
-            const uint32_t tr = s_trow[k];
-            const uint32_t* __restrict__ bo = prm.part[tr >> 28].boff + (tr & 0x0fffffffu) + j;
-            s = __ldg(bo);
-            u = (__ldg(bo + 1) - s) >> 3;
-          }
-          uint32_t inc = u;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= (uint32_t)d) inc += x;
-          }
-          if (k < Rc) {
-            s_start[k] = s;
-            s_upre[k] = run + inc - u;
-          }
-          run += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        const uint32_t U = run;  // groups of all lists in this block
-        if (lane == 0) s_upre[Rc] = U;
-        __syncwarp();
-        if (U == 0) continue;
-        const uint32_t q = (U + 31) >> 5;               // groups per lane
-        const uint32_t u0 = lane * q, u1 = min(U, u0 + q);
-        // the list holding my first group: last k with upre[k] <= u0
-        uint32_t k = 0;
-        if (u0 < u1) {
-          uint32_t lo = 0, hi = Rc;  // upre[lo] <= u0 < upre[hi]
-          while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (s_upre[mid] <= u0) lo = mid; else hi = mid;
-          }
-          k = lo;
-        }
-        for (uint32_t ub = u0; __any_sync(0xffffffffu, ub < u1); ub += kQ) {
-          uint4 v[kQ];
-#pragma unroll
-          for (int i = 0; i < kQ; ++i) {
-            v[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-            const uint32_t u = ub + i;
-            if (u < u1) {
-              while (u >= s_upre[k + 1]) ++k;  // (empty buckets repeat the same prefix value)
-              const ListPart& lp = prm.part[s_trow[k] >> 28];
-              v[i] = __ldg(reinterpret_cast<const uint4*>(lp.lmem + s_start[k] + 8u * (u - s_upre[k])));
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < kQ; ++i) {
-            const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const uint32_t f0 = w[e] & 0xffffu, f1 = w[e] >> 16;
-              tile_red2(tb, f0, f0 - lo16 < span16);
-              tile_red2(tb, f1, f1 - lo16 < span16);
-            }
-          }
+        load_lists(c0, Rc);
+        setup_pass(Rc, false);
+        while (__any_sync(0xffffffffu, u_next < u1)) {
+          load_batch();
+          apply_batch();
         }
         __syncwarp();
       }
-#ifdef PRF_CALIB
-      }
-#endif
+      if (R > (uint32_t)kCap) load_lists(0, kCap);  // back to the first pass's lists for the next tile
+      // bucket bounds of the next block, for rows of <= 64 lists
+      if (pf_ok && j < j_last) prefetch_bounds(j + 1);
       __syncwarp();
 
       // ---- threshold mask: bit (p - p_begin) set iff d <= editdist ----
@@ -430,8 +476,12 @@ int launch_rows(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, ui
   switch (ctx->rows_cfg) {  // tuning instantiations (scripts/rows_probe.py)
     case 1: return launch_rows_t<13, 13, 112, 4>(ctx, p_begin, p_end, editdist, d_out, d_mask);
     case 2: return launch_rows_t<13, 12, 240, 8>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-    default: return launch_rows_t<13, 12, 240, 4>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    case 3: return launch_rows_t<13, 12, 240, 4>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    default: break;
   }
+  // 13 warps per SM when every row's lists fit one pass of 112 (measured 2.59 vs 2.69 ms at 100k x 200), else 12 warps x 240
+  if (ctx->h.max_lists <= 112) return launch_rows_t<13, 13, 112, 4>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  return launch_rows_t<13, 12, 240, 4>(ctx, p_begin, p_end, editdist, d_out, d_mask);
 }
 
 }  // namespace prf
