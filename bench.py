@@ -5,9 +5,11 @@
 
 One "step" = one pass of the hot path over the whole batch: canonical bipartitions resident in HBM
 -> dedup -> incidence -> matrix kernel -> packed uint16 upper triangle resident in HBM.  With N > 1
-(torchrun, one rank per GPU) the trees are sharded across ranks, an NCCL all-gather rebuilds the full
-bipartition table on every rank, and each rank computes a contiguous, aligned slice of the packed
-triangle (fixed total work => "strong" scaling).  Rank 0 prints ONE JSON line.
+(torchrun, one rank per GPU) the trees are sharded across ranks, the build is hash-partitioned over the
+GPUs (prf_team_load: the library's own kernels store keys and list structures into the peers' memory
+over NVLink; torch.distributed only carries the 64-byte arena handles once, outside the timed region),
+and each rank computes a contiguous, aligned slice of the packed triangle (fixed total work => "strong"
+scaling).  Rank 0 prints ONE JSON line.
 
 `e2e` is the same metric through the public host-buffer call prf_hashrf (pinned host input, H2D,
 compute, D2H of the whole matrix into pinned host memory).  `cpu_baseline` / `--impl reference` time
@@ -165,7 +167,7 @@ def run_gpu(args, wl, wl_name):
     import torch.distributed as dist
     from phybin_b200.host import Forest
     from phybin_b200.rfdistance import MEM_DEVICE, RFContext, shard_range
-    from phybin_b200.distributed import KeyGather, shard_rows as key_shard_rows, tree_shard
+    from phybin_b200.distributed import KeyGather, shard_rows as key_shard_rows, team_load, team_setup, tree_shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -209,9 +211,13 @@ def run_gpu(args, wl, wl_name):
         d_leaf = torch.from_numpy(leaf_all.view(np.int64)).to(dev) if mode == "tolerant" else None
         gather = KeyGather(key_shard_rows(off_all, T, world), W, dev)
         d_off_my = torch.from_numpy((off_all[t_lo:t_hi + 1] - off_all[t_lo]).astype(np.int64)).to(dev)
-    # N = 2: all-gathering the keys and building twice is cheaper than the partitioned build's fixed latencies
-    build = args.build if args.build != "auto" else ("sharded" if world >= 4 else "replicated")
-    sharded = False
+    # N > 1, hashRF: hash-partitioned build over the ranks' GPUs (prf_team.cuh); --build replicated = NCCL all-gather
+    # of the keys + the whole build on every rank (kept for comparison)
+    build = args.build if args.build != "auto" else "sharded"
+    sharded = world > 1 and mode == "hashrf" and build == "sharded"
+    if sharded:
+        rows_per_rank = key_shard_rows(off_all, T, world)
+        team_setup(ctx, T, W, nnz, max(rows_per_rank), int(counts.max()) if len(counts) else 0)
     with torch.cuda.stream(ext):
         p_begin, p_end = shard_range(T, rank, world)
         d_out = torch.empty(max(p_end - p_begin, 8), dtype=torch.int16, device=dev)
@@ -224,7 +230,7 @@ def run_gpu(args, wl, wl_name):
         """dedup + incidence + matrix for this rank's slice; inputs and outputs stay in HBM."""
         if sharded:
             # hash-partitioned build: all-to-all of keys, per-class dedup, all-gather + merge of the structures
-            raise RuntimeError("unreachable")
+            team_load(ctx, d_my, d_off_my, T)
         else:
             with torch.cuda.stream(ext):
                 d_full = gather(d_my)     # NCCL all-gather over NVLink when world > 1
@@ -303,6 +309,8 @@ def run_gpu(args, wl, wl_name):
         pos = np.sort(rng.integers(0, n_slice, size=256)) if n_slice else np.zeros(0, dtype=np.int64)
         vals = d_out[torch.from_numpy(pos).to(dev)].cpu().numpy().view(np.uint16) if n_slice else []
         row_starts = np.array([r * T - r * (r + 1) // 2 for r in range(T)], dtype=np.int64)
+        row_first = int(np.searchsorted(row_starts, p_begin, side="right") - 1)
+        row_last = min(T - 2, int(np.searchsorted(row_starts, max(p_end - 1, p_begin), side="right") - 1))
         for p, v in zip(pos, vals):
             gp = p_begin + int(p)
             a = int(np.searchsorted(row_starts, gp, side="right") - 1)
@@ -311,11 +319,74 @@ def run_gpu(args, wl, wl_name):
             sb = {tuple(x) for x in bips_all[int(off_all[b]):int(off_all[b + 1])].tolist()}
             assert int(v) == len(sa ^ sb), f"self-check failed at pair ({a},{b}): {int(v)} != {len(sa ^ sb)}"
         selfcheck = {"sampled_pairs": int(len(pos))}
+        if not args.quick_check:
+            # independent of the library: the multiset of 32-byte keys -> Map bip -> trees on the host (numpy)
+            t_chk = time.perf_counter()
+            void = np.ascontiguousarray(bips_all).view(np.dtype((np.void, bips_all.shape[1] * 8))).ravel()
+            _, inv, mult = np.unique(void, return_inverse=True, return_counts=True)
+            inv = inv.ravel()
+            tree_of = np.repeat(np.arange(T, dtype=np.int64), counts)
+            # a tree's entries are a set: count every (key, tree) once
+            pair = np.unique(inv.astype(np.int64) * T + tree_of)
+            m = np.bincount(pair // T, minlength=len(mult)).astype(np.int64)
+            host_hits = int((m * (m - 1) // 2).sum())
+            nb_host = np.bincount(pair % T, minlength=T).astype(np.int64)
+            selfcheck["host_n_unique"] = int(len(mult))
+            selfcheck["host_n_hits"] = host_hits
+            assert int(st["n_unique"]) == len(mult), f"n_unique {st['n_unique']} != host {len(mult)}"
+            if not st.get("n_flipped"):
+                assert int(st["n_hits"]) == host_hits, f"n_hits {st['n_hits']} != host {host_hits}"
+            # 8 full rows of this rank's slice recomputed on the host from the key ids
+            key_of, tr_of = pair // T, pair % T
+            rows_chk = []
+            for a in sorted(set(int(x) for x in rng.integers(row_first, row_last + 1, size=8))):
+                mark = np.zeros(len(mult), dtype=bool)
+                mark[key_of[tr_of == a]] = True
+                shared = np.bincount(tr_of[mark[key_of]], minlength=T).astype(np.int64)
+                want = nb_host[a] + nb_host[a + 1:] - 2 * shared[a + 1:]
+                g0 = int(row_starts[a]); lo = max(g0, p_begin); hi = min(g0 + (T - 1 - a), p_end)
+                if hi <= lo:
+                    continue
+                got = d_out[lo - p_begin:hi - p_begin].cpu().numpy().view(np.uint16).astype(np.int64)
+                assert np.array_equal(got, want[lo - g0:hi - g0]), f"row {a} differs from the host recomputation"
+                rows_chk.append(a)
+            selfcheck["host_rows_checked"] = rows_chk
+            selfcheck["host_check_s"] = round(time.perf_counter() - t_chk, 1)
         if world == 1 and not st.get("n_flipped"):
             total = int(d_out[:P].view(torch.int16).to(torch.int64).bitwise_and(0xFFFF).sum().item()) if P else 0
-            want = (T - 1) * int(counts.sum()) - 2 * int(st["n_hits"])
+            hits_ref = selfcheck.get("host_n_hits", int(st["n_hits"]))
+            want = (T - 1) * int(counts.sum()) - 2 * hits_ref
             assert total == want, f"checksum identity failed: {total} != {want}"
             selfcheck["checksum"] = total
+            selfcheck["checksum_uses"] = "host n_hits" if "host_n_hits" in selfcheck else "library n_hits"
+        if world > 1:
+            # every rank's slice against the same slice of a single-GPU compute (rank 0 redoes the whole job alone)
+            def slice_sums(t):
+                v = t.view(torch.int16).to(torch.int64).bitwise_and(0xFFFF)
+                w = (torch.arange(v.numel(), device=v.device, dtype=torch.int64) % 65521) + 1
+                return [int(v.sum().item()), int((v * w).sum().item() & 0x7FFFFFFFFFFFFFFF)]
+            mine = slice_sums(d_out[:p_end - p_begin]) + [p_begin, p_end]
+            allsums = [None] * world
+            dist.all_gather_object(allsums, mine)
+            if rank == 0:
+                with torch.cuda.stream(ext):
+                    d_all = torch.from_numpy(bips_all.view(np.int64)).to(dev)
+                ext.synchronize()
+                ctx1 = RFContext(local_rank)
+                ext1 = torch.cuda.ExternalStream(ctx1.stream, device=dev)
+                ctx1.hashrf_load(d_all.data_ptr(), d_off.data_ptr(), T, W, MEM_DEVICE)
+                ok = []
+                for r, (s0, s1, pb, pe) in enumerate(allsums):
+                    with torch.cuda.stream(ext1):
+                        buf = torch.empty(max(pe - pb, 8), dtype=torch.int16, device=dev)
+                    ctx1.hashrf_compute(pb, pe, -1, 1, buf.data_ptr(), 0)
+                    ref = slice_sums(buf[:pe - pb])
+                    assert ref == [s0, s1], f"slice of rank {r} differs from the single-GPU compute"
+                    ok.append(r)
+                    del buf
+                ctx1.close()
+                del d_all
+                selfcheck["slices_equal_single_gpu"] = ok
 
     # ---- what the mask feeds (untimed, N = 1): flat clusters at --editdist, as doCluster / sliceDendro use it ------
     consumer = None
@@ -339,7 +410,7 @@ def run_gpu(args, wl, wl_name):
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
-                "kernel": "sparse_rows_kernel" if mode == "hashrf" else "tolerant_kernel",
+                "kernel": "rows_kernel" if mode == "hashrf" else "tolerant_kernel",
                 "kernel_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_share_of_step": avg_ms * 1e-3 / step_s}
     if mode == "hashrf" and st.get("variant_used") == 2:
@@ -399,7 +470,7 @@ def run_gpu(args, wl, wl_name):
         del pin_in, pin_out, pin_mask  # before the library's stream goes away (the host allocator records events on it)
         e2e = {"value": P / float(dt[0]), "unit": UNIT, "h2d_bytes_per_step": int(nbytes[0]), "d2h_bytes_per_step": int(nbytes[1]),
                "ms_per_step": float(dt[0]) * 1e3, "steps": n_e2e,
-               "note": "per rank: pinned tree shard -> HBM, NCCL all-gather of keys, build, own slice, slice -> pinned host; bytes summed over ranks"}
+               "note": "per rank: pinned tree shard -> HBM, hash-partitioned build over NVLink, own slice, slice -> pinned host; bytes summed over ranks"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -416,7 +487,7 @@ def run_gpu(args, wl, wl_name):
             "config": {"workload": wl_name, "trees": T, "taxa": n, "mode": mode, "editdist": editdist,
                        "pairs": P, "nnz": nnz, "words": W, "n_unique": st.get("n_unique"), "n_hits": st.get("n_hits"),
                        "variant": {1: "sparse", 2: "dense"}.get(st.get("variant_used"), mode), "n_shared": st.get("n_shared"),
-                       "parallelism": f"packed-range shard x{world}" + ((" + hash-partitioned build (NCCL all-to-all of keys, all-gather of the per-class structures)" if sharded else " + NCCL all-gather of bipartition keys") if world > 1 else ""),
+                       "parallelism": f"packed-range shard x{world}" + ((" + hash-partitioned build (prf_team_load: keys and per-class list structures stored into the peers' memory over NVLink by the library's kernels)" if sharded else " + NCCL all-gather of bipartition keys, whole build on every rank") if world > 1 else ""),
                        "l2": "output per step (>= 2 B/pair) far exceeds the 126 MB L2; no explicit flush"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "device_s": dev_s, "wall_s": wall, "selfcheck": selfcheck, "consumer": consumer,
@@ -507,6 +578,7 @@ def main():
     ap.add_argument("--ref-trees", type=int, default=0, help="CPU sample size in trees")
     ap.add_argument("--build", default="auto", choices=["auto", "sharded", "replicated"],
                     help="N > 1: hash-partitioned build, or all-gather of the keys + replicated build (auto: sharded from 4 GPUs)")
+    ap.add_argument("--quick-check", action="store_true", help="skip the host-side recomputation of n_hits and of 8 full rows")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

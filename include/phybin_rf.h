@@ -94,7 +94,8 @@ typedef struct prf_stats {
 /* ---- lifetime ------------------------------------------------------------------------------- */
 
 /* Creates a context on CUDA device `device` (>= 0).  Returns NULL when there is no such device or
- * CUDA is unavailable (there is no CPU fallback). */
+ * CUDA is unavailable (there is no CPU fallback).  One context drives one GPU; prf_multi_create (below) drives
+ * every GPU of the box behind the same kind of call. */
 PRF_API prf_ctx* prf_create(int device);
 PRF_API void prf_destroy(prf_ctx* ctx);
 /* Message of the last failure on this context ("" if none).  ctx may be NULL: returns the message
@@ -141,6 +142,44 @@ PRF_API int prf_fetch(prf_ctx* ctx, uint64_t p_begin, uint64_t p_end, uint16_t* 
 PRF_API int prf_fetch_mask(prf_ctx* ctx, uint64_t p_begin, uint64_t p_end, uint32_t* dst);
 /* Copies the packed entries of upper-triangle rows [row0, row1) (row a holds d(a, a+1..T-1)). */
 PRF_API int prf_fetch_rows(prf_ctx* ctx, uint32_t row0, uint32_t row1, uint16_t* dst);
+
+/* ---- hashRF on all GPUs of one box ------------------------------------------------------------ */
+/* The `build` phase (RFDistance.hs:289-297) is hash-partitioned: GPU r deduplicates the bipartitions of hash class r
+ * and builds their inverted lists; the classes' structures are exchanged by kernels that store straight into the
+ * peers' memory over NVLink (no NCCL call, no host-side size exchange); the `ingest` phase (RFDistance.hs:300-341)
+ * then needs no exchange at all: GPU r computes the aligned slice prf_shard_range(T, r, world) of the packed triangle.
+ * Results are bit-identical to the single-GPU path.  The tensor-core (dense) variant is single-GPU only.
+ *
+ * (a) One process drives every GPU -- what a drop-in `hashRF` binds: */
+typedef struct prf_multi prf_multi;
+/* n_gpus <= 0: every visible GPU.  devices: n_gpus CUDA device indices or NULL for 0 .. n_gpus-1.  NULL on failure. */
+PRF_API prf_multi* prf_multi_create(int n_gpus, const int* devices);
+PRF_API void prf_multi_destroy(prf_multi* m);
+PRF_API const char* prf_multi_last_error(const prf_multi* m);
+PRF_API int prf_multi_gpus(const prf_multi* m);
+/* The context of rank `rank` (its slice of the last result stays there: prf_fetch / prf_fetch_mask, consumers). */
+PRF_API prf_ctx* prf_multi_ctx(prf_multi* m, int rank);
+/* Arguments as prf_hashrf (host buffers).  Trees are dealt to the GPUs in contiguous shards; every GPU copies its
+ * slice of the matrix (and mask) into out_upper / out_mask over its own PCIe link. */
+PRF_API int prf_multi_hashrf(prf_multi* m, const uint64_t* bips, const uint64_t* tree_off, uint32_t T, uint32_t W,
+                             int32_t editdist, uint16_t* out_upper, uint32_t* out_mask, prf_stats* stats);
+
+/* (b) One context per GPU, in one process or one process per GPU (MPI / torchrun style):
+ *   prf_team_init     every rank, same T / W / nnz_total / max_local_entries / max_tree_entries: allocates the rank's
+ *                     exchange arena and returns its handle (prf_team_handle_bytes() bytes, a cudaIpcMemHandle_t);
+ *   prf_team_connect  with the handles of all ranks in rank order (exchanged by the caller, e.g. an all-gather);
+ *   prf_team_load     collective: rank r passes the canonical bipartitions of ITS trees, trees
+ *                     [T r / world, T (r + 1) / world), laid out like prf_hashrf_load's input, in DEVICE memory.
+ *                     Afterwards every rank holds the whole structure: prf_hashrf_compute on any range.
+ * nnz_total = entries over all ranks; max_local_entries = most entries one rank holds; max_tree_entries = most entries
+ * of one tree.  A hash class that outgrows its region (2 x the mean + 64 K entries) is reported as PRF_E_NOMEM. */
+PRF_API size_t prf_team_handle_bytes(void);
+PRF_API int prf_team_init(prf_ctx* ctx, uint32_t rank, uint32_t world, uint32_t T, uint32_t W, uint64_t nnz_total,
+                          uint64_t max_local_entries, uint32_t max_tree_entries, void* handle_out);
+PRF_API int prf_team_connect(prf_ctx* ctx, const void* handles);
+PRF_API int prf_team_load(prf_ctx* ctx, const uint64_t* d_bips, const uint64_t* d_tree_off, uint32_t T_local,
+                          prf_stats* stats);
+PRF_API void prf_team_release(prf_ctx* ctx);
 
 /* ---- tolerant mode (replaces fst . naiveDistMatrix, RFDistance.hs:168-198) ------------------- */
 

@@ -131,6 +131,20 @@ def rf_lib():
         L.prf_tolerant.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int32, vp, vp, st]
         L.prf_tolerant_load.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int, st]
         L.prf_tolerant_compute.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int32, vp, vp, st]
+        L.prf_team_handle_bytes.restype = C.c_size_t
+        L.prf_team_init.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, vp]
+        L.prf_team_connect.argtypes = [vp, vp]
+        L.prf_team_load.argtypes = [vp, vp, vp, C.c_uint32, st]
+        L.prf_team_release.argtypes = [vp]
+        L.prf_multi_create.restype = vp
+        L.prf_multi_create.argtypes = [C.c_int, C.POINTER(C.c_int)]
+        L.prf_multi_destroy.argtypes = [vp]
+        L.prf_multi_last_error.restype = C.c_char_p
+        L.prf_multi_last_error.argtypes = [vp]
+        L.prf_multi_gpus.argtypes = [vp]
+        L.prf_multi_ctx.restype = vp
+        L.prf_multi_ctx.argtypes = [vp, C.c_int]
+        L.prf_multi_hashrf.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int32, vp, vp, st]
         L.prf_allbips.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
                                   C.POINTER(prf_extract_info)]
         L.prf_hashrf_trees.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int32, vp, vp, st,
@@ -166,7 +180,7 @@ def rf_lib():
 # Every symbol include/phybin_rf.h declares (tests check the built library exports them all).
 RF_SYMBOLS = [
     "prf_create", "prf_destroy", "prf_last_error", "prf_version", "prf_stream", "prf_hashrf",
-    "prf_hashrf_load", "prf_hashrf_compute", "prf_fetch", "prf_fetch_mask", "prf_fetch_rows",
+    "prf_hashrf_load", "prf_hashrf_compute", "prf_multi_create", "prf_multi_destroy", "prf_multi_last_error", "prf_multi_gpus", "prf_multi_ctx", "prf_multi_hashrf", "prf_team_handle_bytes", "prf_team_init", "prf_team_connect", "prf_team_load", "prf_team_release", "prf_fetch", "prf_fetch_mask", "prf_fetch_rows",
     "prf_tolerant", "prf_tolerant_load", "prf_tolerant_compute", "prf_allbips", "prf_allbips_result", "prf_allbips_fetch", "prf_hashrf_trees", "prf_tolerant_trees", "prf_consensus", "prf_consensus_fetch", "prf_fetch_submatrix",
     "prf_mask_components", "prf_packed_index",
     "prf_shard_align", "prf_shard_range", "prf_limits", "prf_launch_count",

@@ -17,15 +17,18 @@ static thread_local std::string g_create_error;
 // ext[0] = tree_off[T]; ext[1] = most entries of one tree; ext[2] != 0 when the offsets do not start at 0 or descend
 __global__ void __launch_bounds__(256) tree_extent_kernel(const uint64_t* __restrict__ off, uint32_t T, unsigned long long* ext) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t > T) return;
+  unsigned long long m = 0;
   if (t == T) {
     ext[0] = off[T];
     if (off[0] != 0) ext[2] = 1;
-    return;
+  } else if (t < T) {
+    const uint64_t a = off[t], b = off[t + 1];
+    if (b < a) ext[2] = 1;
+    else m = b - a;
   }
-  const uint64_t a = off[t], b = off[t + 1];
-  if (b < a) ext[2] = 1;
-  else atomicMax(&ext[1], (unsigned long long)(b - a));
+#pragma unroll
+  for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(&ext[1], m);
 }
 
 
@@ -85,6 +88,7 @@ PRF_API void prf_destroy(prf_ctx* h) {
   if (!h) return;
   Ctx& c = h->c;
   cudaSetDevice(c.device);
+  team_release_ctx(&c);
   c.h = HashRFState{};
   c.tol = TolerantState{};
   c.ext = ExtractState{};

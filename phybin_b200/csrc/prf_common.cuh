@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdarg>
 #include <cstdlib>
@@ -88,6 +89,7 @@ struct HashRFState {
   DevBuf<uint16_t> lmem;
   uint32_t n_long = 0;           // long lists
   uint64_t n_lmem = 0;           // entries of lmem (with padding)
+  uint64_t rlist_n = 0, singles_n = 0;  // entries of rlist / singles
   // tree-major incidence over ALL shared bipartitions (dense variant input; single-context builds only)
   DevBuf<uint32_t> ent_lid;      // [entry] dense id (0 .. n_shared-1) of the entry's list, 0xffffffff = bipartition of one tree only
   DevBuf<uint64_t> ent_tb, ent_te;  // [T] entry range of every tree
@@ -150,6 +152,68 @@ struct ConsensusState {
   DevBuf<uint64_t> off;   // [T + 1]
 };
 
+constexpr size_t kTeamHandleBytes = 64;  // cudaIpcMemHandle_t
+
+struct TeamPartHeader {  // what rank p tells everybody about its class (first bytes of part region p)
+  unsigned long long n_unique, n_hits, n_entries, nnz;
+  uint32_t n_lists2, n_long, n_flipped, n_rlist, n_boff, n_lmem, n_singles, max_lists;
+  uint32_t err;          // != 0: the class did not fit its region
+  uint32_t pad[3];
+};
+
+struct TeamLayout {
+  uint32_t world = 0, T = 0, W = 0, NB = 0;
+  uint64_t cap_e = 0;      // most entries one rank holds locally = capacity of a key region
+  uint64_t cap_class = 0;  // most entries one hash class is sized for
+  uint64_t cap_r = 0, cap_b = 0, cap_l = 0, cap_s = 0;  // rlist, boff, lmem (u16), singles entries per part
+  size_t off_flags = 0, off_keys = 0, off_tb = 0, off_te = 0, off_parts = 0, part_bytes = 0, bytes = 0;
+  size_t p_nb = 0, p_roff = 0, p_soff = 0, p_rlist = 0, p_boff = 0, p_lmem = 0, p_singles = 0;  // inside a part region
+  static size_t up(size_t x) { return (x + 255) & ~(size_t)255; }
+  void compute(uint32_t world_, uint32_t T_, uint32_t W_, uint32_t NB_, uint64_t nnz_total, uint64_t cap_e_, uint32_t short_max) {
+    world = world_; T = T_; W = W_; NB = NB_; cap_e = cap_e_;
+    cap_class = nnz_total <= (4u << 20) ? nnz_total : std::min<uint64_t>(nnz_total, 2 * nnz_total / world + 65536);
+    cap_class = std::max<uint64_t>(cap_class, 16);
+    cap_r = 2 * cap_class + 16;  // (majority lists stored as complements add at most as many again)
+    cap_b = (cap_class / (short_max + 1) + 2) * NB + 16;
+    cap_l = 2 * cap_class + 7 * std::min<uint64_t>(cap_b, 2 * cap_class) + 16;
+    cap_s = cap_class * (short_max > 1 ? (short_max - 1) : 0) / 2 + 16;
+    size_t o = 0;
+    off_flags = o; o += 4096;
+    off_keys = o; o += up((size_t)world * cap_e * W * 8);
+    off_tb = o; o += up((size_t)T * 8 + 8);
+    off_te = o; o += up((size_t)T * 8 + 8);
+    off_parts = o;
+    size_t q = up(sizeof(TeamPartHeader));
+    p_nb = q; q += up(((size_t)T + 16) * 2);
+    p_roff = q; q += up(((size_t)T + 1) * 4);
+    p_soff = q; q += up(((size_t)T + 1) * 4);
+    p_rlist = q; q += up(cap_r * 4);
+    p_boff = q; q += up(cap_b * 4);
+    p_lmem = q; q += up(cap_l * 2);
+    p_singles = q; q += up(cap_s * 4);
+    part_bytes = q;
+    bytes = off_parts + (size_t)world * part_bytes;
+  }
+};
+
+struct TeamShared;  // single-process teams: host barrier + events (prf_team.cu)
+
+struct Team {
+  bool active = false, connected = false;
+  uint32_t rank = 0, world = 1, max_entries = 0;
+  uint64_t nnz_total = 0;
+  TeamLayout lay;
+  uint8_t* arena = nullptr;           // mine (cudaMalloc)
+  uint8_t* peer[kMaxParts] = {};      // every rank's arena as mapped here (peer[rank] == arena)
+  bool ipc_open[kMaxParts] = {};
+  uint64_t epoch = 0;                 // barriers passed
+  TeamShared* shared = nullptr;       // non-null: single-process team (events instead of flag kernels)
+  cudaEvent_t ev = nullptr;           // single-process: my arrival event
+  DevBuf<uint32_t> cls_cnt, cls_pos, err;  // partition scratch
+  DevBuf<uint8_t> cls;
+  DevBuf<uint64_t> peers_dev;         // [world] peer arena addresses (device copy for the kernels)
+};
+
 struct Ctx {
   int device = 0;
   int sm_count = 148;
@@ -162,6 +226,7 @@ struct Ctx {
   ExtractState ext;
   ConsensusState cons;
   RowPlan plan;
+  Team team;
   DevBuf<unsigned long long> scan_status;  // decoupled look-back scan: tile status words (prf_primitives.cuh)
   DevBuf<uint32_t> scan_counter;
   uint32_t scan_gen = 0;

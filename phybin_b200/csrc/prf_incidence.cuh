@@ -592,8 +592,8 @@ int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* tb, const uin
                         (size_t)warps * set_slots * 4, s>>>(tb, te, T, H.ent_lid.p, shared_bits.p, wrank.p, set_slots, lcnt.p, nb32.p);
     PRF_LAUNCHED(ctx);
   }
-  if ((rc = exclusive_scan(ctx, IsLong{lcnt.p, cnts.p, short_max}, Lmax, llid.p, &cnts.p->n_long))) return rc;
-  if ((rc = exclusive_scan(ctx, ShortLen{lcnt.p, cnts.p, short_max}, Lmax, sbase.p, &cnts.p->short_members))) return rc;
+  if ((rc = exclusive_scan(ctx, IsLong{lcnt.p, cnts.p, short_max}, Lmax, llid.p, &cnts.p->n_long, &cnts.p->n_lists))) return rc;
+  if ((rc = exclusive_scan(ctx, ShortLen{lcnt.p, cnts.p, short_max}, Lmax, sbase.p, &cnts.p->short_members, &cnts.p->n_lists))) return rc;
   const int flip_ok = ctx->debug_no_flip ? 0 : 1;
   list_stats_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(lcnt.p, short_max, T, flip_ok, cnts.p);
   PRF_LAUNCHED(ctx);
@@ -616,7 +616,7 @@ int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* tb, const uin
     PRF_CK(ctx, fbits.alloc((size_t)n_heavy * fwords, s));
     PRF_CK(ctx, hcnt.alloc((size_t)T + 1, s));
     PRF_CK(ctx, cudaMemsetAsync(fbits.p, 0, fbits.bytes(), s));
-    if ((rc = exclusive_scan(ctx, IsHeavy{lcnt.p, cnts.p, T, short_max}, Lmax, fid.p, nullptr))) return rc;
+    if ((rc = exclusive_scan(ctx, IsHeavy{lcnt.p, cnts.p, T, short_max}, Lmax, fid.p, nullptr, &cnts.p->n_lists))) return rc;
     flip_ids_kernel<<<grid_for(hc.n_lists), 256, 0, s>>>(lcnt.p, llid.p, fid.p, cnts.p, T, short_max, fll.p);
     PRF_LAUNCHED(ctx);
   }
@@ -698,6 +698,8 @@ int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* tb, const uin
   H.n_shared_nnz = hc.n_entries;
   H.n_long = hc.n_long;
   H.n_lmem = hc.n_lmem;
+  H.rlist_n = hc.long_members;
+  H.singles_n = hc.short_pairs;
   H.max_lists = hc.max_lists;
   H.n_parts = 1;
   H.part[0] = ListPart{H.roff.p, H.rlist.p, H.boff.p, H.lmem.p, H.soff.p, H.singles.p};

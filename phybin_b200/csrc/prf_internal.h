@@ -7,6 +7,7 @@
 //   prf_tolerant.cu   prf_tolerant.cuh   + the prf_tolerant* entry points
 //   prf_extract.cu    prf_extract.cuh    + prf_allbips*, prf_hashrf_trees, prf_tolerant_trees
 //   prf_consumers.cu  prf_cluster.cuh, prf_consensus.cuh + their entry points
+//   prf_team.cu       prf_team.cuh       multi-GPU build (prf_team_*, prf_multi_*)
 #pragma once
 
 #include <algorithm>
@@ -26,6 +27,7 @@ namespace prf {
 int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* tb, const uint64_t* te, uint32_t T, uint32_t W,
                  uint64_t span, uint64_t nnz, uint32_t max_entries);
 int build_nb_shift(Ctx* ctx);
+void team_release_ctx(Ctx* ctx);  // prf_team.cu: frees a context's team arena (prf_destroy)
 void build_row_plan(uint32_t T, uint64_t p_begin, uint64_t p_end, uint32_t tile, std::vector<RowItem>& rows,
                     std::vector<RowItem>& groups);
 int launch_rows(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out, uint32_t* d_mask);

@@ -46,16 +46,20 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t& t
 // flag << 32 | value (flag 1 = aggregate, 2 = inclusive prefix): the generation (one per scan call of the
 // context) makes stale words read as "not ready", so the status array never needs clearing.
 template <class F>
-__global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(F f, uint64_t n, uint32_t* out, uint32_t* total,
-                                                                      volatile unsigned long long* status,
-                                                                      uint32_t* tile_counter, uint32_t gen, uint32_t tiles) {
+__global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(F f, uint64_t n_max, const uint32_t* n_dev, uint32_t* out,
+                                                                      uint32_t* total, volatile unsigned long long* status,
+                                                                      uint32_t* tile_counter, uint32_t gen, uint32_t tiles_max) {
   __shared__ uint32_t s_tile, s_prefix;
   if (threadIdx.x == 0) {
     s_tile = atomicAdd(tile_counter, 1u);
-    if (s_tile == tiles - 1) *tile_counter = 0u;  // every id has been handed out: ready for the next scan
+    if (s_tile == tiles_max - 1) *tile_counter = 0u;  // every id has been handed out: ready for the next scan
   }
   __syncthreads();
   const uint32_t tile = s_tile;
+  // n_dev (optional): the number of elements, known only on the device (<= n_max); tiles beyond it leave at once
+  const uint64_t n = n_dev ? min((uint64_t)*n_dev, n_max) : n_max;
+  const uint32_t tiles = n ? (uint32_t)((n + kScanTile - 1) / kScanTile) : 1u;
+  if (tile >= tiles) return;
   const uint64_t base = (uint64_t)tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
   uint32_t v[kScanItems];
   uint32_t s = 0;
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(F f, uint64
 // out must not alias anything f reads unless f reads element i only (in-place is then safe:
 // every tile is fully read into registers before it is written).
 template <class F>
-int exclusive_scan(Ctx* ctx, F f, uint64_t n, uint32_t* out, uint32_t* d_total) {
+int exclusive_scan(Ctx* ctx, F f, uint64_t n, uint32_t* out, uint32_t* d_total, const uint32_t* n_dev = nullptr) {
   cudaStream_t s = ctx->stream;
   if (n == 0) {
     if (d_total) PRF_CK(ctx, cudaMemsetAsync(d_total, 0, sizeof(uint32_t), s));
@@ -120,7 +124,7 @@ int exclusive_scan(Ctx* ctx, F f, uint64_t n, uint32_t* out, uint32_t* d_total) 
     PRF_CK(ctx, cudaMemsetAsync(ctx->scan_status.p, 0, ctx->scan_status.bytes(), s));
     ctx->scan_gen = 1;
   }
-  scan_lookback_kernel<F><<<tiles, kScanThreads, 0, s>>>(f, n, out, d_total, ctx->scan_status.p, ctx->scan_counter.p,
+  scan_lookback_kernel<F><<<tiles, kScanThreads, 0, s>>>(f, n, n_dev, out, d_total, ctx->scan_status.p, ctx->scan_counter.p,
                                                          ctx->scan_gen, tiles);
   PRF_LAUNCHED(ctx);
   return PRF_OK;

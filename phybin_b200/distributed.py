@@ -48,3 +48,26 @@ class KeyGather:
         return self.full
 
 
+
+
+# ---------------------------------------------------------------------------------------------------
+# Hash-partitioned build over the ranks' GPUs (prf_team.cuh): torch.distributed only carries the 64-byte
+# arena handles once; the data path is the library's own kernels storing into the peers' memory over NVLink.
+# ---------------------------------------------------------------------------------------------------
+
+def team_setup(ctx, T: int, W: int, nnz_total: int, max_local_entries: int, max_tree_entries: int) -> None:
+    """Collective, once per problem shape: every rank allocates its exchange arena (prf_team_init) and opens the
+    peers' (prf_team_connect).  `ctx` is an RFContext on this rank's GPU."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    handle = ctx.team_init(rank, world, T, W, nnz_total, max_local_entries, max_tree_entries)
+    handles = [None] * world
+    dist.all_gather_object(handles, handle)
+    ctx.team_connect(b"".join(handles))
+    dist.barrier()  # every rank has opened every arena before anybody writes into one
+
+
+def team_load(ctx, keys: torch.Tensor, off: torch.Tensor, T: int) -> dict:
+    """Collective: `keys` [nnz_local, W] int64 and `off` [T_local + 1] int64 describe THIS rank's trees
+    tree_shard(T, rank, world) (device tensors visible to ctx's stream).  On return ctx holds the whole structure:
+    ctx.hashrf_compute works on any range."""
+    return ctx.team_load(keys.data_ptr(), off.data_ptr(), off.numel() - 1, T)

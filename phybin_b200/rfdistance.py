@@ -94,6 +94,46 @@ class DistanceMatrix:
         return str(self.rows()).replace(" ", "")
 
 
+class MultiRF:
+    """prf_multi: one process driving several GPUs of the box (the trees are dealt to the GPUs, the build is
+    hash-partitioned over them, every GPU computes and returns a slice of the matrix)."""
+
+    def __init__(self, n_gpus: int = 0, devices=None):
+        self._L = rf_lib()
+        arr = (C.c_int * len(devices))(*devices) if devices else None
+        self._m = self._L.prf_multi_create(len(devices) if devices else n_gpus, arr)
+        if not self._m:
+            raise PhyBinRFError(-2, "prf_multi_create failed (no CUDA device, or more than 16 GPUs)")
+
+    @property
+    def n_gpus(self) -> int:
+        return int(self._L.prf_multi_gpus(self._m))
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self._L.prf_multi_destroy(self._m)
+            self._m = None
+
+    def __del__(self):
+        self.close()
+
+    def hashrf(self, bips: np.ndarray, tree_off: np.ndarray, editdist: int = -1):
+        """prf_multi_hashrf on host arrays: (upper uint16[P], mask uint32[...] | None, stats)."""
+        bips = np.ascontiguousarray(bips, dtype=np.uint64)
+        tree_off = np.ascontiguousarray(tree_off, dtype=np.uint64)
+        T = len(tree_off) - 1
+        W = bips.shape[1] if bips.ndim == 2 else 1
+        P = T * (T - 1) // 2 if T else 0
+        out = np.empty(P, dtype=np.uint16)
+        mask = np.zeros((P + 31) // 32, dtype=np.uint32) if editdist >= 0 else None
+        st = prf_stats()
+        rc = self._L.prf_multi_hashrf(self._m, bips.ctypes.data, tree_off.ctypes.data, T, W, editdist, out.ctypes.data,
+                                      mask.ctypes.data if mask is not None else None, C.byref(st))
+        if rc != 0:
+            raise PhyBinRFError(rc, self._L.prf_multi_last_error(self._m).decode())
+        return out, mask, st.as_dict()
+
+
 class RFContext:
     """One prf_ctx: a CUDA device, a stream, and the device-resident state of one problem."""
 
@@ -177,6 +217,26 @@ class RFContext:
         self._ck(self._L.prf_hashrf_compute(self._h, p_begin, p_end, editdist, variant, d_out or None,
                                             d_mask or None, C.byref(st) if want_stats else None))
         return st.as_dict() if want_stats else None
+
+    # ---- hashRF over several GPUs (one context per GPU; phybin_b200.distributed has the torch.distributed driver) ----
+    def team_init(self, rank: int, world: int, T: int, W: int, nnz_total: int, max_local_entries: int,
+                  max_tree_entries: int) -> bytes:
+        """prf_team_init: allocates this rank's exchange arena; returns its handle (pass all ranks' handles, in rank
+        order, to team_connect)."""
+        buf = C.create_string_buffer(self._L.prf_team_handle_bytes())
+        self._ck(self._L.prf_team_init(self._h, rank, world, T, W, nnz_total, max_local_entries, max_tree_entries, buf))
+        return buf.raw
+
+    def team_connect(self, handles: bytes):
+        self._ck(self._L.prf_team_connect(self._h, handles))
+
+    def team_load(self, d_bips: int, d_tree_off: int, T_local: int, T: int) -> dict:
+        """prf_team_load (collective): device pointers of THIS rank's trees' bipartitions and offsets."""
+        st = prf_stats()
+        self._ck(self._L.prf_team_load(self._h, d_bips, d_tree_off, T_local, C.byref(st)))
+        self.T = T
+        self.P = T * (T - 1) // 2 if T else 0
+        return st.as_dict()
 
     # ---- tolerant ----------------------------------------------------------------------------
     def tolerant(self, clades: np.ndarray, tree_off: np.ndarray, leafsets: np.ndarray, editdist: int = -1,
