@@ -491,6 +491,9 @@ def run_gpu(args, wl, wl_name):
                        "l2": "output per step (>= 2 B/pair) far exceeds the 126 MB L2; no explicit flush"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "device_s": dev_s, "wall_s": wall, "selfcheck": selfcheck, "consumer": consumer,
+            "phases_ms": {("key_exchange" if sharded else "dedup"): st.get("ms_dedup"),
+                          ("class_build_and_part_exchange" if sharded else "lists"): st.get("ms_incidence"),
+                          "matrix": avg_ms, "note": "CUDA-event times of the last step on rank 0"},
         }
         print(json.dumps(line), flush=True)
     torch.cuda.synchronize(dev)

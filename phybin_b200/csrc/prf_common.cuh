@@ -268,6 +268,14 @@ inline void trace_mark(const char* what) {
   last = now;
 }
 
+// PRF_TRACE=1: additionally waits for the stream, so that the mark's time is the GPU time of what was queued since
+// the previous mark (serialises the phases: for diagnosis only).
+inline void trace_sync(cudaStream_t s, const char* what) {
+  if (!trace_on()) return;
+  cudaStreamSynchronize(s);
+  trace_mark(what);
+}
+
 #define PRF_CK(ctx, call)                                                                      \
   do {                                                                                         \
     cudaError_t _e = (call);                                                                   \

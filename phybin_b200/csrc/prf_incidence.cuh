@@ -68,22 +68,28 @@ __global__ void __launch_bounds__(256) dedup_insert_kernel(const uint64_t* __res
 
 // Compact variant for nnz < 2^25 - 1 entries: 4-byte slots ( tag:7 | representative entry + 1 : 25, 0 = free )
 // and a table of 1.25 * nnz slots addressed by multiply-shift instead of a power-of-two mask.  At the
-// headline shape the table is 98 MB instead of 268 MB: it stays in the 126 MB L2 (the key stream is
+// headline shape the table is 98 MB instead of 268 MB: it mostly stays in the 126 MB L2 (the key stream is
 // loaded with an evict-first policy), so the random probes and CAS are L2 hits instead of DRAM sectors.
+// One thread per entry over up to kMaxParts dense entry segments (one for a single-GPU build; one per source rank
+// for a class build of a multi-GPU team, whose trees have too few entries each to fill a warp).
+struct DedupSegs {
+  uint64_t begin[kMaxParts];
+  uint64_t start[kMaxParts + 1];  // entries of the segments before this one
+  uint32_t n;
+};
 template <int W>
-__global__ void __launch_bounds__(256) dedup_insert32_kernel(const uint64_t* __restrict__ bips,
-                                                             const uint64_t* __restrict__ tb,
-                                                             const uint64_t* __restrict__ te, uint32_t T,
+__global__ void __launch_bounds__(256) dedup_insert32_kernel(const uint64_t* __restrict__ bips, const DedupSegs segs,
                                                              uint32_t* slots, uint32_t* shared_bits, uint32_t cap,
                                                              uint32_t* __restrict__ ent_slot,
                                                              unsigned long long* counters) {
-  const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (t >= T) return;
   uint64_t policy;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-  const uint64_t e0 = tb[t], e1 = te[t];
+  const uint64_t total = segs.start[segs.n];
   uint32_t claims = 0;
-  for (uint64_t e = e0 + lane_id(); e < e1; e += 32) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t sg = 0;
+    while (sg + 1 < segs.n && i >= segs.start[sg + 1]) ++sg;
+    const uint64_t e = segs.begin[sg] + (i - segs.start[sg]);
     uint64_t k[W];
     {
       const uint64_t* p = bips + e * W;
@@ -135,46 +141,48 @@ struct PopcWord {
 // shared slots) or 0xffffffff when the bipartition is held by this tree only.  A tree's entries are a SET
 // (S.Set DenseLabelSet): an exact per-warp hash set in shared memory drops a list id the tree already has.
 // lcnt[l] = trees holding list l; nb32[t] = |B_t| (distinct entries).
+template <int G>  // lanes per tree: 32, or 8 (four trees per warp) when the trees have few entries (class builds)
 __global__ void __launch_bounds__(256) list_count_kernel(const uint64_t* __restrict__ tb, const uint64_t* __restrict__ te,
                                                          uint32_t T, uint32_t* __restrict__ ent,
                                                          const uint32_t* __restrict__ shared_bits,
                                                          const uint32_t* __restrict__ wrank, uint32_t set_slots,
                                                          uint32_t* lcnt, uint32_t* __restrict__ nb32) {
   extern __shared__ uint32_t s_sets[];
-  const uint32_t warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = lane_id();
-  uint32_t* set = s_sets + (size_t)warp * set_slots;
-  for (uint32_t t = blockIdx.x * warps + warp; t < T; t += gridDim.x * warps) {
-    const uint64_t e0 = tb[t], e1 = te[t];
-    for (uint32_t i = lane; i < set_slots; i += 32) set[i] = 0xffffffffu;
+  constexpr uint32_t kPer = 32 / G;
+  const uint32_t warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = lane_id(), sub = lane % G, grp = lane / G;
+  uint32_t* set = s_sets + ((size_t)warp * kPer + grp) * set_slots;
+  for (uint32_t t0 = (blockIdx.x * warps + warp) * kPer; t0 < T; t0 += gridDim.x * warps * kPer) {
+    const uint32_t t = t0 + grp;
+    const bool live = t < T;
+    const uint64_t e0 = live ? tb[t] : 0, e1 = live ? te[t] : 0;
+    for (uint32_t i = sub; i < set_slots; i += G) set[i] = 0xffffffffu;
     __syncwarp();
     uint32_t dups = 0;
-    for (uint64_t eb = e0; eb < e1; eb += 32) {
-      const uint64_t e = eb + lane;
-      if (e < e1) {
-        const uint32_t s = ent[e];
-        const uint32_t word = shared_bits[s >> 5];
-        uint32_t l = 0xffffffffu;
-        if ((word >> (s & 31)) & 1u) {
-          l = wrank[s >> 5] + __popc(word & ((1u << (s & 31)) - 1u));
-          uint32_t h = (l * 0x9E3779B1u) & (set_slots - 1);
-          for (;;) {
-            const uint32_t old = atomicCAS(&set[h], 0xffffffffu, l);
-            if (old == 0xffffffffu) break;
-            if (old == l) {  // the tree listed this bipartition before
-              l = 0xffffffffu;
-              ++dups;
-              break;
-            }
-            h = (h + 1) & (set_slots - 1);
+    for (uint64_t e = e0 + sub; e < e1; e += G) {
+      const uint32_t s = ent[e];
+      const uint32_t word = shared_bits[s >> 5];
+      uint32_t l = 0xffffffffu;
+      if ((word >> (s & 31)) & 1u) {
+        l = wrank[s >> 5] + __popc(word & ((1u << (s & 31)) - 1u));
+        uint32_t h = (l * 0x9E3779B1u) & (set_slots - 1);
+        for (;;) {
+          const uint32_t old = atomicCAS(&set[h], 0xffffffffu, l);
+          if (old == 0xffffffffu) break;
+          if (old == l) {  // the tree listed this bipartition before
+            l = 0xffffffffu;
+            ++dups;
+            break;
           }
-          if (l != 0xffffffffu) atomicAdd(&lcnt[l], 1u);
+          h = (h + 1) & (set_slots - 1);
         }
-        ent[e] = l;
+        if (l != 0xffffffffu) atomicAdd(&lcnt[l], 1u);
       }
+      ent[e] = l;
     }
+    __syncwarp();
 #pragma unroll
-    for (int d = 16; d; d >>= 1) dups += __shfl_xor_sync(0xffffffffu, dups, d);
-    if (lane == 0) nb32[t] = (uint32_t)(e1 - e0) - dups;
+    for (int d = G / 2; d; d >>= 1) dups += __shfl_xor_sync(0xffffffffu, dups, d);
+    if (sub == 0 && live) nb32[t] = (uint32_t)(e1 - e0) - dups;
     __syncwarp();
   }
 }
@@ -257,6 +265,7 @@ __global__ void __launch_bounds__(256) list_stats_kernel(const uint32_t* __restr
 // One warp per tree over ent (list ids).  bcnt[ll * NB + (t >> block_log2)] counts the members of long list ll
 // inside t's column block; a short list's members go to sraw[sbase[l] ..) in arrival order; rcnt[t] = long lists
 // of tree t.
+template <int G>
 __global__ void __launch_bounds__(256) bucket_count_kernel(const uint64_t* __restrict__ tb, const uint64_t* __restrict__ te,
                                                            uint32_t T, const uint32_t* __restrict__ ent,
                                                            const uint32_t* __restrict__ lcnt, const uint32_t* __restrict__ llid,
@@ -265,11 +274,14 @@ __global__ void __launch_bounds__(256) bucket_count_kernel(const uint64_t* __res
                                                            uint32_t* __restrict__ sraw, uint32_t* __restrict__ rcnt,
                                                            const uint32_t* __restrict__ fid, uint32_t* fbits, uint32_t fwords,
                                                            uint32_t* __restrict__ hcnt) {
-  const uint32_t warps = blockDim.x >> 5, lane = lane_id();
-  for (uint32_t t = blockIdx.x * warps + (threadIdx.x >> 5); t < T; t += gridDim.x * warps) {
-    const uint64_t e0 = tb[t], e1 = te[t];
+  constexpr uint32_t kPer = 32 / G;
+  const uint32_t warps = blockDim.x >> 5, lane = lane_id(), sub = lane % G, grp = lane / G;
+  for (uint32_t t0 = (blockIdx.x * warps + (threadIdx.x >> 5)) * kPer; t0 < T; t0 += gridDim.x * warps * kPer) {
+    const uint32_t t = t0 + grp;
+    const bool live = t < T;
+    const uint64_t e0 = live ? tb[t] : 0, e1 = live ? te[t] : 0;
     uint32_t nl = 0, nh = 0;
-    for (uint64_t e = e0 + lane; e < e1; e += 32) {
+    for (uint64_t e = e0 + sub; e < e1; e += G) {
       const uint32_t l = ent[e];
       if (l == 0xffffffffu) continue;
       const uint32_t m = lcnt[l];
@@ -283,12 +295,13 @@ __global__ void __launch_bounds__(256) bucket_count_kernel(const uint64_t* __res
         sraw[sbase[l] + atomicAdd(&sfill[l], 1u)] = t;
       }
     }
+    __syncwarp();
 #pragma unroll
-    for (int d = 16; d; d >>= 1) {
+    for (int d = G / 2; d; d >>= 1) {
       nl += __shfl_xor_sync(0xffffffffu, nl, d);
       nh += __shfl_xor_sync(0xffffffffu, nh, d);
     }
-    if (lane == 0) {
+    if (sub == 0 && live) {
       rcnt[t] = nl;
       if (hcnt) hcnt[t] = nh;
     }
@@ -392,6 +405,7 @@ struct Pad8 {  // bucket sizes rounded up to the 16-byte groups the matrix kerne
 
 // ---- K2d: fill the buckets and the trees' list arrays ------------------------------------------------------
 // bcnt doubles as the fill cursor (counted down); lmem was preset to 0xffff (the padding value).
+template <int G>
 __global__ void __launch_bounds__(256) bucket_fill_kernel(const uint64_t* __restrict__ tb, const uint64_t* __restrict__ te,
                                                           uint32_t T, const uint32_t* __restrict__ ent,
                                                           const uint32_t* __restrict__ lcnt, const uint32_t* __restrict__ llid,
@@ -399,19 +413,26 @@ __global__ void __launch_bounds__(256) bucket_fill_kernel(const uint64_t* __rest
                                                           const uint32_t* __restrict__ boff, uint16_t* __restrict__ lmem,
                                                           const uint32_t* __restrict__ roff, uint32_t* __restrict__ rlist,
                                                           int flip) {
-  const uint32_t warps = blockDim.x >> 5, lane = lane_id(), lt = lanemask_lt();
-  for (uint32_t t = blockIdx.x * warps + (threadIdx.x >> 5); t < T; t += gridDim.x * warps) {
-    const uint64_t e0 = tb[t], e1 = te[t];
-    uint32_t pos = roff[t];
-    for (uint64_t eb = e0; eb < e1; eb += 32) {
-      const uint64_t e = eb + lane;
+  constexpr uint32_t kPer = 32 / G;
+  const uint32_t warps = blockDim.x >> 5, lane = lane_id(), sub = lane % G, grp = lane / G;
+  const uint32_t gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u) << (G * grp)), lt = lanemask_lt() & gmask;
+  for (uint32_t t0 = (blockIdx.x * warps + (threadIdx.x >> 5)) * kPer; t0 < T; t0 += gridDim.x * warps * kPer) {
+    const uint32_t t = t0 + grp;
+    const bool live = t < T;
+    const uint64_t e0 = live ? tb[t] : 0, e1 = live ? te[t] : 0;
+    uint32_t pos = live ? roff[t] : 0;
+    uint32_t len = (uint32_t)(e1 - e0);  // the longest tree of the warp sets the (warp-uniform) trip count
+#pragma unroll
+    for (int d = 16; d; d >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, d));
+    for (uint64_t i = 0; i < len; i += G) {
+      const uint64_t e = e0 + i + sub;
       uint32_t ll = 0xffffffffu;
       if (e < e1) {
         const uint32_t l = ent[e];
         if (l != 0xffffffffu && lcnt[l] > short_max && !(flip && 2ull * lcnt[l] > T)) ll = llid[l];
       }
       const bool is = ll != 0xffffffffu;
-      const uint32_t bal = __ballot_sync(0xffffffffu, is);
+      const uint32_t bal = __ballot_sync(0xffffffffu, is) & gmask;
       if (is) {
         const size_t b = (size_t)ll * NB + (t >> block_log2);
         lmem[boff[b] + (atomicSub(&bcnt[b], 1u) - 1u)] = (uint16_t)(t & ((1u << block_log2) - 1u));
@@ -499,7 +520,8 @@ int build_nb_shift(Ctx* ctx) {
 // d_bips: keys (W words per entry); tree t's entries are [tb[t], te[t]) (device arrays); `span` = one past the
 // largest entry index; max_entries = most entries of one tree.
 int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* tb, const uint64_t* te, uint32_t T, uint32_t W,
-                 uint64_t span, uint64_t nnz, uint32_t max_entries) {
+                 uint64_t span, uint64_t nnz, uint32_t max_entries, const uint64_t* seg_begin, const uint64_t* seg_len,
+                 uint32_t n_segs) {
   cudaStream_t s = ctx->stream;
   HashRFState& H = ctx->h;
   H = HashRFState{};
@@ -560,13 +582,26 @@ int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* tb, const uin
   trace_mark("build: temporaries allocated");
   PRF_CK(ctx, cudaEventRecord(ctx->ev[1], s));
   // ---- K1: dedup ----
+  DedupSegs segs{};  // the dense entry segments: the whole array, or one per source rank of a team
+  if (n_segs == 0) {
+    segs.n = 1;
+    segs.begin[0] = 0;
+    segs.start[1] = nnz;
+  } else {
+    segs.n = n_segs;
+    for (uint32_t i = 0; i < n_segs; ++i) {
+      segs.begin[i] = seg_begin[i];
+      segs.start[i + 1] = segs.start[i] + seg_len[i];
+    }
+  }
+  const int dedup_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((segs.start[segs.n] + 255) / 256, (uint64_t)ctx->sm_count * 64));
   if (T) {
     switch (W) {
 #define PRF_W_CASE(w)                                                                                                  \
   case w:                                                                                                              \
     if (compact)                                                                                                       \
-      dedup_insert32_kernel<w><<<(T + 7) / 8, 256, 0, s>>>(d_bips, tb, te, T, slots32.p, shared_bits.p, (uint32_t)cap,  \
-                                                           H.ent_lid.p, counters.p);                                   \
+      dedup_insert32_kernel<w><<<dedup_grid, 256, 0, s>>>(d_bips, segs, slots32.p, shared_bits.p, (uint32_t)cap,        \
+                                                          H.ent_lid.p, counters.p);                                    \
     else                                                                                                               \
       launch_dedup<w>(ctx, d_bips, tb, te, T, slots.p, shared_bits.p, cap - 1, H.ent_lid.p, counters.p);               \
     break;
@@ -579,19 +614,26 @@ int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* tb, const uin
     PRF_LAUNCHED(ctx);
   }
   PRF_CK(ctx, cudaEventRecord(ctx->ev[2], s));
+  trace_sync(s, "build:   dedup kernel");
 
   // ---- K2: lists ----
   int rc;
-  const int grid_t = std::max(1, std::min<int>((int)((T + 7) / 8), ctx->sm_count * 8));
+  // lanes per tree in the tree-major kernels: a class build of a multi-GPU team sees every tree with few entries
+  const bool narrow = T && nnz / T < 48;
+  const uint32_t tpw = narrow ? 4 : 1;  // trees per warp
+  const int grid_t = std::max(1, std::min<int>((int)((T + 8 * tpw - 1) / (8 * tpw)), ctx->sm_count * 8));
   if ((rc = exclusive_scan(ctx, PopcWord{shared_bits.p}, cap / 32, wrank.p, &cnts.p->n_lists))) return rc;
   uint32_t set_slots = 64;
   while (set_slots < 2 * max_entries) set_slots <<= 1;
   if (T) {
-    const int warps = (int)std::min<uint32_t>(8, (48 * 1024) / (set_slots * 4));
-    list_count_kernel<<<std::max(1, std::min<int>((int)((T + warps - 1) / warps), ctx->sm_count * 8)), 32 * warps,
-                        (size_t)warps * set_slots * 4, s>>>(tb, te, T, H.ent_lid.p, shared_bits.p, wrank.p, set_slots, lcnt.p, nb32.p);
+    const int warps = (int)std::max<uint32_t>(1, std::min<uint32_t>(8, (48 * 1024) / (set_slots * 4 * tpw)));
+    const int grid_l = std::max(1, std::min<int>((int)((T + warps * tpw - 1) / (warps * tpw)), ctx->sm_count * 8));
+    const size_t smem_l = (size_t)warps * tpw * set_slots * 4;
+    if (narrow) list_count_kernel<8><<<grid_l, 32 * warps, smem_l, s>>>(tb, te, T, H.ent_lid.p, shared_bits.p, wrank.p, set_slots, lcnt.p, nb32.p);
+    else list_count_kernel<32><<<grid_l, 32 * warps, smem_l, s>>>(tb, te, T, H.ent_lid.p, shared_bits.p, wrank.p, set_slots, lcnt.p, nb32.p);
     PRF_LAUNCHED(ctx);
   }
+  trace_sync(s, "build:   rank scan + list_count");
   if ((rc = exclusive_scan(ctx, IsLong{lcnt.p, cnts.p, short_max}, Lmax, llid.p, &cnts.p->n_long, &cnts.p->n_lists))) return rc;
   if ((rc = exclusive_scan(ctx, ShortLen{lcnt.p, cnts.p, short_max}, Lmax, sbase.p, &cnts.p->short_members, &cnts.p->n_lists))) return rc;
   const int flip_ok = ctx->debug_no_flip ? 0 : 1;
@@ -641,8 +683,12 @@ int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* tb, const uin
   PRF_CK(ctx, cudaMemsetAsync(scur.p, 0, scur.bytes(), s));
   PRF_CK(ctx, cudaMemsetAsync(H.lmem.p, 0xff, H.lmem.bytes(), s));
   if (T) {
-    bucket_count_kernel<<<grid_t, 256, 0, s>>>(tb, te, T, H.ent_lid.p, lcnt.p, llid.p, sbase.p, short_max, H.block_log2, NB,
-                                               bcnt.p, sfill.p, sraw.p, rcnt.p, fid.p, fbits.p, fwords, hcnt.p);
+    if (narrow)
+      bucket_count_kernel<8><<<grid_t, 256, 0, s>>>(tb, te, T, H.ent_lid.p, lcnt.p, llid.p, sbase.p, short_max, H.block_log2, NB,
+                                                    bcnt.p, sfill.p, sraw.p, rcnt.p, fid.p, fbits.p, fwords, hcnt.p);
+    else
+      bucket_count_kernel<32><<<grid_t, 256, 0, s>>>(tb, te, T, H.ent_lid.p, lcnt.p, llid.p, sbase.p, short_max, H.block_log2, NB,
+                                                     bcnt.p, sfill.p, sraw.p, rcnt.p, fid.p, fbits.p, fwords, hcnt.p);
     PRF_LAUNCHED(ctx);
     if (n_heavy) {
       flip_buckets_kernel<<<(n_heavy * NB + 7) / 8, 256, 0, s>>>(fbits.p, fwords, fll.p, n_heavy, T, H.block_log2, NB, 0, bcnt.p,
@@ -656,11 +702,16 @@ int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* tb, const uin
       PRF_LAUNCHED(ctx);
     }
   }
+  trace_sync(s, "build:   memsets + bucket_count");
   if ((rc = exclusive_scan(ctx, Pad8{bcnt.p, n_buckets}, n_buckets + 1, H.boff.p, &cnts.p->n_lmem))) return rc;
   if ((rc = exclusive_scan(ctx, LoadU32{rcnt.p}, (uint64_t)T + 1, H.roff.p, nullptr))) return rc;
   if (T) {
-    bucket_fill_kernel<<<grid_t, 256, 0, s>>>(tb, te, T, H.ent_lid.p, lcnt.p, llid.p, short_max, H.block_log2, NB, bcnt.p,
-                                              H.boff.p, H.lmem.p, H.roff.p, H.rlist.p, n_heavy ? 1 : 0);
+    if (narrow)
+      bucket_fill_kernel<8><<<grid_t, 256, 0, s>>>(tb, te, T, H.ent_lid.p, lcnt.p, llid.p, short_max, H.block_log2, NB, bcnt.p,
+                                                   H.boff.p, H.lmem.p, H.roff.p, H.rlist.p, n_heavy ? 1 : 0);
+    else
+      bucket_fill_kernel<32><<<grid_t, 256, 0, s>>>(tb, te, T, H.ent_lid.p, lcnt.p, llid.p, short_max, H.block_log2, NB, bcnt.p,
+                                                    H.boff.p, H.lmem.p, H.roff.p, H.rlist.p, n_heavy ? 1 : 0);
     PRF_LAUNCHED(ctx);
     if (n_heavy) {
       flip_buckets_kernel<<<(n_heavy * NB + 7) / 8, 256, 0, s>>>(fbits.p, fwords, fll.p, n_heavy, T, H.block_log2, NB, 1, bcnt.p,
@@ -674,6 +725,7 @@ int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* tb, const uin
       PRF_LAUNCHED(ctx);
     }
   }
+  trace_sync(s, "build:   scans + bucket_fill + singles count");
   if ((rc = exclusive_scan(ctx, LoadU32{scount.p}, (uint64_t)T + 1, H.soff.p, nullptr))) return rc;
   if (T) {
     if (hc.short_members) {

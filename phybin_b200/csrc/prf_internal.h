@@ -24,8 +24,10 @@ namespace prf {
 
 // kernel launchers (defined next to their kernels)
 // tree t's entries are [tb[t], te[t]) of d_bips (W words each); span = one past the largest entry index
+// seg_*: the dense entry segments holding all entries (n_segs = 0: the one segment [0, nnz))
 int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* tb, const uint64_t* te, uint32_t T, uint32_t W,
-                 uint64_t span, uint64_t nnz, uint32_t max_entries);
+                 uint64_t span, uint64_t nnz, uint32_t max_entries, const uint64_t* seg_begin = nullptr,
+                 const uint64_t* seg_len = nullptr, uint32_t n_segs = 0);
 int build_nb_shift(Ctx* ctx);
 void team_release_ctx(Ctx* ctx);  // prf_team.cu: frees a context's team arena (prf_destroy)
 void build_row_plan(uint32_t T, uint64_t p_begin, uint64_t p_end, uint32_t tile, std::vector<RowItem>& rows,

@@ -53,18 +53,23 @@ void team_release_ctx(Ctx* ctx) {
   tm = Team{};
 }
 
-static int team_barrier(Ctx* ctx) {
+static int team_barrier(Ctx* ctx, const uint32_t* payload = nullptr) {
   Team& tm = ctx->team;
   cudaStream_t s = ctx->stream;
   ++tm.epoch;
   if (tm.shared) {  // single process: events + a host rendezvous of the ranks' threads
     PRF_CK(ctx, cudaEventRecord(tm.ev, s));
+    if (payload) {  // same delivery as the flag kernel's, by a stream-ordered kernel before the event
+      team_payload_kernel<<<1, 32, 0, s>>>(tm.peers_dev.p, tm.lay.off_flags, tm.rank, tm.world, payload);
+      PRF_LAUNCHED(ctx);
+      PRF_CK(ctx, cudaEventRecord(tm.ev, s));
+    }
     tm.shared->wait();  // every rank has recorded its event
     for (uint32_t p = 0; p < tm.world; ++p)
       if (p != tm.rank) PRF_CK(ctx, cudaStreamWaitEvent(s, tm.shared->ev[p], 0));
     tm.shared->wait();  // nobody re-records its event before everybody has queued its waits
   } else {
-    team_barrier_kernel<<<1, 32, 0, s>>>(tm.peers_dev.p, tm.lay.off_flags, tm.rank, tm.world, tm.epoch, tm.err.p);
+    team_barrier_kernel<<<1, 32, 0, s>>>(tm.peers_dev.p, tm.lay.off_flags, tm.rank, tm.world, tm.epoch, payload, tm.err.p);
     PRF_LAUNCHED(ctx);
   }
   return PRF_OK;
@@ -202,34 +207,42 @@ static int team_load(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off, ui
   ctx->out_valid = ctx->mask_valid = false;
   PRF_CK(ctx, cudaEventRecord(ctx->ev[0], s));
 
-  // ---- hash classes of my keys, positions inside every (class, me) region, keys and entry ranges to their owners ----
-  const size_t ncnt = (size_t)world * (Tl + 1);
-  if (tm.cls.n < nnz_local + 1) PRF_CK(ctx, tm.cls.alloc(nnz_local + 1, s));
-  if (tm.cls_cnt.n < ncnt) PRF_CK(ctx, tm.cls_cnt.alloc(ncnt, s));
-  if (tm.cls_pos.n < ncnt) PRF_CK(ctx, tm.cls_pos.alloc(ncnt, s));
-  switch (W) {
-#define PRF_W_CASE(w) case w: team_class_kernel<w><<<(Tl + 1 + 7) / 8, 256, 0, s>>>(d_bips, d_off, Tl, world, tm.cls.p, tm.cls_cnt.p); break;
-    PRF_W_CASE(1) PRF_W_CASE(2) PRF_W_CASE(3) PRF_W_CASE(4) PRF_W_CASE(5) PRF_W_CASE(6) PRF_W_CASE(7) PRF_W_CASE(8)
-    PRF_W_CASE(9) PRF_W_CASE(10) PRF_W_CASE(11) PRF_W_CASE(12) PRF_W_CASE(13) PRF_W_CASE(14) PRF_W_CASE(15) PRF_W_CASE(16)
-#undef PRF_W_CASE
-    default: return ctx->fail(PRF_E_UNSUPPORTED, "W=%u", W);
-  }
-  PRF_LAUNCHED(ctx);
-  int rc;
-  if ((rc = exclusive_scan(ctx, LoadU32{tm.cls_cnt.p}, ncnt, tm.cls_pos.p, nullptr))) return rc;
+  // ---- my keys to their owners: one kernel (classes, reserved ranges, stores into the peers' arenas) ----
+  if (tm.cls_cnt.n < (size_t)kMaxParts) PRF_CK(ctx, tm.cls_cnt.alloc(kMaxParts, s));  // per-class cursors of my key regions
+  PRF_CK(ctx, cudaMemsetAsync(tm.cls_cnt.p, 0, kMaxParts * 4, s));
   if (Tl) {
-    team_push_keys_kernel<<<(Tl + 7) / 8, 256, 0, s>>>(d_bips, d_off, Tl, t_lo, W, world, rank, tm.cls.p, tm.cls_pos.p, tm.peers_dev.p, L,
-                                                       tm.err.p);
+    switch (W) {
+#define PRF_W_CASE(w) case w: team_partition_kernel<w><<<(Tl + 7) / 8, 256, 0, s>>>(d_bips, d_off, Tl, t_lo, world, rank, tm.peers_dev.p, L, tm.cls_cnt.p, tm.err.p); break;
+      PRF_W_CASE(1) PRF_W_CASE(2) PRF_W_CASE(3) PRF_W_CASE(4) PRF_W_CASE(5) PRF_W_CASE(6) PRF_W_CASE(7) PRF_W_CASE(8)
+      PRF_W_CASE(9) PRF_W_CASE(10) PRF_W_CASE(11) PRF_W_CASE(12) PRF_W_CASE(13) PRF_W_CASE(14) PRF_W_CASE(15) PRF_W_CASE(16)
+#undef PRF_W_CASE
+      default: return ctx->fail(PRF_E_UNSUPPORTED, "W=%u", W);
+    }
     PRF_LAUNCHED(ctx);
   }
-  if ((rc = team_barrier(ctx))) return rc;
+  trace_sync(s, "team:   partition kernel");
+  int rc;
+  if ((rc = team_barrier(ctx, tm.cls_cnt.p))) return rc;  // (+ how many entries every class got from me)
+  trace_sync(s, "team:   barrier 1");
   PRF_CK(ctx, cudaEventRecord(ctx->ev[1], s));
+  trace_mark("team: keys pushed, barrier queued");
 
   // ---- the ordinary build on my class (keys, tb, te now sit in my arena) ----
   const uint64_t* keys = reinterpret_cast<const uint64_t*>(tm.arena + L.off_keys);
   const uint64_t* tb = reinterpret_cast<const uint64_t*>(tm.arena + L.off_tb);
   const uint64_t* te = reinterpret_cast<const uint64_t*>(tm.arena + L.off_te);
-  if ((rc = hashrf_build(ctx, keys, tb, te, T, W, (uint64_t)world * L.cap_e, L.cap_class, tm.max_entries))) {
+  // entries every source rank sent me: the dense segments of my key space, and the size of the dedup table
+  unsigned long long seg_cnt[kMaxParts] = {};
+  PRF_CK(ctx, cudaMemcpyAsync(seg_cnt, tm.arena + L.off_flags + 2048, (size_t)world * 8, cudaMemcpyDeviceToHost, s));
+  PRF_CK(ctx, cudaStreamSynchronize(s));
+  uint64_t seg_begin[kMaxParts], seg_len[kMaxParts], class_entries = 0;
+  for (uint32_t p = 0; p < world; ++p) {
+    seg_begin[p] = (uint64_t)p * L.cap_e;
+    seg_len[p] = seg_cnt[p];
+    class_entries += seg_cnt[p];
+  }
+  trace_mark("team: class size known");
+  if ((rc = hashrf_build(ctx, keys, tb, te, T, W, (uint64_t)world * L.cap_e, class_entries, tm.max_entries, seg_begin, seg_len, world))) {
     if (tm.shared) tm.shared->failed = 1;
     // keep the peers' barriers matched: fall through with an error part
   }
@@ -274,8 +287,11 @@ static int team_load(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off, ui
   }
   team_push_part_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(cp, tm.peers_dev.p, L.off_parts + (size_t)rank * L.part_bytes, world);
   PRF_LAUNCHED(ctx);
+  trace_sync(s, "team:   push part kernel");
   if ((rc = team_barrier(ctx))) return rc;
+  trace_sync(s, "team:   barrier 2");
   PRF_CK(ctx, cudaEventRecord(ctx->ev[2], s));
+  trace_mark("team: part pushed, barrier queued");
 
   // ---- every part is here: |B_t| = sum over the parts, install the parts as the loaded problem ----
   DevBuf<uint16_t> nb;
@@ -352,6 +368,7 @@ static int team_load(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off, ui
   st.gpu_launches = (int32_t)(ctx->launches - launches0);
   if ((rc = build_nb_shift(ctx))) return rc;
   H.loaded = true;
+  trace_mark("team: parts installed");
   if (stats) *stats = st;
   return PRF_OK;
 }

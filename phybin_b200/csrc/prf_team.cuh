@@ -38,79 +38,69 @@ __device__ __forceinline__ uint32_t key_class(const uint64_t* __restrict__ bips,
   return (uint32_t)((mix64(h ^ 0xA5A5A5A5A5A5A5A5ull) >> 33) % world);
 }
 
-// One warp per local tree: cls[e] = hash class of entry e; cnt[c * (Tl + 1) + t] = entries of tree t in class c.
+// One warp per local tree, one kernel: hash classes of the tree's keys, a contiguous range reserved for them in
+// every class's (class, me) key region (atomic cursor per class: the trees of a region are in arrival order, every
+// tree's entries contiguous), then every key stored straight into its owner's arena (peer memory over NVLink) and
+// the tree's entry range into that class's tb / te.  The keys are read twice; the second read hits L1 / L2.
 template <int W>
-__global__ void __launch_bounds__(256) team_class_kernel(const uint64_t* __restrict__ bips, const uint64_t* __restrict__ off,
-                                                         uint32_t Tl, uint32_t world, uint8_t* __restrict__ cls,
-                                                         uint32_t* __restrict__ cnt) {
-  const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = lane_id();
-  if (t > Tl) return;
-  if (t == Tl) {  // the scan's last column
-    if (lane < world) cnt[(size_t)lane * (Tl + 1) + Tl] = 0;
-    return;
-  }
+__global__ void __launch_bounds__(256) team_partition_kernel(const uint64_t* __restrict__ bips, const uint64_t* __restrict__ off,
+                                                             uint32_t Tl, uint32_t t_lo, uint32_t world, uint32_t rank,
+                                                             const uint64_t* __restrict__ peers, TeamLayout lay, uint32_t* cursor,
+                                                             uint32_t* err) {
+  const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = lane_id(), lt = lanemask_lt();
+  if (t >= Tl) return;
   const uint64_t e0 = off[t], e1 = off[t + 1];
-  uint32_t mine = 0;  // lane c accumulates class c
+  uint32_t mine = 0;  // lane c: entries of class c
   for (uint64_t eb = e0; eb < e1; eb += 32) {
     const uint64_t e = eb + lane;
-    uint32_t c = 0xffffffffu;
-    if (e < e1) {
-      c = key_class<W>(bips, e, world);
-      cls[e] = (uint8_t)c;
-    }
+    const uint32_t c = e < e1 ? key_class<W>(bips, e, world) : 0xffffffffu;
     for (uint32_t k = 0; k < world; ++k) {
       const uint32_t n = __popc(__ballot_sync(0xffffffffu, c == k));
       if (lane == k) mine += n;
     }
   }
-  if (lane < world) cnt[(size_t)lane * (Tl + 1) + t] = mine;
-}
-
-// One warp per local tree: every key goes straight into its owner's arena (peer memory), tree order kept inside
-// a (class, source) region; the tree's entry range in every class goes to that class's tb / te.
-__global__ void __launch_bounds__(256) team_push_keys_kernel(const uint64_t* __restrict__ bips, const uint64_t* __restrict__ off,
-                                                             uint32_t Tl, uint32_t t_lo, uint32_t W, uint32_t world, uint32_t rank,
-                                                             const uint8_t* __restrict__ cls, const uint32_t* __restrict__ pos,
-                                                             const uint64_t* __restrict__ peers, TeamLayout lay, uint32_t* err) {
-  const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = lane_id(), lt = lanemask_lt();
-  if (t >= Tl) return;
-  const uint64_t e0 = off[t], e1 = off[t + 1];
-  // where tree t's entries of class c start inside region `rank` of rank c's key space
-  uint32_t run = 0;  // lane c: entries of class c written so far
   uint64_t first = 0;
-  if (lane < world) first = (uint64_t)rank * lay.cap_e + (pos[(size_t)lane * (Tl + 1) + t] - pos[(size_t)lane * (Tl + 1)]);
+  if (lane < world) {
+    const uint32_t at = atomicAdd(&cursor[lane], mine);
+    if ((uint64_t)at + mine > lay.cap_e) *err = 1;  // (cannot happen: a region holds all of a rank's entries)
+    first = (uint64_t)rank * lay.cap_e + at;
+    reinterpret_cast<uint64_t*>(peers[lane] + lay.off_tb)[t_lo + t] = first;
+    reinterpret_cast<uint64_t*>(peers[lane] + lay.off_te)[t_lo + t] = first + mine;
+  }
+  uint32_t run = 0;  // lane c: entries of class c written so far
   for (uint64_t eb = e0; eb < e1; eb += 32) {
     const uint64_t e = eb + lane;
-    const uint32_t c = e < e1 ? cls[e] : 0xffffffffu;
+    const uint32_t c = e < e1 ? key_class<W>(bips, e, world) : 0xffffffffu;
     for (uint32_t k = 0; k < world; ++k) {
       const uint32_t bal = __ballot_sync(0xffffffffu, c == k);
       if (!bal) continue;
       const uint64_t f = __shfl_sync(0xffffffffu, first, k);
       const uint32_t r = __shfl_sync(0xffffffffu, run, k);
       if (c == k) {
-        const uint64_t dst = f + r + __popc(bal & lt);
-        if (dst >= (uint64_t)(rank + 1) * lay.cap_e) {
-          *err = 1;  // (cannot happen: a region holds all of a rank's entries)
+        uint64_t* out = reinterpret_cast<uint64_t*>(peers[k] + lay.off_keys) + (f + r + __popc(bal & lt)) * W;
+        const uint64_t* in = bips + e * W;
+        if ((W & 1u) == 0) {  // 16-byte stores over NVLink (key regions and the caller's keys are 16-byte aligned)
+#pragma unroll
+          for (int w = 0; w < W; w += 2) *reinterpret_cast<ulonglong2*>(out + w) = *reinterpret_cast<const ulonglong2*>(in + w);
         } else {
-          uint64_t* out = reinterpret_cast<uint64_t*>(peers[k] + lay.off_keys) + dst * W;
-          for (uint32_t w = 0; w < W; ++w) out[w] = bips[e * W + w];
+#pragma unroll
+          for (int w = 0; w < W; ++w) out[w] = in[w];
         }
       }
       if (lane == k) run += __popc(bal);
     }
   }
-  if (lane < world) {
-    reinterpret_cast<uint64_t*>(peers[lane] + lay.off_tb)[t_lo + t] = first;
-    reinterpret_cast<uint64_t*>(peers[lane] + lay.off_te)[t_lo + t] = first + run;
-  }
   __threadfence_system();
 }
 
 // Multi-process barrier: tell every peer that I arrived (epoch), then wait until every peer has told me.
+// `payload` (optional, [world] uint32 in my memory): payload[p] is delivered to rank p's arena (slot `rank` of its
+// payload area) before the flag -- the key exchange uses it to tell every class how many entries I sent it.
 __global__ void team_barrier_kernel(const uint64_t* __restrict__ peers, size_t off_flags, uint32_t rank, uint32_t world,
-                                    unsigned long long epoch, uint32_t* err) {
+                                    unsigned long long epoch, const uint32_t* payload, uint32_t* err) {
   const uint32_t p = threadIdx.x;
   if (p >= world) return;
+  if (payload) reinterpret_cast<unsigned long long*>(peers[p] + off_flags + 2048)[rank] = payload[p];
   __threadfence_system();
   unsigned long long* theirs = reinterpret_cast<unsigned long long*>(peers[p] + off_flags) + rank;
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
@@ -126,6 +116,13 @@ __global__ void team_barrier_kernel(const uint64_t* __restrict__ peers, size_t o
     }
     __nanosleep(200);
   }
+}
+
+// single-process teams: the payload delivery of team_barrier_kernel as a stream-ordered kernel of its own
+__global__ void team_payload_kernel(const uint64_t* __restrict__ peers, size_t off_flags, uint32_t rank, uint32_t world,
+                                    const uint32_t* payload) {
+  const uint32_t p = threadIdx.x;
+  if (p < world) reinterpret_cast<unsigned long long*>(peers[p] + off_flags + 2048)[rank] = payload[p];
 }
 
 struct TeamCopy {  // one array of my finished part

@@ -70,4 +70,7 @@ def team_load(ctx, keys: torch.Tensor, off: torch.Tensor, T: int) -> dict:
     """Collective: `keys` [nnz_local, W] int64 and `off` [T_local + 1] int64 describe THIS rank's trees
     tree_shard(T, rank, world) (device tensors visible to ctx's stream).  On return ctx holds the whole structure:
     ctx.hashrf_compute works on any range."""
+    # the tensors may have been produced on torch's current stream: the library's stream waits for it first
+    lib_stream = torch.cuda.ExternalStream(ctx.stream, device=keys.device)
+    lib_stream.wait_stream(torch.cuda.current_stream(keys.device))
     return ctx.team_load(keys.data_ptr(), off.data_ptr(), off.numel() - 1, T)

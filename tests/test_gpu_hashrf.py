@@ -121,6 +121,26 @@ def test_config2_shape_vs_closed_form_oracle(ctx):
     assert st["gpu_launches"] > 0 and st["variant_used"] == 1
 
 
+def test_config3_shape_w4_vs_closed_form_oracle(ctx):
+    # BASELINE config 3 family (200 taxa, W = 4 words per set) at a size the oracle finishes in seconds: the matrix through
+    # the sparse kernel, through the tensor-core variant, and the threshold mask of both
+    T, n = 2500, 200
+    f = Forest.synthetic(T, n, seed=0x5EED0003)
+    assert f.words == 4
+    o = orc.Forest([f.to_newick()])
+    small = orc.Forest([f.to_newick(0, 300)])
+    assert np.array_equal(small.hashrf(n, "closed"), small.hashrf(n, "literal"))  # closed form is trusted only after this
+    want = oracle_packed(o, "hashrf", "closed")
+    bips, off = f.all_bips()
+    for variant in (1, 2):
+        up, mask, st = run_variant(ctx, bips, off, variant, editdist=388)
+        assert st["variant_used"] == variant
+        assert np.array_equal(up.astype(np.int64), want)
+        bits = np.unpackbits(mask.view(np.uint8), bitorder="little")[: len(want)]
+        assert np.array_equal(bits.astype(bool), want <= 388)
+        assert 0 < bits.sum() < len(want)
+
+
 def test_multifurcating_nonuniform_bip_counts(ctx):
     rng = random.Random(11)
     text = [random_multifurcating_newicks(rng, 500, 40)]
