@@ -86,17 +86,43 @@ __global__ void __launch_bounds__(256) dedup_insert32_kernel(const uint64_t* __r
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
   const uint64_t total = segs.start[segs.n];
   uint32_t claims = 0;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+  // a warp's 32 keys are read with coalesced 16-byte loads and handed to their lanes through shared memory (a lane
+  // loading its own 8 W bytes would touch one sector per lane and load: the L1 wavefronts were a third of the kernel)
+  __shared__ __align__(16) uint64_t s_keys[8][32 * W + 2];
+  const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+  for (uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; i0 < total; i0 += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = i0 + lane;
     uint32_t sg = 0;
     while (sg + 1 < segs.n && i >= segs.start[sg + 1]) ++sg;
     const uint64_t e = segs.begin[sg] + (i - segs.start[sg]);
+    const bool valid = i < total;
     uint64_t k[W];
-    {
+    const uint32_t sg0 = __shfl_sync(0xffffffffu, sg, 0);
+    const uint32_t nv = __popc(__ballot_sync(0xffffffffu, valid));
+    if (W % 2 == 0 && __all_sync(0xffffffffu, !valid || sg == sg0)) {  // one segment: the keys are contiguous
+      const uint64_t ef = __shfl_sync(0xffffffffu, e, 0);
+      const ulonglong2* src = reinterpret_cast<const ulonglong2*>(bips + ef * W);
+      ulonglong2* dst = reinterpret_cast<ulonglong2*>(&s_keys[warp][0]);
+#pragma unroll
+      for (int c = 0; c < W / 2; ++c) {
+        const uint32_t ch = c * 32 + lane;
+        if (ch < nv * (W / 2)) {
+          ulonglong2 q;
+          asm volatile("ld.global.nc.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(q.x), "=l"(q.y) : "l"(src + ch), "l"(policy));
+          dst[ch] = q;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int w = 0; w < W; ++w) k[w] = s_keys[warp][lane * W + w];
+      __syncwarp();
+    } else if (valid) {
       const uint64_t* p = bips + e * W;
 #pragma unroll
       for (int w = 0; w < W; ++w)
         asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(k[w]) : "l"(p + w), "l"(policy));
     }
+    if (!valid) continue;
     uint64_t h = 0x9E3779B97F4A7C15ull;
 #pragma unroll
     for (int w = 0; w < W; ++w) h = mix64(h ^ (k[w] + 0x632BE59BD9B4E019ull * (w + 1)));
@@ -539,7 +565,8 @@ int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* tb, const uin
   // compact 4-byte slots whenever the entry index fits 25 bits (see dedup_insert32_kernel)
   const bool compact = span < (1ull << 25) - 1 && !ctx->debug_wide_slots;
   uint64_t cap = 1024;
-  if (compact) cap = std::max<uint64_t>(1024, ((uint64_t)(nnz * 1.25) + 31) / 32 * 32);  // load factor <= 0.8, multiple of the bitmap word
+  // load factor <= 0.8 where the table has to fight for the L2 (above 8 M entries), <= 0.5 (shorter probe chains) below
+  if (compact) cap = std::max<uint64_t>(1024, ((uint64_t)(nnz * (nnz > (8u << 20) ? 1.25 : 2.0)) + 31) / 32 * 32);
   else while (cap < nnz + nnz / 2) cap <<= 1;  // load factor <= 2/3 even if every key is distinct
   if (!compact && cap > (1ull << 32)) return ctx->fail(PRF_E_UNSUPPORTED, "nnz=%llu entries: the dedup table would exceed 2^32 slots", (unsigned long long)nnz);
 
