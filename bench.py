@@ -109,35 +109,77 @@ class ClockSampler:
 # CPU reference arm: the oracle's literal hashRF / naiveDistMatrix on a bounded sample
 # ---------------------------------------------------------------------------------------------------
 
-def cpu_sample(wl: dict, budget_trees: int):
-    """Times the oracle (literal restatement of RFDistance.hs:284-341 / :168-198) on the first
-    `budget_trees` trees of the workload.  Returns (pairs_per_s, seconds, sample description)."""
+def cpu_sample(wl: dict, budget_trees: int, all_cores: bool = False):
+    """Times the oracle (literal restatement of RFDistance.hs:284-341 / :168-198) on the first `budget_trees` trees of
+    the workload: on one thread, like the reference's sequential runST ingest (RFDistance.hs:300-341), or -- hashRF
+    only -- the same algorithm parallelised over all host cores (oracle: hashRFAllCores).
+    Returns (pairs_per_s, seconds, threads, sample description)."""
     from oracle import oracle as orc
     from phybin_b200.host import Forest
     Ts = min(budget_trees, wl["T"])
     f = Forest.synthetic(Ts, wl["n"], wl["seed"], wl["family"], 8, wl.get("p_missing", 0.0))
     text = f.to_newick()
     of = orc.Forest([text])
+    threads = 1
     t0 = time.perf_counter()
     if wl["mode"] == "tolerant":
         of.naive()
+    elif all_cores:
+        of.hashrf(wl["n"], "literal_all_cores")
+        threads = orc.max_threads()
     else:
         of.hashrf(wl["n"], "literal")
     dt = time.perf_counter() - t0
     pairs = Ts * (Ts - 1) // 2
-    return pairs / dt, dt, f"first {Ts} of {wl['T']} trees x {wl['n']} taxa, all {pairs} pairs, literal {wl['mode']} restatement (allBips + table + matrix)"
+    how = f"literal {wl['mode']} restatement (allBips + table + matrix), " + (f"OpenMP on {threads} threads" if all_cores and wl["mode"] != "tolerant" else "1 thread like the reference")
+    return pairs / dt, dt, threads, f"first {Ts} of {wl['T']} trees x {wl['n']} taxa, all {pairs} pairs, {how}"
+
+
+def cpu_baseline_report(wl: dict, ref_trees: int, full_sweep: bool) -> dict:
+    """cpu_baseline of the GPU arm's line: the all-cores variant at the largest sampled T is the
+    value; the single-threaded run (what the reference's runtime does) and the T sweep are listed beside it."""
+    if wl["mode"] == "tolerant":
+        v, s, th, desc = cpu_sample(wl, ref_trees or 150)
+        return {"value": v, "unit": UNIT, "cores": th, "kind": "port", "sample": desc, "seconds": s, "host_cores": os.cpu_count()}
+    sweep = []
+    sizes = [1000, 2000, 5000] + ([10000] if full_sweep else [])
+    if ref_trees:
+        sizes = [ref_trees]
+    for Ts in sizes:
+        v, s, th, desc = cpu_sample(wl, Ts, all_cores=True)
+        sweep.append({"trees": min(Ts, wl["T"]), "cores": th, "value": v, "seconds": s})
+    v1, s1, _, desc1 = cpu_sample(wl, min(sizes[-1], 2000))
+    return {"value": v, "unit": UNIT, "cores": th, "kind": "port", "sample": desc, "seconds": s, "host_cores": os.cpu_count(),
+            "single_thread": {"value": v1, "unit": UNIT, "cores": 1, "sample": desc1, "seconds": s1},
+            "sweep": sweep}
+
+
+def workload_config(wl: dict, wl_name: str, editdist: int, nnz: int, words: int) -> dict:
+    """The `config` object: the same for both arms (what was sampled or measured is reported elsewhere in the line)."""
+    T = wl["T"]
+    return {"workload": wl_name, "trees": T, "taxa": wl["n"], "mode": wl["mode"], "editdist": editdist,
+            "pairs": T * (T - 1) // 2, "nnz": int(nnz), "words": int(words)}
 
 
 def run_reference(args, wl, wl_name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sample_T = args.ref_trees or (2000 if wl["mode"] == "hashrf" else 150)
+    from phybin_b200.host import Forest
+    hashrf = wl["mode"] == "hashrf"
+    sample_T = args.ref_trees or (4000 if hashrf else 150)
+    f = Forest.synthetic(wl["T"], wl["n"], wl["seed"], wl["family"], 8, wl.get("p_missing", 0.0))
+    if hashrf:
+        _, off = f.all_bips()
+    else:
+        _, _, off = f.clades()
+    cfg = workload_config(wl, wl_name, wl["editdist"], int(off[-1]), f.words)
+    del f, off
     for _ in range(args.warmup):
-        cpu_sample(wl, max(100, sample_T // 8))
-    vals, secs, desc = [], [], ""
+        cpu_sample(wl, max(100, sample_T // 8), all_cores=True)
+    vals, secs, desc, th = [], [], "", 1
     for _ in range(args.steps):
-        v, s, desc = cpu_sample(wl, sample_T)
+        v, s, th, desc = cpu_sample(wl, sample_T, all_cores=True)
         vals.append(v); secs.append(s)
     total_pairs = len(vals) * (min(sample_T, wl["T"]) * (min(sample_T, wl["T"]) - 1) // 2)
     value = total_pairs / sum(secs)
@@ -145,10 +187,13 @@ def run_reference(args, wl, wl_name):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64",
-        "data": "synthetic",
-        "config": {"workload": wl_name, "trees": wl["T"], "taxa": wl["n"], "mode": wl["mode"],
-                   "note": "reference arm = CPU oracle (C++ restatement of PhyBin's hashRF); GHC is absent so the Haskell binary cannot be built; the reference path is single-threaded (runST, RFDistance.hs:300-341)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc,
+        "data": "synthetic", "config": cfg,
+        "sampled_trees": min(sample_T, wl["T"]),
+        "note": "reference arm = CPU oracle (C++ restatement of PhyBin's hashRF; GHC is absent so the Haskell binary cannot be built). "
+                "Each step runs the whole path on the first `sampled_trees` trees of the workload and the rate is in tree-pairs/s "
+                "(the reference's cost per pair does not fall with T). The reference's own ingest is single-threaded "
+                "(runST, RFDistance.hs:300-341); this arm uses every host core (cpu_baseline.cores).",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": th, "kind": "port", "sample": desc,
                          "host_cores": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -474,9 +519,7 @@ def run_gpu(args, wl, wl_name):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, s, desc = cpu_sample(wl, args.ref_trees or (2000 if mode == "hashrf" else 150))
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc, "seconds": s,
-                        "host_cores": os.cpu_count()}
+        cpu_baseline = cpu_baseline_report(wl, args.ref_trees, args.cpu_sweep_full)
 
     if rank == 0:
         line = {
@@ -484,8 +527,8 @@ def run_gpu(args, wl, wl_name):
             "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u16" if mode == "hashrf" else "u64",
             "data": "synthetic",
-            "config": {"workload": wl_name, "trees": T, "taxa": n, "mode": mode, "editdist": editdist,
-                       "pairs": P, "nnz": nnz, "words": W, "n_unique": st.get("n_unique"), "n_hits": st.get("n_hits"),
+            "config": workload_config(wl, wl_name, editdist, nnz, W),
+            "details": {"n_unique": st.get("n_unique"), "n_hits": st.get("n_hits"),
                        "variant": {1: "sparse", 2: "dense"}.get(st.get("variant_used"), mode), "n_shared": st.get("n_shared"),
                        "parallelism": f"packed-range shard x{world}" + ((" + hash-partitioned build (prf_team_load: keys and per-class list structures stored into the peers' memory over NVLink by the library's kernels)" if sharded else " + NCCL all-gather of bipartition keys, whole build on every rank") if world > 1 else ""),
                        "l2": "output per step (>= 2 B/pair) far exceeds the 126 MB L2; no explicit flush"},
@@ -584,6 +627,7 @@ def main():
     ap.add_argument("--quick-check", action="store_true", help="skip the host-side recomputation of n_hits and of 8 full rows")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-sweep-full", action="store_true", help="cpu_baseline: add T = 10000 to the all-cores sweep")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     wl = dict(WORKLOADS[args.workload])

@@ -53,6 +53,13 @@ def lib():
     return _lib
 
 
+def max_threads():
+    """Threads the "literal_all_cores" variant of Forest.hashrf uses."""
+    f = lib().orc_max_threads
+    f.restype = C.c_int
+    return int(f())
+
+
 class Forest:
     """Parsed trees + global label table, as parseNewicks returns them (Parser.hs:57)."""
 
@@ -108,12 +115,13 @@ class Forest:
         out = np.zeros(T * (T - 1) // 2 if T else 0, dtype=np.int64)
         nu = C.c_int64(0)
         b, g = C.c_double(0), C.c_double(0)
-        rc = lib().orc_hashrf(self._h, num_taxa, 0 if variant == "literal" else 1, out.ctypes.data,
-                              C.byref(nu), C.byref(b), C.byref(g))
+        code = {"literal": 0, "closed": 1, "literal_all_cores": 2}[variant]
+        rc = lib().orc_hashrf(self._h, num_taxa, code, out.ctypes.data, C.byref(nu), C.byref(b), C.byref(g))
         if rc:
             raise RuntimeError("oracle hashRF failed")
         if stats is not None:
             stats.update(n_unique=nu.value, build_s=b.value, ingest_s=g.value)
+            stats.update(threads=max_threads() if code == 2 else 1)
         return out
 
     def consensus_bips(self, members: Sequence[int]) -> List[Tuple[int, ...]]:

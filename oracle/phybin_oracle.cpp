@@ -16,6 +16,9 @@
 //
 // Build: make -C oracle   (g++ -O2 -shared -fPIC; no dependencies)
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <algorithm>
 #include <cctype>
 #include <chrono>
@@ -380,6 +383,104 @@ static Matrix hashRF(int /*num_taxa*/, const std::vector<Tree>& trees, size_t* n
   return matr;
 }
 
+// The same algorithm on ALL HOST CORES (variant ii): the reference's ingest loop is a sequential
+// runST (RFDistance.hs:300-341, "Not concurrency safe yet" :319); this is what a straightforward parallelisation of
+// it gives -- bipartition extraction parallel over the trees, the bump loop parallel over the table's bipartitions
+// with atomic increments.  Same result as hashRF above (tests/test_oracle_golden.py); used only as a CPU baseline.
+static Matrix hashRFAllCores(const std::vector<Tree>& trees, size_t* n_unique = nullptr, double* build_s = nullptr,
+                             double* ingest_s = nullptr) {
+  const int num_trees = (int)trees.size();
+  std::vector<BipSet> per_tree((size_t)num_trees);
+  const bool trace = getenv("ORC_TRACE") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  double secs[3] = {0, 0, 0};
+  int phase = 0;
+  auto lap = [&](const char* what) {
+    auto t1 = std::chrono::steady_clock::now();
+    secs[phase++] = std::chrono::duration<double>(t1 - t0).count();
+    if (trace) fprintf(stderr, "[orc all-cores] %s %.3f s\n", what, secs[phase - 1]);
+    t0 = t1;
+  };
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int ix = 0; ix < num_trees; ++ix) per_tree[ix] = allBips(trees[ix]);
+  lap("allBips");
+  // the table, sharded by a hash of the bipartition: every thread owns the shards s = thread (mod threads) and
+  // inserts, in tree order, the bipartitions that fall into them (same lists as the sequential insertWith)
+  int shards = 1;
+#ifdef _OPENMP
+  shards = omp_get_max_threads();
+#endif
+  std::vector<std::map<IntSet, IntSet>> tables((size_t)shards);
+#pragma omp parallel for schedule(static, 1)
+  for (int s = 0; s < shards; ++s)
+    for (int ix = 0; ix < num_trees; ++ix)
+      for (const IntSet& bip : per_tree[ix]) {
+        uint64_t h = 0x9E3779B97F4A7C15ull;
+        for (int l : bip) h = (h ^ (uint64_t)l) * 0x100000001B3ull;
+        if ((int)((h >> 20) % (uint64_t)shards) == s) tables[(size_t)s][bip].push_back(ix);
+      }
+  std::vector<const IntSet*> lists;
+  size_t n_keys = 0;
+  for (const auto& tb : tables) n_keys += tb.size();
+  lists.reserve(n_keys);
+  for (const auto& tb : tables)
+    for (const auto& kv : tb) lists.push_back(&kv.second);
+  lap("table");
+  const size_t T = (size_t)num_trees;
+  Matrix matr(T * (T - (T ? 1 : 0)) / 2, 0);
+  int threads = 1;
+#ifdef _OPENMP
+  threads = omp_get_max_threads();
+#endif
+  // every thread bumps a private matrix (no atomics), summed afterwards; atomics on the shared one if they would not fit
+  const bool priv = matr.size() * sizeof(uint32_t) * (size_t)threads <= (size_t)8 << 30;
+  std::vector<std::vector<uint32_t>> mine(priv ? (size_t)threads : 0);
+#pragma omp parallel num_threads(threads)
+  {
+    int me = 0;
+#ifdef _OPENMP
+    me = omp_get_thread_num();
+#endif
+    uint32_t* m32 = nullptr;
+    if (priv) {
+      mine[(size_t)me].assign(matr.size(), 0);
+      m32 = mine[(size_t)me].data();
+    }
+    std::vector<char> have(T);
+#pragma omp for schedule(dynamic, 64)
+    for (long long b = 0; b < (long long)lists.size(); ++b) {
+      const IntSet& haveIt = *lists[(size_t)b];
+      std::fill(have.begin(), have.end(), 0);
+      for (int t : haveIt) have[t] = 1;
+      for (int i : haveIt)
+        for (int j = 0; j < num_trees; ++j) {
+          if (have[j]) continue;
+          const size_t at = j < i ? lowerIx(i, j) : lowerIx(j, i);
+          if (priv) {
+            ++m32[at];
+          } else {
+            int64_t* cell = &matr[at];
+#pragma omp atomic
+            ++*cell;
+          }
+        }
+    }
+    if (priv) {
+#pragma omp for schedule(static)
+      for (long long c = 0; c < (long long)matr.size(); ++c) {
+        int64_t v = 0;
+        for (int t = 0; t < threads; ++t) v += mine[(size_t)t][(size_t)c];
+        matr[(size_t)c] = v;
+      }
+    }
+  }
+  lap("matrix");
+  if (n_unique) *n_unique = n_keys;
+  if (build_s) *build_s = secs[0] + secs[1];
+  if (ingest_s) *ingest_s = secs[2];
+  return matr;
+}
+
 // A DERIVED (not literal) evaluation of the same matrix used only to make large parity cases
 // finish in seconds: d(i,j) = |B_i| + |B_j| - 2 |B_i n B_j|, the closed form of the bump loop
 // (each bip in exactly one of the two trees bumps the pair once).  Checked against the literal
@@ -482,14 +583,25 @@ int orc_all_bips_total_labels(const orc_forest* h, int t) {
   return pos;
 }
 
-// out: T(T-1)/2 int64, (i,j), j<i at i(i-1)/2+j.  variant 0 = literal hashRF, 1 = closed form.
+// threads the all-cores variant uses (1 when the oracle was built without OpenMP)
+int orc_max_threads() {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+// out: T(T-1)/2 int64, (i,j), j<i at i(i-1)/2+j.  variant 0 = literal hashRF, 1 = closed form, 2 = the literal
+// algorithm on all host cores (orc_max_threads() of them).
 int orc_hashrf(const orc_forest* h, int num_taxa, int variant, int64_t* out, int64_t* n_unique,
                double* build_s, double* ingest_s) {
   try {
     size_t nu = 0;
     double b = 0, g = 0;
-    orc::Matrix m = variant == 0 ? orc::hashRF(num_taxa, h->f->trees, &nu, &b, &g)
-                                 : orc::hashRFClosedForm(h->f->trees, &nu);
+    orc::Matrix m = variant == 0   ? orc::hashRF(num_taxa, h->f->trees, &nu, &b, &g)
+                    : variant == 2 ? orc::hashRFAllCores(h->f->trees, &nu, &b, &g)
+                                   : orc::hashRFClosedForm(h->f->trees, &nu);
     if (out) std::copy(m.begin(), m.end(), out);
     if (n_unique) *n_unique = (int64_t)nu;
     if (build_s) *build_s = b;

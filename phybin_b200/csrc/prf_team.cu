@@ -210,25 +210,7 @@ static int team_load(Ctx* ctx, const uint64_t* d_bips, const uint64_t* d_off, ui
   // ---- my keys to their owners: one kernel (classes, reserved ranges, stores into the peers' arenas) ----
   if (tm.cls_cnt.n < (size_t)kMaxParts) PRF_CK(ctx, tm.cls_cnt.alloc(kMaxParts, s));  // per-class cursors of my key regions
   PRF_CK(ctx, cudaMemsetAsync(tm.cls_cnt.p, 0, kMaxParts * 4, s));
-  // through shared memory when a tree's keys fit twice in a warp's share of 96 KB (W even), else straight stores
-  const size_t per_warp = 2 * (size_t)std::max<uint32_t>(tm.max_entries, 1) * W * 8;
-  const int pw = W % 2 == 0 && per_warp <= 96 * 1024 ? (int)std::min<size_t>(8, (96 * 1024) / per_warp) : 0;
-  if (Tl && pw) {
-    const size_t smem = (size_t)pw * per_warp;
-    const int grid = (int)((Tl + pw - 1) / pw);
-    switch (W) {
-#define PRF_W_CASE(w)                                                                                                       \
-  case w:                                                                                                                   \
-    PRF_CK(ctx, cudaFuncSetAttribute(team_partition_smem_kernel<w>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    team_partition_smem_kernel<w><<<grid, 32 * pw, smem, s>>>(d_bips, d_off, Tl, t_lo, world, rank, tm.peers_dev.p, L,       \
-                                                              tm.cls_cnt.p, tm.err.p, std::max<uint32_t>(tm.max_entries, 1)); \
-    break;
-      PRF_W_CASE(2) PRF_W_CASE(4) PRF_W_CASE(6) PRF_W_CASE(8) PRF_W_CASE(10) PRF_W_CASE(12) PRF_W_CASE(14) PRF_W_CASE(16)
-#undef PRF_W_CASE
-      default: return ctx->fail(PRF_E_UNSUPPORTED, "W=%u", W);
-    }
-    PRF_LAUNCHED(ctx);
-  } else if (Tl) {
+  if (Tl) {
     switch (W) {
 #define PRF_W_CASE(w) case w: team_partition_kernel<w><<<(Tl + 7) / 8, 256, 0, s>>>(d_bips, d_off, Tl, t_lo, world, rank, tm.peers_dev.p, L, tm.cls_cnt.p, tm.err.p); break;
       PRF_W_CASE(1) PRF_W_CASE(2) PRF_W_CASE(3) PRF_W_CASE(4) PRF_W_CASE(5) PRF_W_CASE(6) PRF_W_CASE(7) PRF_W_CASE(8)

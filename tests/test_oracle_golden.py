@@ -46,7 +46,7 @@ def test_naive_matches_golden(golden, name):
 
 
 @pytest.mark.parametrize("name", ALL)
-@pytest.mark.parametrize("variant", ["literal", "closed"])
+@pytest.mark.parametrize("variant", ["literal", "closed", "literal_all_cores"])
 def test_hashrf_matches_golden(golden, name, variant):
     c = golden[name]
     f = orc.Forest(c["texts"], c["name_prefix"])
