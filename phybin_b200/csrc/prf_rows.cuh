@@ -132,6 +132,25 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
     uint32_t S = pS;
 #pragma unroll
     for (int d = 16; d; d >>= 1) S += __shfl_xor_sync(0xffffffffu, S, d);
+    // rows with <= 32 singles keep them in a register for all of the row's tiles (lane i: the i-th single over the
+    // parts); loading them per tile left a global-load latency between the fill and the lists (8 % of the kernel's
+    // stall samples at 100k x 200)
+    uint32_t my_single = 0xffffffffu;
+    const bool s_reg = S <= 32;
+    if (S && s_reg) {
+      uint32_t pSx = pS;
+#pragma unroll
+      for (int d = 1; d < kMaxParts; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, pSx, d);
+        if (lane >= (uint32_t)d) pSx += o;
+      }
+      pSx -= pS;
+      uint32_t p = 0;
+      for (uint32_t q = 1; q < prm.n_parts; ++q)
+        if (__shfl_sync(0xffffffffu, pSx, q) <= lane) p = q;
+      const uint32_t s0 = __shfl_sync(0xffffffffu, ps0, p), x = __shfl_sync(0xffffffffu, pSx, p);
+      if (lane < S) my_single = __ldg(prm.part[p].singles + s0 + (lane - x));
+    }
     // lists [c0, c0 + Rc) of the row -> s_trow
     auto load_lists = [&](uint32_t c0, uint32_t Rc) {
       for (uint32_t kb = 0; kb < Rc; kb += 32) {
@@ -310,7 +329,12 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
       __syncwarp();
 
       // ---- singles ----
-      if (S) {
+      if (S && s_reg) {
+        if (my_single - c_lo < cnt) {  // (0xffffffff - c_lo >= cnt: lanes without a single stay out)
+          const uint32_t idx = (uint32_t)(base + (int32_t)my_single);
+          atomicSub(&tile32[idx >> 1], 2u << ((idx & 1u) * 16u));
+        }
+      } else if (S) {
         for (uint32_t p = 0; p < prm.n_parts; ++p) {
           const uint32_t s0 = __shfl_sync(0xffffffffu, ps0, p), sn = __shfl_sync(0xffffffffu, pS, p);
           const uint32_t* __restrict__ sg = prm.part[p].singles + s0;
@@ -344,7 +368,8 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
         __syncwarp();
       }
       if (R > (uint32_t)kCap) load_lists(0, kCap);  // back to the first pass's lists for the next tile
-      // bucket bounds of the next block, for rows of <= 64 lists
+      // bucket bounds of the next block, for rows of <= 64 lists (requesting them earlier, right after this block's
+      // were consumed, measured slower: 2.68 vs 2.58 ms)
       if (pf_ok && j < j_last) prefetch_bounds(j + 1);
       __syncwarp();
 
@@ -474,14 +499,15 @@ int launch_rows(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, ui
   // the tiny-block build exists so that small test inputs exercise multi-tile rows and several passes over a row's lists
   if (ctx->debug_small_tiles) return launch_rows_t<8, 2, 8, 2>(ctx, p_begin, p_end, editdist, d_out, d_mask);
   switch (ctx->rows_cfg) {  // tuning instantiations (scripts/rows_probe.py)
-    case 1: return launch_rows_t<13, 13, 112, 4>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-    case 2: return launch_rows_t<13, 12, 240, 8>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-    case 3: return launch_rows_t<13, 12, 240, 4>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    case 1: return launch_rows_t<13, 13, 112, 6>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    case 2: return launch_rows_t<13, 12, 240, 6>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    case 3: return launch_rows_t<13, 13, 112, 4>(ctx, p_begin, p_end, editdist, d_out, d_mask);
     default: break;
   }
-  // 13 warps per SM when every row's lists fit one pass of 112 (measured 2.59 vs 2.69 ms at 100k x 200), else 12 warps x 240
-  if (ctx->h.max_lists <= 112) return launch_rows_t<13, 13, 112, 4>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-  return launch_rows_t<13, 12, 240, 4>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  // 13 warps per SM when every row's lists fit one pass of 112 (measured 2.53 vs 2.60 ms at 100k x 200), else 12 warps
+  // x 240; 6 groups per lane in flight (4: 2.57 ms, 8: 2.54 ms)
+  if (ctx->h.max_lists <= 112) return launch_rows_t<13, 13, 112, 6>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  return launch_rows_t<13, 12, 240, 6>(ctx, p_begin, p_end, editdist, d_out, d_mask);
 }
 
 }  // namespace prf
