@@ -463,9 +463,14 @@ def run_gpu(args, wl, wl_name):
         kpad = (int(st["n_shared"]) + 127) // 128 * 128
         ops = 2.0 * kpad * my_pairs
         tops = ops / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
-        peak_i8 = 2.0 * peaks["bf16_tflops"]
+        peak_i8, i8_src = 2.0 * peaks["bf16_tflops"], peak_src + " bf16 x2 (nominal ratio; profiles/int8_peak.json missing)"
+        try:
+            with open(os.path.join(ROOT, "profiles", "int8_peak.json")) as fh:
+                peak_i8, i8_src = float(json.load(fh)["int8_tops"]), "measured: cuBLASLt int8 GEMM on a B200 of this pool (scripts/int8_peak.py, profiles/int8_peak.json)"
+        except Exception:
+            pass
         roofline = {"bound": "tensor", "achieved": tops, "peak": peak_i8, "unit": "TFLOP/s", "frac": tops / peak_i8,
-                    "traffic": None, "peak_source": peak_src + " bf16 x2 (int8 dense peak is not in MEASURED_PEAKS.json; nominal ratio)",
+                    "traffic": None, "peak_source": i8_src,
                     "kernel": "dense_gram_kernel", "kernel_ms": avg_ms, "algorithmic_ops_per_launch": ops,
                     "k_columns": kpad, "output_gbs": alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0,
                     "kernel_share_of_step": avg_ms * 1e-3 / step_s}
@@ -473,7 +478,9 @@ def run_gpu(args, wl, wl_name):
     if os.path.exists(traffic_file):
         try:
             with open(traffic_file) as fh:
-                roofline["traffic"] = json.load(fh).get(wl_name if world == 1 else "", None)
+                # measured for the sparse matrix kernel at N = 1 (per-rank captures at N > 1 are not taken: ncu must not
+                # wrap a multi-rank job)
+                roofline["traffic"] = json.load(fh).get(wl_name if world == 1 and roofline["bound"] == "hbm" and mode == "hashrf" else "", None)
         except Exception:
             pass
 
