@@ -279,7 +279,13 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_gram_kernel(const DensePar
                              r3 = __vsetleu2(o.w, thr2);
               const uint32_t bits = ((r0 | (r0 >> 15)) & 3u) | (((r1 | (r1 >> 15)) & 3u) << 2) |
                                     (((r2 | (r2 >> 15)) & 3u) << 4) | (((r3 | (r3 >> 15)) & 3u) << 6);
-              reinterpret_cast<uint8_t*>(prm.mask)[((e_lo & ~7ull) - prm.p_begin + g) >> 3] = (uint8_t)bits;
+              // every mask write of this kernel is a 32-bit atomicOr into the pre-zeroed mask: a group's byte shares
+              // its word with groups of other rows / warps / CTAs, and a plain byte store next to their word-sized
+              // atomics would be a mixed-size race
+              if (bits) {
+                const uint64_t byte = ((e_lo & ~7ull) - prm.p_begin + g) >> 3;
+                atomicOr(&prm.mask[byte >> 2], bits << ((byte & 3) * 8));
+              }
             }
           } else {
             uint32_t bits = 0;
