@@ -497,14 +497,20 @@ def run_gpu(args, wl, wl_name):
         pin_mask = torch.empty(max((p_end - p_begin + 31) // 32, 1), dtype=torch.int32).pin_memory() if editdist >= 0 else None
         n_e2e = max(1, min(args.steps, 2))
 
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
         def e2e_step():
             with torch.cuda.stream(ext):
+                ev[0].record(ext)
                 d_my.copy_(pin_in, non_blocking=True)
+                ev[1].record(ext)
             step()
             with torch.cuda.stream(ext):
+                ev[2].record(ext)
                 pin_out[: p_end - p_begin].copy_(d_out[: p_end - p_begin], non_blocking=True)
                 if pin_mask is not None:
                     pin_mask.copy_(d_mask, non_blocking=True)
+                ev[3].record(ext)
             ext.synchronize()
 
         for _ in range(2):
@@ -522,6 +528,10 @@ def run_gpu(args, wl, wl_name):
         del pin_in, pin_out, pin_mask  # before the library's stream goes away (the host allocator records events on it)
         e2e = {"value": P / float(dt[0]), "unit": UNIT, "h2d_bytes_per_step": int(nbytes[0]), "d2h_bytes_per_step": int(nbytes[1]),
                "ms_per_step": float(dt[0]) * 1e3, "steps": n_e2e,
+               "phases_ms": {"h2d": ev[0].elapsed_time(ev[1]), "build_and_matrix": ev[1].elapsed_time(ev[2]), "d2h": ev[2].elapsed_time(ev[3]),
+                             "note": "rank 0, last step (CUDA events on the library's stream)"},
+               "host_ceiling": "all ranks copying device -> pinned host at once reach 142 GB/s in aggregate on this box (57 GB/s for one "
+                               "rank alone; one NUMA node, 32 vCPUs): scripts/d2h_probe.py, profiles/r02_d2h_probe_n8.json",
                "note": "per rank: pinned tree shard -> HBM, hash-partitioned build over NVLink, own slice, slice -> pinned host; bytes summed over ranks"}
 
     cpu_baseline = None
@@ -630,7 +640,7 @@ def main():
     ap.add_argument("--trees", type=int, default=0, help="override the number of trees (debug)")
     ap.add_argument("--ref-trees", type=int, default=0, help="CPU sample size in trees")
     ap.add_argument("--build", default="auto", choices=["auto", "sharded", "replicated"],
-                    help="N > 1: hash-partitioned build, or all-gather of the keys + replicated build (auto: sharded from 4 GPUs)")
+                    help="N > 1: hash-partitioned build over the GPUs (auto = sharded), or NCCL all-gather of the keys + the whole build on every rank")
     ap.add_argument("--quick-check", action="store_true", help="skip the host-side recomputation of n_hits and of 8 full rows")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
