@@ -78,14 +78,18 @@ struct DedupSegs {
   uint32_t n;
 };
 template <int W>
-__global__ void __launch_bounds__(256) dedup_insert32_kernel(const uint64_t* __restrict__ bips, const DedupSegs segs,
+__global__ void __launch_bounds__(256, (W <= 6 ? 8 : W <= 10 ? 6 : 4)) dedup_insert32_kernel(const uint64_t* __restrict__ bips, const DedupSegs segs,
                                                              uint32_t* slots, uint32_t* shared_bits, uint32_t cap,
                                                              uint32_t* __restrict__ ent_slot,
-                                                             unsigned long long* counters) {
+                                                             unsigned long long* counters, int mode) {
   uint64_t policy;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
   const uint64_t total = segs.start[segs.n];
   uint32_t claims = 0;
+  // (the kernel is bound by the number of random accesses in flight, i.e. by resident threads: the launch bounds keep
+  // W <= 6 at 32 registers = 2048 threads per SM, 0.55 vs 0.62 ms at 100k x 200.  Several keys in flight per thread --
+  // first-slot loads issued back to back, keys read back on a tag match -- measured 0.98 ms: the per-thread chains of
+  // the later probes serialise; prefetching the next key's slot into L2: 0.78 ms at 46 registers)
   // a warp's 32 keys are read with coalesced 16-byte loads and handed to their lanes through shared memory (a lane
   // loading its own 8 W bytes would touch one sector per lane and load: the L1 wavefronts were a third of the kernel)
   __shared__ __align__(16) uint64_t s_keys[8][32 * W + 2];
@@ -130,10 +134,16 @@ __global__ void __launch_bounds__(256) dedup_insert32_kernel(const uint64_t* __r
     const uint32_t mine = (tag << 25) | ((uint32_t)e + 1u);
     uint32_t s = (uint32_t)(((h & 0xffffffffull) * (uint64_t)cap) >> 32);
     for (;;) {
-      uint32_t cur = slots[s];
-      if (cur == 0u) {
+      uint32_t cur;
+      if (mode & 1) {  // small table: see hashrf_build
         cur = atomicCAS(&slots[s], 0u, mine);
-        if (cur == 0u) { ++claims; break; }  // claimed: this entry is the representative
+        if (cur == 0u) { ++claims; break; }
+      } else {
+        cur = slots[s];
+        if (cur == 0u) {
+          cur = atomicCAS(&slots[s], 0u, mine);
+          if (cur == 0u) { ++claims; break; }  // claimed: this entry is the representative
+        }
       }
       if ((cur >> 25) == tag) {  // same tag: decide on the full key
         uint64_t r[W];
@@ -621,6 +631,10 @@ int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* tb, const uin
       segs.start[i + 1] = segs.start[i] + seg_len[i];
     }
   }
+  // a table that stays in L2 is probed with the compare-and-swap itself (one round trip for a new key: 0.047 vs 0.071 ms
+  // at 10k x 100); a larger one with a plain load first (an atomic on a line that misses L2 is slower: 0.85 vs 0.62 ms
+  // at 100k x 200)
+  const int dedup_mode = compact && cap * 4 <= (32ull << 20) ? 1 : 0;
   const int dedup_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((segs.start[segs.n] + 255) / 256, (uint64_t)ctx->sm_count * 64));
   if (T) {
     switch (W) {
@@ -628,7 +642,7 @@ int hashrf_build(Ctx* ctx, const uint64_t* d_bips, const uint64_t* tb, const uin
   case w:                                                                                                              \
     if (compact)                                                                                                       \
       dedup_insert32_kernel<w><<<dedup_grid, 256, 0, s>>>(d_bips, segs, slots32.p, shared_bits.p, (uint32_t)cap,        \
-                                                          H.ent_lid.p, counters.p);                                    \
+                                                          H.ent_lid.p, counters.p, dedup_mode);                        \
     else                                                                                                               \
       launch_dedup<w>(ctx, d_bips, tb, te, T, slots.p, shared_bits.p, cap - 1, H.ent_lid.p, counters.p);               \
     break;
