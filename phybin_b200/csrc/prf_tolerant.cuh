@@ -75,13 +75,19 @@ __device__ __forceinline__ uint32_t norm_bip(const BitSet<W>& m, uint32_t pc, co
 
 template <int W>
 __device__ __forceinline__ uint32_t hash_set(const BitSet<W>& s) {
-  uint64_t h = 0x9E3779B97F4A7C15ull;
+  // routes only (equality is decided on the full key): a multiply-add per 32-bit half word, then an avalanche
+  uint32_t h = 0x9E3779B9u;
 #pragma unroll
-  for (int i = 0; i < W; ++i) h = (h ^ s.w[i]) * 0xD6E8FEB86659FD93ull + (h >> 29);
-  h ^= h >> 32;
-  h *= 0xD6E8FEB86659FD93ull;
-  h ^= h >> 29;
-  return (uint32_t)h;
+  for (int i = 0; i < W; ++i) {
+    h = h * 0x85EBCA6Bu + (uint32_t)s.w[i];
+    h = h * 0xC2B2AE35u + (uint32_t)(s.w[i] >> 32);
+  }
+  h ^= h >> 16;
+  h *= 0x7FEB352Du;
+  h ^= h >> 15;
+  h *= 0x846CA68Bu;
+  h ^= h >> 16;
+  return h;
 }
 
 // Everything a lane needs to (re)build the canonical set of any clade of the pair.
@@ -132,9 +138,11 @@ __device__ __forceinline__ bool make_key(const PairCtx<W>& P, uint32_t idx, BitS
 // slot word: [31:30] flags (1 = in a, 2 = in b), [29:11] tag, [10:0] key number + 1; 0 = empty.
 // The table holds no keys: on a tag match the other key is rebuilt from its number (its raw clade is
 // an L1/L2 hit), so a warp needs only 4 bytes of shared memory per slot and many warps fit on an SM.
+// Returns, packed, what the insertion changed: bit 0 / bit 1 = the slot gained flag 1 / 2 for the first time, bit 2 = the
+// slot now has both flags and did not before.  Summed over a pair's keys: |F_a|, |F_b| and |F_a n F_b|.
 template <int W>
-__device__ __forceinline__ void table_insert(uint32_t* table, uint32_t tmask, const PairCtx<W>& P, uint32_t idx,
-                                             const BitSet<W>& key, uint32_t flag) {
+__device__ __forceinline__ uint32_t table_insert(uint32_t* table, uint32_t tmask, const PairCtx<W>& P, uint32_t idx,
+                                                 const BitSet<W>& key, uint32_t flag) {
   const uint32_t h = hash_set<W>(key);
   const uint32_t tag = (h >> 13) & 0x7ffffu;
   const uint32_t mine = (flag << 30) | (tag << 11) | (idx + 1);
@@ -143,7 +151,7 @@ __device__ __forceinline__ void table_insert(uint32_t* table, uint32_t tmask, co
     uint32_t cur = *((volatile uint32_t*)&table[s]);
     if (cur == 0) {
       cur = atomicCAS(&table[s], 0u, mine);
-      if (cur == 0) return;
+      if (cur == 0) return flag | (flag == 3u ? 4u : 0u);
     }
     if (((cur >> 11) & 0x7ffffu) == tag) {
       BitSet<W> other;
@@ -152,8 +160,9 @@ __device__ __forceinline__ void table_insert(uint32_t* table, uint32_t tmask, co
 #pragma unroll
       for (int i = 0; i < W; ++i) eq &= (other.w[i] == key.w[i]);
       if (eq) {
-        atomicOr(&table[s], flag << 30);
-        return;
+        const uint32_t old = atomicOr(&table[s], flag << 30) >> 30;
+        const uint32_t gained = flag & ~old;
+        return gained | ((old | flag) == 3u && old != 3u ? 4u : 0u);
       }
     }
     s = (s + 1) & tmask;
@@ -170,9 +179,7 @@ __global__ void __launch_bounds__(512) tolerant_kernel(uint32_t T, uint64_t p_be
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t warps = blockDim.x >> 5;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // layout: per-warp tables (uint32), then the CTA's results
-  uint32_t* table = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * tsize;
-  uint16_t* res = reinterpret_cast<uint16_t*>(reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warps * tsize);
+  uint32_t* table = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * tsize;  // per-warp tables
   const uint32_t tmask = tsize - 1;
   for (uint32_t s = lane; s < tsize; s += 32) table[s] = 0;
   __syncwarp();
@@ -181,10 +188,11 @@ __global__ void __launch_bounds__(512) tolerant_kernel(uint32_t T, uint64_t p_be
   const uint64_t n_blocks = (p_end - p_begin + per_cta - 1) / per_cta;
   for (uint64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
     const uint64_t pb = p_begin + blk * per_cta;
+    uint32_t my_d = 0;
     for (int q = 0; q < kTolPairsPerWarp; ++q) {
       const uint32_t local = warp * kTolPairsPerWarp + q;
       const uint64_t p = pb + local;
-      if (p >= p_end) break;
+      if (p >= p_end) break;  // (warp-uniform)
       const uint32_t a = row_of(p, T);
       const uint32_t b = a + 1 + (uint32_t)(p - row_start(a, T));
       PairCtx<W> P;
@@ -218,35 +226,43 @@ __global__ void __launch_bounds__(512) tolerant_kernel(uint32_t T, uint64_t p_be
           const uint32_t idx = c0 + lane;
           BitSet<W> key;
           const bool have = idx < n_keys && make_key<W>(P, idx, key);
-          if (have) table_insert<W>(table, tmask, P, idx, key, idx < P.na ? 1u : (idx < P.na + P.nb ? 2u : 3u));
+          if (have) {
+            const uint32_t g = table_insert<W>(table, tmask, P, idx, key, idx < P.na ? 1u : (idx < P.na + P.nb ? 2u : 3u));
+            d += (g & 1u) + ((g >> 1) & 1u) - ((g >> 1) & 2u);  // |F_a| + |F_b| - 2 |F_a n F_b| = |F_a xor F_b|
+          }
         }
         __syncwarp();
-        // count slots seen in exactly one tree, and clear the table for the next pair
-        for (uint32_t s = lane; s < tsize; s += 32) {
-          const uint32_t fl = table[s] >> 30;
-          d += (fl == 1u) | (fl == 2u);
-          table[s] = 0;
-        }
+        // clear the table for the next pair
+        for (uint32_t s = lane; s < tsize / 4; s += 32) reinterpret_cast<uint4*>(table)[s] = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
         for (int sh = 16; sh; sh >>= 1) d += __shfl_xor_sync(0xffffffffu, d, sh);
         __syncwarp();
       }
-      if (lane == 0) res[local] = (uint16_t)d;
+      // lane q keeps the q-th result of this warp
+      if (lane == (uint32_t)q) my_d = d;
     }
-    __syncthreads();
-    const uint32_t nvalid = (uint32_t)min((uint64_t)per_cta, p_end - pb);
-    const uint64_t rel = pb - p_begin;
-    for (uint32_t i = threadIdx.x; i < nvalid; i += blockDim.x) out[rel + i] = res[i];
-    if (editdist >= 0) {
-      // per_cta is a multiple of 32 and so is rel
-      for (uint32_t g = warp; g * 32 < nvalid; g += warps) {
-        const uint32_t i = g * 32 + lane;
-        const bool hit = i < nvalid && (int32_t)res[i] <= editdist;
-        const uint32_t bits = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) mask[rel / 32 + g] = bits;
+    // the warp's kTolPairsPerWarp consecutive results: one 16-byte store and one mask byte, no CTA-wide barrier (warps of
+    // a CTA differ in how long their pairs take; waiting for the slowest one was ~10 % of the kernel)
+    const uint64_t p0 = pb + (uint64_t)warp * kTolPairsPerWarp;  // (p0 - p_begin) is a multiple of 8
+    if (p0 < p_end) {
+      const uint32_t nv = (uint32_t)min((uint64_t)kTolPairsPerWarp, p_end - p0);
+      uint32_t v[kTolPairsPerWarp];
+#pragma unroll
+      for (int q = 0; q < kTolPairsPerWarp; ++q) v[q] = __shfl_sync(0xffffffffu, my_d, q);
+      if (lane == 0) {
+        uint16_t* o = out + (p0 - p_begin);
+        if (nv == kTolPairsPerWarp && (reinterpret_cast<uintptr_t>(o) & 15u) == 0) {
+          *reinterpret_cast<uint4*>(o) = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+        } else {
+          for (uint32_t q = 0; q < nv; ++q) o[q] = (uint16_t)v[q];
+        }
+        if (editdist >= 0) {
+          uint32_t bits = 0;
+          for (uint32_t q = 0; q < nv; ++q) bits |= ((int32_t)v[q] <= editdist ? 1u : 0u) << q;
+          reinterpret_cast<uint8_t*>(mask)[(p0 - p_begin) >> 3] = (uint8_t)bits;  // every mask byte has one writer
+        }
       }
     }
-    __syncthreads();
   }
 }
 
@@ -256,11 +272,13 @@ static int launch_tolerant_w(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t
   const TolerantState& S = ctx->tol;
   const uint32_t key_cap = 2 * S.max_clades + 4;
   uint32_t tsize = 64;
-  while (tsize < key_cap + key_cap / 2) tsize <<= 1;  // load factor <= 2/3 even if no key repeats
-  // pairs per CTA must be a multiple of 32 so mask words never straddle CTAs: 8 pairs/warp -> warps % 4 == 0
+  // load factor <= 1/3 even if no key repeats: a warp's 32 insertions finish with the longest of their probe chains, and
+  // the registers (2 CTAs of 16 warps per SM) leave the shared memory for it
+  while (tsize < 3 * key_cap) tsize <<= 1;
+  if (tsize > 2048) tsize >>= 1;  // (very large trees: back to <= 2/3)
   uint32_t warps = 16;
-  while (warps > 4 && (size_t)warps * tsize * 4 + warps * kTolPairsPerWarp * 2 > 64 * 1024) warps -= 4;
-  const size_t smem = (size_t)warps * tsize * 4 + warps * kTolPairsPerWarp * 2;
+  while (warps > 4 && (size_t)warps * tsize * 4 > 96 * 1024) warps -= 4;
+  const size_t smem = (size_t)warps * tsize * 4;
   PRF_CK(ctx, cudaFuncSetAttribute(tolerant_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int ctas = 0;
   PRF_CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, tolerant_kernel<W>, (int)(warps * 32), smem));
@@ -268,6 +286,8 @@ static int launch_tolerant_w(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t
   const uint32_t per_cta = warps * kTolPairsPerWarp;
   const uint64_t n_blocks = (p_end - p_begin + per_cta - 1) / per_cta;
   const uint32_t grid = (uint32_t)std::min<uint64_t>(n_blocks, (uint64_t)ctx->sm_count * ctas * 8);
+  // every mask byte is written by the warp that owns its 8 pairs; the bytes after p_end in the last word are not
+  if (d_mask) PRF_CK(ctx, cudaMemsetAsync(d_mask + (p_end - p_begin) / 32, 0, ((p_end - p_begin) % 32) ? 4 : 0, ctx->stream));
   tolerant_kernel<W><<<grid, warps * 32, smem, ctx->stream>>>(S.T, p_begin, p_end, S.clades.p, S.off.p, S.leafsets.p,
                                                              tsize, editdist, d_out, d_mask);
   PRF_LAUNCHED(ctx);
