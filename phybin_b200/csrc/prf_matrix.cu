@@ -2,6 +2,7 @@
 #include "prf_common.cuh"
 #include "prf_internal.h"
 #include "prf_rows.cuh"
+#include "prf_rows_pair.cuh"
 
 namespace prf {
 
@@ -43,6 +44,27 @@ void build_row_plan(uint32_t T, uint64_t p_begin, uint64_t p_end, uint32_t tile,
   }
   std::stable_sort(rows.begin(), rows.end(),
                    [](const RowItem& x, const RowItem& y) { return x.ce - x.cb > y.ce - y.cb; });
+}
+
+int launch_rows(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out, uint32_t* d_mask) {
+  // the tiny-block builds exist so that small test inputs exercise multi-tile rows and several passes over a row's lists
+  if (ctx->debug_small_tiles)
+    return ctx->rows_cfg >= 4 ? launch_rows_pair_t<8, 2, 8, 2>(ctx, p_begin, p_end, editdist, d_out, d_mask)
+                              : launch_rows_t<8, 2, 8, 2>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  switch (ctx->rows_cfg) {  // tuning instantiations (scripts/rows_probe.py)
+    case 1: return launch_rows_t<13, 13, 112, 6>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    case 2: return launch_rows_t<13, 12, 240, 6>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    case 3: return launch_rows_t<13, 13, 112, 4>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    case 4: return launch_rows_pair_t<13, 13, 112, 3>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    case 5: return launch_rows_pair_t<13, 12, 240, 3>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    case 6: return launch_rows_pair_t<13, 13, 112, 2>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    case 7: return launch_rows_pair_t<13, 13, 112, 4>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+    default: break;
+  }
+  // 13 warps per SM when every row's lists fit one pass of 112 (measured 2.53 vs 2.60 ms at 100k x 200), else 12 warps
+  // x 240; 6 groups per lane in flight (4: 2.57 ms, 8: 2.54 ms)
+  if (ctx->h.max_lists <= 112) return launch_rows_t<13, 13, 112, 6>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  return launch_rows_t<13, 12, 240, 6>(ctx, p_begin, p_end, editdist, d_out, d_mask);
 }
 
 }  // namespace prf

@@ -435,16 +435,10 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-template <int kLog2B, int kWarps, int kCap, int kQ>
-static int launch_rows_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out, uint32_t* d_mask) {
+// The cut of [p_begin, p_end) into whole-row work items (longest first), cached in the context.
+static int prepare_row_plan(Ctx* ctx, uint64_t p_begin, uint64_t p_end) {
   const HashRFState& H = ctx->h;
   cudaStream_t s = ctx->stream;
-  constexpr int kThreads = 32 * kWarps;
-  constexpr size_t smem = (size_t)kWarps * (((1 << kLog2B) + 8) * 2 + kCap * 12 + 16);
-  static_assert(smem + 256 <= 232448, "rows kernel: shared memory per CTA");
-  if (H.block_log2 != (uint32_t)kLog2B) return ctx->fail(PRF_E_STATE, "list structure was built for another column block size");
-  auto kern = rows_kernel<kLog2B, kWarps, kCap, kQ>;
-  PRF_CK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   RowPlan& plan = ctx->plan;
   if (!plan.valid || plan.T != H.T || plan.p_begin != p_begin || plan.p_end != p_end || plan.tile != 0) {
     plan.valid = false;
@@ -462,8 +456,12 @@ static int launch_rows_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t edi
     plan.tile = 0;
     plan.valid = true;
   }
-  if (plan.n_items == 0) return PRF_OK;
-  const uint32_t grid = std::min<uint32_t>((plan.n_items + kWarps - 1) / kWarps, (uint32_t)ctx->sm_count);
+  return PRF_OK;
+}
+
+static RowsParams make_rows_params(Ctx* ctx, uint64_t p_begin, int32_t editdist, uint16_t* d_out, uint32_t* d_mask) {
+  const HashRFState& H = ctx->h;
+  const RowPlan& plan = ctx->plan;
   RowsParams prm{};
   prm.T = H.T;
   prm.p_begin = p_begin;
@@ -483,6 +481,27 @@ static int launch_rows_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t edi
   prm.counter = plan.counter.p;
 #ifdef PRF_CALIB
   prm.calib = ctx->calib;
+#endif
+  return prm;
+}
+
+template <int kLog2B, int kWarps, int kCap, int kQ>
+static int launch_rows_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out, uint32_t* d_mask) {
+  const HashRFState& H = ctx->h;
+  cudaStream_t s = ctx->stream;
+  constexpr int kThreads = 32 * kWarps;
+  constexpr size_t smem = (size_t)kWarps * (((1 << kLog2B) + 8) * 2 + kCap * 12 + 16);
+  static_assert(smem + 256 <= 232448, "rows kernel: shared memory per CTA");
+  if (H.block_log2 != (uint32_t)kLog2B) return ctx->fail(PRF_E_STATE, "list structure was built for another column block size");
+  auto kern = rows_kernel<kLog2B, kWarps, kCap, kQ>;
+  PRF_CK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int rc = prepare_row_plan(ctx, p_begin, p_end);
+  if (rc) return rc;
+  RowPlan& plan = ctx->plan;
+  if (plan.n_items == 0) return PRF_OK;
+  const uint32_t grid = std::min<uint32_t>((plan.n_items + kWarps - 1) / kWarps, (uint32_t)ctx->sm_count);
+  RowsParams prm = make_rows_params(ctx, p_begin, editdist, d_out, d_mask);
+#ifdef PRF_CALIB
   {
     const int no_red = ctx->calib == 2;
     PRF_CK(ctx, cudaMemcpyToSymbolAsync(g_calib_no_red, &no_red, sizeof(int), 0, cudaMemcpyHostToDevice, s));
@@ -493,21 +512,6 @@ static int launch_rows_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t edi
   kern<<<grid, kThreads, smem, s>>>(prm);
   PRF_LAUNCHED(ctx);
   return PRF_OK;
-}
-
-int launch_rows(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out, uint32_t* d_mask) {
-  // the tiny-block build exists so that small test inputs exercise multi-tile rows and several passes over a row's lists
-  if (ctx->debug_small_tiles) return launch_rows_t<8, 2, 8, 2>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-  switch (ctx->rows_cfg) {  // tuning instantiations (scripts/rows_probe.py)
-    case 1: return launch_rows_t<13, 13, 112, 6>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-    case 2: return launch_rows_t<13, 12, 240, 6>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-    case 3: return launch_rows_t<13, 13, 112, 4>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-    default: break;
-  }
-  // 13 warps per SM when every row's lists fit one pass of 112 (measured 2.53 vs 2.60 ms at 100k x 200), else 12 warps
-  // x 240; 6 groups per lane in flight (4: 2.57 ms, 8: 2.54 ms)
-  if (ctx->h.max_lists <= 112) return launch_rows_t<13, 13, 112, 6>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-  return launch_rows_t<13, 12, 240, 6>(ctx, p_begin, p_end, editdist, d_out, d_mask);
 }
 
 }  // namespace prf
