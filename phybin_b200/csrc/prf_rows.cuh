@@ -54,13 +54,29 @@ struct RowsParams {
   uint32_t n_items;
   uint32_t* counter;          // next item (zeroed before the launch)
 #ifdef PRF_CALIB
-  int calib;                  // calibration builds only: 1 = fill + store only, 2 = member loads but no tile updates
+  int calib;                  // calibration builds only (scripts/rows_calib.py): 1 = fill + store only, 2 = everything but the
+                              // reductions add 0, 3 = no group loads, 4 = no reduction instructions, 5 = bounds + scan only
 #endif
 };
 
 #ifdef PRF_CALIB
 __device__ int g_calib_no_red;
 #endif
+
+// L2 residency: the list structure (~45 MB at 100k x 200) is re-read by every row that uses it and fits the 126 MB L2,
+// but the 10 GB stream of matrix tiles passing through L2 evicts it; every evicted sector comes back as a small random
+// DRAM read in the middle of the write stream (0.39 GB per launch, and the kernel 0.7 ms slower than on an input whose
+// structure is tiny).  So the structure is loaded with an evict-last policy and the tiles are stored evict-first.
+__device__ __forceinline__ uint32_t ldg_keep(const uint32_t* p, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint4 ldg_keep(const uint4* p, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
 
 // tile entry of column offset `off` (relative to the block) -= 2 when `on`; tb = byte address of the entry of the
 // block's column 0 (mod 2^32).  One shared-memory reduction on the entry's 32-bit word, issued UNCONDITIONALLY (a
@@ -69,6 +85,7 @@ __device__ int g_calib_no_red;
 // scripts/rows_calib.py).
 __device__ __forceinline__ void tile_red2(uint32_t tb, uint32_t safe, uint32_t off, bool on) {
 #ifdef PRF_CALIB
+  if (g_calib_no_red == 2) return;
   if (g_calib_no_red) on = false;
 #endif
   const uint32_t A = tb + 2u * off;
@@ -101,6 +118,9 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
   __syncwarp();
   uint32_t fill_phase = 0;
 
+  uint64_t pol_keep, pol_stream;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
   const uint32_t vv = (2u * prm.nb_uniform) | ((2u * prm.nb_uniform) << 16);
   const uint4 q4 = make_uint4(vv, vv, vv, vv);
 
@@ -116,10 +136,10 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
     uint32_t pk0 = 0, pR = 0, ps0 = 0, pS = 0;
     if (lane < prm.n_parts) {
       const ListPart& q = prm.part[lane];
-      pk0 = __ldg(q.roff + a);
-      pR = __ldg(q.roff + a + 1) - pk0;
-      ps0 = __ldg(q.soff + a);
-      pS = __ldg(q.soff + a + 1) - ps0;
+      pk0 = ldg_keep(q.roff + a, pol_keep);
+      pR = ldg_keep(q.roff + a + 1, pol_keep) - pk0;
+      ps0 = ldg_keep(q.soff + a, pol_keep);
+      pS = ldg_keep(q.soff + a + 1, pol_keep) - ps0;
     }
     uint32_t pRx = pR;  // inclusive scan over parts (n_parts <= 16)
 #pragma unroll
@@ -149,7 +169,7 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
       for (uint32_t q = 1; q < prm.n_parts; ++q)
         if (__shfl_sync(0xffffffffu, pSx, q) <= lane) p = q;
       const uint32_t s0 = __shfl_sync(0xffffffffu, ps0, p), x = __shfl_sync(0xffffffffu, pSx, p);
-      if (lane < S) my_single = __ldg(prm.part[p].singles + s0 + (lane - x));
+      if (lane < S) my_single = ldg_keep(prm.part[p].singles + s0 + (lane - x), pol_keep);
     }
     // lists [c0, c0 + Rc) of the row -> s_trow
     auto load_lists = [&](uint32_t c0, uint32_t Rc) {
@@ -159,7 +179,7 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
         for (uint32_t q = 1; q < prm.n_parts; ++q)  // warp-uniform loop, per-lane k
           if (__shfl_sync(0xffffffffu, pRx, q) <= k) p = q;
         const uint32_t k0 = __shfl_sync(0xffffffffu, pk0, p), x = __shfl_sync(0xffffffffu, pRx, p);
-        if (kb + lane < Rc) s_trow[kb + lane] = (p << 28) | (__ldg(prm.part[p].rlist + k0 + (k - x)) * NB);
+        if (kb + lane < Rc) s_trow[kb + lane] = (p << 28) | (ldg_keep(prm.part[p].rlist + k0 + (k - x), pol_keep) * NB);
       }
       __syncwarp();
     };
@@ -175,8 +195,8 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
         if (kk < R) {
           const uint32_t tr = s_trow[kk];
           const uint32_t* __restrict__ bo = prm.part[tr >> 28].boff + (tr & 0x0fffffffu) + jn;
-          pf_s[c] = __ldg(bo);
-          pf_e[c] = __ldg(bo + 1);
+          pf_s[c] = ldg_keep(bo, pol_keep);
+          pf_e[c] = ldg_keep(bo + 1, pol_keep);
         }
       }
     };
@@ -214,8 +234,8 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
           } else if (kk < Rc) {
             const uint32_t tr = s_trow[kk];
             const uint32_t* __restrict__ bo = prm.part[tr >> 28].boff + (tr & 0x0fffffffu) + j;
-            sb = __ldg(bo);
-            eb = __ldg(bo + 1);
+            sb = ldg_keep(bo, pol_keep);
+            eb = ldg_keep(bo + 1, pol_keep);
           }
           const uint32_t u = (eb - sb) >> 3;
           uint32_t inc = u;
@@ -250,10 +270,16 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
         for (int i = 0; i < kQ; ++i) {
           v[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
           const uint32_t u = u_next + i;
+#ifdef PRF_CALIB
+          if (prm.calib == 3 && u < u1) {
+            while (u >= s_upre[k + 1]) ++k;
+            continue;
+          }
+#endif
           if (u < u1) {
             while (u >= s_upre[k + 1]) ++k;  // (empty buckets repeat the same prefix value)
             const ListPart& lp = prm.part[s_trow[k] >> 28];
-            v[i] = __ldg(reinterpret_cast<const uint4*>(lp.lmem + s_start[k] + 8u * (u - s_upre[k])));
+            v[i] = ldg_keep(reinterpret_cast<const uint4*>(lp.lmem + s_start[k] + 8u * (u - s_upre[k])), pol_keep);
           }
         }
       };
@@ -277,6 +303,9 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
 #endif
       if (R0) {
         setup_pass(R0, pf_ok);
+#ifdef PRF_CALIB
+        if (prm.calib == 5) u1 = u_next = 0;
+#endif
         load_batch();
       }
 
@@ -340,7 +369,7 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
           const uint32_t* __restrict__ sg = prm.part[p].singles + s0;
           for (uint32_t sb = 0; sb < sn; sb += 32) {
             const uint32_t i = sb + lane;
-            const uint32_t b = i < sn ? __ldg(sg + i) : 0xffffffffu;
+            const uint32_t b = i < sn ? ldg_keep(sg + i, pol_keep) : 0xffffffffu;
             if (b >= c_lo && b < c_hi) {
               const uint32_t idx = (uint32_t)(base + (int32_t)b);
               atomicSub(&tile32[idx >> 1], 2u << ((idx & 1u) * 16u));
@@ -423,8 +452,8 @@ __global__ void __launch_bounds__(32 * kWarps, 1) rows_kernel(const RowsParams p
         }
         if (lane == 0) {
           if (ib > ia)
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gp + ia),
-                         "r"(smem_addr(tile + ia)), "r"((ib - ia) * 2u)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gp + ia),
+                         "r"(smem_addr(tile + ia)), "r"((ib - ia) * 2u), "l"(pol_stream)
                          : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -503,7 +532,7 @@ static int launch_rows_t(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t edi
   RowsParams prm = make_rows_params(ctx, p_begin, editdist, d_out, d_mask);
 #ifdef PRF_CALIB
   {
-    const int no_red = ctx->calib == 2;
+    const int no_red = ctx->calib == 2 ? 1 : ctx->calib == 4 ? 2 : 0;
     PRF_CK(ctx, cudaMemcpyToSymbolAsync(g_calib_no_red, &no_red, sizeof(int), 0, cudaMemcpyHostToDevice, s));
   }
 #endif

@@ -44,7 +44,8 @@ def main():
     res = {"workload": name}
     for cfg in cfgs:
         L.prf_debug_rows_cfg(ctx._h, cfg)
-        for mode, label in ((0, "full"), (1, "fill_store_only"), (2, "loads_no_updates")):
+        for mode, label in ((0, "full"), (1, "fill_store_only"), (2, "loads_no_updates"), (3, "no_group_loads"), (4, "no_red_instructions"),
+                            (5, "bounds_and_scan_only")):
             if mode not in modes:
                 continue
             L.prf_debug_calib(ctx._h, mode)
