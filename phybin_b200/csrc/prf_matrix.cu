@@ -64,7 +64,7 @@ int launch_rows(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, ui
   // 13 warps per SM when every row's lists fit one pass of 112 (measured 2.53 vs 2.60 ms at 100k x 200), else 12 warps
   // x 240; 6 groups per lane in flight (4: 2.57 ms, 8: 2.54 ms)
   if (ctx->h.max_lists <= 112) return launch_rows_t<13, 13, 112, 6>(ctx, p_begin, p_end, editdist, d_out, d_mask);
-  return launch_rows_t<13, 12, 240, 6>(ctx, p_begin, p_end, editdist, d_out, d_mask);
+  return launch_rows_pair_t<13, 12, 240, 3>(ctx, p_begin, p_end, editdist, d_out, d_mask);
 }
 
 }  // namespace prf

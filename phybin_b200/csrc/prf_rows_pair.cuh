@@ -40,6 +40,9 @@ __global__ void __launch_bounds__(64 * kPairs, 1) rows_pair_kernel(const RowsPar
   pair_sync();
   uint32_t fill_phase = 0;
 
+  uint64_t pol_keep, pol_stream;  // see ldg_keep in prf_rows.cuh
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
   const uint32_t vv = (2u * prm.nb_uniform) | ((2u * prm.nb_uniform) << 16);
   const uint4 q4 = make_uint4(vv, vv, vv, vv);
 
@@ -55,10 +58,10 @@ __global__ void __launch_bounds__(64 * kPairs, 1) rows_pair_kernel(const RowsPar
     uint32_t pk0 = 0, pR = 0, ps0 = 0, pS = 0;
     if (lane < prm.n_parts) {
       const ListPart& q = prm.part[lane];
-      pk0 = __ldg(q.roff + a);
-      pR = __ldg(q.roff + a + 1) - pk0;
-      ps0 = __ldg(q.soff + a);
-      pS = __ldg(q.soff + a + 1) - ps0;
+      pk0 = ldg_keep(q.roff + a, pol_keep);
+      pR = ldg_keep(q.roff + a + 1, pol_keep) - pk0;
+      ps0 = ldg_keep(q.soff + a, pol_keep);
+      pS = ldg_keep(q.soff + a + 1, pol_keep) - ps0;
     }
     uint32_t pRx = pR, pSx = pS;  // inclusive scans over the parts (n_parts <= 16)
 #pragma unroll
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(64 * kPairs, 1) rows_pair_kernel(const RowsPar
       for (uint32_t q = 1; q < prm.n_parts; ++q)
         if (__shfl_sync(0xffffffffu, pSx, q) <= L) p = q;
       const uint32_t s0 = __shfl_sync(0xffffffffu, ps0, p), x = __shfl_sync(0xffffffffu, pSx, p);
-      if (L < S) my_single = __ldg(prm.part[p].singles + s0 + (L - x));
+      if (L < S) my_single = ldg_keep(prm.part[p].singles + s0 + (L - x), pol_keep);
     }
     // lists [c0, c0 + Rc) of the row -> s_trow (the pair's warps take alternate chunks of 32)
     auto load_lists = [&](uint32_t c0, uint32_t Rc) {
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(64 * kPairs, 1) rows_pair_kernel(const RowsPar
         for (uint32_t q = 1; q < prm.n_parts; ++q)  // warp-uniform loop, per-lane k
           if (__shfl_sync(0xffffffffu, pRx, q) <= k) p = q;
         const uint32_t k0 = __shfl_sync(0xffffffffu, pk0, p), x = __shfl_sync(0xffffffffu, pRx, p);
-        if (kb + lane < Rc) s_trow[kb + lane] = (p << 28) | (__ldg(prm.part[p].rlist + k0 + (k - x)) * NB);
+        if (kb + lane < Rc) s_trow[kb + lane] = (p << 28) | (ldg_keep(prm.part[p].rlist + k0 + (k - x), pol_keep) * NB);
       }
       pair_sync();
     };
@@ -106,8 +109,8 @@ __global__ void __launch_bounds__(64 * kPairs, 1) rows_pair_kernel(const RowsPar
         if (kk < R) {
           const uint32_t tr = s_trow[kk];
           const uint32_t* __restrict__ bo = prm.part[tr >> 28].boff + (tr & 0x0fffffffu) + jn;
-          pf_s[c] = __ldg(bo);
-          pf_e[c] = __ldg(bo + 1);
+          pf_s[c] = ldg_keep(bo, pol_keep);
+          pf_e[c] = ldg_keep(bo + 1, pol_keep);
         }
       }
     };
@@ -143,8 +146,8 @@ __global__ void __launch_bounds__(64 * kPairs, 1) rows_pair_kernel(const RowsPar
           } else if (kk < Rc) {
             const uint32_t tr = s_trow[kk];
             const uint32_t* __restrict__ bo = prm.part[tr >> 28].boff + (tr & 0x0fffffffu) + j;
-            sb = __ldg(bo);
-            eb = __ldg(bo + 1);
+            sb = ldg_keep(bo, pol_keep);
+            eb = ldg_keep(bo + 1, pol_keep);
           }
           const uint32_t u = (eb - sb) >> 3;
           uint32_t inc = u;
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(64 * kPairs, 1) rows_pair_kernel(const RowsPar
           if (u < u1) {
             while (u >= s_upre[k + 1]) ++k;  // (empty buckets repeat the same prefix value)
             const ListPart& lp = prm.part[s_trow[k] >> 28];
-            v[i] = __ldg(reinterpret_cast<const uint4*>(lp.lmem + s_start[k] + 8u * (u - s_upre[k])));
+            v[i] = ldg_keep(reinterpret_cast<const uint4*>(lp.lmem + s_start[k] + 8u * (u - s_upre[k])), pol_keep);
           }
         }
       };
@@ -266,7 +269,7 @@ __global__ void __launch_bounds__(64 * kPairs, 1) rows_pair_kernel(const RowsPar
           const uint32_t* __restrict__ sg = prm.part[p].singles + s0;
           for (uint32_t sb = 0; sb < sn; sb += 64) {
             const uint32_t i = sb + L;
-            const uint32_t b = i < sn ? __ldg(sg + i) : 0xffffffffu;
+            const uint32_t b = i < sn ? ldg_keep(sg + i, pol_keep) : 0xffffffffu;
             if (b >= c_lo && b < c_hi) {
               const uint32_t idx = (uint32_t)(base + (int32_t)b);
               atomicSub(&tile32[idx >> 1], 2u << ((idx & 1u) * 16u));
@@ -347,8 +350,8 @@ __global__ void __launch_bounds__(64 * kPairs, 1) rows_pair_kernel(const RowsPar
         }
         if (lane == 0) {
           if (ib > ia)
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gp + ia),
-                         "r"(smem_addr(tile + ia)), "r"((ib - ia) * 2u)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gp + ia),
+                         "r"(smem_addr(tile + ia)), "r"((ib - ia) * 2u), "l"(pol_stream)
                          : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
