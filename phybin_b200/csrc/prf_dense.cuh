@@ -45,10 +45,20 @@ constexpr size_t kDSmem = (size_t)kDStages * kDStageBytes + 4 * 32 * kDRowWords 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
 }
+// Operand tiles are re-read by every output tile of their row / column panel: they are loaded with an evict-last L2
+// policy and the matrix is stored evict-first, so that the output stream does not push the operand out of L2.
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
                    smem_addr(dst)),
-               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void store_stream(uint4* p, const uint4& v) {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
                : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -272,7 +282,7 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_gram_kernel(const DensePar
             o.y = __funnelshift_r(w1, w2, sh);
             o.z = __funnelshift_r(w2, w3, sh);
             o.w = __funnelshift_r(w3, w4, sh);
-            *reinterpret_cast<uint4*>(gout + g) = o;
+            store_stream(reinterpret_cast<uint4*>(gout + g), o);
             if (prm.editdist >= 0) {
               const uint32_t thr = (uint32_t)prm.editdist, thr2 = thr | (thr << 16);
               const uint32_t r0 = __vsetleu2(o.x, thr2), r1 = __vsetleu2(o.y, thr2), r2 = __vsetleu2(o.z, thr2),
