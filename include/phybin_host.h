@@ -108,6 +108,21 @@ PHB_API int phb_cluster_component(const uint16_t* sub, uint32_t m, int linkage, 
 /* Same on doubles (tests against scipy use tie-free real distances). */
 PHB_API int phb_cluster_component_f64(const double* sub, uint32_t m, int linkage, double thresh, uint32_t* labels);
 
+/* The whole agglomeration with its merge list (the host twin of prf_agglomerate, phybin_rf.h; same rule, same
+ * IEEE-double arithmetic): step k merged the clusters with smallest members merge_a[k] < merge_b[k] at distance
+ * merge_d[k]; *n_merges steps were taken before the smallest distance exceeded thresh (m - 1 with
+ * thresh = INFINITY).  labels / merge_* (m - 1 entries each) / n_merges may be NULL. */
+PHB_API int phb_agglomerate(const uint16_t* sub, uint32_t m, int linkage, double thresh, uint32_t* labels,
+                            uint32_t* merge_a, uint32_t* merge_b, double* merge_d, uint32_t* n_merges);
+
+/* dendrogram.txt: `show (fmap treename dendro)` (PhyBin.hs:238-243) for a FULL merge list (n_merges == m - 1) --
+ * the derived Show of hierarchical-clustering's `Dendrogram String`,
+ *   Leaf "name"   |   Branch <show Double> (<left>) (<right>)
+ * with the cluster that kept its key (merge_a) as the left child.  names: m tree names.  NULL on an incomplete
+ * or malformed merge list; free with phb_free_buf. */
+PHB_API char* phb_dendrogram_text(const char* const* names, uint32_t m, const uint32_t* merge_a,
+                                  const uint32_t* merge_b, const double* merge_d, uint32_t n_merges);
+
 /* printDistMat text of a packed uint16 upper triangle; free with phb_free_buf. */
 PHB_API char* phb_print_dist_mat(const uint16_t* upper, uint32_t T);
 /* Streams the same text to a file; returns 0 on success. */

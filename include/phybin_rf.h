@@ -272,6 +272,35 @@ PRF_API int prf_mask_components(prf_ctx* ctx, const uint32_t* d_mask, uint32_t T
 PRF_API int prf_fetch_submatrix(prf_ctx* ctx, const uint16_t* d_matrix, uint32_t T, const uint32_t* ids, uint32_t m,
                                 uint16_t* out);
 
+/* ---- the agglomeration itself: C.dendrogram linkage trees dist (PhyBin.hs:358) ------------------- */
+
+typedef struct prf_agglo_info {
+  uint32_t n_merges;    /* merges performed (m - 1 for a full dendrogram) */
+  uint32_t n_clusters;  /* m - n_merges */
+  int32_t gpu_launches;
+  float ms_kernels;     /* gather + agglomeration kernel */
+} prf_agglo_info;
+
+/* Agglomerative clustering of m trees on the device, replacing hierarchical-clustering-0.4.6's C.dendrogram
+ * (stack.yaml:9, called at PhyBin.hs:358) and, through `thresh`, sliceDendro (PhyBin.hs:415-422).
+ *   d_matrix, T   as for prf_fetch_submatrix: a DEVICE buffer with the whole packed triangle, or NULL for the
+ *                 context-owned result of the last compute
+ *   ids, m        ascending tree ids (host) -- e.g. one component of prf_mask_components; NULL = all T trees
+ *   linkage       0 single, 1 complete, 2 UPGMA (C.SingleLinkage / C.CompleteLinkage / C.UPGMA, Main.hs:96-98)
+ *   thresh        merging stops when the smallest distance exceeds it (sliceDendro's `dist > dstThresh`);
+ *                 INFINITY = the full dendrogram (dendrogram.txt, PhyBin.hs:238-243)
+ *   labels        out (host, m entries, may be NULL): smallest LOCAL index of every tree's cluster at the cut
+ *   merge_a/b/d   out (host, m-1 entries each, may be NULL): step k merged the clusters whose smallest local
+ *                 members are merge_a[k] < merge_b[k] at distance merge_d[k]; the merged cluster keeps merge_a[k]
+ * Every step merges the pair at minimal distance, the first in (lower key, higher key) order among ties, and
+ * updates distances by Lance-Williams in IEEE double -- the same rule and arithmetic as the host restatement
+ * phb_cluster_component, so both produce the same merges.  One persistent cooperative kernel, one grid barrier
+ * per merge; the working matrix is m x m uint16 (single / complete) or double (UPGMA) in HBM: PRF_E_NOMEM when
+ * that does not fit. */
+PRF_API int prf_agglomerate(prf_ctx* ctx, const uint16_t* d_matrix, uint32_t T, const uint32_t* ids, uint32_t m,
+                            int linkage, double thresh, uint32_t* labels, uint32_t* merge_a, uint32_t* merge_b,
+                            double* merge_d, prf_agglo_info* info);
+
 /* ---- strict consensus of every cluster (replaces the intersection inside consensusTree) -------- */
 
 typedef struct prf_consensus_info {

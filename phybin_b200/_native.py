@@ -32,6 +32,14 @@ class prf_consensus_info(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
+class prf_agglo_info(C.Structure):
+    _fields_ = [("n_merges", C.c_uint32), ("n_clusters", C.c_uint32), ("gpu_launches", C.c_int32),
+                ("ms_kernels", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 class prf_stats(C.Structure):
     _fields_ = [
         ("n_trees", C.c_uint64), ("n_words", C.c_uint64), ("nnz", C.c_uint64),
@@ -91,6 +99,9 @@ def host_lib():
         L.phb_consensus_newick.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32]
         L.phb_cluster_component.argtypes = [vp, C.c_uint32, C.c_int, C.c_double, vp]
         L.phb_cluster_component_f64.argtypes = [vp, C.c_uint32, C.c_int, C.c_double, vp]
+        L.phb_agglomerate.argtypes = [vp, C.c_uint32, C.c_int, C.c_double, vp, vp, vp, vp, u32p]
+        L.phb_dendrogram_text.restype = vp
+        L.phb_dendrogram_text.argtypes = [C.POINTER(C.c_char_p), C.c_uint32, vp, vp, vp, C.c_uint32]
         L.phb_print_dist_mat.restype = vp
         L.phb_print_dist_mat.argtypes = [vp, C.c_uint32]
         L.phb_write_dist_mat.argtypes = [C.c_char_p, vp, C.c_uint32]
@@ -153,6 +164,8 @@ def rf_lib():
         L.prf_allbips_result.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), u64p]
         L.prf_allbips_fetch.argtypes = [vp, vp, vp, vp]
         L.prf_fetch_submatrix.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, vp]
+        L.prf_agglomerate.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, C.c_int, C.c_double, vp, vp, vp, vp,
+                                      C.POINTER(prf_agglo_info)]
         L.prf_consensus.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int, vp, C.POINTER(prf_consensus_info)]
         L.prf_consensus_fetch.argtypes = [vp, vp, vp]
         L.prf_mask_components.argtypes = [vp, vp, C.c_uint32, vp, u32p]
@@ -181,7 +194,7 @@ def rf_lib():
 RF_SYMBOLS = [
     "prf_create", "prf_destroy", "prf_last_error", "prf_version", "prf_stream", "prf_hashrf",
     "prf_hashrf_load", "prf_hashrf_compute", "prf_multi_create", "prf_multi_destroy", "prf_multi_last_error", "prf_multi_gpus", "prf_multi_ctx", "prf_multi_hashrf", "prf_team_handle_bytes", "prf_team_init", "prf_team_connect", "prf_team_load", "prf_team_release", "prf_fetch", "prf_fetch_mask", "prf_fetch_rows",
-    "prf_tolerant", "prf_tolerant_load", "prf_tolerant_compute", "prf_allbips", "prf_allbips_result", "prf_allbips_fetch", "prf_hashrf_trees", "prf_tolerant_trees", "prf_consensus", "prf_consensus_fetch", "prf_fetch_submatrix",
+    "prf_tolerant", "prf_tolerant_load", "prf_tolerant_compute", "prf_allbips", "prf_allbips_result", "prf_allbips_fetch", "prf_hashrf_trees", "prf_tolerant_trees", "prf_consensus", "prf_consensus_fetch", "prf_fetch_submatrix", "prf_agglomerate",
     "prf_mask_components", "prf_packed_index",
     "prf_shard_align", "prf_shard_range", "prf_limits", "prf_launch_count",
 ]

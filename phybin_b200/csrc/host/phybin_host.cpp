@@ -779,7 +779,8 @@ char* phb_consensus_newick(const phb_forest* h, const uint64_t* keys, uint64_t k
 namespace {
 
 // Agglomerative clustering of m items cut at `thresh`; see phybin_host.h.  d: packed upper triangle, modified.
-int agglomerate(std::vector<double>& d, uint32_t m, int linkage, double thresh, uint32_t* labels) {
+int agglomerate(std::vector<double>& d, uint32_t m, int linkage, double thresh, uint32_t* labels, uint32_t* merge_a = nullptr,
+                uint32_t* merge_b = nullptr, double* merge_d = nullptr, uint32_t* n_merges = nullptr) {
   auto at = [&](uint32_t i, uint32_t j) -> double& {  // i < j
     return d[(uint64_t)i * (2ull * m - i - 1) / 2 + (j - i - 1)];
   };
@@ -796,6 +797,7 @@ int agglomerate(std::vector<double>& d, uint32_t m, int linkage, double thresh, 
       if (active[j] && at(i, j) < nnd[i]) { nnd[i] = at(i, j); nn[i] = j; }
   };
   for (uint32_t i = 0; i < m; ++i) rescan(i);
+  uint32_t step = 0;
   for (uint32_t left = m; left > 1; --left) {
     uint32_t a = NONE;
     double best = inf;
@@ -803,6 +805,10 @@ int agglomerate(std::vector<double>& d, uint32_t m, int linkage, double thresh, 
       if (active[i] && nn[i] != NONE && nnd[i] < best) { best = nnd[i]; a = i; }
     if (a == NONE || best > thresh) break;  // sliceDendro: dist > dstThresh splits (PhyBin.hs:418-419)
     const uint32_t b = nn[a];
+    if (merge_a) merge_a[step] = a;
+    if (merge_b) merge_b[step] = b;
+    if (merge_d) merge_d[step] = best;
+    ++step;
     const double na = size[a], nb = size[b];
     for (uint32_t x = 0; x < m; ++x) {
       if (!active[x] || x == a || x == b) continue;
@@ -821,12 +827,72 @@ int agglomerate(std::vector<double>& d, uint32_t m, int linkage, double thresh, 
       }
     }
   }
-  for (uint32_t i = 0; i < m; ++i) {
+  if (n_merges) *n_merges = step;
+  for (uint32_t i = 0; labels && i < m; ++i) {
     uint32_t r = i;
     while (parent[r] != r) r = parent[r];
     labels[i] = r;  // merges keep the lower key, so the root is the cluster's smallest index
   }
   return 0;
+}
+
+// `show` of a Haskell Double (Numeric.showFloat via floatToDigits): the shortest digits that read back to the
+// same double; plain decimal for 0.1 <= x < 10^7, d.ddde<n> otherwise.
+void show_double(std::string& o, double x) {
+  if (x != x) { o += "NaN"; return; }
+  if (x < 0) { o += '-'; x = -x; }
+  if (x == std::numeric_limits<double>::infinity()) { o += "Infinity"; return; }
+  if (x == 0) { o += "0.0"; return; }
+  char buf[40];
+  int prec = 0;
+  for (prec = 0; prec < 17; ++prec) {
+    std::snprintf(buf, sizeof buf, "%.*e", prec, x);
+    if (std::strtod(buf, nullptr) == x) break;
+  }
+  std::string digits;
+  const char* e = std::strchr(buf, 'e');
+  for (const char* c = buf; c < e; ++c)
+    if (*c != '.') digits += *c;
+  const int exp10 = std::atoi(e + 1);  // x = d.ddd * 10^exp10
+  if (x >= 0.1 && x < 1e7) {
+    if (exp10 < 0) {  // 0.1 <= x < 1
+      o += "0.";
+      o += digits;
+    } else {
+      for (int i = 0; i <= exp10; ++i) o += i < (int)digits.size() ? digits[i] : '0';
+      o += '.';
+      if ((int)digits.size() > exp10 + 1) o.append(digits, exp10 + 1, std::string::npos);
+      else o += '0';
+    }
+  } else {
+    o += digits[0];
+    o += '.';
+    if (digits.size() > 1) o.append(digits, 1, std::string::npos);
+    else o += '0';
+    o += 'e';
+    o += std::to_string(exp10);
+  }
+}
+
+// `show` of a Haskell String.
+void show_string(std::string& o, const char* s) {
+  o += '"';
+  bool num_escape = false;  // the previous character was a numeric escape: a following digit needs "\&"
+  for (const unsigned char* c = (const unsigned char*)s; *c; ++c) {
+    if (num_escape && *c >= '0' && *c <= '9') o += "\\&";
+    num_escape = false;
+    switch (*c) {
+      case '"': o += "\\\""; break;
+      case '\\': o += "\\\\"; break;
+      case '\n': o += "\\n"; break;
+      case '\t': o += "\\t"; break;
+      case '\r': o += "\\r"; break;
+      default:
+        if (*c < 32 || *c >= 127) { o += '\\'; o += std::to_string((unsigned)*c); num_escape = true; }
+        else o += (char)*c;
+    }
+  }
+  o += '"';
 }
 
 }  // namespace
@@ -843,6 +909,62 @@ int phb_cluster_component(const uint16_t* sub, uint32_t m, int linkage, double t
   if (m > 46000) return -2;
   std::vector<double> d(sub, sub + (uint64_t)m * (m ? m - 1 : 0) / 2);  // fromIntegral (PhyBin.hs:355-356)
   return agglomerate(d, m, linkage, thresh, labels);
+}
+
+int phb_agglomerate(const uint16_t* sub, uint32_t m, int linkage, double thresh, uint32_t* labels, uint32_t* merge_a,
+                    uint32_t* merge_b, double* merge_d, uint32_t* n_merges) {
+  if ((m > 1 && !sub) || linkage < 0 || linkage > 2) return -1;
+  if (m > 46000) return -2;
+  std::vector<double> d(sub, sub + (uint64_t)m * (m ? m - 1 : 0) / 2);
+  return agglomerate(d, m, linkage, thresh, labels, merge_a, merge_b, merge_d, n_merges);
+}
+
+char* phb_dendrogram_text(const char* const* names, uint32_t m, const uint32_t* merge_a, const uint32_t* merge_b,
+                          const double* merge_d, uint32_t n_merges) {
+  if (!m || !names || n_merges + 1 != m || (n_merges && (!merge_a || !merge_b || !merge_d))) return nullptr;
+  // node k < m: Leaf k; node m + k: the Branch made by merge k.  cur[key] = node currently standing for that cluster.
+  std::vector<uint32_t> cur(m), left(n_merges), right(n_merges);
+  for (uint32_t i = 0; i < m; ++i) cur[i] = i;
+  for (uint32_t k = 0; k < n_merges; ++k) {
+    const uint32_t a = merge_a[k], b = merge_b[k];
+    if (a >= b || b >= m || cur[a] == NONE || cur[b] == NONE) return nullptr;
+    left[k] = cur[a];
+    right[k] = cur[b];
+    cur[a] = m + k;
+    cur[b] = NONE;
+  }
+  // derived Show, showsPrec 0: "Branch d (l) (r)" / "Leaf \"name\""; iterative (a chain dendrogram is m deep)
+  std::string o;
+  struct It { uint32_t node; int state; };
+  std::vector<It> st;
+  st.push_back({n_merges ? m + n_merges - 1 : 0u, 0});
+  while (!st.empty()) {
+    It& it = st.back();
+    if (it.node < m) {
+      o += "Leaf ";
+      show_string(o, names[it.node] ? names[it.node] : "");
+      st.pop_back();
+      continue;
+    }
+    const uint32_t k = it.node - m;
+    if (it.state == 0) {
+      o += "Branch ";
+      show_double(o, merge_d[k]);
+      o += " (";
+      it.state = 1;
+      st.push_back({left[k], 0});
+    } else if (it.state == 1) {
+      o += ") (";
+      it.state = 2;
+      st.push_back({right[k], 0});
+    } else {
+      o += ')';
+      st.pop_back();
+    }
+  }
+  char* r = (char*)std::malloc(o.size() + 1);
+  if (r) std::memcpy(r, o.c_str(), o.size() + 1);
+  return r;
 }
 
 static void append_uint(std::string& o, unsigned x) {

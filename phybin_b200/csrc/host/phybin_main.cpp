@@ -17,6 +17,7 @@
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -236,15 +237,39 @@ int main(int argc, char** argv) {
         const std::vector<uint32_t>& ids = members[c];
         const uint32_t m = (uint32_t)ids.size();
         if (m < 3) continue;  // two trees within D of each other are one cluster under every linkage
-        sub.resize((size_t)m * (m - 1) / 2);
         local.resize(m);
-        if ((rc = prf_fetch_submatrix(ctx, nullptr, T, ids.data(), m, sub.data()))) die(std::string("phybin_rf error: ") + prf_last_error(ctx));
-        if (phb_cluster_component(sub.data(), m, opt.linkage, (double)opt.editdist, local.data()))
-          die("component of " + std::to_string(m) + " trees is too large for the host clustering step");
+        if (m >= 64) {  // a large component: the agglomeration itself runs on the device (same rule, same arithmetic)
+          if ((rc = prf_agglomerate(ctx, nullptr, T, ids.data(), m, opt.linkage, (double)opt.editdist, local.data(), nullptr, nullptr,
+                                    nullptr, nullptr)))
+            die(std::string("phybin_rf error: ") + prf_last_error(ctx));
+        } else {
+          sub.resize((size_t)m * (m - 1) / 2);
+          if ((rc = prf_fetch_submatrix(ctx, nullptr, T, ids.data(), m, sub.data()))) die(std::string("phybin_rf error: ") + prf_last_error(ctx));
+          if (phb_cluster_component(sub.data(), m, opt.linkage, (double)opt.editdist, local.data()))
+            die("component of " + std::to_string(m) + " trees is too large for the host clustering step");
+        }
         for (uint32_t i = 0; i < m; ++i) label[ids[i]] = ids[local[i]];
       }
       for (auto& v : members) v.clear();
       for (uint32_t t = 0; t < T; ++t) members[label[t]].push_back(t);
+    }
+    // dendrogram.txt = show (fmap treename dendro) (PhyBin.hs:238-243): the full agglomeration of every tree, on the device
+    if (T >= 1 && T <= 40000) {
+      std::vector<uint32_t> ma(T), mb(T);
+      std::vector<double> md(T);
+      prf_agglo_info ai;
+      if ((rc = prf_agglomerate(ctx, nullptr, T, nullptr, T, opt.linkage, INFINITY, nullptr, ma.data(), mb.data(), md.data(), &ai)))
+        die(std::string("phybin_rf error: ") + prf_last_error(ctx));
+      std::vector<const char*> nptr;
+      for (uint32_t t = 0; t < T; ++t) nptr.push_back(t < names.size() ? names[t].c_str() : "");
+      char* txt = phb_dendrogram_text(nptr.data(), T, ma.data(), mb.data(), md.data(), ai.n_merges);
+      if (!txt) die("could not format the dendrogram");
+      std::ofstream(opt.out_dir + "/dendrogram.txt") << txt;
+      phb_free_buf(txt);
+      std::printf("Time for clustering was: %.3fs\n", ai.ms_kernels / 1e3);
+      std::printf(" [finished] Wrote full dendrogram to file dendrogram.txt\n");  // PhyBin.hs:246
+    } else {
+      std::printf("dendrogram.txt skipped: the full dendrogram of %u trees needs a %u x %u working matrix (flat clusters below are exact)\n", T, T, T);
     }
     std::printf("Combining all clusters at distance less than or equal to %d\n", opt.editdist);  // PhyBin.hs:276
     // sorted0 = reverse (sortBy (compare `on` fst) wlens)  (PhyBin.hs:281): sizes descending.  The order of

@@ -4,9 +4,55 @@
 #include "prf_internal.h"
 #include "prf_primitives.cuh"
 #include "prf_cluster.cuh"
+#include "prf_agglo.cuh"
 #include "prf_consensus.cuh"
 
 using namespace prf;
+
+namespace {
+
+template <class Tv>
+int run_agglo(Ctx* ctx, const uint16_t* src, uint64_t src_begin, uint32_t T, const uint32_t* d_ids, uint32_t m, int linkage,
+              double thresh, uint32_t* d_ma, uint32_t* d_mb, double* d_md, uint32_t* d_nm) {
+  cudaStream_t s = ctx->stream;
+  constexpr uint32_t E = AggloVal<Tv>::kPerVec;
+  const uint32_t ld = (m + E - 1) / E * E;
+  uint32_t G = std::min<uint32_t>((uint32_t)ctx->sm_count, (m + 15) / 16);
+  const uint32_t R0 = (m + G - 1) / G;
+  const size_t smem = (size_t)R0 * 20 + 512;
+  PRF_CK(ctx, cudaFuncSetAttribute(agglo_kernel<Tv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  PRF_CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agglo_kernel<Tv>, (int)kAggloThreads, smem));
+  if (per_sm < 1) return ctx->fail(PRF_E_UNSUPPORTED, "agglomeration of %u trees does not fit a CTA's shared memory", m);
+  DevBuf<Tv> D;
+  DevBuf<uint32_t> sizes;
+  DevBuf<AggloRecord> rec;
+  if (D.alloc((size_t)m * ld, s) != cudaSuccess || sizes.alloc((size_t)G * m, s) != cudaSuccess) {
+    cudaGetLastError();
+    return ctx->fail(PRF_E_NOMEM, "no device memory for a %u x %u matrix of %zu-byte distances", m, m, sizeof(Tv));
+  }
+  PRF_CK(ctx, rec.alloc((size_t)2 * G, s));
+  agglo_gather_kernel<Tv><<<dim3((ld + 255) / 256, m), 256, 0, s>>>(src, src_begin, T, d_ids, m, ld, D.p);
+  PRF_LAUNCHED(ctx);
+  AggloParams prm;
+  prm.D = D.p;
+  prm.m = m;
+  prm.ld = ld;
+  prm.linkage = linkage;
+  prm.thresh = thresh;
+  prm.sizes = sizes.p;
+  prm.rec = rec.p;
+  prm.merge_a = d_ma;
+  prm.merge_b = d_mb;
+  prm.merge_d = d_md;
+  prm.n_merges = d_nm;
+  void* args[] = {&prm};
+  PRF_CK(ctx, cudaLaunchCooperativeKernel((const void*)agglo_kernel<Tv>, dim3(G), dim3(kAggloThreads), args, smem, s));
+  PRF_LAUNCHED(ctx);
+  return PRF_OK;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -86,6 +132,94 @@ PRF_API int prf_fetch_submatrix(prf_ctx* h, const uint16_t* d_matrix, uint32_t T
   PRF_LAUNCHED(ctx);
   PRF_CK(ctx, cudaMemcpyAsync(out, d_out.p, n_out * 2, cudaMemcpyDeviceToHost, s));
   PRF_CK(ctx, cudaStreamSynchronize(s));
+  return PRF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// agglomerative clustering of one set of trees (the dendrogram)
+// ---------------------------------------------------------------------------------------------
+
+PRF_API int prf_agglomerate(prf_ctx* h, const uint16_t* d_matrix, uint32_t T, const uint32_t* ids, uint32_t m, int linkage,
+                            double thresh, uint32_t* labels, uint32_t* merge_a, uint32_t* merge_b, double* merge_d,
+                            prf_agglo_info* info) {
+  if (!h) return PRF_E_INVALID;
+  Ctx* ctx = &h->c;
+  ctx->err.clear();
+  const uint16_t* src = d_matrix;
+  uint64_t src_begin = 0;
+  if (!src) {
+    if (!ctx->out_valid) return ctx->fail(PRF_E_STATE, "no context-owned result to cluster");
+    T = ctx->h.loaded ? ctx->h.T : (ctx->tol.loaded ? ctx->tol.T : 0);
+    src = ctx->out.p;
+    src_begin = ctx->out_begin;
+  }
+  if (!ids) m = T;
+  if (linkage < 0 || linkage > 2) return ctx->fail(PRF_E_INVALID, "linkage must be 0 (single), 1 (complete) or 2 (UPGMA)");
+  if (thresh != thresh) return ctx->fail(PRF_E_INVALID, "thresh is NaN");
+  if (ids)
+    for (uint32_t i = 0; i < m; ++i)
+      if (ids[i] >= T || (i && ids[i] <= ids[i - 1])) return ctx->fail(PRF_E_INVALID, "ids must be ascending tree ids below %u", T);
+  if (m >= 2 && !d_matrix) {
+    const uint32_t i0 = ids ? ids[0] : 0, i1 = ids ? ids[1] : 1, y0 = ids ? ids[m - 2] : m - 2, y1 = ids ? ids[m - 1] : m - 1;
+    const uint64_t lo = row_start(i0, T) + (i1 - i0 - 1), hi = row_start(y0, T) + (y1 - y0 - 1);
+    if (lo < ctx->out_begin || hi >= ctx->out_end) return ctx->fail(PRF_E_INVALID, "the computed range does not cover these pairs");
+  }
+  if (info) *info = prf_agglo_info{};
+  uint32_t n_merges = 0;
+  std::vector<uint32_t> ha, hb;
+  float ms = 0.f;
+  const uint64_t launches0 = ctx->launches;
+  if (m >= 2) {
+    PRF_CK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    int coop = 0;
+    PRF_CK(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+    if (!coop) return ctx->fail(PRF_E_UNSUPPORTED, "device does not support cooperative launches");
+    DevBuf<uint32_t> d_ids, d_ma, d_mb, d_nm;
+    DevBuf<double> d_md;
+    if (ids) {
+      PRF_CK(ctx, d_ids.alloc(m, s));
+      PRF_CK(ctx, cudaMemcpyAsync(d_ids.p, ids, (size_t)m * 4, cudaMemcpyHostToDevice, s));
+    }
+    PRF_CK(ctx, d_ma.alloc(m - 1, s));
+    PRF_CK(ctx, d_mb.alloc(m - 1, s));
+    PRF_CK(ctx, d_md.alloc(m - 1, s));
+    PRF_CK(ctx, d_nm.alloc(1, s));
+    PRF_CK(ctx, cudaMemsetAsync(d_nm.p, 0, 4, s));
+    PRF_CK(ctx, cudaEventRecord(ctx->ev[0], s));
+    // single / complete linkage only ever hold input values: the matrix stays uint16; UPGMA averages in double
+    const int rc = linkage == 2 ? run_agglo<double>(ctx, src, src_begin, T, ids ? d_ids.p : nullptr, m, linkage, thresh, d_ma.p, d_mb.p, d_md.p, d_nm.p)
+                                : run_agglo<uint16_t>(ctx, src, src_begin, T, ids ? d_ids.p : nullptr, m, linkage, thresh, d_ma.p, d_mb.p, d_md.p, d_nm.p);
+    if (rc) return rc;
+    PRF_CK(ctx, cudaEventRecord(ctx->ev[1], s));
+    PRF_CK(ctx, cudaMemcpyAsync(&n_merges, d_nm.p, 4, cudaMemcpyDeviceToHost, s));
+    PRF_CK(ctx, cudaStreamSynchronize(s));
+    if (n_merges > m - 1) return ctx->fail(PRF_E_CUDA, "agglomeration returned %u merges for %u trees", n_merges, m);
+    ha.resize(n_merges);
+    hb.resize(n_merges);
+    if (n_merges) {
+      PRF_CK(ctx, cudaMemcpyAsync(ha.data(), d_ma.p, (size_t)n_merges * 4, cudaMemcpyDeviceToHost, s));
+      PRF_CK(ctx, cudaMemcpyAsync(hb.data(), d_mb.p, (size_t)n_merges * 4, cudaMemcpyDeviceToHost, s));
+      if (merge_d) PRF_CK(ctx, cudaMemcpyAsync(merge_d, d_md.p, (size_t)n_merges * 8, cudaMemcpyDeviceToHost, s));
+      PRF_CK(ctx, cudaStreamSynchronize(s));
+    }
+    ms = ev_ms(ctx->ev[0], ctx->ev[1]);
+  }
+  if (merge_a && n_merges) std::memcpy(merge_a, ha.data(), (size_t)n_merges * 4);
+  if (merge_b && n_merges) std::memcpy(merge_b, hb.data(), (size_t)n_merges * 4);
+  if (labels) {
+    // a merge keeps the lower key, so a cluster's key is its smallest member
+    std::vector<uint32_t> parent(m);
+    for (uint32_t i = 0; i < m; ++i) parent[i] = i;
+    for (uint32_t k = 0; k < n_merges; ++k) parent[hb[k]] = ha[k];
+    for (uint32_t i = 0; i < m; ++i) labels[i] = parent[i] == i ? i : labels[parent[i]];  // parent[i] < i: already final
+  }
+  if (info) {
+    info->n_merges = n_merges;
+    info->n_clusters = m - n_merges;
+    info->gpu_launches = (int32_t)(ctx->launches - launches0);
+    info->ms_kernels = ms;
+  }
   return PRF_OK;
 }
 

@@ -167,6 +167,42 @@ def cluster_component(sub: np.ndarray, m: int, linkage: str, thresh: float) -> n
     return labels
 
 
+def agglomerate(sub: np.ndarray, m: int, linkage: str, thresh: float = float("inf")):
+    """phb_agglomerate: the whole agglomeration of m items from the packed upper triangle `sub` (uint16), cut at
+    `thresh` (inf = full dendrogram).  Returns (labels[m], merge_a, merge_b, merge_d): step k merged the clusters with
+    smallest members merge_a[k] < merge_b[k] at distance merge_d[k] (C.dendrogram, PhyBin.hs:358)."""
+    L = host_lib()
+    sub = np.ascontiguousarray(sub, dtype=np.uint16)
+    labels = np.empty(m, dtype=np.uint32)
+    ma = np.empty(max(m - 1, 1), dtype=np.uint32)
+    mb = np.empty(max(m - 1, 1), dtype=np.uint32)
+    md = np.empty(max(m - 1, 1), dtype=np.float64)
+    n = C.c_uint32(0)
+    rc = L.phb_agglomerate(sub.ctypes.data, m, LINKAGE[linkage], float(thresh), labels.ctypes.data, ma.ctypes.data,
+                           mb.ctypes.data, md.ctypes.data, C.byref(n))
+    if rc:
+        raise ValueError("phb_agglomerate: %s" % ("too large for a dense matrix" if rc == -2 else "bad arguments"))
+    return labels, ma[:n.value], mb[:n.value], md[:n.value]
+
+
+def dendrogram_text(names: Sequence[str], merge_a, merge_b, merge_d) -> str:
+    """phb_dendrogram_text: `show (fmap treename dendro)` as the reference writes it to dendrogram.txt
+    (PhyBin.hs:238-243) from a full merge list."""
+    L = host_lib()
+    m = len(names)
+    arr = (C.c_char_p * m)(*[n.encode() for n in names])
+    ma = np.ascontiguousarray(merge_a, dtype=np.uint32)
+    mb = np.ascontiguousarray(merge_b, dtype=np.uint32)
+    md = np.ascontiguousarray(merge_d, dtype=np.float64)
+    p = L.phb_dendrogram_text(arr, m, ma.ctypes.data, mb.ctypes.data, md.ctypes.data, len(ma))
+    if not p:
+        raise ValueError("phb_dendrogram_text: the merge list is not a full dendrogram of %d items" % m)
+    try:
+        return C.string_at(p).decode()
+    finally:
+        L.phb_free_buf(p)
+
+
 def bits_to_labels(row: np.ndarray) -> Tuple[int, ...]:
     """One W-word bit set -> ascending label tuple (for tests and debugging)."""
     out = []

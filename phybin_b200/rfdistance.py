@@ -16,8 +16,8 @@ from typing import IO, List, Optional, Tuple
 import numpy as np
 
 from . import _native
-from ._native import prf_consensus_info, prf_extract_info, prf_stats, rf_lib, host_lib
-from .host import Forest, bits_to_labels, cluster_component
+from ._native import prf_agglo_info, prf_consensus_info, prf_extract_info, prf_stats, rf_lib, host_lib
+from .host import LINKAGE, Forest, bits_to_labels, cluster_component, dendrogram_text
 
 VARIANT_AUTO, VARIANT_SPARSE, VARIANT_DENSE = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -368,12 +368,34 @@ class RFContext:
         self._ck(self._L.prf_fetch_submatrix(self._h, d_matrix or None, self.T, ids.ctypes.data, m, out.ctypes.data))
         return out
 
-    def flat_clusters(self, editdist: int, linkage: str = "UPGMA", d_mask: int = 0, d_matrix: int = 0) -> Tuple[np.ndarray, int]:
+    def agglomerate(self, ids=None, linkage: str = "UPGMA", thresh: float = float("inf"), d_matrix: int = 0):
+        """prf_agglomerate: C.dendrogram linkage trees dist (PhyBin.hs:358) on the device for the ascending tree ids
+        `ids` (None = every tree), cut at `thresh` (inf = the full dendrogram).  Returns (labels[m] = smallest local
+        index of each tree's cluster, merge_a, merge_b, merge_d, info): step k merged the clusters with smallest local
+        members merge_a[k] < merge_b[k] at distance merge_d[k]."""
+        if ids is None:
+            m, ids_p = self.T, None
+        else:
+            ids = np.ascontiguousarray(ids, dtype=np.uint32)
+            m, ids_p = len(ids), ids.ctypes.data
+        labels = np.empty(max(m, 1), dtype=np.uint32)
+        ma = np.empty(max(m - 1, 1), dtype=np.uint32)
+        mb = np.empty(max(m - 1, 1), dtype=np.uint32)
+        md = np.empty(max(m - 1, 1), dtype=np.float64)
+        info = prf_agglo_info()
+        self._ck(self._L.prf_agglomerate(self._h, d_matrix or None, self.T, ids_p, m, LINKAGE[linkage], float(thresh),
+                                         labels.ctypes.data, ma.ctypes.data, mb.ctypes.data, md.ctypes.data, C.byref(info)))
+        n = info.n_merges
+        return labels[:m], ma[:n], mb[:n], md[:n], info.as_dict()
+
+    def flat_clusters(self, editdist: int, linkage: str = "UPGMA", d_mask: int = 0, d_matrix: int = 0,
+                      device_min: int = 64) -> Tuple[np.ndarray, int]:
         """sliceDendro editdist (C.dendrogram linkage trees dist)  (PhyBin.hs:358,415-422) as flat labels: labels[t] =
         smallest tree id of t's cluster.  Needs a full-triangle compute with this editdist (its mask; context-owned,
         or the caller's device buffers d_mask / d_matrix).  The device splits the trees into the connected components
-        of {d <= editdist}; single linkage is done there, the other linkages agglomerate every component on the host
-        from its fetched sub-matrix (cluster_component)."""
+        of {d <= editdist}; single linkage is done there.  For the other linkages every component of at least
+        `device_min` trees is agglomerated on the device (prf_agglomerate), smaller ones on the host from their fetched
+        sub-matrix (cluster_component: same rule, same arithmetic)."""
         labels, n = self.mask_components(d_mask)
         if linkage == "single":
             return labels, n
@@ -384,9 +406,18 @@ class RFContext:
             if len(ids) < 3:  # a component of two trees is one cluster under every linkage
                 continue
             ids = np.sort(ids).astype(np.uint32)
-            local = cluster_component(self.fetch_submatrix(ids, d_matrix), len(ids), linkage, editdist)
+            if len(ids) >= device_min:
+                local = self.agglomerate(ids, linkage, editdist, d_matrix)[0]
+            else:
+                local = cluster_component(self.fetch_submatrix(ids, d_matrix), len(ids), linkage, editdist)
             out[ids] = ids[local]
         return out, int(np.count_nonzero(out == np.arange(len(out))))
+
+    def dendrogram(self, names, linkage: str = "UPGMA", d_matrix: int = 0) -> str:
+        """dendrogram.txt (PhyBin.hs:238-243): the full agglomeration of every tree on the device, shown as the
+        reference's `show (fmap treename dendro)`."""
+        _, ma, mb, md, _ = self.agglomerate(None, linkage, float("inf"), d_matrix)
+        return dendrogram_text(names, ma, mb, md)
 
     def consensus(self, labels: np.ndarray, bips=None, tree_off=None) -> Tuple[np.ndarray, np.ndarray, dict]:
         """prf_consensus: for every cluster (labels[t] = smallest tree id of t's cluster, as mask_components returns)
