@@ -77,6 +77,19 @@ PHB_API int phb_allbips(const phb_forest* f, uint32_t W, int threads, uint64_t**
 PHB_API int phb_raw_clades(const phb_forest* f, uint32_t W, int threads, uint64_t** clades,
                            uint64_t** tree_off, uint64_t** leafsets, uint64_t* nnz);
 
+/* Tolerant-mode inputs for forests in which a tree may REPEAT a leaf label (prf_tolerant_load_dups, phybin_rf.h).
+ * The reference counts such leaves twice in numLeaves (CoreTypes.hs:289-291) -- normBip's size -- while its
+ * label sets stay sets, so the device also needs
+ *   *outsets    nnz*W: per clade, the label set of the leaves OUTSIDE that node (decides whether pruneTreeLeaves,
+ *               PreProcessor.hs:21-32, leaves the node below the pruned root)
+ *   *dup_off    T+1 offsets into dup_label / dup_extra: tree t's labels that occur more than once and how many
+ *               extra times.
+ * Clades are every non-root interior node in pre-order (not made unique).  All arrays malloc'd, free with
+ * phb_free_buf. */
+PHB_API int phb_raw_clades_ex(const phb_forest* f, uint32_t W, uint64_t** clades, uint64_t** outsets,
+                              uint64_t** tree_off, uint64_t** leafsets, uint64_t** dup_off, uint32_t** dup_label,
+                              uint32_t** dup_extra, uint64_t* nnz);
+
 /* The trees as the flat pre-order arrays prf_allbips (phybin_rf.h) takes: BORROWED pointers into the
  * forest, valid until it is modified or freed.  node_label[v] >= 0: leaf label, -1: interior node;
  * node_parent[v]: index of the parent (undefined for a tree's first node, its root); the nodes of tree

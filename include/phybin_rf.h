@@ -188,7 +188,8 @@ PRF_API void prf_team_release(prf_ctx* ctx);
  *           leaf sets need not be passed (the kernel derives them from `leafsets`).
  * tree_off  T+1 offsets into clades.
  * leafsets  T*W words: the tree's taxon set (treeLabels, RFDistance.hs:200-203).
- * Each tree's leaf labels must be distinct.  Per pair the kernel restricts both trees to the
+ * Each tree's leaf labels must be distinct (forests where a tree repeats a label: prf_tolerant_load_dups).
+ * Per pair the kernel restricts both trees to the
  * shared taxa, re-normalises (normBip with size = #shared, RFDistance.hs:229-239, including its
  * [0,size) complement universe and odd-size tie rule) and counts the symmetric difference. */
 PRF_API int prf_tolerant(prf_ctx* ctx, const uint64_t* clades, const uint64_t* tree_off,
@@ -199,6 +200,19 @@ PRF_API int prf_tolerant_load(prf_ctx* ctx, const uint64_t* clades, const uint64
                               prf_stats* stats);
 PRF_API int prf_tolerant_compute(prf_ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist,
                                  uint16_t* d_out, uint32_t* d_mask, prf_stats* stats);
+/* Load for forests in which a tree may REPEAT a leaf label.  The reference's label sets stay sets, but numLeaves
+ * -- normBip's size, RFDistance.hs:215 -- counts such leaves twice (CoreTypes.hs:289-291), and whether
+ * pruneTreeLeaves (PreProcessor.hs:21-32) leaves a node below the pruned root is no longer visible from its own
+ * label set.  Additional inputs (phb_raw_clades_ex produces them):
+ *   clades     every non-root interior node of a tree, NOT made unique (equal sets may differ in outsets)
+ *   outsets    nnz*W words: per clade the label set of the leaves OUTSIDE that node      (`kind` memory)
+ *   dup_off    T+1 offsets into dup_label / dup_extra                                     (HOST memory)
+ *   dup_label, dup_extra   per tree its labels that occur more than once, and how many extra times
+ * Followed by prf_tolerant_compute as usual (a slower instantiation of the same kernel: per-tree sizes). */
+PRF_API int prf_tolerant_load_dups(prf_ctx* ctx, const uint64_t* clades, const uint64_t* outsets,
+                                   const uint64_t* tree_off, const uint64_t* leafsets, const uint64_t* dup_off,
+                                   const uint32_t* dup_label, const uint32_t* dup_extra, uint32_t T, uint32_t W,
+                                   int kind, prf_stats* stats);
 
 /* ---- bipartition extraction on the device (replaces allBips, RFDistance.hs:207-248) ------------ */
 

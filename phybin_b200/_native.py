@@ -94,6 +94,8 @@ def host_lib():
         L.phb_allbips.argtypes = [vp, C.c_uint32, C.c_int, C.POINTER(u64p), C.POINTER(u64p), u64p]
         L.phb_raw_clades.argtypes = [vp, C.c_uint32, C.c_int, C.POINTER(u64p), C.POINTER(u64p),
                                      C.POINTER(u64p), u64p]
+        L.phb_raw_clades_ex.argtypes = [vp, C.c_uint32, C.POINTER(u64p), C.POINTER(u64p), C.POINTER(u64p), C.POINTER(u64p),
+                                        C.POINTER(u64p), C.POINTER(u32p), C.POINTER(u32p), u64p]
         L.phb_tree_arrays.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), u64p]
         L.phb_consensus_newick.restype = vp
         L.phb_consensus_newick.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32]
@@ -141,6 +143,7 @@ def rf_lib():
         L.prf_fetch_rows.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
         L.prf_tolerant.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int32, vp, vp, st]
         L.prf_tolerant_load.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int, st]
+        L.prf_tolerant_load_dups.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int, st]
         L.prf_tolerant_compute.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int32, vp, vp, st]
         L.prf_team_handle_bytes.restype = C.c_size_t
         L.prf_team_init.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, vp]
@@ -194,7 +197,7 @@ def rf_lib():
 RF_SYMBOLS = [
     "prf_create", "prf_destroy", "prf_last_error", "prf_version", "prf_stream", "prf_hashrf",
     "prf_hashrf_load", "prf_hashrf_compute", "prf_multi_create", "prf_multi_destroy", "prf_multi_last_error", "prf_multi_gpus", "prf_multi_ctx", "prf_multi_hashrf", "prf_team_handle_bytes", "prf_team_init", "prf_team_connect", "prf_team_load", "prf_team_release", "prf_fetch", "prf_fetch_mask", "prf_fetch_rows",
-    "prf_tolerant", "prf_tolerant_load", "prf_tolerant_compute", "prf_allbips", "prf_allbips_result", "prf_allbips_fetch", "prf_hashrf_trees", "prf_tolerant_trees", "prf_consensus", "prf_consensus_fetch", "prf_fetch_submatrix", "prf_agglomerate",
+    "prf_tolerant", "prf_tolerant_load", "prf_tolerant_load_dups", "prf_tolerant_compute", "prf_allbips", "prf_allbips_result", "prf_allbips_fetch", "prf_hashrf_trees", "prf_tolerant_trees", "prf_consensus", "prf_consensus_fetch", "prf_fetch_submatrix", "prf_agglomerate",
     "prf_mask_components", "prf_packed_index",
     "prf_shard_align", "prf_shard_range", "prf_limits", "prf_launch_count",
 ]

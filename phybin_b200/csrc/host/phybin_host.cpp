@@ -678,6 +678,66 @@ int phb_raw_clades(const phb_forest* h, uint32_t W, int threads, uint64_t** clad
   return 0;
 }
 
+int phb_raw_clades_ex(const phb_forest* h, uint32_t W, uint64_t** clades, uint64_t** outsets, uint64_t** tree_off,
+                      uint64_t** leafsets, uint64_t** dup_off, uint32_t** dup_label, uint32_t** dup_extra, uint64_t* nnz) {
+  const Forest& f = h->f;
+  if (!clades || !outsets || !tree_off || !leafsets || !dup_off || !dup_label || !dup_extra || !nnz || W < phb_words(h) || W > 64)
+    return -1;
+  const uint32_t T = f.T();
+  std::vector<uint64_t> cl, ou, off(1, 0), ls((uint64_t)T * W, 0), doff(1, 0), bits, out, acc(W);
+  std::vector<uint32_t> dlab, dext, count(f.label_names.size(), 0), kids;
+  for (uint32_t t = 0; t < T; ++t) {
+    clade_bits(f, t, W, bits);
+    const uint64_t b = f.tree_begin[t], e = f.tree_begin[t + 1];
+    std::memcpy(&ls[(uint64_t)t * W], &bits[0], W * 8);
+    // out(root) = {}; out(child c of v) = out(v) | clades of c's siblings (label SETS: with repeated labels
+    // out(c) may intersect clade(c))
+    out.assign((e - b) * W, 0);
+    for (uint64_t v = b; v < e; ++v) {   // pre-order: parents first
+      kids.clear();
+      for (uint32_t c = f.first_child[v]; c != NONE; c = f.next_sib[c]) kids.push_back(c);
+      if (kids.empty()) continue;
+      std::vector<uint64_t> suffix((kids.size() + 1) * W, 0);
+      for (size_t i = kids.size(); i-- > 0;)
+        for (uint32_t w = 0; w < W; ++w) suffix[i * W + w] = suffix[(i + 1) * W + w] | bits[(kids[i] - b) * W + w];
+      for (uint32_t w = 0; w < W; ++w) acc[w] = out[(v - b) * W + w];
+      for (size_t i = 0; i < kids.size(); ++i) {
+        for (uint32_t w = 0; w < W; ++w) {
+          out[(kids[i] - b) * W + w] = acc[w] | suffix[(i + 1) * W + w];
+          acc[w] |= bits[(kids[i] - b) * W + w];
+        }
+      }
+    }
+    for (uint64_t v = b + 1; v < e; ++v)   // every non-root interior node, NOT made unique: equal clades can differ in out
+      if (f.label[v] < 0) {
+        cl.insert(cl.end(), &bits[(v - b) * W], &bits[(v - b) * W] + W);
+        ou.insert(ou.end(), &out[(v - b) * W], &out[(v - b) * W] + W);
+      }
+    off.push_back(cl.size() / W);
+    for (uint64_t v = b; v < e; ++v)
+      if (f.label[v] >= 0) ++count[f.label[v]];
+    for (uint64_t v = b; v < e; ++v)
+      if (f.label[v] >= 0 && count[f.label[v]]) {
+        if (count[f.label[v]] > 1) { dlab.push_back((uint32_t)f.label[v]); dext.push_back(count[f.label[v]] - 1); }
+        count[f.label[v]] = 0;
+      }
+    doff.push_back(dlab.size());
+  }
+  auto give = [](const auto& v, auto** dst) -> bool {
+    using E = typename std::remove_reference<decltype(v)>::type::value_type;
+    E* p = (E*)std::malloc(std::max<size_t>(v.size(), 1) * sizeof(E));
+    if (!p) return false;
+    if (!v.empty()) std::memcpy(p, v.data(), v.size() * sizeof(E));
+    *dst = p;
+    return true;
+  };
+  if (!give(cl, clades) || !give(ou, outsets) || !give(off, tree_off) || !give(ls, leafsets) || !give(doff, dup_off) ||
+      !give(dlab, dup_label) || !give(dext, dup_extra))
+    return -1;
+  *nnz = cl.size() / W;
+  return 0;
+}
+
 int phb_tree_arrays(const phb_forest* h, const int32_t** node_label, const uint32_t** node_parent,
                     const uint64_t** tree_begin, const uint32_t** num_leaves, uint64_t* n_nodes) {
   if (!h) return -1;

@@ -138,9 +138,8 @@ int main(int argc, char** argv) {
     names.swap(kept_names);
     const uint32_t before = phb_num_trees(forest), kept = phb_filter_num_leaves(forest, n_taxa);
     if (kept != before) std::printf("WARNING: dropped %u trees whose leaf count differs from %u\n", before - kept, n_taxa);
-  } else if (phb_has_duplicate_leaves(forest)) {
-    die("--tolerant on the device needs distinct leaf labels within each tree");
   }
+  const bool dup_leaves = opt.tolerant && phb_has_duplicate_leaves(forest);  // numLeaves counts them twice (CoreTypes.hs:289-291)
   const uint32_t T = phb_num_trees(forest), W = phb_words(forest);
   const uint64_t P = (uint64_t)T * (T ? T - 1 : 0) / 2;
 
@@ -168,7 +167,13 @@ int main(int argc, char** argv) {
     }
     if (!rc) rc = prf_hashrf_compute(ctx, 0, P, opt.editdist, opt.variant, nullptr, nullptr, &st);
   } else {
-    if (opt.host_bips) {
+    if (dup_leaves) {
+      uint64_t *clades = nullptr, *outs = nullptr, *off = nullptr, *leaf = nullptr, *doff = nullptr, nnz = 0;
+      uint32_t *dlab = nullptr, *dext = nullptr;
+      if (phb_raw_clades_ex(forest, W, &clades, &outs, &off, &leaf, &doff, &dlab, &dext, &nnz)) die("clade extraction failed");
+      rc = prf_tolerant_load_dups(ctx, clades, outs, off, leaf, doff, dlab, dext, T, W, PRF_MEM_HOST, &st);
+      for (void* p : {(void*)clades, (void*)outs, (void*)off, (void*)leaf, (void*)doff, (void*)dlab, (void*)dext}) phb_free_buf(p);
+    } else if (opt.host_bips) {
       uint64_t *clades = nullptr, *off = nullptr, *leaf = nullptr, nnz = 0;
       if (phb_raw_clades(forest, W, 0, &clades, &off, &leaf, &nnz)) die("clade extraction failed");
       rc = prf_tolerant_load(ctx, clades, off, leaf, T, W, PRF_MEM_HOST, &st);

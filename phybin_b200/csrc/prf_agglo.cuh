@@ -248,15 +248,17 @@ template <class Tv>
 __global__ void __launch_bounds__(256) agglo_gather_kernel(const uint16_t* __restrict__ src, uint64_t src_begin, uint32_t T,
                                                            const uint32_t* __restrict__ ids, uint32_t m, uint32_t ld,
                                                            Tv* __restrict__ D) {
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= ld) return;
-  Tv v = AggloVal<Tv>::dead();
-  if (j < m && j != i) {
-    const uint32_t ti = ids ? ids[i] : i, tj = ids ? ids[j] : j;
-    const uint32_t lo = min(ti, tj), hi = max(ti, tj);
-    v = (Tv)src[row_start(lo, T) + (hi - lo - 1) - src_begin];
+  for (uint32_t i = blockIdx.y; i < m; i += gridDim.y) {
+    Tv v = AggloVal<Tv>::dead();
+    if (j < m && j != i) {
+      const uint32_t ti = ids ? ids[i] : i, tj = ids ? ids[j] : j;
+      const uint32_t lo = min(ti, tj), hi = max(ti, tj);
+      v = (Tv)src[row_start(lo, T) + (hi - lo - 1) - src_begin];
+    }
+    D[(size_t)i * ld + j] = v;
   }
-  D[(size_t)i * ld + j] = v;
 }
 
 }  // namespace prf

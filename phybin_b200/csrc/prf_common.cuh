@@ -129,6 +129,11 @@ struct TolerantState {
   DevBuf<uint64_t> clades;    // [nnz*W]
   DevBuf<uint64_t> off;       // [T+1]
   DevBuf<uint64_t> leafsets;  // [T*W]
+  DevBuf<uint16_t> par;       // [nnz]   parent clade of every clade inside its tree (prf_tolerant.cuh), 0xffff = root
+  bool dups = false;          // some tree repeats a leaf label (prf_tolerant_load_dups): the arrays below are set
+  DevBuf<uint64_t> outsets;   // [nnz*W] label set of the leaves outside each clade's node
+  DevBuf<uint64_t> dup_off;   // [T+1]
+  DevBuf<uint32_t> dup_label, dup_extra;
   prf_stats stats{};
 };
 

@@ -32,7 +32,7 @@ int run_agglo(Ctx* ctx, const uint16_t* src, uint64_t src_begin, uint32_t T, con
     return ctx->fail(PRF_E_NOMEM, "no device memory for a %u x %u matrix of %zu-byte distances", m, m, sizeof(Tv));
   }
   PRF_CK(ctx, rec.alloc((size_t)2 * G, s));
-  agglo_gather_kernel<Tv><<<dim3((ld + 255) / 256, m), 256, 0, s>>>(src, src_begin, T, d_ids, m, ld, D.p);
+  agglo_gather_kernel<Tv><<<dim3((ld + 255) / 256, std::min<uint32_t>(m, 65535u)), 256, 0, s>>>(src, src_begin, T, d_ids, m, ld, D.p);
   PRF_LAUNCHED(ctx);
   AggloParams prm;
   prm.D = D.p;

@@ -175,6 +175,20 @@ static int trees_one_shot(prf_ctx* h, bool tolerant, const int32_t* node_label, 
                           uint16_t* out_upper, uint32_t* out_mask, prf_stats* stats, prf_extract_info* extract) {
   if (!h) return PRF_E_INVALID;
   Ctx* ctx = &h->c;
+  if (tolerant && node_label && tree_begin && W && W <= 64) {
+    // the one-shot path extracts label SETS; a tree that repeats a leaf label needs prf_tolerant_load_dups' extra inputs
+    std::vector<uint32_t> stamp((size_t)W * 64, 0xffffffffu);
+    for (uint32_t t = 0; t < T; ++t)
+      for (uint64_t v = tree_begin[t]; v < tree_begin[t + 1]; ++v) {
+        const int32_t l = node_label[v];
+        if (l < 0 || (uint32_t)l >= W * 64) continue;
+        if (stamp[l] == t) {
+          ctx->err.clear();
+          return ctx->fail(PRF_E_UNSUPPORTED, "tree %u repeats leaf label %d: use prf_tolerant_load_dups (inputs from phb_raw_clades_ex)", t, l);
+        }
+        stamp[l] = t;
+      }
+  }
   prf_extract_info ei{};
   int rc = prf_allbips(h, node_label, node_parent, tree_begin, num_leaves, T, W, PRF_MEM_HOST,
                        tolerant ? PRF_EXTRACT_CLADES : PRF_EXTRACT_BIPS, &ei);

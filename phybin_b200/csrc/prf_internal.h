@@ -34,6 +34,7 @@ void build_row_plan(uint32_t T, uint64_t p_begin, uint64_t p_end, uint32_t tile,
                     std::vector<RowItem>& groups);
 int launch_rows(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out, uint32_t* d_mask);
 int launch_dense(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out, uint32_t* d_mask);
+int launch_tol_parents(Ctx* ctx);  // parent clade of every clade of the loaded tolerant problem
 int launch_tolerant(Ctx* ctx, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out, uint32_t* d_mask);
 uint32_t dense_kpad(uint32_t n_shared);     // shared bipartitions padded to the dense variant's k-block
 uint32_t dense_tpad(uint32_t T);            // trees padded to its column tile

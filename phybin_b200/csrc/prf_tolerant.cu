@@ -12,12 +12,14 @@ extern "C" {
 // tolerant
 // ---------------------------------------------------------------------------------------------
 
-PRF_API int prf_tolerant_load(prf_ctx* h, const uint64_t* clades, const uint64_t* tree_off,
-                              const uint64_t* leafsets, uint32_t T, uint32_t W, int kind, prf_stats* stats) {
+static int tolerant_load_impl(prf_ctx* h, const uint64_t* clades, const uint64_t* outsets, const uint64_t* tree_off,
+                              const uint64_t* leafsets, const uint64_t* dup_off, const uint32_t* dup_label,
+                              const uint32_t* dup_extra, bool dups, uint32_t T, uint32_t W, int kind, prf_stats* stats) {
   if (!h) return PRF_E_INVALID;
   Ctx* ctx = &h->c;
   ctx->err.clear();
   if (!tree_off || (T && !leafsets)) return ctx->fail(PRF_E_INVALID, "tree_off / leafsets is NULL");
+  if (dups && !dup_off) return ctx->fail(PRF_E_INVALID, "dup_off is NULL");
   if (W == 0 || W > kTolMaxWords) return ctx->fail(PRF_E_UNSUPPORTED, "tolerant mode supports W in 1..%u, got %u", kTolMaxWords, W);
   if (kind != PRF_MEM_HOST && kind != PRF_MEM_DEVICE) return ctx->fail(PRF_E_INVALID, "bad memory kind %d", kind);
   PRF_CK(ctx, cudaSetDevice(ctx->device));
@@ -42,6 +44,19 @@ PRF_API int prf_tolerant_load(prf_ctx* h, const uint64_t* clades, const uint64_t
   }
   uint64_t nnz = hoff[T];
   if (nnz && !clades) return ctx->fail(PRF_E_INVALID, "clades is NULL");
+  if (dups && nnz && !outsets) return ctx->fail(PRF_E_INVALID, "outsets is NULL");
+  std::vector<uint64_t> hdoff;
+  uint64_t n_dup = 0;
+  if (dups) {  // (host arrays in both memory kinds: a handful of entries)
+    hdoff.assign(dup_off, dup_off + T + 1);
+    if (hdoff[0] != 0) return ctx->fail(PRF_E_INVALID, "dup_off[0] must be 0");
+    for (uint32_t t = 0; t < T; ++t)
+      if (hdoff[t + 1] < hdoff[t]) return ctx->fail(PRF_E_INVALID, "dup_off is not ascending at tree %u", t);
+    n_dup = hdoff[T];
+    if (n_dup && (!dup_label || !dup_extra)) return ctx->fail(PRF_E_INVALID, "dup_label / dup_extra is NULL");
+    for (uint64_t x = 0; x < n_dup; ++x)
+      if (dup_label[x] >= 64u * W) return ctx->fail(PRF_E_INVALID, "dup_label[%llu]=%u does not fit %u words", (unsigned long long)x, dup_label[x], W);
+  }
   if (maxc > kTolMaxClades)
     return ctx->fail(PRF_E_UNSUPPORTED, "a tree has %u interior clades; tolerant mode supports <= %u", maxc, kTolMaxClades);
   PRF_CK(ctx, S.off.alloc((size_t)T + 1, s));
@@ -51,10 +66,24 @@ PRF_API int prf_tolerant_load(prf_ctx* h, const uint64_t* clades, const uint64_t
   if ((rc = upload(ctx, S.off.p, hoff.data(), ((size_t)T + 1) * 8, PRF_MEM_HOST))) return rc;
   if ((rc = upload(ctx, S.clades.p, clades, nnz * W * 8, kind))) return rc;
   if ((rc = upload(ctx, S.leafsets.p, leafsets, (size_t)T * W * 8, kind))) return rc;
-  PRF_CK(ctx, cudaEventRecord(ctx->ev[1], s));
-  PRF_CK(ctx, cudaStreamSynchronize(s));
   S.T = T;
   S.W = W;
+  S.dups = dups;
+  if (dups) {
+    PRF_CK(ctx, S.outsets.alloc(nnz * W, s));
+    PRF_CK(ctx, S.dup_off.alloc((size_t)T + 1, s));
+    PRF_CK(ctx, S.dup_label.alloc(n_dup, s));
+    PRF_CK(ctx, S.dup_extra.alloc(n_dup, s));
+    if ((rc = upload(ctx, S.outsets.p, outsets, nnz * W * 8, kind))) return rc;
+    if ((rc = upload(ctx, S.dup_off.p, hdoff.data(), ((size_t)T + 1) * 8, PRF_MEM_HOST))) return rc;
+    if ((rc = upload(ctx, S.dup_label.p, dup_label, n_dup * 4, PRF_MEM_HOST))) return rc;
+    if ((rc = upload(ctx, S.dup_extra.p, dup_extra, n_dup * 4, PRF_MEM_HOST))) return rc;
+  } else {
+    PRF_CK(ctx, S.par.alloc(nnz, s));
+    if ((rc = launch_tol_parents(ctx))) return rc;
+  }
+  PRF_CK(ctx, cudaEventRecord(ctx->ev[1], s));
+  PRF_CK(ctx, cudaStreamSynchronize(s));
   S.nnz = nnz;
   S.max_clades = maxc;
   S.P = (uint64_t)T * (T ? T - 1 : 0) / 2;
@@ -70,6 +99,17 @@ PRF_API int prf_tolerant_load(prf_ctx* h, const uint64_t* clades, const uint64_t
   S.stats.gpu_launches = (int32_t)(ctx->launches - launches0);
   if (stats) *stats = S.stats;
   return PRF_OK;
+}
+
+PRF_API int prf_tolerant_load(prf_ctx* h, const uint64_t* clades, const uint64_t* tree_off,
+                              const uint64_t* leafsets, uint32_t T, uint32_t W, int kind, prf_stats* stats) {
+  return tolerant_load_impl(h, clades, nullptr, tree_off, leafsets, nullptr, nullptr, nullptr, false, T, W, kind, stats);
+}
+
+PRF_API int prf_tolerant_load_dups(prf_ctx* h, const uint64_t* clades, const uint64_t* outsets, const uint64_t* tree_off,
+                                   const uint64_t* leafsets, const uint64_t* dup_off, const uint32_t* dup_label,
+                                   const uint32_t* dup_extra, uint32_t T, uint32_t W, int kind, prf_stats* stats) {
+  return tolerant_load_impl(h, clades, outsets, tree_off, leafsets, dup_off, dup_label, dup_extra, true, T, W, kind, stats);
 }
 
 PRF_API int prf_tolerant_compute(prf_ctx* h, uint64_t p_begin, uint64_t p_end, int32_t editdist, uint16_t* d_out,

@@ -10,7 +10,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from ._native import host_lib, u64p
+from ._native import host_lib, u32p, u64p
 
 RANDOM_TOPOLOGY = 0
 NNI_FAMILY = 1
@@ -130,6 +130,30 @@ class Forest:
         return (_take(cp, nnz.value * W).reshape(-1, W), _take(op, T + 1),
                 _take(lp, T * W).reshape(T, W))
 
+
+    def raw_clades_ex(self, W: Optional[int] = None):
+        """phb_raw_clades_ex: the tolerant path's inputs for a forest whose trees may repeat a leaf label:
+        (clades[nnz, W], outsets[nnz, W], tree_off[T+1], leafsets[T, W], dup_off[T+1], dup_label, dup_extra)."""
+        L = host_lib()
+        W = W or self.words
+        T = len(self)
+        c, o, off, ls, doff = u64p(), u64p(), u64p(), u64p(), u64p()
+        dl, de = u32p(), u32p()
+        nnz = C.c_uint64(0)
+        rc = L.phb_raw_clades_ex(self._h, W, C.byref(c), C.byref(o), C.byref(off), C.byref(ls), C.byref(doff), C.byref(dl),
+                                 C.byref(de), C.byref(nnz))
+        if rc:
+            raise ValueError("phb_raw_clades_ex failed (W too small?)")
+        n = nnz.value
+        off_a = _take(off, T + 1)
+        doff_a = _take(doff, T + 1)
+        nd = int(doff_a[T])
+        dl_a = np.ctypeslib.as_array(dl, shape=(max(nd, 1),))[:nd].copy()
+        de_a = np.ctypeslib.as_array(de, shape=(max(nd, 1),))[:nd].copy()
+        L.phb_free_buf(dl)
+        L.phb_free_buf(de)
+        return (_take(c, n * W).reshape(n, W), _take(o, n * W).reshape(n, W), off_a, _take(ls, T * W).reshape(T, W),
+                doff_a, dl_a, de_a)
 
     def consensus_newick(self, keys: np.ndarray, num_taxa: Optional[int] = None) -> str:
         """bipsToTree num_taxa keys (RFDistance.hs:410-445) printed on one line with this forest's label names

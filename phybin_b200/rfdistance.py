@@ -272,6 +272,25 @@ class RFContext:
         self.P = T * (T - 1) // 2 if T else 0
         return st.as_dict()
 
+    def tolerant_load_dups(self, clades, outsets, tree_off, leafsets, dup_off, dup_label, dup_extra) -> dict:
+        """prf_tolerant_load_dups (host arrays, as Forest.raw_clades_ex returns them): trees may repeat a leaf label."""
+        st = prf_stats()
+        clades = np.ascontiguousarray(clades, dtype=np.uint64)
+        outsets = np.ascontiguousarray(outsets, dtype=np.uint64)
+        tree_off = np.ascontiguousarray(tree_off, dtype=np.uint64)
+        leafsets = np.ascontiguousarray(leafsets, dtype=np.uint64)
+        dup_off = np.ascontiguousarray(dup_off, dtype=np.uint64)
+        dup_label = np.ascontiguousarray(dup_label, dtype=np.uint32)
+        dup_extra = np.ascontiguousarray(dup_extra, dtype=np.uint32)
+        T = len(tree_off) - 1
+        W = leafsets.shape[1] if leafsets.ndim == 2 else 1
+        self._ck(self._L.prf_tolerant_load_dups(self._h, clades.ctypes.data, outsets.ctypes.data, tree_off.ctypes.data,
+                                                leafsets.ctypes.data, dup_off.ctypes.data, dup_label.ctypes.data,
+                                                dup_extra.ctypes.data, T, W, MEM_HOST, C.byref(st)))
+        self.T = T
+        self.P = T * (T - 1) // 2 if T else 0
+        return st.as_dict()
+
     def tolerant_compute(self, p_begin: int = 0, p_end: Optional[int] = None, editdist: int = -1,
                          d_out: int = 0, d_mask: int = 0, want_stats: bool = True) -> Optional[dict]:
         p_end = self.P if p_end is None else p_end
@@ -507,12 +526,14 @@ def hashRF(num_taxa: int, trees: Forest, ctx: Optional[RFContext] = None, extrac
 
 def naiveDistMatrix(trees: Forest, ctx: Optional[RFContext] = None):
     """naiveDistMatrix trees (RFDistance.hs:168): (matrix, per-tree allBips as sets of label tuples)."""
-    if trees.has_duplicate_leaves():
-        raise PhyBinRFError(-6, "tolerant mode on the device needs distinct leaf labels within a tree")
     ctx = ctx or default_context()
     ctx.allbips(trees, EXTRACT_BIPS)  # the second component of the result: every tree's allBips
     bips, boff = ctx.allbips_fetch()
-    ctx.tolerant_load_trees(trees)
+    if trees.has_duplicate_leaves():
+        # numLeaves counts a repeated label twice (CoreTypes.hs:289-291): per-tree sizes and outside sets from the host
+        ctx.tolerant_load_dups(*trees.raw_clades_ex())
+    else:
+        ctx.tolerant_load_trees(trees)
     ctx.tolerant_compute(want_stats=False)
     upper = ctx.fetch()
     eachbips = [frozenset(bits_to_labels(b) for b in bips[int(boff[t]):int(boff[t + 1])])

@@ -93,3 +93,45 @@ def test_agglomerate_argument_errors(ctx):
         ctx._ck(ctx._L.prf_agglomerate(ctx._h, None, 50, None, 50, 3, 1.0, None, None, None, None, None))  # bad linkage
     labels, ma, mb, md, info = ctx.agglomerate(np.array([7], dtype=np.uint32))
     assert labels.tolist() == [0] and len(ma) == 0 and info["n_clusters"] == 1
+
+
+# ---- --tolerant with repeated leaf labels (prf_tolerant_load_dups) ---------------------------------------------
+
+@pytest.mark.parametrize("seed", range(8))
+def test_tolerant_repeated_leaf_labels_vs_oracle(ctx, seed):
+    """numLeaves counts a repeated label twice (CoreTypes.hs:289-291) while label sets stay sets: the DUPS
+    instantiation of the tolerant kernel against the oracle's literal naiveDistMatrix."""
+    import random
+    from oracle import oracle as orc
+    from tests.test_tolerant_model_cpu import dup_newicks
+    from tests.util import oracle_packed
+    rng = random.Random(500 + seed)
+    n = rng.choice([2, 3, 4, 7, 30, 66, 130, 200])
+    text = dup_newicks(rng, 40, n, p_missing=rng.choice([0.0, 0.15, 0.4]), p_dup=rng.choice([0.02, 0.3]))
+    f, o = Forest.parse([text]), orc.Forest([text])
+    assert f.has_duplicate_leaves()
+    want = oracle_packed(o, "naive")
+    ctx.tolerant_load_dups(*f.raw_clades_ex())
+    ctx.tolerant_compute(editdist=3)
+    assert np.array_equal(ctx.fetch().astype(np.int64), want)
+    P = len(want)
+    bits = np.unpackbits(ctx.fetch_mask().view(np.uint8), bitorder="little")[:P].astype(bool)
+    assert np.array_equal(bits, want <= 3)
+    # the public mirror routes there by itself; the one-shot device extraction refuses such trees loudly
+    from phybin_b200.rfdistance import naiveDistMatrix
+    mat, _ = naiveDistMatrix(f, ctx)
+    assert np.array_equal(mat.upper.astype(np.int64), want)
+    with pytest.raises(PhyBinRFError) as e:
+        ctx.hashrf_trees(f, tolerant=True)
+    assert e.value.code == -6
+
+
+def test_tolerant_dups_form_equals_plain_form_without_repeats(ctx):
+    import random
+    from tests.util import random_multifurcating_newicks
+    rng = random.Random(9)
+    f = Forest.parse([random_multifurcating_newicks(rng, 300, 90, p_missing=0.2, unary=0.2)])
+    want, _, _ = ctx.tolerant(*f.raw_clades())
+    ctx.tolerant_load_dups(*f.raw_clades_ex())
+    ctx.tolerant_compute()
+    assert np.array_equal(ctx.fetch(), want)
