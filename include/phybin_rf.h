@@ -161,6 +161,9 @@ PRF_API int prf_multi_gpus(const prf_multi* m);
 PRF_API prf_ctx* prf_multi_ctx(prf_multi* m, int rank);
 /* Arguments as prf_hashrf (host buffers).  Trees are dealt to the GPUs in contiguous shards; every GPU copies its
  * slice of the matrix (and mask) into out_upper / out_mask over its own PCIe link. */
+/* Flat single-linkage clusters after a prf_multi_hashrf with editdist >= 0: every GPU runs the union-find over its
+ * resident mask shard, GPU 0 merges the label arrays (prf_mask_components_shard).  labels: host, T entries. */
+PRF_API int prf_multi_components(prf_multi* m, uint32_t* labels, uint32_t* n_components);
 PRF_API int prf_multi_hashrf(prf_multi* m, const uint64_t* bips, const uint64_t* tree_off, uint32_t T, uint32_t W,
                              int32_t editdist, uint16_t* out_upper, uint32_t* out_mask, prf_stats* stats);
 
@@ -277,6 +280,16 @@ PRF_API int prf_tolerant_trees(prf_ctx* ctx, const int32_t* node_label, const ui
  * PhyBin.hs:415-422); complete linkage / UPGMA clusters are subsets of them. */
 PRF_API int prf_mask_components(prf_ctx* ctx, const uint32_t* d_mask, uint32_t T, uint32_t* labels,
                                 uint32_t* n_components);
+
+/* Shard form (the mask is sharded like the matrix).  The mask covers [p_begin, p_end) -- a device pointer
+ * whose first bit is pair p_begin, or NULL for the context-owned mask of the last compute, which must cover exactly
+ * that range; an empty range reads no mask at all (pure merge of the seeds).
+ * seed (host, n_seed x T, may be NULL): label arrays other shards / ranks returned; their components are merged in as
+ * edges (t, seed[i][t]).  So every rank calls this on its own shard, the label arrays are exchanged (all-gather), and
+ * one more call with an empty range and all of them as seeds yields the components of the whole graph -- the
+ * all-reduce(min) of labels, done as a union-find on the device. */
+PRF_API int prf_mask_components_shard(prf_ctx* ctx, const uint32_t* d_mask, uint64_t p_begin, uint64_t p_end, uint32_t T,
+                                      const uint32_t* seed, uint32_t n_seed, uint32_t* labels, uint32_t* n_components);
 
 /* Sub-matrix for m trees ids[0] < ids[1] < ... (host array): out (host, m*(m-1)/2 uint16) is the packed upper
  * triangle of the m x m matrix d(ids[i], ids[j]) -- what the host-side complete-linkage / UPGMA step needs for

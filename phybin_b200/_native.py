@@ -172,6 +172,8 @@ def rf_lib():
         L.prf_consensus.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_int, vp, C.POINTER(prf_consensus_info)]
         L.prf_consensus_fetch.argtypes = [vp, vp, vp]
         L.prf_mask_components.argtypes = [vp, vp, C.c_uint32, vp, u32p]
+        L.prf_mask_components_shard.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, vp, C.c_uint32, vp, u32p]
+        L.prf_multi_components.argtypes = [vp, vp, u32p]
         L.prf_packed_index.restype = C.c_uint64
         L.prf_packed_index.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
         L.prf_shard_align.restype = C.c_uint64
@@ -198,6 +200,6 @@ RF_SYMBOLS = [
     "prf_create", "prf_destroy", "prf_last_error", "prf_version", "prf_stream", "prf_hashrf",
     "prf_hashrf_load", "prf_hashrf_compute", "prf_multi_create", "prf_multi_destroy", "prf_multi_last_error", "prf_multi_gpus", "prf_multi_ctx", "prf_multi_hashrf", "prf_team_handle_bytes", "prf_team_init", "prf_team_connect", "prf_team_load", "prf_team_release", "prf_fetch", "prf_fetch_mask", "prf_fetch_rows",
     "prf_tolerant", "prf_tolerant_load", "prf_tolerant_load_dups", "prf_tolerant_compute", "prf_allbips", "prf_allbips_result", "prf_allbips_fetch", "prf_hashrf_trees", "prf_tolerant_trees", "prf_consensus", "prf_consensus_fetch", "prf_fetch_submatrix", "prf_agglomerate",
-    "prf_mask_components", "prf_packed_index",
+    "prf_mask_components", "prf_mask_components_shard", "prf_multi_components", "prf_packed_index",
     "prf_shard_align", "prf_shard_range", "prf_limits", "prf_launch_count",
 ]

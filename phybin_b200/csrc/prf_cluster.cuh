@@ -61,6 +61,14 @@ __global__ void __launch_bounds__(256) cc_hook_kernel(const uint32_t* __restrict
   }
 }
 
+// Edges (t, seed[i * T + t]): the components another shard (rank) found, merged into this union-find.
+__global__ void __launch_bounds__(256) cc_seed_kernel(const uint32_t* __restrict__ seed, uint64_t n, uint32_t T, uint32_t* parent) {
+  const uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n) return;
+  const uint32_t t = (uint32_t)(x % T), l = seed[x];
+  if (l != t) cc_unite(parent, t, l);
+}
+
 // label[t] = smallest tree id of t's component; counts the roots.
 __global__ void __launch_bounds__(256) cc_flatten_kernel(uint32_t* parent, uint32_t T, uint32_t* __restrict__ label,
                                                          uint32_t* n_roots) {

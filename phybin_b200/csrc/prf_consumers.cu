@@ -60,6 +60,43 @@ extern "C" {
 // flat clusters from the threshold mask
 // ---------------------------------------------------------------------------------------------
 
+// Union-find over the mask bits of [p_begin, p_end) plus the edges (t, seed[i][t]) of n_seed label arrays.
+static int components_impl(Ctx* ctx, const uint32_t* d_mask, uint64_t p_begin, uint64_t p_end, uint32_t T, const uint32_t* seed,
+                           uint32_t n_seed, uint32_t* labels, uint32_t* n_components) {
+  PRF_CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  DevBuf<uint32_t> parent, label, roots, d_seed;
+  PRF_CK(ctx, parent.alloc(T, s));
+  PRF_CK(ctx, label.alloc(T, s));
+  PRF_CK(ctx, roots.alloc(1, s));
+  PRF_CK(ctx, cudaMemsetAsync(roots.p, 0, 4, s));
+  uint32_t hroots = 0;
+  if (T) {
+    cc_init_kernel<<<grid_for(T), 256, 0, s>>>(parent.p, T);
+    PRF_LAUNCHED(ctx);
+    const uint64_t n_words = (p_end - p_begin + 31) / 32;
+    if (n_words) {
+      if (n_words > 0x7fffffffull * 256) return ctx->fail(PRF_E_UNSUPPORTED, "mask too large for one launch");
+      cc_hook_kernel<<<(uint32_t)((n_words + 255) / 256), 256, 0, s>>>(d_mask, n_words, p_begin, p_end, T, parent.p);
+      PRF_LAUNCHED(ctx);
+    }
+    if (n_seed) {  // another shard's components as edges (t, its label of t): the union is the graph of both shards
+      const uint64_t n = (uint64_t)n_seed * T;
+      PRF_CK(ctx, d_seed.alloc(n, s));
+      PRF_CK(ctx, cudaMemcpyAsync(d_seed.p, seed, n * 4, cudaMemcpyHostToDevice, s));
+      cc_seed_kernel<<<grid_for(n), 256, 0, s>>>(d_seed.p, n, T, parent.p);
+      PRF_LAUNCHED(ctx);
+    }
+    cc_flatten_kernel<<<grid_for(T), 256, 0, s>>>(parent.p, T, label.p, roots.p);
+    PRF_LAUNCHED(ctx);
+    PRF_CK(ctx, cudaMemcpyAsync(labels, label.p, (size_t)T * 4, cudaMemcpyDeviceToHost, s));
+  }
+  PRF_CK(ctx, cudaMemcpyAsync(&hroots, roots.p, 4, cudaMemcpyDeviceToHost, s));
+  PRF_CK(ctx, cudaStreamSynchronize(s));
+  if (n_components) *n_components = hroots;
+  return PRF_OK;
+}
+
 PRF_API int prf_mask_components(prf_ctx* h, const uint32_t* d_mask, uint32_t T, uint32_t* labels, uint32_t* n_components) {
   if (!h) return PRF_E_INVALID;
   Ctx* ctx = &h->c;
@@ -71,31 +108,28 @@ PRF_API int prf_mask_components(prf_ctx* h, const uint32_t* d_mask, uint32_t T, 
       return ctx->fail(PRF_E_STATE, "no context-owned mask covering the whole triangle (compute with editdist >= 0 first)");
     d_mask = ctx->mask.p;
   }
-  PRF_CK(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t s = ctx->stream;
-  DevBuf<uint32_t> parent, label, roots;
-  PRF_CK(ctx, parent.alloc(T, s));
-  PRF_CK(ctx, label.alloc(T, s));
-  PRF_CK(ctx, roots.alloc(1, s));
-  PRF_CK(ctx, cudaMemsetAsync(roots.p, 0, 4, s));
-  uint32_t hroots = 0;
-  if (T) {
-    cc_init_kernel<<<grid_for(T), 256, 0, s>>>(parent.p, T);
-    PRF_LAUNCHED(ctx);
-    const uint64_t n_words = (P + 31) / 32;
-    if (n_words) {
-      if (n_words > 0x7fffffffull * 256) return ctx->fail(PRF_E_UNSUPPORTED, "mask too large for one launch");
-      cc_hook_kernel<<<(uint32_t)((n_words + 255) / 256), 256, 0, s>>>(d_mask, n_words, 0, P, T, parent.p);
-      PRF_LAUNCHED(ctx);
-    }
-    cc_flatten_kernel<<<grid_for(T), 256, 0, s>>>(parent.p, T, label.p, roots.p);
-    PRF_LAUNCHED(ctx);
-    PRF_CK(ctx, cudaMemcpyAsync(labels, label.p, (size_t)T * 4, cudaMemcpyDeviceToHost, s));
+  return components_impl(ctx, d_mask, 0, P, T, nullptr, 0, labels, n_components);
+}
+
+PRF_API int prf_mask_components_shard(prf_ctx* h, const uint32_t* d_mask, uint64_t p_begin, uint64_t p_end, uint32_t T,
+                                      const uint32_t* seed, uint32_t n_seed, uint32_t* labels, uint32_t* n_components) {
+  if (!h) return PRF_E_INVALID;
+  Ctx* ctx = &h->c;
+  ctx->err.clear();
+  if (!labels && T) return ctx->fail(PRF_E_INVALID, "labels is NULL");
+  if (n_seed && !seed) return ctx->fail(PRF_E_INVALID, "seed is NULL");
+  const uint64_t P = (uint64_t)T * (T ? T - 1 : 0) / 2;
+  if (!d_mask && p_end > p_begin) {
+    if (!ctx->mask_valid || ctx->mask_begin != p_begin || ctx->mask_end != p_end)
+      return ctx->fail(PRF_E_STATE, "the context-owned mask does not cover exactly [%llu, %llu)", (unsigned long long)p_begin,
+                       (unsigned long long)p_end);
+    d_mask = ctx->mask.p;
   }
-  PRF_CK(ctx, cudaMemcpyAsync(&hroots, roots.p, 4, cudaMemcpyDeviceToHost, s));
-  PRF_CK(ctx, cudaStreamSynchronize(s));
-  if (n_components) *n_components = hroots;
-  return PRF_OK;
+  int rc = check_range(ctx, P, p_begin, p_end);
+  if (rc) return rc;
+  for (uint64_t x = 0; x < (uint64_t)n_seed * T; ++x)
+    if (seed[x] >= T) return ctx->fail(PRF_E_INVALID, "seed label %u is not a tree id", seed[x]);
+  return components_impl(ctx, d_mask, p_begin, p_end, T, seed, n_seed, labels, n_components);
 }
 
 PRF_API int prf_fetch_submatrix(prf_ctx* h, const uint16_t* d_matrix, uint32_t T, const uint32_t* ids, uint32_t m,

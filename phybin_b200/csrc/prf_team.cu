@@ -531,4 +531,30 @@ PRF_API int prf_multi_hashrf(prf_multi* m, const uint64_t* bips, const uint64_t*
   return PRF_OK;
 }
 
+PRF_API int prf_multi_components(prf_multi* m, uint32_t* labels, uint32_t* n_components) {
+  if (!m) return PRF_E_INVALID;
+  m->err.clear();
+  const uint32_t world = m->world, T = m->T;
+  if (!T || !labels) { m->err = "no problem loaded (prf_multi_hashrf with editdist >= 0 first) or labels is NULL"; return PRF_E_STATE; }
+  std::vector<uint32_t> all((size_t)world * T);
+  int rcs[kMaxParts] = {};
+  auto worker = [&](uint32_t r) {
+    uint64_t pb = 0, pe = 0;
+    prf_shard_range(T, r, world, &pb, &pe);
+    uint32_t n = 0;
+    if (pe > pb) rcs[r] = prf_mask_components_shard(m->ctx[r], nullptr, pb, pe, T, nullptr, 0, all.data() + (size_t)r * T, &n);
+    else for (uint32_t t = 0; t < T; ++t) all[(size_t)r * T + t] = t;
+  };
+  std::vector<std::thread> th;
+  for (uint32_t r = 1; r < world; ++r) th.emplace_back(worker, r);
+  worker(0);
+  for (auto& t : th) t.join();
+  for (uint32_t r = 0; r < world; ++r)
+    if (rcs[r]) { m->err = "rank " + std::to_string(r) + ": " + prf_last_error(m->ctx[r]); return rcs[r]; }
+  int rc = prf_mask_components_shard(m->ctx[0], nullptr, 0, 0, T, all.data(),
+                                     world, labels, n_components);
+  if (rc) m->err = std::string("merge: ") + prf_last_error(m->ctx[0]);
+  return rc;
+}
+
 }  // extern "C"

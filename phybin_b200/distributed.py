@@ -74,3 +74,27 @@ def team_load(ctx, keys: torch.Tensor, off: torch.Tensor, T: int) -> dict:
     lib_stream = torch.cuda.ExternalStream(ctx.stream, device=keys.device)
     lib_stream.wait_stream(torch.cuda.current_stream(keys.device))
     return ctx.team_load(keys.data_ptr(), off.data_ptr(), off.numel() - 1, T)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Flat clusters from a SHARDED threshold mask: every rank runs the union-find over its own shard,
+# the label arrays are all-gathered (T x 4 bytes per rank) and merged by one more union-find on the device --
+# the all-reduce(min) of labels without its iteration to a fixed point.
+# ---------------------------------------------------------------------------------------------------
+
+def gather_labels(labels: np.ndarray, device: torch.device | None = None) -> np.ndarray:
+    """All-gathers every rank's label array: [world, T] uint32 (NCCL on `device`, gloo when None)."""
+    world = dist.get_world_size()
+    mine = torch.from_numpy(labels.astype(np.int64))
+    if device is not None:
+        mine = mine.to(device)
+    out = torch.empty((world, mine.numel()), dtype=torch.int64, device=mine.device)
+    dist.all_gather_into_tensor(out.view(-1), mine)
+    return out.cpu().numpy().astype(np.uint32)
+
+
+def sharded_components(ctx, p_begin: int, p_end: int, device: torch.device | None = None, d_mask: int = 0):
+    """Collective: components of { d <= editdist } when rank r computed (and holds the mask of) the packed range
+    [p_begin, p_end) = prf_shard_range(T, r, world).  Returns (labels[T], n_components), identical on every rank."""
+    mine, _ = ctx.mask_components_shard(p_begin, p_end, d_mask=d_mask)
+    return ctx.mask_components_shard(0, 0, seeds=gather_labels(mine, device))

@@ -131,7 +131,18 @@ class MultiRF:
                                       mask.ctypes.data if mask is not None else None, C.byref(st))
         if rc != 0:
             raise PhyBinRFError(rc, self._L.prf_multi_last_error(self._m).decode())
+        self.T = T
         return out, mask, st.as_dict()
+
+    def components(self) -> Tuple[np.ndarray, int]:
+        """prf_multi_components after hashrf(editdist >= 0): every GPU's union-find over its resident mask shard,
+        merged on GPU 0 -- (labels[T] = smallest tree id of each tree's component, number of components)."""
+        labels = np.empty(self.T, dtype=np.uint32)
+        n = C.c_uint32(0)
+        rc = self._L.prf_multi_components(self._m, labels.ctypes.data, C.byref(n))
+        if rc != 0:
+            raise PhyBinRFError(rc, self._L.prf_multi_last_error(self._m).decode())
+        return labels, n.value
 
 
 class RFContext:
@@ -376,6 +387,18 @@ class RFContext:
         labels = np.empty(self.T, dtype=np.uint32)
         n = C.c_uint32(0)
         self._ck(self._L.prf_mask_components(self._h, d_mask or None, self.T, labels.ctypes.data, C.byref(n)))
+        return labels, n.value
+
+    def mask_components_shard(self, p_begin: int, p_end: int, seeds=None, d_mask: int = 0) -> Tuple[np.ndarray, int]:
+        """prf_mask_components_shard: union-find over the mask bits of the packed range [p_begin, p_end) (the
+        context-owned mask of a sharded compute, or a device pointer), merged with the label arrays `seeds`
+        ([n, T]) that other shards returned; an empty range merges the seeds only."""
+        labels = np.empty(self.T, dtype=np.uint32)
+        n = C.c_uint32(0)
+        seeds = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint32).reshape(-1, self.T)
+        self._ck(self._L.prf_mask_components_shard(self._h, d_mask or None, p_begin, p_end, self.T,
+                                                   seeds.ctypes.data if seeds is not None else None,
+                                                   len(seeds) if seeds is not None else 0, labels.ctypes.data, C.byref(n)))
         return labels, n.value
 
     def fetch_submatrix(self, ids, d_matrix: int = 0) -> np.ndarray:

@@ -84,3 +84,43 @@ def test_team_of_one_through_the_staged_entry_points():
         assert np.array_equal(out, ref)
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 5, 8])
+def test_sharded_mask_components_equal_whole_mask_components(world):
+    """the mask is sharded like the matrix; per-shard union-find + merge of the label arrays gives the
+    components of the whole graph (prf_mask_components_shard, prf_multi_components)."""
+    from phybin_b200.rfdistance import shard_range
+    T, thr = 900, 6
+    f = Forest.synthetic(T, 40, 0x5EED0200 + world, NNI_FAMILY, 6, 0.0)
+    bips, off = f.all_bips()
+    ctx = RFContext(0)
+    try:
+        ctx.hashrf_load(bips, off)
+        ctx.hashrf_compute(editdist=thr)
+        want, n_want = ctx.mask_components()
+        assert 1 < n_want < T
+        # shard by shard on one context: each range computed (context-owned mask of exactly that range), then merged
+        parts = []
+        for r in range(world):
+            b, e = shard_range(T, r, world)
+            ctx.hashrf_compute(b, e, editdist=thr)
+            parts.append(ctx.mask_components_shard(b, e)[0])
+        got, n_got = ctx.mask_components_shard(0, 0, seeds=np.stack(parts))
+        assert np.array_equal(got, want) and n_got == n_want
+        # chained form: a shard's components seeded with the previous shards' labels
+        acc = None
+        for r in range(world):
+            b, e = shard_range(T, r, world)
+            ctx.hashrf_compute(b, e, editdist=thr)
+            acc, n_acc = ctx.mask_components_shard(b, e, seeds=None if acc is None else acc[None, :])
+        assert np.array_equal(acc, want) and n_acc == n_want
+    finally:
+        ctx.close()
+    m = MultiRF(devices=[0] * world)
+    try:
+        m.hashrf(bips, off, thr)
+        got, n_got = m.components()
+    finally:
+        m.close()
+    assert np.array_equal(got, want) and n_got == n_want
