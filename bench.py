@@ -458,6 +458,23 @@ def run_gpu(args, wl, wl_name):
                 "kernel": "rows_kernel" if mode == "hashrf" else "tolerant_kernel",
                 "kernel_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_share_of_step": avg_ms * 1e-3 / step_s}
+    if mode == "tolerant":
+        # HBM is not what binds this kernel: per pair it restricts, re-normalises and hashes both trees' clades --
+        # 2 * (2n - 2) * W word-ops (64-bit AND + popcount) by the survey's count.  Reported against the MEASURED word-op peak.
+        n_taxa = wl["n"]
+        wordops = 2.0 * (2 * n_taxa - 2) * W * my_pairs
+        got = wordops / (avg_ms * 1e-3) if avg_ms > 0 else 0.0
+        peak_w, w_src = 8.0 * 148 * 1.965e9, "nominal: 16 POPC/clk/SM -> 8 word-ops/clk/SM x 148 SMs x 1965 MHz (profiles/wordop_peak.json missing)"
+        try:
+            with open(os.path.join(ROOT, "profiles", "wordop_peak.json")) as fh:
+                peak_w, w_src = float(json.load(fh)["wordops_per_s"]), "measured: scripts/wordop_peak.py on a B200 of this pool (profiles/wordop_peak.json)"
+        except Exception:
+            pass
+        roofline = {"bound": "alu", "achieved": got / 1e9, "peak": peak_w / 1e9, "unit": "Gword-op/s", "frac": got / peak_w,
+                    "traffic": None, "peak_source": w_src, "kernel": "tolerant_kernel", "kernel_ms": avg_ms,
+                    "algorithmic_wordops_per_launch": wordops, "wordops_per_pair": 2.0 * (2 * n_taxa - 2) * W,
+                    "kernel_share_of_step": avg_ms * 1e-3 / step_s,
+                    "hbm": {"achieved_gbs": achieved, "frac": achieved / peaks["hbm_gbs"], "note": "2 B per pair out; not the binding limit"}}
     if mode == "hashrf" and st.get("variant_used") == 2:
         # tensor-core variant: 2 * Kpad int8 ops per pair (Kpad = shared bipartitions padded to the 128-column k-block)
         kpad = (int(st["n_shared"]) + 127) // 128 * 128

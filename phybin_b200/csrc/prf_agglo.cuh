@@ -33,7 +33,8 @@ struct AggloRecord {   // what a CTA publishes per step
   double best_d;       // its best own row: nnd, row, nn   (row a of the step excluded)
   uint32_t best_i, best_j;
   double rowa_d;       // its share of row a's new nearest neighbour: min over its rows x > a of the new D[a][x]
-  uint32_t rowa_j, pad;
+  uint32_t rowa_j;
+  uint32_t stamp;      // step + 1 (debugging aid)
 };
 
 struct AggloParams {
@@ -90,6 +91,38 @@ __device__ __forceinline__ void agglo_block_min(double& d, uint32_t& i, uint32_t
   }
 }
 
+// Two reductions at once: (d1, i1, payload j1) and (d2, i2), each min by (d, i).  scratch: the arrays of agglo_block_min
+// plus s_d2 / s_i2 (32 entries each).
+__device__ __forceinline__ void agglo_block_min2(double& d1, uint32_t& i1, uint32_t& j1, double& d2, uint32_t& i2, double* s_d,
+                                                 uint32_t* s_i, uint32_t* s_j, double* s_d2, uint32_t* s_i2) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+#pragma unroll
+  for (int sh = 16; sh; sh >>= 1) {
+    const double od = __shfl_xor_sync(0xffffffffu, d1, sh), pd = __shfl_xor_sync(0xffffffffu, d2, sh);
+    const uint32_t oi = __shfl_xor_sync(0xffffffffu, i1, sh), oj = __shfl_xor_sync(0xffffffffu, j1, sh);
+    const uint32_t pi = __shfl_xor_sync(0xffffffffu, i2, sh);
+    if (agglo_less(od, oi, d1, i1)) { d1 = od; i1 = oi; j1 = oj; }
+    if (agglo_less(pd, pi, d2, i2)) { d2 = pd; i2 = pi; }
+  }
+  __syncthreads();  // the scratch of the previous call has been read
+  if (lane == 0) { s_d[warp] = d1; s_i[warp] = i1; s_j[warp] = j1; s_d2[warp] = d2; s_i2[warp] = i2; }
+  __syncthreads();
+  d1 = lane < n_warps ? s_d[lane] : inf;
+  i1 = lane < n_warps ? s_i[lane] : kAggloNone;
+  j1 = lane < n_warps ? s_j[lane] : kAggloNone;
+  d2 = lane < n_warps ? s_d2[lane] : inf;
+  i2 = lane < n_warps ? s_i2[lane] : kAggloNone;
+#pragma unroll
+  for (int sh = 16; sh; sh >>= 1) {
+    const double od = __shfl_xor_sync(0xffffffffu, d1, sh), pd = __shfl_xor_sync(0xffffffffu, d2, sh);
+    const uint32_t oi = __shfl_xor_sync(0xffffffffu, i1, sh), oj = __shfl_xor_sync(0xffffffffu, j1, sh);
+    const uint32_t pi = __shfl_xor_sync(0xffffffffu, i2, sh);
+    if (agglo_less(od, oi, d1, i1)) { d1 = od; i1 = oi; j1 = oj; }
+    if (agglo_less(pd, pi, d2, i2)) { d2 = pd; i2 = pi; }
+  }
+}
+
 // First minimal entry of row x among the columns j > x (dead columns hold the sentinel = +inf): the whole CTA
 // reads the row with 16-byte L2 loads; returns (value, column) in every thread, (+inf, NONE) when there is none.
 template <class Tv>
@@ -132,6 +165,8 @@ __global__ void __launch_bounds__(kAggloThreads, 1) agglo_kernel(const AggloPara
   uint32_t* s_j = s_i + 32;                                 // [32]
   uint32_t* s_list = s_j + 32;                              // [R] rows to rescan
   uint32_t* s_act = s_list + R;                             // [R] row still a cluster
+  uint32_t* s_i2 = s_act + R;                               // [32]
+  double* s_d2 = reinterpret_cast<double*>(s_i2 + 32 + ((R & 1) ? 1 : 0));  // [32], 8-byte aligned: 4 R words + 32 words (+1)
   __shared__ uint32_t s_n_list;
   Tv* D = reinterpret_cast<Tv*>(prm.D);
   uint32_t* size = prm.sizes + (size_t)cta * m;
@@ -158,27 +193,27 @@ __global__ void __launch_bounds__(kAggloThreads, 1) agglo_kernel(const AggloPara
         const uint32_t x = r * G + cta;
         if (s_act[r] && x != a_prev && s_nn[r] != kAggloNone && agglo_less(s_nnd[r], x, d, i)) { d = s_nnd[r]; i = x; j = s_nn[r]; }
       }
-      agglo_block_min(d, i, j, s_d, s_i, s_j);
+      agglo_block_min2(d, i, j, pa_d, pa_j, s_d, s_i, s_j, s_d2, s_i2);
       if (tid == 0) {
         AggloRecord rc;
         rc.best_d = d; rc.best_i = i; rc.best_j = j;
-        rc.rowa_d = pa_d; rc.rowa_j = pa_j; rc.pad = 0;
+        rc.rowa_d = pa_d; rc.rowa_j = pa_j; rc.stamp = step + 1;
         prm.rec[(size_t)(step & 1) * G + cta] = rc;
       }
     }
     grid.sync();
-    // ---- every CTA derives the same winner
+    // ---- every CTA derives the same winner from the G records
     double bd = inf, ad = inf;
-    uint32_t bi = kAggloNone, bj = kAggloNone, aj = kAggloNone, dummy = 0;
+    uint32_t bi = kAggloNone, bj = kAggloNone, aj = kAggloNone;
     for (uint32_t c = tid; c < G; c += blockDim.x) {
-      const AggloRecord* rp = prm.rec + (size_t)(step & 1) * G + c;
-      const double d1 = __ldcg(&rp->best_d), d2 = __ldcg(&rp->rowa_d);
-      const uint32_t i1 = __ldcg(&rp->best_i), j1 = __ldcg(&rp->best_j), j2 = __ldcg(&rp->rowa_j);
+      const uint4* rp = reinterpret_cast<const uint4*>(prm.rec + (size_t)(step & 1) * G + c);
+      const uint4 lo = __ldcg(rp), hi = __ldcg(rp + 1);
+      const double d1 = __longlong_as_double(((long long)lo.y << 32) | lo.x), d2 = __longlong_as_double(((long long)hi.y << 32) | hi.x);
+      const uint32_t i1 = lo.z, j1 = lo.w, j2 = hi.z;
       if (agglo_less(d1, i1, bd, bi)) { bd = d1; bi = i1; bj = j1; }
       if (agglo_less(d2, j2, ad, aj)) { ad = d2; aj = j2; }
     }
-    agglo_block_min(bd, bi, bj, s_d, s_i, s_j);
-    agglo_block_min(ad, aj, dummy, s_d, s_i, s_j);
+    agglo_block_min2(bd, bi, bj, ad, aj, s_d, s_i, s_j, s_d2, s_i2);
     if (a_prev != kAggloNone) {
       if (a_prev % G == cta && tid == 0) { s_nnd[a_prev / G] = ad; s_nn[a_prev / G] = aj; }
       if (aj != kAggloNone && agglo_less(ad, a_prev, bd, bi)) { bd = ad; bi = a_prev; bj = aj; }
@@ -189,10 +224,11 @@ __global__ void __launch_bounds__(kAggloThreads, 1) agglo_kernel(const AggloPara
     }
     const uint32_t a = bi, b = bj;   // a < b
     if (cta == 0 && tid == 0) { prm.merge_a[step] = a; prm.merge_b[step] = b; prm.merge_d[step] = bd; }
-    const double na = (double)size[a], nb = (double)size[b];
+    // cluster sizes only enter UPGMA's weights
+    const double na = prm.linkage == 2 ? (double)size[a] : 1.0, nb = prm.linkage == 2 ? (double)size[b] : 1.0;
     if (tid == 0) s_n_list = 0;
     __syncthreads();   // sizes read, list counter cleared, a_prev's nn stored
-    if (tid == 0) size[a] += size[b];
+    if (tid == 0 && prm.linkage == 2) size[a] += size[b];
     // ---- update the own rows
     pa_d = inf;
     pa_j = kAggloNone;
@@ -224,10 +260,7 @@ __global__ void __launch_bounds__(kAggloThreads, 1) agglo_kernel(const AggloPara
         }
       }
     }
-    {  // the CTA's share of row a's nearest neighbour (published with the next record)
-      uint32_t dummy2 = 0;
-      agglo_block_min(pa_d, pa_j, dummy2, s_d, s_i, s_j);
-    }
+    // (pa_d, pa_j: this thread's share of row a's nearest neighbour, reduced and published with the next record)
     __syncthreads();   // list complete, own-row stores ordered before the rescans of this CTA
     const uint32_t n_list = s_n_list;
     for (uint32_t q = 0; q < n_list; ++q) {

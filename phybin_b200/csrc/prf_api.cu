@@ -32,6 +32,24 @@ __global__ void __launch_bounds__(256) tree_extent_kernel(const uint64_t* __rest
 }
 
 
+namespace prf {
+__global__ void __launch_bounds__(1024) wordop_peak_kernel(unsigned long long* sink, uint32_t iters, uint64_t seed) {
+  uint64_t x[8], acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { x[i] = seed * (2 * i + 1) + threadIdx.x; acc[i] = 0; }
+  uint64_t m = seed ^ blockIdx.x;
+  for (uint32_t it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += __popcll(x[i] & m);
+    m += 0x9E3779B97F4A7C15ull;
+  }
+  uint64_t t = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += acc[i];
+  if (t == 0x7fffffffffffffffull) *sink = t;  // keeps the loop alive
+}
+}  // namespace prf
+
 extern "C" {
 
 PRF_API const char* prf_version(void) { return "phybin_rf 0.1 (sm_100a)"; }
@@ -423,6 +441,27 @@ PRF_API int prf_debug_scan(prf_ctx* h, const uint32_t* host_in, uint64_t n, uint
   PRF_CK(ctx, cudaMemcpyAsync(host_out, out.p, n * 4, cudaMemcpyDeviceToHost, s));
   PRF_CK(ctx, cudaMemcpyAsync(total, tot.p, 4, cudaMemcpyDeviceToHost, s));
   PRF_CK(ctx, cudaStreamSynchronize(s));
+  return PRF_OK;
+}
+
+// Measured integer "word-op" peak of the device (the tolerant mode's roofline denominator): one word-op =
+// AND + popcount + accumulate of one 64-bit word, 8 independent chains per thread.  Returns word-ops per second.
+PRF_API int prf_debug_wordop_peak(prf_ctx* h, double* wordops_per_s) {
+  if (!h || !wordops_per_s) return PRF_E_INVALID;
+  Ctx* ctx = &h->c;
+  PRF_CK(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  DevBuf<unsigned long long> sink;
+  PRF_CK(ctx, sink.alloc(1, s));
+  const uint32_t grid = (uint32_t)ctx->sm_count * 2, iters = 1 << 14;
+  wordop_peak_kernel<<<grid, 1024, 0, s>>>(sink.p, iters, 0x0123456789abcdefull);  // warm-up
+  PRF_CK(ctx, cudaEventRecord(ctx->ev[0], s));
+  wordop_peak_kernel<<<grid, 1024, 0, s>>>(sink.p, iters, 0x0123456789abcdefull);
+  PRF_CK(ctx, cudaEventRecord(ctx->ev[1], s));
+  PRF_CK(ctx, cudaStreamSynchronize(s));
+  ctx->launches += 2;
+  const double ms = ev_ms(ctx->ev[0], ctx->ev[1]);
+  *wordops_per_s = ms > 0 ? (double)grid * 1024 * iters * 8 / (ms * 1e-3) : 0.0;
   return PRF_OK;
 }
 

@@ -19,7 +19,7 @@ int run_agglo(Ctx* ctx, const uint16_t* src, uint64_t src_begin, uint32_t T, con
   const uint32_t ld = (m + E - 1) / E * E;
   uint32_t G = std::min<uint32_t>((uint32_t)ctx->sm_count, (m + 15) / 16);
   const uint32_t R0 = (m + G - 1) / G;
-  const size_t smem = (size_t)R0 * 20 + 512;
+  const size_t smem = (size_t)R0 * 20 + 512 + 4 + 128 + 256;
   PRF_CK(ctx, cudaFuncSetAttribute(agglo_kernel<Tv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   PRF_CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agglo_kernel<Tv>, (int)kAggloThreads, smem));
@@ -32,6 +32,7 @@ int run_agglo(Ctx* ctx, const uint16_t* src, uint64_t src_begin, uint32_t T, con
     return ctx->fail(PRF_E_NOMEM, "no device memory for a %u x %u matrix of %zu-byte distances", m, m, sizeof(Tv));
   }
   PRF_CK(ctx, rec.alloc((size_t)2 * G, s));
+  PRF_CK(ctx, cudaMemsetAsync(rec.p, 0, (size_t)2 * G * sizeof(AggloRecord), s));  // stamp 0 = not yet published
   agglo_gather_kernel<Tv><<<dim3((ld + 255) / 256, std::min<uint32_t>(m, 65535u)), 256, 0, s>>>(src, src_begin, T, d_ids, m, ld, D.p);
   PRF_LAUNCHED(ctx);
   AggloParams prm;

@@ -188,25 +188,45 @@ __device__ __forceinline__ bool key_equals(const PairCtx<W, DUPS>& P, uint32_t i
 // an L1/L2 hit), so a warp needs only 4 bytes of shared memory per slot and many warps fit on an SM.
 // Returns, packed, what the insertion changed: bit 0 / bit 1 = the slot gained flag 1 / 2 for the first time, bit 2 = the
 // slot now has both flags and did not before.  Summed over a pair's keys: |F_a|, |F_b| and |F_a n F_b|.
+__device__ __forceinline__ uint32_t tol_lds(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t tol_cas(uint32_t addr, uint32_t cmp, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(addr), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+__device__ __forceinline__ uint32_t tol_or(uint32_t addr, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(val) : "memory");
+  return old;
+}
+
+// tbase: shared-window byte address of the warp's table; bmask = (tsize - 1) * 4.  The probe loop carries two
+// registers (the slot's byte offset and the word to store); the asm barrier below stops ptxas from re-deriving them
+// -- i.e. from re-hashing the key -- on every probe, which it otherwise does under the 64-register cap (ncu: the
+// loop was 45 instructions long and 40 % of the kernel).
 template <int W, bool DUPS>
-__device__ __forceinline__ uint32_t table_insert(uint32_t* table, uint32_t tmask, const PairCtx<W, DUPS>& P, uint32_t idx,
+__device__ __forceinline__ uint32_t table_insert(uint32_t tbase, uint32_t bmask, const PairCtx<W, DUPS>& P, uint32_t idx,
                                                  const BitSet<W>& key, uint32_t flag) {
   const uint32_t h = hash_set<W>(key);
-  const uint32_t tag = (h >> 13) & 0x7ffffu;
-  const uint32_t mine = (flag << 30) | (tag << 11) | (idx + 1);
-  uint32_t s = h & tmask;
+  uint32_t mine = (flag << 30) | (((h >> 13) & 0x7ffffu) << 11) | (idx + 1);
+  uint32_t s4 = (h << 2) & bmask;
+  asm volatile("" : "+r"(mine), "+r"(s4));
   for (;;) {
-    uint32_t cur = *((volatile uint32_t*)&table[s]);
+    uint32_t cur = tol_lds(tbase + s4);
     if (cur == 0) {
-      cur = atomicCAS(&table[s], 0u, mine);
+      cur = tol_cas(tbase + s4, 0u, mine);
       if (cur == 0) return flag | (flag == 3u ? 4u : 0u);
     }
-    if (((cur >> 11) & 0x7ffffu) == tag && key_equals<W, DUPS>(P, (cur & 0x7ffu) - 1, key)) {
-      const uint32_t old = atomicOr(&table[s], flag << 30) >> 30;
+    if (((cur ^ mine) & 0x3ffff800u) == 0 && key_equals<W, DUPS>(P, (cur & 0x7ffu) - 1, key)) {
+      const uint32_t old = tol_or(tbase + s4, flag << 30) >> 30;
       const uint32_t gained = flag & ~old;
       return gained | ((old | flag) == 3u && old != 3u ? 4u : 0u);
     }
-    s = (s + 1) & tmask;
+    s4 = (s4 + 4) & bmask;
   }
 }
 
@@ -253,7 +273,8 @@ __global__ void __launch_bounds__(512, (W <= 3 && !DUPS) ? 2 : 1) tolerant_kerne
   const uint64_t* __restrict__ leafsets = prm.leafsets;
   const uint64_t* __restrict__ off = prm.off;
   uint32_t* table = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * tsize;  // per-warp tables
-  const uint32_t tmask = tsize - 1;
+  uint32_t tbase = (uint32_t)__cvta_generic_to_shared(table), bmask = (tsize - 1) * 4;
+  asm volatile("" : "+r"(tbase), "+r"(bmask));  // kept in registers (ptxas otherwise re-derives the address on every probe)
   for (uint32_t s = lane; s < tsize; s += 32) table[s] = 0;
   __syncwarp();
 
@@ -339,7 +360,7 @@ __global__ void __launch_bounds__(512, (W <= 3 && !DUPS) ? 2 : 1) tolerant_kerne
             }
           }
           if (have) {
-            const uint32_t g = table_insert<W, DUPS>(table, tmask, P, idx, key, isb ? 2u : 1u);
+            const uint32_t g = table_insert<W, DUPS>(tbase, bmask, P, idx, key, isb ? 2u : 1u);
             d += (g & 1u) + ((g >> 1) & 1u) - ((g >> 1) & 2u);  // |F_a| + |F_b| - 2 |F_a n F_b| = |F_a xor F_b|
           }
         }
@@ -354,7 +375,7 @@ __global__ void __launch_bounds__(512, (W <= 3 && !DUPS) ? 2 : 1) tolerant_kerne
               BitSet<W> key;
               rebuild_key<W, DUPS>(P, n_cl + lane, key);
               if (popc_set<W>(key) > 1) {
-                const uint32_t g = table_insert<W, DUPS>(table, tmask, P, n_cl + lane, key, DUPS ? (sideb ? 2u : 1u) : 3u);
+                const uint32_t g = table_insert<W, DUPS>(tbase, bmask, P, n_cl + lane, key, DUPS ? (sideb ? 2u : 1u) : 3u);
                 d += (g & 1u) + ((g >> 1) & 1u) - ((g >> 1) & 2u);
               }
             }

@@ -10,7 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from phybin_b200 import _native
-from phybin_b200.distributed import KeyGather, shard_rows, tree_shard
+from phybin_b200.distributed import KeyGather, gather_labels, shard_rows, tree_shard
 from phybin_b200.host import Forest
 
 
@@ -42,6 +42,9 @@ def _worker(rank, world, port, T, n, out_dir):
         assert L.prf_shard_range(T, rank, world, ctypes.byref(b), ctypes.byref(e)) == 0
         ranges = [None] * world
         dist.all_gather_object(ranges, (b.value, e.value))
+        # the exchange step of the sharded flat clusters: every rank's label array, in rank order, on every rank
+        labs = gather_labels(np.arange(T, dtype=np.uint32) // (rank + 2))
+        ok = ok and labs.shape == (world, T) and all(np.array_equal(labs[r], np.arange(T) // (r + 2)) for r in range(world))
         with open(os.path.join(out_dir, f"r{rank}.txt"), "w") as fh:
             fh.write(f"{int(ok)} {ranges}")
     finally:
