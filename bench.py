@@ -38,6 +38,8 @@ WORKLOADS = {
     "cfg2_nni": dict(T=10_000, n=100, seed=0x5EED0002, family=1, editdist=-1, mode="hashrf"),
     "cfg3_nni": dict(T=100_000, n=200, seed=0x5EED0003, family=1, editdist=-1, mode="hashrf"),
     "cfg4": dict(T=50_000, n=500, seed=0x5EED0004, family=0, editdist=4, mode="hashrf"),
+    # cfg4's shape on the similar-trees family: the mask's consumer (components + UPGMA flat clusters) is non-trivial here
+    "cfg4_nni": dict(T=50_000, n=500, seed=0x5EED0004, family=1, editdist=4, mode="hashrf"),
     "cfg5": dict(T=20_000, n=150, seed=0x5EED0005, family=0, editdist=-1, mode="tolerant", p_missing=0.10),
 }
 METRIC = "rf_tree_pairs_per_sec"
@@ -441,9 +443,12 @@ def run_gpu(args, wl, wl_name):
         t1 = time.perf_counter()
         _, nclu = ctx.flat_clusters(editdist, "UPGMA", d_mask.data_ptr(), d_out.data_ptr())
         t2 = time.perf_counter()
+        lab_c, _ = ctx.mask_components(d_mask.data_ptr())
         consumer = {"what": "connected components of {d <= editdist} on the device (prf_mask_components), then UPGMA flat "
-                            "clusters per component on the host (sliceDendro editdist . C.dendrogram UPGMA)",
+                            "clusters (sliceDendro editdist . C.dendrogram UPGMA): components of >= 64 trees agglomerated on the "
+                            "device (prf_agglomerate), smaller ones by the host restatement of the same rule",
                     "components_ms": (t1 - t0) * 1e3, "n_components": int(ncomp),
+                    "largest_component": int(np.bincount(lab_c).max()) if len(lab_c) else 0,
                     "upgma_flat_clusters_ms": (t2 - t1) * 1e3, "n_clusters": int(nclu)}
 
     # ---- roofline of the dominant kernel (the matrix kernel), per launch ---------------------------

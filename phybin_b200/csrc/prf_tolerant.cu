@@ -44,6 +44,7 @@ static int tolerant_load_impl(prf_ctx* h, const uint64_t* clades, const uint64_t
   }
   uint64_t nnz = hoff[T];
   if (nnz && !clades) return ctx->fail(PRF_E_INVALID, "clades is NULL");
+  if (nnz >= 0xffffffffull) return ctx->fail(PRF_E_UNSUPPORTED, "nnz=%llu clades; supported < 2^32 - 1", (unsigned long long)nnz);
   if (dups && nnz && !outsets) return ctx->fail(PRF_E_INVALID, "outsets is NULL");
   std::vector<uint64_t> hdoff;
   uint64_t n_dup = 0;

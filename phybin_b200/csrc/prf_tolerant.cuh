@@ -92,15 +92,15 @@ __device__ __forceinline__ BitSet<W> universe(uint32_t k) {
 
 template <int W>
 __device__ __forceinline__ uint32_t hash_set(const BitSet<W>& s) {
-  // routes only (equality is decided on the full key): a multiply-add per 32-bit half word, then an avalanche
-  uint32_t h = 0x9E3779B9u;
+  // routes only (equality is decided on the full key): two independent multiply-add chains over the 32-bit half
+  // words, one avalanche round
+  uint32_t h0 = 0x9E3779B9u, h1 = 0x85EBCA6Bu;
 #pragma unroll
   for (int i = 0; i < W; ++i) {
-    h = h * 0x85EBCA6Bu + (uint32_t)s.w[i];
-    h = h * 0xC2B2AE35u + (uint32_t)(s.w[i] >> 32);
+    h0 = h0 * 0xC2B2AE35u + (uint32_t)s.w[i];
+    h1 = h1 * 0x27D4EB2Fu + (uint32_t)(s.w[i] >> 32);
   }
-  h ^= h >> 16;
-  h *= 0x7FEB352Du;
+  uint32_t h = h0 ^ (h1 * 0x165667B1u);
   h ^= h >> 15;
   h *= 0x846CA68Bu;
   h ^= h >> 16;
@@ -128,7 +128,7 @@ struct TolParams {
 template <int W, bool DUPS>
 struct PairCtx {
   const uint64_t* clades;
-  uint64_t oa, ob;   // first clade of tree a / tree b
+  uint32_t oa, ob;   // first clade of tree a / tree b (nnz < 2^32 is checked at load: 32-bit index arithmetic)
   uint32_t na, nb;   // clade counts
   BitSet<W> S;       // shared taxa
   BitSet<W> R;       // normBip's universe {0..k-1} of side a (both sides when !DUPS)
@@ -147,7 +147,7 @@ __device__ __forceinline__ void rebuild_key(const PairCtx<W, DUPS>& P, uint32_t 
   bool isb;
   if (idx < P.na + P.nb) {
     isb = idx >= P.na;
-    const uint64_t* src = P.clades + (isb ? P.ob + (idx - P.na) : P.oa + idx) * W;
+    const uint64_t* src = P.clades + (size_t)(isb ? P.ob + (idx - P.na) : P.oa + idx) * W;
 #pragma unroll
     for (int i = 0; i < W; ++i) m.w[i] = src[i] & P.S.w[i];
     pc = popc_set<W>(m);
@@ -215,19 +215,20 @@ __device__ __forceinline__ uint32_t table_insert(uint32_t tbase, uint32_t bmask,
   uint32_t mine = (flag << 30) | (((h >> 13) & 0x7ffffu) << 11) | (idx + 1);
   uint32_t s4 = (h << 2) & bmask;
   asm volatile("" : "+r"(mine), "+r"(s4));
-  for (;;) {
+  uint32_t old = 0;  // flags the key had before this insertion
+  for (;;) {         // nothing but the probe in the loop: what the insertion changed is worked out once, after it
     uint32_t cur = tol_lds(tbase + s4);
     if (cur == 0) {
       cur = tol_cas(tbase + s4, 0u, mine);
-      if (cur == 0) return flag | (flag == 3u ? 4u : 0u);
+      if (cur == 0) break;
     }
     if (((cur ^ mine) & 0x3ffff800u) == 0 && key_equals<W, DUPS>(P, (cur & 0x7ffu) - 1, key)) {
-      const uint32_t old = tol_or(tbase + s4, flag << 30) >> 30;
-      const uint32_t gained = flag & ~old;
-      return gained | ((old | flag) == 3u && old != 3u ? 4u : 0u);
+      old = tol_or(tbase + s4, flag << 30) >> 30;
+      break;
     }
     s4 = (s4 + 4) & bmask;
   }
+  return (flag & ~old) | ((old | flag) == 3u && old != 3u ? 4u : 0u);
 }
 
 // Parent of every clade inside its tree, found once per load: the smallest other clade of the tree that contains it
@@ -315,10 +316,10 @@ __global__ void __launch_bounds__(512, (W <= 3 && !DUPS) ? 2 : 1) tolerant_kerne
           }
         }
         P.R = universe<W>(P.ka);
-        P.oa = off[a];
-        P.na = (uint32_t)(off[a + 1] - P.oa);
-        P.ob = off[b];
-        P.nb = (uint32_t)(off[b + 1] - P.ob);
+        P.oa = (uint32_t)off[a];
+        P.na = (uint32_t)off[a + 1] - P.oa;
+        P.ob = (uint32_t)off[b];
+        P.nb = (uint32_t)off[b + 1] - P.ob;
         const uint32_t n_cl = P.na + P.nb;
         for (uint32_t c0 = 0; c0 < n_cl; c0 += 32) {
           const uint32_t idx = c0 + lane;
@@ -327,11 +328,11 @@ __global__ void __launch_bounds__(512, (W <= 3 && !DUPS) ? 2 : 1) tolerant_kerne
           bool isb = false;
           if (idx < n_cl) {
             isb = idx >= P.na;
-            const uint64_t e = isb ? P.ob + (idx - P.na) : P.oa + idx;
+            const uint32_t e = isb ? P.ob + (idx - P.na) : P.oa + idx;
             const bool full = isb ? P.fullB : P.fullA;
             BitSet<W> m;
 #pragma unroll
-            for (int i = 0; i < W; ++i) m.w[i] = clades[e * W + i] & P.S.w[i];
+            for (int i = 0; i < W; ++i) m.w[i] = clades[(size_t)e * W + i] & P.S.w[i];
             const uint32_t pc = popc_set<W>(m);
             bool keep = pc != 0;  // the node lost all its leaves
             if (DUPS) {
@@ -339,17 +340,17 @@ __global__ void __launch_bounds__(512, (W <= 3 && !DUPS) ? 2 : 1) tolerant_kerne
               // (PreProcessor.hs:28-31); the cached bips of an unpruned tree keep every node (RFDistance.hs:186-191)
               uint64_t outside = 0;
 #pragma unroll
-              for (int i = 0; i < W; ++i) outside |= prm.outsets[e * W + i] & P.S.w[i];
+              for (int i = 0; i < W; ++i) outside |= prm.outsets[(size_t)e * W + i] & P.S.w[i];
               keep &= full || outside != 0;
             } else {
               const uint32_t pr = prm.par[e];
               if (pr == 0xffffu) {
                 keep &= full || pc != P.ns;   // the whole of S: the pruned tree's root
               } else {
-                const uint64_t pe = (isb ? P.ob : P.oa) + pr;
+                const uint32_t pe = (isb ? P.ob : P.oa) + pr;
                 bool same = true;
 #pragma unroll
-                for (int i = 0; i < W; ++i) same &= (clades[pe * W + i] & P.S.w[i]) == m.w[i];
+                for (int i = 0; i < W; ++i) same &= (clades[(size_t)pe * W + i] & P.S.w[i]) == m.w[i];
                 keep &= !same;                // same set as its parent clade: the parent stands for both
               }
             }

@@ -6,11 +6,11 @@
 set -u
 O=gpurun_out
 mkdir -p $O
-timeout 600 python -m pytest tests -m gpu -x -q > $O/r02_pytest.log 2>&1; echo "pytest rc=$?" | tee -a $O/r02_rc.log
+timeout 900 python -m pytest tests -m gpu -x -q > $O/r02_pytest.log 2>&1; echo "pytest rc=$?" | tee -a $O/r02_rc.log
 tail -3 $O/r02_pytest.log
 timeout 400 python bench.py > $O/r02_bench_cfg3_default.json 2> $O/r02_bench_cfg3_default.err; echo "bench cfg3 rc=$?" | tee -a $O/r02_rc.log
 cat $O/r02_bench_cfg3_default.json
-for w in ${WORKLOADS:-cfg4 cfg5}; do
+for w in ${WORKLOADS:-cfg4 cfg5 cfg4_nni cfg3_nni cfg2}; do
   timeout 300 python bench.py --workload $w --no-cpu > $O/r02_bench_$w.json 2> $O/r02_bench_$w.err; echo "bench $w rc=$?" | tee -a $O/r02_rc.log
 done
 if [ -n "${REF_ARM:-}" ]; then timeout 300 python bench.py --impl reference > $O/r02_bench_cfg3_reference_arm.json 2> $O/r02_bench_ref.err; echo "ref arm rc=$?" | tee -a $O/r02_rc.log; fi
