@@ -1,7 +1,9 @@
 """Randomised GPU stress of the rows around the matrix (run on a B200; not part of pytest because of its length):
 device extraction (allBips / raw clades) against the host extraction word for word and against the oracle's
 allBips, one-shot from trees against the staged calls, strict consensus of random partitions and of mask components
-against the oracle, flat clusters of every linkage against the naive restatement.
+against the oracle, flat clusters of every linkage against the naive restatement, the device agglomeration
+(prf_agglomerate: merge lists, bit for bit) against the host restatement on tie-heavy random matrices, and the tolerant
+matrix of forests with repeated leaf labels (prf_tolerant_load_dups) against the oracle's literal naiveDistMatrix.
 usage: python scripts/stress_consumers.py [seconds]"""
 import os, random, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -11,13 +13,15 @@ from oracle import oracle as orc
 from oracle import pyref
 from phybin_b200.host import Forest, NNI_FAMILY, bits_to_labels
 from phybin_b200.rfdistance import EXTRACT_BIPS, EXTRACT_CLADES, RFContext, packed_index
-from tests.util import random_multifurcating_newicks
+from phybin_b200 import host as phost
+from tests.test_tolerant_model_cpu import dup_newicks
+from tests.util import oracle_packed, random_multifurcating_newicks
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 90.0
 rng = random.Random(int(os.environ.get("STRESS_SEED", "777")))
 ctx = RFContext(0)
 t_end = time.time() + budget
-n_cases = n_cons = n_clu = 0
+n_cases = n_cons = n_clu = n_agg = n_dup = 0
 while time.time() < t_end:
     kind = rng.choice(["random", "nni", "multi", "multi_missing"])
     T = rng.choice([1, 2, 3, 17, 64, 257, 600])
@@ -72,5 +76,30 @@ while time.time() < t_end:
                 got, _ = ctx.flat_clusters(thr, linkage)
                 assert got.tolist() == pyref.flat_clusters(d, T, linkage, thr), ("clusters", kind, T, n, seed, linkage, thr)
                 n_clu += 1
+                got_dev, _ = ctx.flat_clusters(thr, linkage, device_min=3)
+                assert np.array_equal(got_dev, got), ("clusters on the device", kind, T, n, seed, linkage, thr)
+    # the agglomeration itself: an arbitrary tie-heavy matrix on the device, merge list == host restatement
+    import torch
+    m = rng.choice([2, 3, 5, 31, 100, 333, 800])
+    upper = np.random.default_rng(seed).integers(0, rng.choice([1, 2, 5, 40]) + 1, size=m * (m - 1) // 2).astype(np.uint16)
+    t_up = torch.from_numpy(upper.astype(np.int16)).to("cuda:0")
+    torch.cuda.synchronize()
+    ctx.T = m
+    for linkage in ("single", "complete", "UPGMA"):
+        thresh = rng.choice([float("inf"), 0.0, 1.0, 2.5])
+        hl, ha, hb_, hd = phost.agglomerate(upper, m, linkage, thresh)
+        gl, ga, gb, gd, _ = ctx.agglomerate(None, linkage, thresh, t_up.data_ptr())
+        assert np.array_equal(ga, ha) and np.array_equal(gb, hb_) and np.array_equal(gd, hd) and np.array_equal(gl, hl), ("agglo", m, seed, linkage, thresh)
+        n_agg += 1
+    del t_up
+    # repeated leaf labels in --tolerant
+    Td, nd = rng.choice([2, 9, 40]), rng.choice([2, 3, 4, 6, 20, 64, 65, 140])
+    text = dup_newicks(random.Random(seed), Td, nd, p_missing=rng.choice([0.0, 0.2, 0.5]), p_dup=rng.choice([0.03, 0.3]))
+    fd = Forest.parse([text])
+    ctx.tolerant_load_dups(*fd.raw_clades_ex())
+    ctx.tolerant_compute()
+    assert np.array_equal(ctx.fetch().astype(np.int64), oracle_packed(orc.Forest([text]), "naive")), ("tolerant dups", Td, nd, seed)
+    n_dup += 1
     n_cases += 1
+print(f"agglomerations {n_agg}, repeated-label forests {n_dup};", end=" ")
 print(f"consumer stress ok: {n_cases} inputs, {n_cons} consensus sets, {n_clu} clusterings in {budget:.0f} s")
