@@ -430,6 +430,14 @@ def test_cli_clusters_and_consensus_files(golden, tmp_path, name, thr, linkage, 
         assert cons.strip() == c["consensus_text"].strip()
     members = Forest.parse([(out / f"cluster1_{T}_alltrees.tr").read_text()])
     assert len(members) == T
+    # dendrogram.txt (PhyBin.hs:238-243): the device's full agglomeration, shown as the reference's `show`; the same text
+    # from the host restatement run on the golden matrix
+    from phybin_b200 import host as phost
+    rows = c["hashrf"]   # reference layout: row i holds d(i, j) for j < i
+    upper = np.array([rows[b][a] for a in range(T) for b in range(a + 1, T)], dtype=np.uint16)
+    _, ma, mb, md = phost.agglomerate(upper, T, {"--single": "single", "--complete": "complete", "--UPGMA": "UPGMA"}[linkage])
+    assert (out / "dendrogram.txt").read_text() == phost.dendrogram_text([f"alltrees_{i}" for i in range(T)], ma, mb, md)
+    assert " [finished] Wrote full dendrogram to file dendrogram.txt" in r.stdout
     # a tighter cut splits t5 / t3 into several clusters whose sizes add up
     if thr:
         r = subprocess.run([cli, "--editdist=0", linkage, "-o", str(tmp_path / "out0"), str(tr)], capture_output=True, text=True, timeout=120)

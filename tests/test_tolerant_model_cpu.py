@@ -66,3 +66,16 @@ def test_repeated_label_form_equals_distinct_form_without_repeats():
     f = Forest.parse([text])
     assert not f.has_duplicate_leaves()
     _check(text, True)
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_both_oracles_agree_on_repeated_labels(seed):
+    """The C++ oracle and the independent pure-Python restatement (oracle/pyref.py) on forests that repeat leaf labels:
+    numLeaves counts the repeats (CoreTypes.hs:289-291), label sets do not."""
+    from oracle import pyref
+    rng = random.Random(900 + seed)
+    text = dup_newicks(rng, 9, rng.choice([3, 5, 12, 40]), p_missing=rng.choice([0.0, 0.3]), p_dup=0.3)
+    o = orc.Forest([text])
+    _, trees = pyref.parse_newicks([text])
+    assert orc.lower_to_rows(o.naive(), o.num_trees) == pyref.naive_dist_matrix(trees)
+    assert any(pyref.num_leaves(t) != len(pyref._leafset(t)) for t in trees)
