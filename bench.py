@@ -552,8 +552,10 @@ def run_gpu(args, wl, wl_name):
                "ms_per_step": float(dt[0]) * 1e3, "steps": n_e2e,
                "phases_ms": {"h2d": ev[0].elapsed_time(ev[1]), "build_and_matrix": ev[1].elapsed_time(ev[2]), "d2h": ev[2].elapsed_time(ev[3]),
                              "note": "rank 0, last step (CUDA events on the library's stream)"},
-               "host_ceiling": "all ranks copying device -> pinned host at once reach 142 GB/s in aggregate on this box (57 GB/s for one "
-                               "rank alone; one NUMA node, 32 vCPUs): scripts/d2h_probe.py, profiles/r02_d2h_probe_n8.json",
+               "d2h_aggregate_gbs": float(nbytes[1]) / (ev[2].elapsed_time(ev[3]) * 1e-3) / 1e9,
+               "host_ceiling": "the step is the device -> pinned-host copy of the matrix: d2h_aggregate_gbs = all ranks' slice bytes / rank 0's "
+                               "copy time in this run; scripts/d2h_probe.py measures the same ceiling without the compute (one rank alone: "
+                               "~57 GB/s, one PCIe Gen5 x16 link)",
                "note": "per rank: pinned tree shard -> HBM, hash-partitioned build over NVLink, own slice, slice -> pinned host; bytes summed over ranks"}
 
     cpu_baseline = None
