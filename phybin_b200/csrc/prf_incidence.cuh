@@ -194,45 +194,26 @@ __global__ void __launch_bounds__(256) list_count_kernel(const uint64_t* __restr
     for (uint32_t i = sub; i < set_slots; i += G) set[i] = 0xffffffffu;
     __syncwarp();
     uint32_t dups = 0;
-    // kBatch entries per lane at a time: their slot numbers, bitmap words and word ranks are requested together (three
-    // rounds of independent loads) before the dependent set insertions and counter updates -- one entry at a time the
-    // kernel was a chain of three dependent DRAM/L2 latencies per entry (ent is rewritten in place, so the compiler
-    // cannot hoist the next entry's load over the store)
-    constexpr int kBatch = 4;
-    for (uint64_t eb = e0; eb < e1; eb += (uint64_t)G * kBatch) {
-      uint32_t sl[kBatch], word[kBatch], wr[kBatch];
-#pragma unroll
-      for (int k = 0; k < kBatch; ++k) {
-        const uint64_t e = eb + sub + (uint64_t)k * G;
-        sl[k] = e < e1 ? ent[e] : 0u;
-      }
-#pragma unroll
-      for (int k = 0; k < kBatch; ++k) word[k] = shared_bits[sl[k] >> 5];
-#pragma unroll
-      for (int k = 0; k < kBatch; ++k) wr[k] = wrank[sl[k] >> 5];
-#pragma unroll
-      for (int k = 0; k < kBatch; ++k) {
-        const uint64_t e = eb + sub + (uint64_t)k * G;
-        if (e >= e1) continue;
-        const uint32_t s = sl[k];
-        uint32_t l = 0xffffffffu;
-        if ((word[k] >> (s & 31)) & 1u) {
-          l = wr[k] + __popc(word[k] & ((1u << (s & 31)) - 1u));
-          uint32_t h = (l * 0x9E3779B1u) & (set_slots - 1);
-          for (;;) {
-            const uint32_t old = atomicCAS(&set[h], 0xffffffffu, l);
-            if (old == 0xffffffffu) break;
-            if (old == l) {  // the tree listed this bipartition before
-              l = 0xffffffffu;
-              ++dups;
-              break;
-            }
-            h = (h + 1) & (set_slots - 1);
+    for (uint64_t e = e0 + sub; e < e1; e += G) {
+      const uint32_t s = ent[e];
+      const uint32_t word = shared_bits[s >> 5];
+      uint32_t l = 0xffffffffu;
+      if ((word >> (s & 31)) & 1u) {
+        l = wrank[s >> 5] + __popc(word & ((1u << (s & 31)) - 1u));
+        uint32_t h = (l * 0x9E3779B1u) & (set_slots - 1);
+        for (;;) {
+          const uint32_t old = atomicCAS(&set[h], 0xffffffffu, l);
+          if (old == 0xffffffffu) break;
+          if (old == l) {  // the tree listed this bipartition before
+            l = 0xffffffffu;
+            ++dups;
+            break;
           }
-          if (l != 0xffffffffu) atomicAdd(&lcnt[l], 1u);
+          h = (h + 1) & (set_slots - 1);
         }
-        ent[e] = l;
+        if (l != 0xffffffffu) atomicAdd(&lcnt[l], 1u);
       }
+      ent[e] = l;
     }
     __syncwarp();
 #pragma unroll
@@ -336,37 +317,18 @@ __global__ void __launch_bounds__(256) bucket_count_kernel(const uint64_t* __res
     const bool live = t < T;
     const uint64_t e0 = live ? tb[t] : 0, e1 = live ? te[t] : 0;
     uint32_t nl = 0, nh = 0;
-    constexpr int kBatch = 4;  // list ids, list sizes and the per-list targets of kBatch entries in three rounds of independent loads
-    for (uint64_t eb = e0; eb < e1; eb += (uint64_t)G * kBatch) {
-      uint32_t li[kBatch], mm[kBatch], tg[kBatch];
-#pragma unroll
-      for (int k = 0; k < kBatch; ++k) {
-        const uint64_t e = eb + sub + (uint64_t)k * G;
-        li[k] = e < e1 ? ent[e] : 0xffffffffu;
-      }
-#pragma unroll
-      for (int k = 0; k < kBatch; ++k) mm[k] = li[k] != 0xffffffffu ? lcnt[li[k]] : 0u;
-#pragma unroll
-      for (int k = 0; k < kBatch; ++k) {
-        const uint32_t l = li[k], m = mm[k];
-        tg[k] = 0;
-        if (fid && 2ull * m > T && m > short_max) tg[k] = fid[l];
-        else if (m > short_max) tg[k] = llid[l];
-        else if (m >= 2) tg[k] = sbase[l];
-      }
-#pragma unroll
-      for (int k = 0; k < kBatch; ++k) {
-        const uint32_t l = li[k], m = mm[k];
-        if (l == 0xffffffffu) continue;
-        if (fid && 2ull * m > T && m > short_max) {  // majority list: only its bitmap of holders is kept
-          ++nh;
-          atomicOr(&fbits[(size_t)tg[k] * fwords + (t >> 5)], 1u << (t & 31));
-        } else if (m > short_max) {
-          ++nl;
-          atomicAdd(&bcnt[(size_t)tg[k] * NB + (t >> block_log2)], 1u);
-        } else if (m >= 2) {
-          sraw[tg[k] + atomicAdd(&sfill[l], 1u)] = t;
-        }
+    for (uint64_t e = e0 + sub; e < e1; e += G) {
+      const uint32_t l = ent[e];
+      if (l == 0xffffffffu) continue;
+      const uint32_t m = lcnt[l];
+      if (fid && 2ull * m > T && m > short_max) {  // majority list: only its bitmap of holders is kept
+        ++nh;
+        atomicOr(&fbits[(size_t)fid[l] * fwords + (t >> 5)], 1u << (t & 31));
+      } else if (m > short_max) {
+        ++nl;
+        atomicAdd(&bcnt[(size_t)llid[l] * NB + (t >> block_log2)], 1u);
+      } else if (m >= 2) {
+        sraw[sbase[l] + atomicAdd(&sfill[l], 1u)] = t;
       }
     }
     __syncwarp();
@@ -498,33 +460,21 @@ __global__ void __launch_bounds__(256) bucket_fill_kernel(const uint64_t* __rest
     uint32_t len = (uint32_t)(e1 - e0);  // the longest tree of the warp sets the (warp-uniform) trip count
 #pragma unroll
     for (int d = 16; d; d >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, d));
-    constexpr int kBatch = 4;  // as in the counting kernels: the loads of kBatch entries per lane in independent rounds
-    for (uint64_t i = 0; i < len; i += (uint64_t)G * kBatch) {
-      uint32_t li[kBatch], cc[kBatch], lls[kBatch], bo[kBatch];
-#pragma unroll
-      for (int k = 0; k < kBatch; ++k) {
-        const uint64_t e = e0 + i + (uint64_t)k * G + sub;
-        li[k] = e < e1 ? ent[e] : 0xffffffffu;
+    for (uint64_t i = 0; i < len; i += G) {
+      const uint64_t e = e0 + i + sub;
+      uint32_t ll = 0xffffffffu;
+      if (e < e1) {
+        const uint32_t l = ent[e];
+        if (l != 0xffffffffu && lcnt[l] > short_max && !(flip && 2ull * lcnt[l] > T)) ll = llid[l];
       }
-#pragma unroll
-      for (int k = 0; k < kBatch; ++k) cc[k] = li[k] != 0xffffffffu ? lcnt[li[k]] : 0u;
-#pragma unroll
-      for (int k = 0; k < kBatch; ++k)
-        lls[k] = (cc[k] > short_max && !(flip && 2ull * cc[k] > T)) ? llid[li[k]] : 0xffffffffu;
-#pragma unroll
-      for (int k = 0; k < kBatch; ++k) bo[k] = lls[k] != 0xffffffffu ? boff[(size_t)lls[k] * NB + (t >> block_log2)] : 0u;
-#pragma unroll
-      for (int k = 0; k < kBatch; ++k) {  // entries in the order e0 + i + k G + sub: the same rlist order as one entry at a time
-        const uint32_t ll = lls[k];
-        const bool is = ll != 0xffffffffu;
-        const uint32_t bal = __ballot_sync(0xffffffffu, is) & gmask;
-        if (is) {
-          const size_t b = (size_t)ll * NB + (t >> block_log2);
-          lmem[bo[k] + (atomicSub(&bcnt[b], 1u) - 1u)] = (uint16_t)(t & ((1u << block_log2) - 1u));
-          rlist[pos + __popc(bal & lt)] = ll;
-        }
-        pos += __popc(bal);
+      const bool is = ll != 0xffffffffu;
+      const uint32_t bal = __ballot_sync(0xffffffffu, is) & gmask;
+      if (is) {
+        const size_t b = (size_t)ll * NB + (t >> block_log2);
+        lmem[boff[b] + (atomicSub(&bcnt[b], 1u) - 1u)] = (uint16_t)(t & ((1u << block_log2) - 1u));
+        rlist[pos + __popc(bal & lt)] = ll;
       }
+      pos += __popc(bal);
     }
   }
 }
