@@ -69,3 +69,30 @@ def test_deep_chain_dendrogram_text_is_iterative():
     mb = np.arange(1, m, dtype=np.uint32)
     txt = host.dendrogram_text(["t%d" % i for i in range(m)], ma, mb, np.arange(m - 1, dtype=np.float64))
     assert txt.count("Leaf") == m and txt.count("Branch") == m - 1
+
+
+def _haskell_show_double(x: float) -> str:
+    """Haskell's `show :: Double -> String` (Numeric.showFloat / floatToDigits base 10) from Python's shortest repr digits."""
+    from decimal import Decimal
+    if x == 0:
+        return "0.0"
+    sign, digits, exp = Decimal(repr(x)).as_tuple()
+    ds = "".join(map(str, digits)).rstrip("0") or "0"
+    e = len(digits) + exp          # x = 0.d1d2... * 10^e
+    if 0.1 <= x < 1e7:
+        if e <= 0:
+            return "0." + "0" * (-e) + ds
+        whole = (ds + "0" * e)[:e]
+        frac = ds[e:] or "0"
+        return whole + "." + frac
+    return ds[0] + "." + (ds[1:] or "0") + "e" + str(e - 1)
+
+
+def test_show_double_matches_haskell_rule_on_random_values():
+    rng = np.random.default_rng(11)
+    vals = np.concatenate([rng.integers(0, 1000, 200) / rng.integers(1, 400, 200),       # UPGMA-like averages
+                           rng.random(200) * 10.0 ** rng.integers(-6, 9, 200), [0.1, 0.09999999999999999, 1e7, 9999999.999999998]])
+    for v in vals:
+        v = float(v)
+        want = 'Branch %s (Leaf "p") (Leaf "q")' % _haskell_show_double(v)
+        assert host.dendrogram_text(["p", "q"], [0], [1], [v]) == want, v
