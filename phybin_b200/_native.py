@@ -189,6 +189,7 @@ def rf_lib():
         L.prf_debug_row_plan.restype = C.c_longlong
         L.prf_debug_row_plan.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, vp, C.c_uint64]
         L.prf_debug_wide_slots.argtypes = [vp, C.c_int]
+        L.prf_debug_agglo_ctas.argtypes = [vp, C.c_uint32]
         L.prf_debug_wordop_peak.argtypes = [vp, C.POINTER(C.c_double)]
         L.prf_debug_scan.argtypes = [vp, vp, C.c_uint64, vp, vp]
         L.prf_debug_sort.argtypes = [vp, vp, vp, C.c_uint32, C.c_int]

@@ -374,6 +374,12 @@ PRF_API long long prf_debug_row_plan(uint32_t T, uint64_t p_begin, uint64_t p_en
   return (long long)rows.size();
 }
 
+PRF_API int prf_debug_agglo_ctas(prf_ctx* h, uint32_t n) {
+  if (!h) return PRF_E_INVALID;
+  h->c.debug_agglo_ctas = n;
+  return PRF_OK;
+}
+
 PRF_API int prf_debug_wide_slots(prf_ctx* h, int on) {
   if (!h) return PRF_E_INVALID;
   h->c.debug_wide_slots = on != 0;

@@ -241,6 +241,7 @@ struct Ctx {
   int rows_cfg = 0;                   // tests / tuning: instantiation of the rows kernel
   bool debug_no_flip = false;         // tests: keep majority lists as they are
   bool debug_wide_slots = false;      // tests: force the 8-byte-slot dedup table
+  uint32_t debug_agglo_ctas = 0;      // tuning: CTAs of the agglomeration kernel (0 = default)
   DevBuf<unsigned long long> timing;  // PRF_TIMING builds only
   uint32_t timing_grid = 0;
   // ctx-owned result of the last compute

@@ -18,6 +18,7 @@ int run_agglo(Ctx* ctx, const uint16_t* src, uint64_t src_begin, uint32_t T, con
   constexpr uint32_t E = AggloVal<Tv>::kPerVec;
   const uint32_t ld = (m + E - 1) / E * E;
   uint32_t G = std::min<uint32_t>((uint32_t)ctx->sm_count, (m + 15) / 16);
+  if (ctx->debug_agglo_ctas) G = std::max<uint32_t>(1, std::min<uint32_t>(G, ctx->debug_agglo_ctas));
   const uint32_t R0 = (m + G - 1) / G;
   const size_t smem = (size_t)R0 * 20 + 512 + 4 + 128 + 256;
   PRF_CK(ctx, cudaFuncSetAttribute(agglo_kernel<Tv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
