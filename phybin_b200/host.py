@@ -227,6 +227,42 @@ def dendrogram_text(names: Sequence[str], merge_a, merge_b, merge_d) -> str:
         L.phb_free_buf(p)
 
 
+def slice_dendrogram(m: int, merge_a, merge_b, merge_d, thresh: float) -> np.ndarray:
+    """sliceDendro thresh dendro (PhyBin.hs:415-422) on a FULL merge list: walking down from the root, a Branch whose
+    distance exceeds `thresh` is split into its children, anything else becomes one flat cluster.  Returns labels[m] =
+    smallest member of each item's cluster.  (For the monotone linkages used here this equals stopping the agglomeration
+    at the first distance > thresh, which is what prf_agglomerate / phb_agglomerate do with a finite thresh.)"""
+    n = len(merge_a)
+    if n + 1 != m:
+        raise ValueError("slice_dendrogram needs the full merge list of %d items" % m)
+    cur = list(range(m))            # node standing for each cluster key; node k < m: leaf, m + k: merge k
+    left, right = [0] * n, [0] * n
+    for k in range(n):
+        a, b = int(merge_a[k]), int(merge_b[k])
+        left[k], right[k] = cur[a], cur[b]
+        cur[a] = m + k
+    labels = np.empty(m, dtype=np.uint32)
+    stack = [(m + n - 1 if n else 0, False)]
+    while stack:                     # (node, inside a flat cluster already?)
+        node, flat = stack.pop()
+        if node < m:
+            members = [node]
+        elif not flat and merge_d[node - m] > thresh:
+            stack.append((left[node - m], False))
+            stack.append((right[node - m], False))
+            continue
+        else:
+            members, todo = [], [node]
+            while todo:
+                x = todo.pop()
+                if x < m:
+                    members.append(x)
+                else:
+                    todo += [left[x - m], right[x - m]]
+        labels[members] = min(members)
+    return labels
+
+
 def bits_to_labels(row: np.ndarray) -> Tuple[int, ...]:
     """One W-word bit set -> ascending label tuple (for tests and debugging)."""
     out = []

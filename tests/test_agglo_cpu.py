@@ -96,3 +96,16 @@ def test_show_double_matches_haskell_rule_on_random_values():
         v = float(v)
         want = 'Branch %s (Leaf "p") (Leaf "q")' % _haskell_show_double(v)
         assert host.dendrogram_text(["p", "q"], [0], [1], [v]) == want, v
+
+
+@pytest.mark.parametrize("linkage", LINK)
+def test_slice_of_the_full_dendrogram_equals_the_cut_agglomeration(linkage):
+    """sliceDendro on the full merge list (PhyBin.hs:415-422) == stopping at the first distance > thresh."""
+    rng = np.random.default_rng(23)
+    for m in (1, 2, 7, 40, 90):
+        full = _random_full(rng, m, 5)
+        sub = _packed(full)
+        _, ma, mb, md = host.agglomerate(sub, m, linkage)
+        for thresh in (-1.0, 0.0, 1.0, 2.5, 4.0, 100.0):
+            cut, _, _, _ = host.agglomerate(sub, m, linkage, thresh)
+            assert np.array_equal(host.slice_dendrogram(m, ma, mb, md, thresh), cut), (m, thresh)
