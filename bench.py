@@ -174,7 +174,7 @@ def run_reference(args, wl, wl_name):
     if hashrf:
         _, off = f.all_bips()
     else:
-        _, _, off = f.clades()
+        _, off, _ = f.raw_clades()
     cfg = workload_config(wl, wl_name, wl["editdist"], int(off[-1]), f.words)
     del f, off
     for _ in range(args.warmup):
